@@ -1,0 +1,189 @@
+/* pecs_b200.h -- C ABI of the B200-native PECS per-step IMEX path.
+ *
+ * The reference (mdh266/PECS) has no plugin / FFI layer: its seam is the five argument-less private methods the
+ * time loop calls (reference source/SolarCell.cpp:2057-2075), which talk through public members of the
+ * Carrier / CarrierPair / PoissonData structs.  This header is the C boundary a host that owns
+ * those structs (deal.II in the reference; pecs_b200/csrc/host in this repository) binds instead:
+ *
+ *   one-time  : pecs_ctx_create()  <- everything the reference has after setup_dofs / setup_mappings /
+ *               assemble_Poisson_matrix / assemble_LDG_system (reference source/SolarCell.cpp:1933-1959).
+ *               The LU factorisation the reference does in set_solvers (source/SolarCell.cpp:1964,
+ *               source/Carrier.cpp:26-32, source/Poisson.cpp:92-96) happens inside.
+ *   per step  : the five calls below, 1:1 with the reference methods, or pecs_step() for all five, N times.
+ *
+ * Conventions: plain pointers and sizes, caller-owned host buffers (copied during the call), context-owned
+ * device memory, fp64 everywhere, int32 indices.  Vectors use the reference's component-wise block layout:
+ * carriers [Jx | Jy | rho] with 4 nodal values per cell per block (source/CarrierPair.cpp:29-33), Poisson
+ * [RT0 fluxes | potentials] (source/Poisson.cpp:25-28).  Every function returns a pecs_status; no exception
+ * crosses the boundary; pecs_last_error() gives the message of the calling thread's last failure.
+ * A context is not re-entrant; different contexts (e.g. one per applied bias) are independent.
+ * There is NO CPU fallback: without a CUDA device pecs_ctx_create fails with PECS_ERR_NO_DEVICE.
+ */
+#ifndef PECS_B200_H
+#define PECS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PECS_OK = 0,
+  PECS_ERR_INVALID = 1,   /* bad argument / inconsistent tables */
+  PECS_ERR_NO_DEVICE = 2, /* no CUDA device: there is no CPU fallback */
+  PECS_ERR_CUDA = 3,      /* a CUDA runtime call or kernel failed */
+  PECS_ERR_SINGULAR = 4,  /* a pivot block of a fixed matrix could not be inverted */
+  PECS_ERR_INTERNAL = 5
+} pecs_status;
+
+/* boundary ids, reference include/Grid.hpp:141-147 */
+enum { PECS_INTERFACE = 0, PECS_DIRICHLET = 1, PECS_NEUMANN = 2, PECS_SCHOTTKY = 3 };
+
+/* species / vector selectors */
+enum { PECS_ELECTRONS = 0, PECS_HOLES = 1, PECS_REDUCTANTS = 2, PECS_OXIDANTS = 3, PECS_POISSON = 4 };
+
+/* which right-hand-side functors the kernels evaluate: the production ones (reference
+ * source/SolarCell.cpp:1073-1726, 487-815) or the manufactured-solution ones of the reference's convergence
+ * tests (source/LDG.cpp:681-982, source/MixedFEM.cpp:166-254, source/SolarCell.cpp:2105-2330). */
+enum {
+  PECS_KIND_PRODUCTION = 0,
+  PECS_KIND_TEST_STEADY = 1,    /* tests/Poisson_test.cpp   -> test_steady_state  */
+  PECS_KIND_TEST_TRANSIENT = 2, /* tests/IMEX_LDG_test.cpp  -> test_transient     */
+  PECS_KIND_TEST_DD_POISSON = 3 /* tests/DD_Poisson_test.cpp-> test_DD_Poisson    */
+};
+
+/* scaled scalar parameters, reference include/Parameters.hpp:181-242 and the constants of
+ * source/InitialConditions.cpp:20,43,61,79; indices into pecs_problem_desc.params */
+enum {
+  PECS_P_DELTA_T = 0,
+  PECS_P_PENALTY,      /* tau, reference source/SolarCell.cpp:1944-1945 */
+  PECS_P_MU_N, PECS_P_MU_P, PECS_P_MU_R, PECS_P_MU_O,
+  PECS_P_EPS_S, PECS_P_EPS_E,
+  PECS_P_LAMBDA2,      /* scaled_debeye_length */
+  PECS_P_K_ET, PECS_P_K_HT,
+  PECS_P_V_N, PECS_P_V_P, /* scaled recombination velocities (Schottky) */
+  PECS_P_GEN_FLUX, PECS_P_GEN_ALPHA, PECS_P_GEN_LOCATION, /* Generation, reference source/Generation.cpp:14-44 */
+  PECS_P_RHO_N_E, PECS_P_RHO_P_E, PECS_P_RHO_R_E, PECS_P_RHO_O_E,
+  PECS_P_PHI_BI, PECS_P_PHI_APP, PECS_P_PHI_SCH, PECS_P_SCH_LOCATION,
+  PECS_P_TRANSIENT,    /* transient_or_steady of assemble_LDG_system */
+  PECS_P_COUNT
+};
+
+typedef struct {
+  int32_t n;              /* rows = cols */
+  const int32_t* row_ptr; /* n+1 */
+  const int32_t* col;     /* nnz, sorted within a row */
+  const double* val;      /* nnz */
+} pecs_csr;
+
+/* one carrier subdomain = one reference triangulation + DoFHandler + CarrierPair
+ * (reference include/SolarCell.hpp:351-367, include/CarrierPair.hpp:72-108) */
+typedef struct {
+  int32_t n_cells;
+  const double* vertices;        /* [n_cells][4][2], deal.II lexicographic vertex order */
+  const int32_t* poisson_cell;   /* [n_cells] matched Poisson cell: s_2_p_map / e_2_p_map, SolarCell.cpp:308-369 */
+  int32_t n_boundary_faces;      /* faces with at_boundary() */
+  const int32_t* bface_cell;     /* [n_boundary_faces] */
+  const int32_t* bface_face;     /* [n_boundary_faces] local face number 0..3 */
+  const int32_t* bface_id;       /* [n_boundary_faces] boundary id */
+  pecs_csr system_matrix[2];     /* Carrier::system_matrix of carrier_1, carrier_2 (12*n_cells rows) */
+} pecs_domain_desc;
+
+/* PoissonData (reference include/Poisson.hpp:44-83) on the Poisson triangulation */
+typedef struct {
+  int32_t n_cells;
+  const double* vertices;        /* [n_cells][4][2] */
+  int32_t n_rt;                  /* number of RT0 flux dofs; potential of cell c is dof n_rt + c */
+  const int32_t* face_dof;       /* [n_cells][4] global flux dof of each face */
+  int32_t n_boundary_faces;
+  const int32_t* bface_cell;
+  const int32_t* bface_face;
+  const int32_t* bface_id;
+  pecs_csr system_matrix;        /* constraint-condensed, as assembled by SolarCell.cpp:377-417 */
+  int32_t n_constraints;         /* ConstraintMatrix lines, reference source/Poisson.cpp:33-49 */
+  const int32_t* constraint_dof;
+  const int32_t* constraint_master; /* -1: dof = 0 */
+  const double* constraint_weight;
+} pecs_poisson_desc;
+
+/* matched interface faces, reference source/SolarCell.cpp:165-262 */
+typedef struct {
+  int32_t n_pairs;
+  const int32_t* semi_cell;
+  const int32_t* semi_face;
+  const int32_t* elec_cell;
+  const int32_t* elec_face;
+} pecs_interface_desc;
+
+typedef struct {
+  int32_t kind;         /* PECS_KIND_* */
+  int32_t full_system;  /* 0: semiconductor + Poisson only (the manufactured tests), 1: both subdomains */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t reserved;
+  double params[32];    /* PECS_P_* */
+  pecs_domain_desc semiconductor;
+  pecs_domain_desc electrolyte; /* ignored unless full_system */
+  pecs_poisson_desc poisson;
+  pecs_interface_desc interface_pairs;
+} pecs_problem_desc;
+
+typedef struct pecs_ctx pecs_ctx;
+
+const char* pecs_last_error(void);
+/* number of CUDA devices visible to the library (0 when there is none or the driver is missing) */
+int32_t pecs_device_count(void);
+
+/* replaces: end of setup + SolarCellProblem::set_solvers, reference source/SolarCell.cpp:1733-1747 */
+pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out);
+void pecs_ctx_destroy(pecs_ctx* ctx);
+
+/* host <-> device copies of Carrier::solution / PoissonData::solution / ::system_rhs; which = PECS_ELECTRONS..PECS_POISSON */
+pecs_status pecs_set_state(pecs_ctx* ctx, int32_t which, const double* solution);
+pecs_status pecs_get_state(pecs_ctx* ctx, int32_t which, double* solution);
+pecs_status pecs_get_rhs(pecs_ctx* ctx, int32_t which, double* system_rhs);
+pecs_status pecs_set_rhs(pecs_ctx* ctx, int32_t which, const double* system_rhs);
+int32_t pecs_n_dofs(const pecs_ctx* ctx, int32_t which);
+
+/* time of the manufactured right-hand sides (Function::set_time in the reference's tests) */
+pecs_status pecs_set_time(pecs_ctx* ctx, double time);
+
+/* replaces SolarCellProblem::assemble_semiconductor_rhs, reference source/SolarCell.cpp:1037-1414 */
+pecs_status pecs_assemble_semiconductor_rhs(pecs_ctx* ctx);
+/* replaces SolarCellProblem::assemble_electrolyte_rhs, reference source/SolarCell.cpp:1417-1726 */
+pecs_status pecs_assemble_electrolyte_rhs(pecs_ctx* ctx);
+/* replaces SolarCellProblem::solve_full_system -> Carrier::solve x4, source/SolarCell.cpp:1758-1782, source/Carrier.cpp:34-40 */
+pecs_status pecs_solve_full_system(pecs_ctx* ctx);
+/* one species only (the manufactured tests call carrier_1.solve() directly, source/SolarCell.cpp:2934, 3077) */
+pecs_status pecs_solve_species(pecs_ctx* ctx, int32_t which);
+/* replaces SolarCellProblem::assemble_Poisson_rhs, reference source/SolarCell.cpp:430-815 */
+pecs_status pecs_assemble_poisson_rhs(pecs_ctx* ctx);
+/* replaces SolarCellProblem::solve_Poisson -> PoissonData::solve, source/SolarCell.cpp:1750-1756, source/Poisson.cpp:98-105 */
+pecs_status pecs_solve_poisson(pecs_ctx* ctx);
+/* n_steps iterations of the body of the time loop (reference source/SolarCell.cpp:2055-2080), captured in a CUDA graph */
+pecs_status pecs_step(pecs_ctx* ctx, int32_t n_steps);
+/* all five calls above return after enqueueing; this waits for the context's streams */
+pecs_status pecs_synchronize(pecs_ctx* ctx);
+
+/* measurement support for bench.py: run n_steps and report device times measured with CUDA events on the
+ * context's own streams.  ms[0] = whole region, ms[1..5] = the reference's five TimerOutput sections
+ *  summed over the steps when sectioned != 0 (sections are then serialised), else 0. */
+pecs_status pecs_step_timed(pecs_ctx* ctx, int32_t n_steps, int32_t sectioned, double ms[6]);
+/* repeat one kernel class in isolation: which = 0 carrier RHS (both subdomains), 1 Poisson RHS, 2 carrier solves,
+ * 3 Poisson solve; returns average ms per launch group and the number of kernel launches in one group */
+pecs_status pecs_time_kernel(pecs_ctx* ctx, int32_t which, int32_t repeats, double* avg_ms, int32_t* launches);
+
+/* integer facts about the context: see PECS_INFO_* */
+enum {
+  PECS_INFO_LAUNCHES_PER_STEP = 0,
+  PECS_INFO_FACTOR_BYTES = 1,      /* bytes of all factor tables resident in HBM */
+  PECS_INFO_SOLVE_BYTES_PER_STEP = 2, /* factor bytes streamed by the five solves of one step */
+  PECS_INFO_TREE_LEVELS_MAX = 3,
+  PECS_INFO_RHS_BYTES_PER_STEP = 4 /* algorithmic bytes of the carrier + Poisson RHS kernels of one step */
+};
+int64_t pecs_get_info(const pecs_ctx* ctx, int32_t what);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PECS_B200_H */

@@ -1,0 +1,81 @@
+// Csr.hpp -- minimal compressed-sparse-row matrix for the fixed system matrices
+// (stands in for dealii::SparseMatrix<double> + SparsityPattern on the host side).
+#pragma once
+#include <algorithm>
+#include <cstddef>
+#include <numeric>
+#include <vector>
+
+namespace pecs {
+
+struct CsrMatrix {
+  int n = 0;
+  std::vector<int> row_ptr; // n+1
+  std::vector<int> col;
+  std::vector<double> val;
+  size_t nnz() const { return col.size(); }
+
+  void vmult(double* y, const double* x) const {
+    for (int i = 0; i < n; ++i) {
+      double s = 0;
+      for (int k = row_ptr[i]; k < row_ptr[i + 1]; ++k) s += val[k] * x[col[k]];
+      y[i] = s;
+    }
+  }
+};
+
+// Triplet accumulator; duplicates are summed in insertion order when compressed.
+class TripletList {
+public:
+  explicit TripletList(int n) : n_(n) {}
+  void add(int i, int j, double v) {
+    r_.push_back(i);
+    c_.push_back(j);
+    v_.push_back(v);
+  }
+  void reserve(size_t m) {
+    r_.reserve(m);
+    c_.reserve(m);
+    v_.reserve(m);
+  }
+  CsrMatrix compress(bool drop_zeros = false) const {
+    CsrMatrix A;
+    A.n = n_;
+    std::vector<int> cnt(n_ + 1, 0);
+    for (int i : r_) ++cnt[i + 1];
+    std::partial_sum(cnt.begin(), cnt.end(), cnt.begin());
+    std::vector<int> pos(cnt.begin(), cnt.end() - 1), tc(r_.size());
+    std::vector<double> tv(r_.size());
+    for (size_t k = 0; k < r_.size(); ++k) { // stable bucket by row
+      const int p = pos[r_[k]]++;
+      tc[p] = c_[k];
+      tv[p] = v_[k];
+    }
+    A.row_ptr.assign(n_ + 1, 0);
+    std::vector<int> order;
+    for (int i = 0; i < n_; ++i) {
+      const int b = cnt[i], e = cnt[i + 1];
+      order.resize(e - b);
+      std::iota(order.begin(), order.end(), b);
+      std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return tc[a] < tc[c]; });
+      size_t k = 0;
+      while (k < order.size()) {
+        const int cj = tc[order[k]];
+        double s = 0;
+        while (k < order.size() && tc[order[k]] == cj) s += tv[order[k++]];
+        if (drop_zeros && s == 0.0) continue;
+        A.col.push_back(cj);
+        A.val.push_back(s);
+      }
+      A.row_ptr[i + 1] = (int)A.col.size();
+    }
+    return A;
+  }
+
+private:
+  int n_;
+  std::vector<int> r_, c_;
+  std::vector<double> v_;
+};
+
+} // namespace pecs
