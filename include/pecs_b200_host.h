@@ -68,6 +68,16 @@ pecs_status pecs_solarcell_get_host_solution(const pecs_solarcell* p, int32_t wh
 pecs_status pecs_solarcell_ldg_errors(pecs_solarcell* p, int32_t which, double time, double out[2]);
 pecs_status pecs_solarcell_mixed_errors(pecs_solarcell* p, double out[2]);
 
+/* ---- verification of the setup tables (CPU tests only; not reachable from any per-step entry point) ----
+ * Builds the nested-dissection plan of one constant matrix exactly as pecs_ctx_create does and reports its size:
+ * stats[0] fronts, [1] levels, [2] max np, [3] max nb, [4] forward-table entries, [5] backward-table entries,
+ * [6] update-buffer entries.  which: 0..3 species, 4 Poisson. */
+pecs_status pecs_solarcell_plan_stats(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, int64_t stats[8]);
+/* Additionally runs the HOST numeric factorisation and the host reference of the two solve sweeps on rhs b, so
+ * that the CPU test-suite can check plan + factor tables against the matrix (residual) without a GPU. */
+pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,
+                                                 double* x);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,83 @@
+"""Build libpecs_b200.so in-tree (pecs_b200/lib) with nvcc for sm_100a.
+
+    python -m pecs_b200.build [--force] [--jobs N]
+
+Host C++ (pecs_b200/csrc/host, error.cpp) is compiled with g++ -fopenmp, CUDA sources with
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo; the link step produces one shared library that carries the
+whole C ABI of include/pecs_b200.h and include/pecs_b200_host.h.  nvcc cross-compiles without a GPU.
+"""
+import argparse
+import concurrent.futures as cf
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "lib", "libpecs_b200.so")
+NVCC = os.environ.get("PECS_NVCC", shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc")
+HOST_CXX = os.environ.get("PECS_HOST_CXX", "/usr/bin/g++")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-fopenmp,-O3",
+                     "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+CXX_FLAGS = ["-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-std=c++17", "-Wall", "-I/usr/local/cuda/include"]
+
+
+def sources():
+    cpp = sorted(glob.glob(os.path.join(CSRC, "host", "*.cpp"))) + [os.path.join(CSRC, "error.cpp")]
+    cu = sorted(glob.glob(os.path.join(CSRC, "cuda", "*.cu")))
+    return cpp, cu
+
+
+def headers():
+    pats = ["*.hpp", "*.cuh", "host/*.hpp", "cuda/*.cuh", "../../include/*.h"]
+    return [h for p in pats for h in glob.glob(os.path.join(CSRC, p))]
+
+
+def compile_one(src, force, newest_header):
+    obj = os.path.join(OBJ, os.path.relpath(src, CSRC).replace(os.sep, "_") + ".o")
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), newest_header):
+        return obj, ""
+    if src.endswith(".cu"):
+        cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    else:
+        cmd = [HOST_CXX] + CXX_FLAGS + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"compile failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return obj, r.stderr
+
+
+def build(force=False, jobs=None, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cpp, cu = sources()
+    newest_header = max(os.path.getmtime(h) for h in headers())
+    with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count()) as ex:
+        results = list(ex.map(lambda s: compile_one(s, force, newest_header), cpp + cu))
+    objs = [o for o, _ in results]
+    log = "\n".join(e for _, e in results if e)
+    if verbose and log:
+        print(log)
+    with open(os.path.join(OBJ, "ptxas.log"), "a") as f:
+        f.write(log)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
+        cmd = [NVCC] + ARCH + ["-shared", "-ccbin", HOST_CXX, "-Xcompiler", "-fopenmp", "-o", LIB] + objs + \
+              ["-lcublas", "-lcusolver", "-lgomp"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--jobs", type=int, default=None)
+    ap.add_argument("-v", "--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(a.force, a.jobs, a.verbose))

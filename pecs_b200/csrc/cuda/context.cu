@@ -1,0 +1,727 @@
+// context.cu -- pecs_ctx and the device half of the C ABI (include/pecs_b200.h).
+//
+// A context owns, in HBM: the SoA mesh tables of both carrier subdomains, the four carrier state / rhs vectors and
+// the Poisson state / rhs, the factor tables of the five constant systems, and the work vectors of the solves.
+// Stream layout of one IMEX step (captured once into a CUDA graph, pecs_step replays it):
+//
+//   main : cell+face RHS (semiconductor) -> cell+face RHS (electrolyte) --+--> [join] -> Poisson RHS -> Poisson solve
+//   s0..s3 (fork after the RHS kernels): the four carrier solves, concurrent --+            -> distribute
+//
+// All RHS kernels must finish before any solve writes a solution: the interface terms of one subdomain read the
+// other subdomain's previous densities (reference source/SolarCell.cpp:1290-1311, 1653-1677).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "../../../include/pecs_b200.h"
+#include "../error.hpp"
+#include "../host/Csr.hpp"
+#include "../host/SolverSetup.hpp"
+#include "../host/SparseDirect.hpp"
+#include "device_util.cuh"
+#include "factor_device.cuh"
+#include "rhs_kernels.cuh"
+#include "solve_kernels.cuh"
+
+namespace pecs {
+
+// ------------------------------------------------------------------------------------------------ one factorised system
+struct DeviceSystem {
+  int n = 0;
+  SolvePlan plan;
+  DeviceBuffer<double> fwd, bwd, upd, w_in, w_fin, x_perm;
+  DeviceBuffer<int> bd_index, child_map, perm, iperm;
+  DeviceBuffer<DeviceFront> fronts;
+  struct Level {
+    DeviceBuffer<SolveTile> fwd_tiles, bwd_tiles;
+    int smem_fwd = 0, smem_bwd = 0;
+    bool vec2_fwd = true, vec2_bwd = true;
+  };
+  std::vector<Level> levels;
+  int launches_per_solve = 0;
+
+  int64_t factor_bytes() const { return (int64_t)(fwd.bytes() + bwd.bytes()); }
+  int max_smem_doubles() const {
+    int m = 0;
+    for (const Level& l : levels) m = std::max(m, std::max(l.smem_fwd, l.smem_bwd));
+    return m;
+  }
+
+  void build(const CsrMatrix& A, const NodeLayout& layout, int leaf_nodes, bool factor_on_device) {
+    n = A.n;
+    plan = build_solve_plan(A, layout.node_of_dof, layout.x, layout.y, leaf_nodes);
+    const int nf = (int)plan.fronts.size();
+    std::vector<DeviceFront> df(nf);
+    for (int f = 0; f < nf; ++f) {
+      const Front& F = plan.fronts[f];
+      DeviceFront& D = df[f];
+      D.np = F.np;
+      D.nb = F.nb;
+      D.p0 = F.p0;
+      D.bd_off = F.bd_off;
+      D.fwd_off = F.fwd_off;
+      D.bwd_off = F.bwd_off;
+      D.upd_off = F.upd_off;
+      for (int k = 0; k < 2; ++k) {
+        D.has_child[k] = F.child[k] >= 0;
+        D.cmap_off[k] = F.cmap_off[k];
+        D.child_upd_off[k] = F.child[k] >= 0 ? plan.fronts[F.child[k]].upd_off : 0;
+      }
+    }
+    fronts.upload(df);
+    bd_index.upload(plan.bd_index);
+    child_map.upload(plan.child_map);
+    perm.upload(plan.perm);
+    iperm.upload(plan.iperm);
+    upd.resize((size_t)std::max<int64_t>(plan.upd_entries, 1));
+    upd.zero();
+    w_in.resize(n);
+    w_fin.resize(n);
+    x_perm.resize(n);
+    fwd.resize((size_t)std::max<int64_t>(plan.fwd_entries, 2));
+    bwd.resize((size_t)std::max<int64_t>(plan.bwd_entries, 2));
+    if (factor_on_device) {
+      factorize_device(plan, A, fronts.get(), bd_index.get(), perm.get(), fwd.get(), bwd.get());
+    } else {
+      std::vector<double> hf, hb;
+      factorize_host(plan, A, hf, hb);
+      hf.resize(fwd.size(), 0.0);
+      hb.resize(bwd.size(), 0.0);
+      fwd.upload(hf);
+      bwd.upload(hb);
+    }
+    // tile lists per level
+    levels.resize(plan.levels.size());
+    launches_per_solve = 2; // the two permutation gathers
+    for (size_t d = 0; d < plan.levels.size(); ++d) {
+      std::vector<SolveTile> ft, bt;
+      Level& L = levels[d];
+      for (int f : plan.levels[d]) {
+        const Front& F = plan.fronts[f];
+        const int m = F.np + F.nb;
+        L.smem_fwd = std::max(L.smem_fwd, F.np);
+        L.smem_bwd = std::max(L.smem_bwd, m);
+        if (F.np & 1) L.vec2_fwd = false;
+        if (m & 1) L.vec2_bwd = false;
+        int first = 1;
+        for (int r0 = 0; r0 < std::max(F.nb, 1); r0 += kSolveRowsPerTile) {
+          ft.push_back(SolveTile{f, r0, std::max(0, std::min(kSolveRowsPerTile, F.nb - r0)), first});
+          first = 0;
+        }
+        for (int r0 = 0; r0 < F.np; r0 += kSolveRowsPerTile)
+          bt.push_back(SolveTile{f, r0, std::min(kSolveRowsPerTile, F.np - r0), 0});
+      }
+      L.smem_fwd += L.smem_fwd & 1;
+      L.smem_bwd += L.smem_bwd & 1;
+      L.fwd_tiles.upload(ft);
+      L.bwd_tiles.upload(bt);
+      launches_per_solve += 2;
+    }
+  }
+
+  // solution = A^-1 rhs, all on stream s
+  void solve(const double* rhs, double* solution, cudaStream_t s) {
+    const SolveTables t{fronts.get(), bd_index.get(), child_map.get(), fwd.get(), bwd.get()};
+    launch_gather(n, iperm.get(), rhs, w_in.get(), s);
+    for (int d = (int)levels.size() - 1; d >= 0; --d)
+      launch_forward_level(t, levels[d].fwd_tiles.get(), (int)levels[d].fwd_tiles.size(), levels[d].smem_fwd,
+                           levels[d].vec2_fwd, w_in.get(), w_fin.get(), upd.get(), s);
+    for (size_t d = 0; d < levels.size(); ++d)
+      launch_backward_level(t, levels[d].bwd_tiles.get(), (int)levels[d].bwd_tiles.size(), levels[d].smem_bwd,
+                            levels[d].vec2_bwd, w_fin.get(), x_perm.get(), s);
+    launch_gather(n, perm.get(), x_perm.get(), solution, s);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ one carrier subdomain
+struct DeviceDomain {
+  int n_cells = 0, n_bcells = 0;
+  DeviceBuffer<double> vx, vy;
+  DeviceBuffer<int> rt_dof, phi_dof, bcell, bface_id, bnb_cell, bnb_face;
+  DeviceBuffer<double> solution[2], rhs[2];
+  DeviceSystem system[2];
+  DomainView view{};
+  RhsParams prm{};
+  int n_dofs() const { return 12 * n_cells; }
+};
+
+} // namespace pecs
+
+using namespace pecs;
+
+struct pecs_ctx {
+  int device = 0, kind = 0;
+  bool full = true;
+  double params[32] = {};
+  DeviceDomain dom[2];
+  // Poisson
+  int n_rt = 0, n_pcells = 0, n_constraints = 0;
+  DeviceBuffer<double> p_solution, p_rhs, p_static;
+  DeviceBuffer<int> c_dof, c_master;
+  DeviceBuffer<double> c_weight;
+  DeviceSystem p_system;
+  // streams / graph
+  cudaStream_t main = nullptr, side[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaGraphExec_t step_graph = nullptr;
+  DeviceBuffer<char> l2_flush;
+
+  int n_pdofs() const { return n_rt + n_pcells; }
+  int n_domains() const { return full ? 2 : 1; }
+
+  ~pecs_ctx() {
+    cudaSetDevice(device);
+    if (step_graph) cudaGraphExecDestroy(step_graph);
+    for (cudaEvent_t e : join)
+      if (e) cudaEventDestroy(e);
+    if (fork) cudaEventDestroy(fork);
+    for (cudaStream_t s : side)
+      if (s) cudaStreamDestroy(s);
+    if (main) cudaStreamDestroy(main);
+  }
+};
+
+namespace {
+
+template <class F>
+pecs_status guarded(F&& f) {
+  try {
+    f();
+    return PECS_OK;
+  } catch (const StatusError& e) {
+    set_last_error(e.what());
+    return e.status;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return PECS_ERR_INTERNAL;
+  }
+}
+
+void require(bool ok, const char* what) {
+  if (!ok) throw StatusError(PECS_ERR_INVALID, what);
+}
+
+CsrMatrix copy_csr(const pecs_csr& a, int expected_n, const char* name) {
+  require(a.n == expected_n && a.row_ptr && a.col && a.val, name);
+  CsrMatrix A;
+  A.n = a.n;
+  A.row_ptr.assign(a.row_ptr, a.row_ptr + a.n + 1);
+  const size_t nnz = (size_t)A.row_ptr[a.n];
+  A.col.assign(a.col, a.col + nnz);
+  A.val.assign(a.val, a.val + nnz);
+  return A;
+}
+
+void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pecs_poisson_desc& P,
+                  const pecs_interface_desc& I, bool factor_on_device) {
+  DeviceDomain& D = ctx.dom[which];
+  const int n = d.n_cells;
+  require(n > 0 && d.vertices && d.poisson_cell, "domain: empty mesh tables");
+  D.n_cells = n;
+  std::vector<double> vx(4 * (size_t)n), vy(4 * (size_t)n);
+  std::vector<int> rt(4 * (size_t)n), phi(n);
+  for (int c = 0; c < n; ++c) {
+    const int pc = d.poisson_cell[c];
+    require(pc >= 0 && pc < P.n_cells, "domain: poisson_cell out of range");
+    for (int a = 0; a < 4; ++a) {
+      vx[(size_t)a * n + c] = d.vertices[8 * (size_t)c + 2 * a];
+      vy[(size_t)a * n + c] = d.vertices[8 * (size_t)c + 2 * a + 1];
+      rt[(size_t)a * n + c] = P.face_dof[4 * (size_t)pc + a];
+    }
+    phi[c] = P.n_rt + pc;
+  }
+  D.vx.upload(vx);
+  D.vy.upload(vy);
+  D.rt_dof.upload(rt);
+  D.phi_dof.upload(phi);
+  // boundary faces grouped by cell
+  std::map<int, int> record_of;
+  std::vector<int> bcell, bid, nbc, nbf;
+  for (int k = 0; k < d.n_boundary_faces; ++k) {
+    const int c = d.bface_cell[k], f = d.bface_face[k];
+    require(c >= 0 && c < n && f >= 0 && f < 4, "domain: boundary face out of range");
+    auto it = record_of.find(c);
+    if (it == record_of.end()) {
+      it = record_of.emplace(c, (int)bcell.size()).first;
+      bcell.push_back(c);
+      bid.insert(bid.end(), {-1, -1, -1, -1});
+      nbc.push_back(-1);
+      nbf.push_back(0);
+    }
+    bid[4 * (size_t)it->second + f] = d.bface_id[k];
+  }
+  if (ctx.full)
+    for (int k = 0; k < I.n_pairs; ++k) {
+      const int c = which == 0 ? I.semi_cell[k] : I.elec_cell[k];
+      auto it = record_of.find(c);
+      require(it != record_of.end(), "interface pair refers to a cell without boundary faces");
+      nbc[it->second] = which == 0 ? I.elec_cell[k] : I.semi_cell[k];
+      nbf[it->second] = which == 0 ? I.elec_face[k] : I.semi_face[k];
+    }
+  if (ctx.kind == PECS_KIND_PRODUCTION)
+    for (size_t r = 0; r < bcell.size(); ++r)
+      for (int f = 0; f < 4; ++f)
+        if (bid[4 * r + f] == PECS_INTERFACE) require(nbc[r] >= 0, "interface face without a matched neighbour");
+  D.n_bcells = (int)bcell.size();
+  D.bcell.upload(bcell);
+  D.bface_id.upload(bid);
+  D.bnb_cell.upload(nbc);
+  D.bnb_face.upload(nbf);
+  for (int k = 0; k < 2; ++k) {
+    D.solution[k].resize((size_t)D.n_dofs());
+    D.solution[k].zero();
+    D.rhs[k].resize((size_t)D.n_dofs());
+    D.rhs[k].zero();
+  }
+  D.view = DomainView{n,          D.vx.get(),       D.vy.get(),       D.rt_dof.get(),  D.phi_dof.get(),
+                      D.n_bcells, D.bcell.get(), D.bface_id.get(), D.bnb_cell.get(), D.bnb_face.get()};
+  // factorise the two fixed carrier matrices
+  const NodeLayout layout = carrier_nodes(d);
+  for (int k = 0; k < 2; ++k) {
+    if (ctx.kind != PECS_KIND_PRODUCTION && k == 1) break; // the manufactured tests only solve carrier_1
+    const CsrMatrix A = copy_csr(d.system_matrix[k], 12 * n, "domain: system matrix size");
+    D.system[k].build(A, layout, default_leaf_nodes(false), factor_on_device);
+  }
+}
+
+void fill_rhs_params(pecs_ctx& ctx) {
+  const double* p = ctx.params;
+  for (int w = 0; w < 2; ++w) {
+    RhsParams& r = ctx.dom[w].prm;
+    r.kind = ctx.kind;
+    r.is_semiconductor = w == 0;
+    r.inv_dt = 1.0 / p[PECS_P_DELTA_T];
+    r.tau = p[PECS_P_PENALTY];
+    r.charge1 = -1.0; // reference SolarCell.cpp:54,59,71,76
+    r.charge2 = 1.0;
+    r.inv_eps = 1.0 / (w == 0 ? p[PECS_P_EPS_S] : p[PECS_P_EPS_E]);
+    r.gen_scale = w == 0 ? p[PECS_P_GEN_ALPHA] * p[PECS_P_GEN_FLUX] : 0.0;
+    r.gen_alpha = p[PECS_P_GEN_ALPHA];
+    r.gen_location = p[PECS_P_GEN_LOCATION];
+    r.rho1_e = w == 0 ? p[PECS_P_RHO_N_E] : p[PECS_P_RHO_R_E];
+    r.rho2_e = w == 0 ? p[PECS_P_RHO_P_E] : p[PECS_P_RHO_O_E];
+    r.other1_e = p[PECS_P_RHO_N_E];
+    r.other2_e = p[PECS_P_RHO_P_E];
+    r.k_et = p[PECS_P_K_ET];
+    r.k_ht = p[PECS_P_K_HT];
+    r.v_n = p[PECS_P_V_N];
+    r.v_p = p[PECS_P_V_P];
+    r.doping = w == 0 ? p[PECS_P_RHO_N_E] - p[PECS_P_RHO_P_E] : 0.0; // N_D = electrons_e, N_A = holes_e (SolarCell.cpp:542-548)
+    r.time = 0.0;
+  }
+}
+
+void sync_all(pecs_ctx* ctx) {
+  PECS_CUDA(cudaSetDevice(ctx->device));
+  PECS_CUDA(cudaStreamSynchronize(ctx->main));
+  for (cudaStream_t s : ctx->side) PECS_CUDA(cudaStreamSynchronize(s));
+}
+
+double* vector_of(pecs_ctx* ctx, int which, bool rhs) {
+  if (which == PECS_POISSON) return rhs ? ctx->p_rhs.get() : ctx->p_solution.get();
+  require(which >= 0 && which <= 3, "vector selector must be PECS_ELECTRONS..PECS_POISSON");
+  require(which < 2 || ctx->full, "electrolyte vectors do not exist in a semiconductor-only context");
+  DeviceDomain& D = ctx->dom[which / 2];
+  return rhs ? D.rhs[which % 2].get() : D.solution[which % 2].get();
+}
+int n_dofs_of(const pecs_ctx* ctx, int which) {
+  if (which == PECS_POISSON) return ctx->n_pdofs();
+  if (which < 0 || which > 3 || (which >= 2 && !ctx->full)) return 0;
+  return ctx->dom[which / 2].n_dofs();
+}
+
+// ---- enqueue helpers (no synchronisation) ----
+void enqueue_carrier_rhs(pecs_ctx* ctx, int w, cudaStream_t s) {
+  DeviceDomain& D = ctx->dom[w];
+  DeviceDomain& O = ctx->dom[1 - w];
+  launch_carrier_cell_rhs(D.view, D.prm, D.solution[0].get(), D.solution[1].get(), ctx->p_solution.get(), D.rhs[0].get(),
+                          D.rhs[1].get(), s);
+  launch_carrier_boundary_rhs(D.view, O.view, D.prm, D.solution[0].get(), D.solution[1].get(), O.solution[0].get(),
+                              O.solution[1].get(), D.rhs[0].get(), D.rhs[1].get(), s);
+}
+void enqueue_poisson_rhs(pecs_ctx* ctx, cudaStream_t s) {
+  // flux rows: the static Dirichlet data; potential rows: the charge integrals
+  PECS_CUDA(cudaMemcpyAsync(ctx->p_rhs.get(), ctx->p_static.get(), ctx->p_rhs.bytes(), cudaMemcpyDeviceToDevice, s));
+  for (int w = 0; w < ctx->n_domains(); ++w) {
+    DeviceDomain& D = ctx->dom[w];
+    launch_poisson_cell_rhs(D.view, D.prm, D.solution[0].get(), D.solution[1].get(), ctx->p_rhs.get(), s);
+  }
+}
+void enqueue_poisson_solve(pecs_ctx* ctx, cudaStream_t s) {
+  ctx->p_system.solve(ctx->p_rhs.get(), ctx->p_solution.get(), s);
+  launch_distribute(ctx->n_constraints, ctx->c_dof.get(), ctx->c_master.get(), ctx->c_weight.get(),
+                    ctx->p_solution.get(), s);
+}
+void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s) {
+  DeviceDomain& D = ctx->dom[which / 2];
+  require(D.system[which % 2].n > 0, "this species has no factorised system in this context");
+  D.system[which % 2].solve(D.rhs[which % 2].get(), D.solution[which % 2].get(), s);
+}
+void enqueue_full_solve(pecs_ctx* ctx) {
+  // four concurrent solves, reference SolarCell.cpp:1763-1781 (Threads::new_task x4 + join_all)
+  const int n_species = ctx->full ? 4 : (ctx->kind == PECS_KIND_PRODUCTION ? 2 : 1);
+  PECS_CUDA(cudaEventRecord(ctx->fork, ctx->main));
+  for (int k = 0; k < n_species; ++k) {
+    PECS_CUDA(cudaStreamWaitEvent(ctx->side[k], ctx->fork, 0));
+    enqueue_species_solve(ctx, k, ctx->side[k]);
+    PECS_CUDA(cudaEventRecord(ctx->join[k], ctx->side[k]));
+    PECS_CUDA(cudaStreamWaitEvent(ctx->main, ctx->join[k], 0));
+  }
+}
+void enqueue_step(pecs_ctx* ctx) {
+  for (int w = 0; w < ctx->n_domains(); ++w) enqueue_carrier_rhs(ctx, w, ctx->main);
+  enqueue_full_solve(ctx);
+  enqueue_poisson_rhs(ctx, ctx->main);
+  enqueue_poisson_solve(ctx, ctx->main);
+}
+int launches_per_step(const pecs_ctx* ctx) {
+  int n = 0;
+  for (int w = 0; w < ctx->n_domains(); ++w) {
+    n += 2 + 1; // cell + boundary + Poisson cell kernels
+    for (int k = 0; k < 2; ++k)
+      if (ctx->dom[w].system[k].n > 0) n += ctx->dom[w].system[k].launches_per_solve;
+  }
+  n += ctx->p_system.launches_per_solve + (ctx->n_constraints > 0 ? 1 : 0);
+  return n;
+}
+void build_step_graph(pecs_ctx* ctx) {
+  cudaGraph_t graph = nullptr;
+  PECS_CUDA(cudaStreamBeginCapture(ctx->main, cudaStreamCaptureModeThreadLocal));
+  try {
+    enqueue_step(ctx);
+  } catch (...) {
+    cudaStreamEndCapture(ctx->main, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  PECS_CUDA(cudaStreamEndCapture(ctx->main, &graph));
+  PECS_CUDA(cudaGraphInstantiate(&ctx->step_graph, graph, 0));
+  PECS_CUDA(cudaGraphDestroy(graph));
+}
+
+} // namespace
+
+extern "C" {
+
+int32_t pecs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
+  return guarded([&] {
+    require(desc && out, "pecs_ctx_create: NULL argument");
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+      cudaGetLastError();
+      throw StatusError(PECS_ERR_NO_DEVICE,
+                        "pecs_ctx_create: no CUDA device visible; pecs_b200 has no CPU fallback for the per-step path");
+    }
+    require(desc->device >= 0 && desc->device < n_dev, "pecs_ctx_create: device ordinal out of range");
+    require(desc->kind >= PECS_KIND_PRODUCTION && desc->kind <= PECS_KIND_TEST_DD_POISSON, "pecs_ctx_create: unknown kind");
+    require(desc->params[PECS_P_DELTA_T] > 0.0, "pecs_ctx_create: delta_t must be positive");
+    PECS_CUDA(cudaSetDevice(desc->device));
+    std::unique_ptr<pecs_ctx> ctx(new pecs_ctx());
+    ctx->device = desc->device;
+    ctx->kind = desc->kind;
+    ctx->full = desc->full_system != 0;
+    std::memcpy(ctx->params, desc->params, sizeof(ctx->params));
+    PECS_CUDA(cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; ++k) {
+      PECS_CUDA(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+      PECS_CUDA(cudaEventCreateWithFlags(&ctx->join[k], cudaEventDisableTiming));
+    }
+    PECS_CUDA(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
+
+    const pecs_poisson_desc& P = desc->poisson;
+    require(P.n_cells > 0 && P.vertices && P.face_dof && P.n_rt > 0, "poisson: empty tables");
+    ctx->n_rt = P.n_rt;
+    ctx->n_pcells = P.n_cells;
+    const bool factor_on_device = device_factorization_enabled();
+
+    fill_rhs_params(*ctx);
+    setup_domain(*ctx, 0, desc->semiconductor, P, desc->interface_pairs, factor_on_device);
+    if (ctx->full) setup_domain(*ctx, 1, desc->electrolyte, P, desc->interface_pairs, factor_on_device);
+
+    // Poisson vectors, constraints, static boundary data
+    const int np = ctx->n_pdofs();
+    ctx->p_solution.resize(np);
+    ctx->p_solution.zero();
+    ctx->p_rhs.resize(np);
+    ctx->p_rhs.zero();
+    ctx->p_static.resize(np);
+    ctx->p_static.zero();
+    ctx->n_constraints = P.n_constraints;
+    std::vector<int> master_of(np, -2);
+    std::vector<double> weight_of(np, 0.0);
+    for (int k = 0; k < P.n_constraints; ++k) {
+      require(P.constraint_dof[k] >= 0 && P.constraint_dof[k] < np, "poisson: constraint dof out of range");
+      master_of[P.constraint_dof[k]] = P.constraint_master[k] >= 0 ? P.constraint_master[k] : -1;
+      weight_of[P.constraint_dof[k]] = P.constraint_weight[k];
+    }
+    if (P.n_constraints > 0) {
+      ctx->c_dof.upload(P.constraint_dof, P.n_constraints);
+      ctx->c_master.upload(P.constraint_master, P.n_constraints);
+      ctx->c_weight.upload(P.constraint_weight, P.n_constraints);
+    }
+    {
+      std::vector<double> vx(4 * (size_t)P.n_cells), vy(4 * (size_t)P.n_cells);
+      for (int c = 0; c < P.n_cells; ++c)
+        for (int a = 0; a < 4; ++a) {
+          vx[(size_t)a * P.n_cells + c] = P.vertices[8 * (size_t)c + 2 * a];
+          vy[(size_t)a * P.n_cells + c] = P.vertices[8 * (size_t)c + 2 * a + 1];
+        }
+      std::vector<int> is_semi(P.n_cells, 0);
+      for (int c = 0; c < desc->semiconductor.n_cells; ++c) is_semi[desc->semiconductor.poisson_cell[c]] = 1;
+      DeviceBuffer<double> dvx, dvy, dw;
+      DeviceBuffer<int> dcell, dface, did, dsemi, dfd, dmaster;
+      dvx.upload(vx);
+      dvy.upload(vy);
+      dsemi.upload(is_semi);
+      dfd.upload(P.face_dof, 4 * (size_t)P.n_cells);
+      dmaster.upload(master_of);
+      dw.upload(weight_of);
+      if (P.n_boundary_faces > 0) {
+        dcell.upload(P.bface_cell, P.n_boundary_faces);
+        dface.upload(P.bface_face, P.n_boundary_faces);
+        did.upload(P.bface_id, P.n_boundary_faces);
+      }
+      const PoissonFaceView fv{P.n_boundary_faces, dcell.get(), dface.get(), did.get(), dsemi.get(), dvx.get(),
+                               dvy.get(),          P.n_cells,   dfd.get(),   dmaster.get(), dw.get()};
+      const PoissonFaceParams fp{ctx->kind, ctx->params[PECS_P_PHI_BI], ctx->params[PECS_P_PHI_APP],
+                                 ctx->params[PECS_P_PHI_SCH], ctx->params[PECS_P_SCH_LOCATION]};
+      launch_poisson_face_rhs(fv, fp, ctx->p_static.get(), ctx->main);
+      PECS_CUDA(cudaStreamSynchronize(ctx->main));
+    }
+    {
+      const CsrMatrix A = copy_csr(P.system_matrix, np, "poisson: system matrix size");
+      ctx->p_system.build(A, poisson_nodes(P), default_leaf_nodes(true), factor_on_device);
+    }
+    int smem = ctx->p_system.max_smem_doubles();
+    for (int w = 0; w < ctx->n_domains(); ++w)
+      for (int k = 0; k < 2; ++k) smem = std::max(smem, ctx->dom[w].system[k].max_smem_doubles());
+    int max_optin = 0;
+    PECS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    if ((size_t)smem * sizeof(double) > (size_t)max_optin)
+      throw StatusError(PECS_ERR_INTERNAL, "a front's vector does not fit into shared memory");
+    configure_solve_kernels(max_optin);
+    PECS_CUDA(cudaDeviceSynchronize());
+    if (ctx->kind == PECS_KIND_PRODUCTION) build_step_graph(ctx.get());
+    PECS_CUDA(cudaGetLastError());
+    *out = ctx.release();
+  });
+}
+
+void pecs_ctx_destroy(pecs_ctx* ctx) { delete ctx; }
+
+pecs_status pecs_set_state(pecs_ctx* ctx, int32_t which, const double* solution) {
+  return guarded([&] {
+    require(ctx && solution, "pecs_set_state: NULL argument");
+    sync_all(ctx);
+    PECS_CUDA(cudaMemcpy(vector_of(ctx, which, false), solution, (size_t)n_dofs_of(ctx, which) * sizeof(double),
+                         cudaMemcpyHostToDevice));
+  });
+}
+pecs_status pecs_get_state(pecs_ctx* ctx, int32_t which, double* solution) {
+  return guarded([&] {
+    require(ctx && solution, "pecs_get_state: NULL argument");
+    sync_all(ctx);
+    PECS_CUDA(cudaMemcpy(solution, vector_of(ctx, which, false), (size_t)n_dofs_of(ctx, which) * sizeof(double),
+                         cudaMemcpyDeviceToHost));
+  });
+}
+pecs_status pecs_get_rhs(pecs_ctx* ctx, int32_t which, double* system_rhs) {
+  return guarded([&] {
+    require(ctx && system_rhs, "pecs_get_rhs: NULL argument");
+    sync_all(ctx);
+    PECS_CUDA(cudaMemcpy(system_rhs, vector_of(ctx, which, true), (size_t)n_dofs_of(ctx, which) * sizeof(double),
+                         cudaMemcpyDeviceToHost));
+  });
+}
+pecs_status pecs_set_rhs(pecs_ctx* ctx, int32_t which, const double* system_rhs) {
+  return guarded([&] {
+    require(ctx && system_rhs, "pecs_set_rhs: NULL argument");
+    sync_all(ctx);
+    PECS_CUDA(cudaMemcpy(vector_of(ctx, which, true), system_rhs, (size_t)n_dofs_of(ctx, which) * sizeof(double),
+                         cudaMemcpyHostToDevice));
+  });
+}
+int32_t pecs_n_dofs(const pecs_ctx* ctx, int32_t which) { return ctx ? n_dofs_of(ctx, which) : 0; }
+
+pecs_status pecs_set_time(pecs_ctx* ctx, double time) {
+  return guarded([&] {
+    require(ctx != nullptr, "pecs_set_time: NULL context");
+    for (DeviceDomain& D : ctx->dom) D.prm.time = time;
+  });
+}
+
+#define PECS_ENQUEUE(name, body)                                     \
+  pecs_status name(pecs_ctx* ctx) {                                  \
+    return guarded([&] {                                             \
+      require(ctx != nullptr, #name ": NULL context");               \
+      PECS_CUDA(cudaSetDevice(ctx->device));                         \
+      body;                                                          \
+      PECS_CUDA(cudaGetLastError());                                 \
+    });                                                              \
+  }
+PECS_ENQUEUE(pecs_assemble_semiconductor_rhs, enqueue_carrier_rhs(ctx, 0, ctx->main))
+PECS_ENQUEUE(pecs_assemble_electrolyte_rhs,
+             { require(ctx->full, "no electrolyte in this context"); enqueue_carrier_rhs(ctx, 1, ctx->main); })
+PECS_ENQUEUE(pecs_solve_full_system, enqueue_full_solve(ctx))
+PECS_ENQUEUE(pecs_assemble_poisson_rhs, enqueue_poisson_rhs(ctx, ctx->main))
+PECS_ENQUEUE(pecs_solve_poisson, enqueue_poisson_solve(ctx, ctx->main))
+
+pecs_status pecs_solve_species(pecs_ctx* ctx, int32_t which) {
+  return guarded([&] {
+    require(ctx != nullptr, "pecs_solve_species: NULL context");
+    require(which >= 0 && which <= 3 && (which < 2 || ctx->full), "pecs_solve_species: species out of range");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    enqueue_species_solve(ctx, which, ctx->main);
+    PECS_CUDA(cudaGetLastError());
+  });
+}
+
+pecs_status pecs_step(pecs_ctx* ctx, int32_t n_steps) {
+  return guarded([&] {
+    require(ctx != nullptr && n_steps >= 0, "pecs_step: bad argument");
+    require(ctx->step_graph != nullptr, "pecs_step: only the production problem has a step graph");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    for (int s = 0; s < n_steps; ++s) PECS_CUDA(cudaGraphLaunch(ctx->step_graph, ctx->main));
+  });
+}
+
+pecs_status pecs_synchronize(pecs_ctx* ctx) {
+  return guarded([&] {
+    require(ctx != nullptr, "pecs_synchronize: NULL context");
+    sync_all(ctx);
+    PECS_CUDA(cudaGetLastError());
+  });
+}
+
+pecs_status pecs_step_timed(pecs_ctx* ctx, int32_t n_steps, int32_t sectioned, double ms[6]) {
+  return guarded([&] {
+    require(ctx != nullptr && n_steps >= 0 && ms, "pecs_step_timed: bad argument");
+    require(ctx->step_graph != nullptr, "pecs_step_timed: only the production problem has a step graph");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    for (int k = 0; k < 6; ++k) ms[k] = 0.0;
+    sync_all(ctx);
+    cudaEvent_t ev[6];
+    for (cudaEvent_t& e : ev) PECS_CUDA(cudaEventCreate(&e));
+    if (!sectioned) {
+      PECS_CUDA(cudaEventRecord(ev[0], ctx->main));
+      for (int s = 0; s < n_steps; ++s) PECS_CUDA(cudaGraphLaunch(ctx->step_graph, ctx->main));
+      PECS_CUDA(cudaEventRecord(ev[1], ctx->main));
+      PECS_CUDA(cudaEventSynchronize(ev[1]));
+      float t = 0;
+      PECS_CUDA(cudaEventElapsedTime(&t, ev[0], ev[1]));
+      ms[0] = t;
+    } else {
+      for (int s = 0; s < n_steps; ++s) {
+        PECS_CUDA(cudaEventRecord(ev[0], ctx->main));
+        enqueue_carrier_rhs(ctx, 0, ctx->main);
+        PECS_CUDA(cudaEventRecord(ev[1], ctx->main));
+        if (ctx->full) enqueue_carrier_rhs(ctx, 1, ctx->main);
+        PECS_CUDA(cudaEventRecord(ev[2], ctx->main));
+        enqueue_full_solve(ctx);
+        PECS_CUDA(cudaEventRecord(ev[3], ctx->main));
+        enqueue_poisson_rhs(ctx, ctx->main);
+        PECS_CUDA(cudaEventRecord(ev[4], ctx->main));
+        enqueue_poisson_solve(ctx, ctx->main);
+        PECS_CUDA(cudaEventRecord(ev[5], ctx->main));
+        PECS_CUDA(cudaEventSynchronize(ev[5]));
+        for (int k = 0; k < 5; ++k) {
+          float t = 0;
+          PECS_CUDA(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+          ms[1 + k] += t;
+          ms[0] += t;
+        }
+      }
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  });
+}
+
+pecs_status pecs_time_kernel(pecs_ctx* ctx, int32_t which, int32_t repeats, double* avg_ms, int32_t* launches) {
+  return guarded([&] {
+    require(ctx != nullptr && repeats > 0 && avg_ms && launches, "pecs_time_kernel: bad argument");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    sync_all(ctx);
+    // flush L2 (126 MB) before every timed launch group so that the figure is an HBM figure
+    if (ctx->l2_flush.size() == 0) ctx->l2_flush.resize((size_t)256 << 20);
+    cudaEvent_t a, b;
+    PECS_CUDA(cudaEventCreate(&a));
+    PECS_CUDA(cudaEventCreate(&b));
+    double total = 0.0;
+    int n_launch = 0;
+    for (int r = 0; r < repeats; ++r) {
+      PECS_CUDA(cudaMemsetAsync(ctx->l2_flush.get(), r & 0xff, ctx->l2_flush.bytes(), ctx->main));
+      PECS_CUDA(cudaEventRecord(a, ctx->main));
+      switch (which) {
+        case 0:
+          for (int w = 0; w < ctx->n_domains(); ++w) enqueue_carrier_rhs(ctx, w, ctx->main);
+          n_launch = 2 * ctx->n_domains();
+          break;
+        case 1:
+          enqueue_poisson_rhs(ctx, ctx->main);
+          n_launch = ctx->n_domains();
+          break;
+        case 2:
+          // solves overwrite the states; their cost does not depend on the values
+          enqueue_full_solve(ctx);
+          n_launch = 0;
+          for (int w = 0; w < ctx->n_domains(); ++w)
+            for (int k = 0; k < 2; ++k)
+              if (ctx->dom[w].system[k].n > 0) n_launch += ctx->dom[w].system[k].launches_per_solve;
+          break;
+        case 3:
+          enqueue_poisson_solve(ctx, ctx->main);
+          n_launch = ctx->p_system.launches_per_solve + (ctx->n_constraints > 0 ? 1 : 0);
+          break;
+        default:
+          throw StatusError(PECS_ERR_INVALID, "pecs_time_kernel: which must be 0..3");
+      }
+      PECS_CUDA(cudaEventRecord(b, ctx->main));
+      PECS_CUDA(cudaEventSynchronize(b));
+      float t = 0;
+      PECS_CUDA(cudaEventElapsedTime(&t, a, b));
+      total += t;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *avg_ms = total / repeats;
+    *launches = n_launch;
+  });
+}
+
+int64_t pecs_get_info(const pecs_ctx* ctx, int32_t what) {
+  if (!ctx) return -1;
+  int64_t factor = ctx->p_system.factor_bytes();
+  int levels = (int)ctx->p_system.levels.size();
+  int64_t cells = 0;
+  for (int w = 0; w < ctx->n_domains(); ++w) {
+    cells += ctx->dom[w].n_cells;
+    for (int k = 0; k < 2; ++k) {
+      factor += ctx->dom[w].system[k].factor_bytes();
+      levels = std::max(levels, (int)ctx->dom[w].system[k].levels.size());
+    }
+  }
+  switch (what) {
+    case PECS_INFO_LAUNCHES_PER_STEP: return launches_per_step(ctx);
+    case PECS_INFO_FACTOR_BYTES: return factor;
+    case PECS_INFO_SOLVE_BYTES_PER_STEP: return factor; // every factor entry is streamed exactly once per step
+    case PECS_INFO_TREE_LEVELS_MAX: return levels;
+    case PECS_INFO_RHS_BYTES_PER_STEP: return cells * (kCarrierRhsBytesPerCell + kPoissonRhsBytesPerCell);
+  }
+  return -1;
+}
+
+} // extern "C"

@@ -1,0 +1,66 @@
+// device_util.cuh -- CUDA error checking and RAII device buffers for the context.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../error.hpp"
+
+namespace pecs {
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+  if (e != cudaSuccess)
+    throw StatusError(PECS_ERR_CUDA, std::string(what) + " failed: " + cudaGetErrorString(e) + " (" + file + ":" +
+                                         std::to_string(line) + ")");
+}
+#define PECS_CUDA(call) ::pecs::cuda_check((call), #call, __FILE__, __LINE__)
+
+template <class T>
+class DeviceBuffer {
+public:
+  DeviceBuffer() = default;
+  explicit DeviceBuffer(size_t n) { resize(n); }
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  DeviceBuffer(DeviceBuffer&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
+    if (this != &o) {
+      release();
+      p_ = o.p_;
+      n_ = o.n_;
+      o.p_ = nullptr;
+      o.n_ = 0;
+    }
+    return *this;
+  }
+  ~DeviceBuffer() { release(); }
+  void resize(size_t n) {
+    release();
+    n_ = n;
+    if (n) PECS_CUDA(cudaMalloc(&p_, n * sizeof(T)));
+  }
+  void upload(const T* h, size_t n) {
+    if (n != n_) resize(n);
+    if (n) PECS_CUDA(cudaMemcpy(p_, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void upload(const std::vector<T>& h) { upload(h.data(), h.size()); }
+  void zero() {
+    if (n_) PECS_CUDA(cudaMemset(p_, 0, n_ * sizeof(T)));
+  }
+  T* get() const { return p_; }
+  size_t size() const { return n_; }
+  size_t bytes() const { return n_ * sizeof(T); }
+
+private:
+  void release() {
+    if (p_) cudaFree(p_);
+    p_ = nullptr;
+    n_ = 0;
+  }
+  T* p_ = nullptr;
+  size_t n_ = 0;
+};
+
+} // namespace pecs

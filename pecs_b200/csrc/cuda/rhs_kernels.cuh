@@ -1,0 +1,79 @@
+// rhs_kernels.cuh -- launch interface of the right-hand-side assembly kernels (rhs_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace pecs {
+
+// one carrier subdomain as the kernels see it (structure of arrays, all device pointers)
+struct DomainView {
+  int n_cells;
+  const double* vx;      // [4][n_cells] vertex x, lexicographic vertex a at vx[a*n + c]
+  const double* vy;      // [4][n_cells]
+  const int* rt_dof;     // [4][n_cells] Poisson flux dof of face f of the matched Poisson cell
+  const int* phi_dof;    // [n_cells]    Poisson potential dof of the matched Poisson cell
+  // boundary cells (cells with at least one boundary face)
+  int n_bcells;
+  const int* bcell;      // [n_bcells] cell index
+  const int* bface_id;   // [n_bcells][4] boundary id of face f, -1 if the face is interior
+  const int* bnb_cell;   // [n_bcells] matched cell of the other subdomain across the interface (or -1)
+  const int* bnb_face;   // [n_bcells] its face number
+};
+
+// scalars of one subdomain pass (see include/pecs_b200.h PECS_P_*)
+struct RhsParams {
+  int kind;            // PECS_KIND_*
+  int is_semiconductor;
+  double inv_dt;       // 1 / delta_t (carried by the mass matrix in the reference, LDG.cpp:77-79)
+  double tau;          // penalty
+  double charge1, charge2;
+  double inv_eps;
+  double gen_scale, gen_alpha, gen_location; // alpha*G0, alpha, H (0 scale = dark)
+  double rho1_e, rho2_e;                     // equilibrium / Dirichlet densities of this subdomain's carriers
+  double other1_e, other2_e;                 // electrons_e, holes_e as seen from the electrolyte side
+  double k_et, k_ht, v_n, v_p;
+  double doping;       // N_D - N_A (semiconductor) or 0 (electrolyte)
+  double time;         // manufactured right-hand sides
+};
+
+// rhs_c = M u_c + cell terms for both carriers of the subdomain
+void launch_carrier_cell_rhs(const DomainView& d, const RhsParams& p, const double* u1, const double* u2,
+                             const double* poisson_solution, double* rhs1, double* rhs2, cudaStream_t s);
+// boundary / interface / Schottky face terms added into rhs; o1, o2 = the other subdomain's carriers
+void launch_carrier_boundary_rhs(const DomainView& d, const DomainView& other, const RhsParams& p, const double* u1,
+                                 const double* u2, const double* o1, const double* o2, double* rhs1, double* rhs2,
+                                 cudaStream_t s);
+// potential rows of the Poisson rhs: -int (doping + z1 rho1 + z2 rho2) per matched cell
+void launch_poisson_cell_rhs(const DomainView& d, const RhsParams& p, const double* u1, const double* u2,
+                             double* poisson_rhs, cudaStream_t s);
+
+// Poisson boundary faces: time-independent, evaluated once into a static vector
+struct PoissonFaceView {
+  int n_faces;
+  const int* cell;
+  const int* face;
+  const int* id;
+  const int* cell_is_semiconductor; // [n_poisson_cells]
+  const double* vx;                 // [4][n_poisson_cells]
+  const double* vy;
+  int n_poisson_cells;
+  const int* face_dof;              // [n_poisson_cells][4]
+  const int* constraint_master;     // [n_dofs] -2 unconstrained, -1 pinned to zero, else master dof
+  const double* constraint_weight;  // [n_dofs]
+};
+struct PoissonFaceParams {
+  int kind;
+  double phi_bi, phi_app, phi_sch, sch_location;
+};
+void launch_poisson_face_rhs(const PoissonFaceView& v, const PoissonFaceParams& p, double* static_rhs, cudaStream_t s);
+
+// ConstraintMatrix::distribute on the device
+void launch_distribute(int n_constraints, const int* dof, const int* master, const double* weight, double* x,
+                       cudaStream_t s);
+
+// algorithmic bytes per cell of the carrier kernel (both carriers): SURVEY section 8(d)
+constexpr int64_t kCarrierRhsBytesPerCell = 368;
+constexpr int64_t kPoissonRhsBytesPerCell = 140;
+
+} // namespace pecs

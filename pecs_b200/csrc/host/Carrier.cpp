@@ -5,9 +5,11 @@
 #include <iostream>
 #include <stdexcept>
 
+#include "../error.hpp"
+
 namespace {
 void check(pecs_status s, const char* what) {
-  if (s != PECS_OK) throw std::runtime_error(std::string(what) + ": " + pecs_last_error());
+  if (s != PECS_OK) throw pecs::StatusError(s, std::string(what) + ": " + pecs_last_error());
 }
 void require_ctx(const pecs_ctx* ctx, const char* who) {
   if (!ctx)

@@ -7,6 +7,8 @@
 #include <iomanip>
 #include <iostream>
 #include <stdexcept>
+
+#include "../error.hpp"
 #include <unordered_map>
 
 #include "../fe.hpp"
@@ -16,7 +18,7 @@ namespace SOLARCELL {
 
 namespace {
 void check(pecs_status s, const char* what) {
-  if (s != PECS_OK) throw std::runtime_error(std::string(what) + ": " + pecs_last_error());
+  if (s != PECS_OK) throw pecs::StatusError(s, std::string(what) + ": " + pecs_last_error());
 }
 void require_ctx(const pecs_ctx* ctx, const char* who) {
   if (!ctx) throw std::runtime_error(std::string(who) + ": set_solvers() has not created a device context");

@@ -1,0 +1,34 @@
+// SolverSetup.hpp -- how the five constant systems are grouped into nodes for nested dissection.
+//
+//   carriers: one node per cell (its 12 LDG unknowns), located at the cell centre;
+//   Poisson : one node per cell = its potential + every unconstrained edge flux the cell "owns"
+//             (an edge is owned by the cell that sees it as face 1 or 3, else by its only cell).  Pairing each
+//             potential with fluxes of its own cell keeps the pivot blocks of the saddle-point matrix
+//             [A  -B^T; -lambda^2 B  0] invertible without pivoting across fronts.  Constrained fluxes (hanging
+//             children, Neumann edges) are decoupled rows; they join the node of their cell as well.
+#pragma once
+#include <vector>
+
+#include "../../../include/pecs_b200.h"
+#include "SparseDirect.hpp"
+
+namespace SOLARCELL {
+class SolarCellProblem;
+}
+
+namespace pecs {
+
+struct NodeLayout {
+  std::vector<int> node_of_dof;
+  std::vector<double> x, y;
+};
+
+// from the C-ABI tables (this is what pecs_ctx_create uses)
+NodeLayout carrier_nodes(const pecs_domain_desc& d);
+NodeLayout poisson_nodes(const pecs_poisson_desc& d);
+int default_leaf_nodes(bool poisson);
+
+// convenience for the host classes / CPU tests: which = 0..3 species, 4 Poisson; leaf_nodes <= 0 -> default
+SolvePlan plan_for_system(SOLARCELL::SolarCellProblem& problem, int which, int leaf_nodes);
+
+} // namespace pecs

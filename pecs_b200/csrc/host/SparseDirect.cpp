@@ -1,0 +1,448 @@
+// SparseDirect.cpp -- see SparseDirect.hpp.
+#include "SparseDirect.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <stdexcept>
+
+#include "../error.hpp"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace pecs {
+
+namespace {
+
+struct NdBuilder {
+  const std::vector<std::vector<int>>& adj;
+  const std::vector<double>&x, &y;
+  int leaf_nodes;
+  std::vector<int> side; // scratch: 0 = outside, 1 = A, 2 = B
+  struct TreeNode {
+    std::vector<int> nodes;
+    int child[2] = {-1, -1};
+  };
+  std::vector<TreeNode> tree; // postorder
+
+  int leaf(std::vector<int>& nodes) {
+    TreeNode t;
+    t.nodes.swap(nodes);
+    tree.push_back(std::move(t));
+    return (int)tree.size() - 1;
+  }
+
+  int build(std::vector<int>& nodes) {
+    if ((int)nodes.size() <= leaf_nodes) return leaf(nodes);
+    std::vector<int> bestA, bestB, bestS;
+    bool have = false;
+    for (int dir = 0; dir < 2; ++dir) {
+      const std::vector<double>& c = dir == 0 ? x : y;
+      std::vector<int> sorted = nodes;
+      const size_t half = sorted.size() / 2;
+      std::nth_element(sorted.begin(), sorted.begin() + half, sorted.end(),
+                       [&](int a, int b) { return c[a] < c[b] || (c[a] == c[b] && a < b); });
+      for (size_t k = 0; k < sorted.size(); ++k) side[sorted[k]] = k < half ? 1 : 2;
+      std::vector<int> A, B, S;
+      for (size_t k = 0; k < sorted.size(); ++k) {
+        const int v = sorted[k];
+        if (k >= half) {
+          B.push_back(v);
+          continue;
+        }
+        bool touches = false;
+        for (int w : adj[v])
+          if (side[w] == 2) {
+            touches = true;
+            break;
+          }
+        (touches ? S : A).push_back(v);
+      }
+      for (int v : sorted) side[v] = 0;
+      if (A.empty() || B.empty() || S.empty()) continue;
+      if (!have || S.size() < bestS.size()) {
+        bestA.swap(A);
+        bestB.swap(B);
+        bestS.swap(S);
+        have = true;
+      }
+    }
+    if (!have) return leaf(nodes);
+    nodes.clear();
+    nodes.shrink_to_fit();
+    TreeNode t;
+    t.child[0] = build(bestA);
+    t.child[1] = build(bestB);
+    std::sort(bestS.begin(), bestS.end());
+    t.nodes.swap(bestS);
+    tree.push_back(std::move(t));
+    return (int)tree.size() - 1;
+  }
+};
+
+} // namespace
+
+SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_dof, const std::vector<double>& node_x,
+                           const std::vector<double>& node_y, int leaf_nodes) {
+  const int n = A.n;
+  const int n_nodes = (int)node_x.size();
+  if ((int)node_of_dof.size() != n) throw StatusError(PECS_ERR_INVALID, "build_solve_plan: node_of_dof size");
+  std::vector<std::vector<int>> node_dofs(n_nodes), adj(n_nodes);
+  for (int i = 0; i < n; ++i) node_dofs[node_of_dof[i]].push_back(i);
+  for (int i = 0; i < n; ++i)
+    for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k) {
+      const int a = node_of_dof[i], b = node_of_dof[A.col[k]];
+      if (a != b) {
+        adj[a].push_back(b);
+        adj[b].push_back(a);
+      }
+    }
+  for (auto& a : adj) {
+    std::sort(a.begin(), a.end());
+    a.erase(std::unique(a.begin(), a.end()), a.end());
+  }
+
+  NdBuilder nd{adj, node_x, node_y, std::max(1, leaf_nodes), std::vector<int>(n_nodes, 0), {}};
+  {
+    std::vector<int> all;
+    for (int v = 0; v < n_nodes; ++v)
+      if (!node_dofs[v].empty()) all.push_back(v);
+    nd.build(all);
+  }
+  const int nf = (int)nd.tree.size();
+
+  SolvePlan plan;
+  plan.n = n;
+  plan.fronts.resize(nf);
+  // node positions in elimination order + dof permutation
+  std::vector<int> node_pos(n_nodes, -1), node_first_dofpos(n_nodes, -1);
+  plan.perm.assign(n, -1);
+  plan.iperm.assign(n, -1);
+  int next_node = 0, next_dof = 0;
+  std::vector<int> last_node_pos(nf);
+  for (int f = 0; f < nf; ++f) {
+    Front& F = plan.fronts[f];
+    F.p0 = next_dof;
+    for (int v : nd.tree[f].nodes) {
+      node_pos[v] = next_node++;
+      node_first_dofpos[v] = next_dof;
+      for (int d : node_dofs[v]) {
+        plan.perm[d] = next_dof;
+        plan.iperm[next_dof] = d;
+        ++next_dof;
+      }
+    }
+    F.np = next_dof - F.p0;
+    last_node_pos[f] = next_node - 1;
+    for (int k = 0; k < 2; ++k) {
+      F.child[k] = nd.tree[f].child[k];
+      if (F.child[k] >= 0) plan.fronts[F.child[k]].parent = f;
+    }
+  }
+  if (next_dof != n) throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: not every unknown was ordered");
+  // depth (root is the last front in postorder)
+  for (int f = nf - 1; f >= 0; --f) plan.fronts[f].depth = plan.fronts[f].parent < 0 ? 0 : plan.fronts[plan.fronts[f].parent].depth + 1;
+
+  // symbolic structure on nodes: boundary nodes as their node positions, ascending
+  std::vector<int> pos_to_node(n_nodes, -1);
+  for (int v = 0; v < n_nodes; ++v)
+    if (node_pos[v] >= 0) pos_to_node[node_pos[v]] = v;
+  std::vector<std::vector<int>> bd_nodes(nf);
+  for (int f = 0; f < nf; ++f) {
+    std::vector<int> s;
+    for (int v : nd.tree[f].nodes)
+      for (int w : adj[v])
+        if (node_pos[w] > last_node_pos[f]) s.push_back(node_pos[w]);
+    for (int k = 0; k < 2; ++k)
+      if (plan.fronts[f].child[k] >= 0) {
+        for (int p : bd_nodes[plan.fronts[f].child[k]])
+          if (p > last_node_pos[f]) s.push_back(p);
+      }
+    std::sort(s.begin(), s.end());
+    s.erase(std::unique(s.begin(), s.end()), s.end());
+    bd_nodes[f].swap(s);
+  }
+  // expand to unknowns, lay out tables
+  for (int f = 0; f < nf; ++f) {
+    Front& F = plan.fronts[f];
+    F.bd_off = (int64_t)plan.bd_index.size();
+    for (int p : bd_nodes[f]) {
+      const int v = pos_to_node[p];
+      for (int k = 0; k < (int)node_dofs[v].size(); ++k) plan.bd_index.push_back(node_first_dofpos[v] + k);
+    }
+    F.nb = (int)((int64_t)plan.bd_index.size() - F.bd_off);
+    F.fwd_off = plan.fwd_entries;
+    plan.fwd_entries += (int64_t)F.nb * F.np;
+    plan.fwd_entries += plan.fwd_entries & 1; // keep every table 16-byte aligned for the device's double2 loads
+    F.bwd_off = plan.bwd_entries;
+    plan.bwd_entries += (int64_t)F.np * (F.np + F.nb);
+    plan.bwd_entries += plan.bwd_entries & 1;
+    F.upd_off = plan.upd_entries;
+    plan.upd_entries += F.nb;
+    plan.max_np = std::max(plan.max_np, F.np);
+    plan.max_nb = std::max(plan.max_nb, F.nb);
+  }
+  // inverse child maps
+  for (int f = 0; f < nf; ++f) {
+    Front& F = plan.fronts[f];
+    const int m = F.np + F.nb;
+    for (int k = 0; k < 2; ++k) {
+      F.cmap_off[k] = (int64_t)plan.child_map.size();
+      if (F.child[k] < 0) continue;
+      plan.child_map.resize(plan.child_map.size() + m, -1);
+      int* cmap = plan.child_map.data() + F.cmap_off[k];
+      const Front& C = plan.fronts[F.child[k]];
+      const int* cbd = plan.bd(C);
+      const int* fbd = plan.bd(F);
+      for (int s = 0; s < C.nb; ++s) {
+        const int pos = cbd[s];
+        int l;
+        if (pos < F.p0 + F.np) {
+          if (pos < F.p0) throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: child boundary below parent pivots");
+          l = pos - F.p0;
+        } else {
+          const int* it = std::lower_bound(fbd, fbd + F.nb, pos);
+          if (it == fbd + F.nb || *it != pos)
+            throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: child boundary not contained in parent front");
+          l = F.np + (int)(it - fbd);
+        }
+        cmap[l] = s;
+      }
+    }
+  }
+  int max_depth = 0;
+  for (const Front& F : plan.fronts) max_depth = std::max(max_depth, F.depth);
+  plan.levels.assign(max_depth + 1, {});
+  for (int f = 0; f < nf; ++f) plan.levels[plan.fronts[f].depth].push_back(f);
+  return plan;
+}
+
+// ---------------------------------------------------------------------------------------------- host numeric
+namespace {
+
+// C (m x n) -= / = A (m x k) * B (k x n), all row-major with leading dimensions
+void gemm_sub(int m, int n, int k, const double* A, int lda, const double* B, int ldb, double* C, int ldc, bool par) {
+#pragma omp parallel for schedule(static) if (par)
+  for (int i = 0; i < m; ++i) {
+    double* c = C + (size_t)i * ldc;
+    for (int p = 0; p < k; ++p) {
+      const double a = A[(size_t)i * lda + p];
+      if (a == 0.0) continue;
+      const double* b = B + (size_t)p * ldb;
+      for (int j = 0; j < n; ++j) c[j] -= a * b[j];
+    }
+  }
+}
+
+// in-place inverse of an n x n row-major matrix by LU with partial pivoting; returns false if singular
+bool invert(int n, double* M, bool par) {
+  std::vector<int> piv(n);
+  for (int k = 0; k < n; ++k) {
+    int p = k;
+    double best = std::fabs(M[(size_t)k * n + k]);
+    for (int r = k + 1; r < n; ++r)
+      if (std::fabs(M[(size_t)r * n + k]) > best) {
+        best = std::fabs(M[(size_t)r * n + k]);
+        p = r;
+      }
+    if (best == 0.0 || !std::isfinite(best)) return false;
+    piv[k] = p;
+    if (p != k)
+      for (int j = 0; j < n; ++j) std::swap(M[(size_t)k * n + j], M[(size_t)p * n + j]);
+    const double inv = 1.0 / M[(size_t)k * n + k];
+#pragma omp parallel for schedule(static) if (par && n - k > 256)
+    for (int r = k + 1; r < n; ++r) {
+      const double l = M[(size_t)r * n + k] * inv;
+      M[(size_t)r * n + k] = l;
+      if (l == 0.0) continue;
+      const double* rk = M + (size_t)k * n;
+      double* rr = M + (size_t)r * n;
+      for (int j = k + 1; j < n; ++j) rr[j] -= l * rk[j];
+    }
+  }
+  // inverse from the factors: solve L U X = P I column block-wise (row-major friendly formulation)
+  std::vector<double> X((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) X[(size_t)i * n + i] = 1.0;
+  for (int k = 0; k < n; ++k)
+    if (piv[k] != k)
+      for (int j = 0; j < n; ++j) std::swap(X[(size_t)k * n + j], X[(size_t)piv[k] * n + j]);
+  // forward: rows of X updated in order (L unit lower)
+  for (int i = 1; i < n; ++i) {
+    double* xi = X.data() + (size_t)i * n;
+    for (int k = 0; k < i; ++k) {
+      const double l = M[(size_t)i * n + k];
+      if (l == 0.0) continue;
+      const double* xk = X.data() + (size_t)k * n;
+      for (int j = 0; j < n; ++j) xi[j] -= l * xk[j];
+    }
+  }
+  // backward
+  for (int i = n - 1; i >= 0; --i) {
+    double* xi = X.data() + (size_t)i * n;
+    for (int k = i + 1; k < n; ++k) {
+      const double u = M[(size_t)i * n + k];
+      if (u == 0.0) continue;
+      const double* xk = X.data() + (size_t)k * n;
+      for (int j = 0; j < n; ++j) xi[j] -= u * xk[j];
+    }
+    const double d = 1.0 / M[(size_t)i * n + i];
+    for (int j = 0; j < n; ++j) xi[j] *= d;
+  }
+  std::copy(X.begin(), X.end(), M);
+  return true;
+}
+
+CsrMatrix permute(const CsrMatrix& A, const std::vector<int>& perm, bool transpose) {
+  TripletList tl(A.n);
+  tl.reserve(A.nnz());
+  for (int i = 0; i < A.n; ++i)
+    for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k) {
+      if (transpose)
+        tl.add(perm[A.col[k]], perm[i], A.val[k]);
+      else
+        tl.add(perm[i], perm[A.col[k]], A.val[k]);
+    }
+  return tl.compress();
+}
+
+} // namespace
+
+void factorize_host(const SolvePlan& plan, const CsrMatrix& A, std::vector<double>& fwd, std::vector<double>& bwd) {
+  const CsrMatrix Ap = permute(A, plan.perm, false), Apt = permute(A, plan.perm, true);
+  fwd.assign((size_t)plan.fwd_entries, 0.0);
+  bwd.assign((size_t)plan.bwd_entries, 0.0);
+  const int nf = (int)plan.fronts.size();
+  std::vector<std::vector<double>> update(nf); // Schur complements waiting for their parent
+  bool singular = false;
+
+  auto process = [&](int f, bool inner_parallel) {
+    const Front& F = plan.fronts[f];
+    const int np = F.np, nb = F.nb, m = np + nb;
+    const int* bd = plan.bd(F);
+    std::vector<double> M((size_t)m * m, 0.0);
+    auto local = [&](int pos) -> int {
+      if (pos < F.p0 + np) return pos - F.p0;
+      const int* it = std::lower_bound(bd, bd + nb, pos);
+      return (it != bd + nb && *it == pos) ? np + (int)(it - bd) : -1;
+    };
+    for (int i = 0; i < np; ++i) {
+      const int r = F.p0 + i;
+      for (int k = Ap.row_ptr[r]; k < Ap.row_ptr[r + 1]; ++k) {
+        const int q = Ap.col[k];
+        if (q < F.p0) continue;
+        const int l = local(q);
+        if (l < 0) throw StatusError(PECS_ERR_INTERNAL, "factorize_host: entry outside the symbolic front");
+        M[(size_t)i * m + l] = Ap.val[k];
+      }
+      for (int k = Apt.row_ptr[r]; k < Apt.row_ptr[r + 1]; ++k) {
+        const int q = Apt.col[k];
+        if (q < F.p0 + np) continue;
+        const int l = local(q);
+        if (l < 0) throw StatusError(PECS_ERR_INTERNAL, "factorize_host: entry outside the symbolic front");
+        M[(size_t)l * m + i] = Apt.val[k];
+      }
+    }
+    for (int c = 0; c < 2; ++c) {
+      if (F.child[c] < 0) continue;
+      const Front& C = plan.fronts[F.child[c]];
+      std::vector<double>& U = update[F.child[c]];
+      std::vector<int> map(C.nb);
+      const int* cbd = plan.bd(C);
+      for (int s = 0; s < C.nb; ++s) map[s] = local(cbd[s]);
+      for (int s = 0; s < C.nb; ++s) {
+        double* row = M.data() + (size_t)map[s] * m;
+        const double* u = U.data() + (size_t)s * C.nb;
+        for (int t = 0; t < C.nb; ++t) row[map[t]] += u[t];
+      }
+      std::vector<double>().swap(U);
+    }
+    // split the frontal matrix
+    std::vector<double> Fpp((size_t)np * np), Fpb((size_t)np * nb), Fbp((size_t)nb * np);
+    for (int i = 0; i < np; ++i) {
+      std::copy(M.begin() + (size_t)i * m, M.begin() + (size_t)i * m + np, Fpp.begin() + (size_t)i * np);
+      std::copy(M.begin() + (size_t)i * m + np, M.begin() + (size_t)(i + 1) * m, Fpb.begin() + (size_t)i * nb);
+    }
+    for (int i = 0; i < nb; ++i)
+      std::copy(M.begin() + (size_t)(np + i) * m, M.begin() + (size_t)(np + i) * m + np, Fbp.begin() + (size_t)i * np);
+    if (!invert(np, Fpp.data(), inner_parallel)) {
+      singular = true;
+      return;
+    }
+    // G = Fbp * Inv (stored positively), H = Inv * Fpb (stored negated next to Inv), U = Fbb - G * Fpb
+    double* G = fwd.data() + F.fwd_off;
+    std::vector<double> negG((size_t)nb * np, 0.0);
+    gemm_sub(nb, np, np, Fbp.data(), np, Fpp.data(), np, negG.data(), np, inner_parallel);
+    for (size_t k = 0; k < negG.size(); ++k) G[k] = -negG[k];
+    double* B = bwd.data() + F.bwd_off;
+    for (int i = 0; i < np; ++i) std::copy(Fpp.begin() + (size_t)i * np, Fpp.begin() + (size_t)(i + 1) * np, B + (size_t)i * m);
+    gemm_sub(np, nb, np, Fpp.data(), np, Fpb.data(), nb, B + np, m, inner_parallel); // writes -H
+    if (F.parent >= 0) {
+      std::vector<double>& U = update[f];
+      U.resize((size_t)nb * nb);
+      for (int i = 0; i < nb; ++i)
+        std::copy(M.begin() + (size_t)(np + i) * m + np, M.begin() + (size_t)(np + i + 1) * m, U.begin() + (size_t)i * nb);
+      gemm_sub(nb, nb, np, G, np, Fpb.data(), nb, U.data(), nb, inner_parallel);
+    }
+  };
+
+  int threads = 1;
+#ifdef _OPENMP
+  threads = omp_get_max_threads();
+#endif
+  for (int d = (int)plan.levels.size() - 1; d >= 0; --d) {
+    const std::vector<int>& lvl = plan.levels[d];
+    if ((int)lvl.size() >= 2 * threads) {
+#pragma omp parallel for schedule(dynamic, 1)
+      for (int k = 0; k < (int)lvl.size(); ++k) process(lvl[k], false);
+    } else {
+      for (int f : lvl) process(f, true);
+    }
+    if (singular) throw StatusError(PECS_ERR_SINGULAR, "factorize_host: singular pivot block");
+  }
+}
+
+void solve_host(const SolvePlan& plan, const std::vector<double>& fwd, const std::vector<double>& bwd, const double* b,
+                double* x) {
+  const int n = plan.n;
+  std::vector<double> w(n), xp(n), upd((size_t)plan.upd_entries, 0.0);
+  for (int i = 0; i < n; ++i) w[plan.perm[i]] = b[i];
+  for (int d = (int)plan.levels.size() - 1; d >= 0; --d)
+    for (int f : plan.levels[d]) {
+      const Front& F = plan.fronts[f];
+      const int np = F.np, nb = F.nb;
+      double* t = upd.data() + F.upd_off;
+      for (int c = 0; c < 2; ++c) {
+        if (F.child[c] < 0) continue;
+        const int* cmap = plan.child_map.data() + F.cmap_off[c];
+        const double* tc = upd.data() + plan.fronts[F.child[c]].upd_off;
+        for (int l = 0; l < np; ++l)
+          if (cmap[l] >= 0) w[F.p0 + l] -= tc[cmap[l]];
+        for (int l = 0; l < nb; ++l)
+          if (cmap[np + l] >= 0) t[l] += tc[cmap[np + l]];
+      }
+      const double* G = fwd.data() + F.fwd_off;
+      for (int i = 0; i < nb; ++i) {
+        double s = 0;
+        for (int j = 0; j < np; ++j) s += G[(size_t)i * np + j] * w[F.p0 + j];
+        t[i] += s;
+      }
+    }
+  for (size_t d = 0; d < plan.levels.size(); ++d)
+    for (int f : plan.levels[d]) {
+      const Front& F = plan.fronts[f];
+      const int np = F.np, nb = F.nb, m = np + nb;
+      const int* bd = plan.bd(F);
+      const double* B = bwd.data() + F.bwd_off;
+      for (int i = 0; i < np; ++i) {
+        double s = 0;
+        for (int j = 0; j < np; ++j) s += B[(size_t)i * m + j] * w[F.p0 + j];
+        for (int j = 0; j < nb; ++j) s += B[(size_t)i * m + np + j] * xp[bd[j]];
+        xp[F.p0 + i] = s;
+      }
+    }
+  for (int i = 0; i < n; ++i) x[i] = xp[plan.perm[i]];
+}
+
+} // namespace pecs

@@ -7,6 +7,7 @@
 #include "../../../include/pecs_b200_host.h"
 #include "../error.hpp"
 #include "SolarCell.hpp"
+#include "SolverSetup.hpp"
 
 struct pecs_solarcell {
   ParameterSpace::ParameterHandler prm;
@@ -215,6 +216,29 @@ pecs_status pecs_solarcell_ldg_errors(pecs_solarcell* p, int32_t which, double t
 }
 pecs_status pecs_solarcell_mixed_errors(pecs_solarcell* p, double out[2]) {
   return guarded([&] { p->problem->mixed_errors(out[0], out[1]); });
+}
+
+pecs_status pecs_solarcell_plan_stats(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, int64_t stats[8]) {
+  return guarded([&] {
+    const pecs::SolvePlan plan = pecs::plan_for_system(*p->problem, which, leaf_nodes);
+    stats[0] = (int64_t)plan.fronts.size();
+    stats[1] = (int64_t)plan.levels.size();
+    stats[2] = plan.max_np;
+    stats[3] = plan.max_nb;
+    stats[4] = plan.fwd_entries;
+    stats[5] = plan.bwd_entries;
+    stats[6] = plan.upd_entries;
+    stats[7] = 0;
+  });
+}
+pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,
+                                                 double* x) {
+  return guarded([&] {
+    const pecs::SolvePlan plan = pecs::plan_for_system(*p->problem, which, leaf_nodes);
+    std::vector<double> fwd, bwd;
+    pecs::factorize_host(plan, matrix(p, which), fwd, bwd);
+    pecs::solve_host(plan, fwd, bwd, b, x);
+  });
 }
 
 } // extern "C"

@@ -261,6 +261,18 @@ class SolarCellProblem:
     def info(self, what):
         return int(self._lib.pecs_get_info(self.ctx, what))
 
+    # ---- verification of the setup tables (CPU tests) ----
+    def plan_stats(self, which, leaf_nodes=0):
+        st = np.zeros(8, np.int64)
+        check(self._lib.pecs_solarcell_plan_stats(self._h, which, leaf_nodes, st.ctypes.data_as(C.POINTER(C.c_int64))))
+        return dict(zip(["fronts", "levels", "max_np", "max_nb", "fwd_entries", "bwd_entries", "upd_entries"], st))
+
+    def selftest_direct_solve(self, which, b, leaf_nodes=0):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros_like(b)
+        check(self._lib.pecs_solarcell_selftest_direct_solve(self._h, which, leaf_nodes, _dp(b), _dp(x)))
+        return x
+
     # ---- post-processing ----
     def ldg_errors(self, which, time):
         e = np.zeros(2)
