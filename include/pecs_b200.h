@@ -165,6 +165,15 @@ pecs_status pecs_step(pecs_ctx* ctx, int32_t n_steps);
 /* all five calls above return after enqueueing; this waits for the context's streams */
 pecs_status pecs_synchronize(pecs_ctx* ctx);
 
+/* The same n_steps with HOST-resident state, as a host that keeps Carrier::solution / PoissonData::solution in its
+ * own memory would call it: uploads the five solution vectors (states[PECS_ELECTRONS..PECS_POISSON], NULL entries
+ * are skipped), runs the steps, downloads the five vectors back and waits.  Pinned buffers (pecs_host_alloc) make
+ * the copies asynchronous DMA transfers. */
+pecs_status pecs_step_host(pecs_ctx* ctx, int32_t n_steps, double* const states[5]);
+/* page-locked host memory for the above */
+void* pecs_host_alloc(uint64_t bytes);
+void pecs_host_free(void* p);
+
 /* measurement support for bench.py: run n_steps and report device times measured with CUDA events on the
  * context's own streams.  ms[0] = whole region, ms[1..5] = the reference's five TimerOutput sections
  *  summed over the steps when sectioned != 0 (sections are then serialised), else 0. */

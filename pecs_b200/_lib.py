@@ -45,6 +45,9 @@ SIGNATURES = {
     "pecs_solve_poisson": (C.c_int, [VOIDP]),
     "pecs_step": (C.c_int, [VOIDP, C.c_int32]),
     "pecs_synchronize": (C.c_int, [VOIDP]),
+    "pecs_step_host": (C.c_int, [VOIDP, C.c_int32, C.POINTER(c_double_p)]),
+    "pecs_host_alloc": (VOIDP, [C.c_uint64]),
+    "pecs_host_free": (None, [VOIDP]),
     "pecs_step_timed": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p]),
     "pecs_time_kernel": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p, c_int32_p]),
     "pecs_get_info": (C.c_int64, [VOIDP, C.c_int32]),

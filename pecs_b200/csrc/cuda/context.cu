@@ -599,6 +599,36 @@ pecs_status pecs_step(pecs_ctx* ctx, int32_t n_steps) {
   });
 }
 
+pecs_status pecs_step_host(pecs_ctx* ctx, int32_t n_steps, double* const states[5]) {
+  return guarded([&] {
+    require(ctx != nullptr && n_steps >= 0 && states, "pecs_step_host: bad argument");
+    require(ctx->step_graph != nullptr, "pecs_step_host: only the production problem has a step graph");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    for (int w = 0; w < 5; ++w)
+      if (states[w] && n_dofs_of(ctx, w) > 0)
+        PECS_CUDA(cudaMemcpyAsync(vector_of(ctx, w, false), states[w], (size_t)n_dofs_of(ctx, w) * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->main));
+    for (int s = 0; s < n_steps; ++s) PECS_CUDA(cudaGraphLaunch(ctx->step_graph, ctx->main));
+    for (int w = 0; w < 5; ++w)
+      if (states[w] && n_dofs_of(ctx, w) > 0)
+        PECS_CUDA(cudaMemcpyAsync(states[w], vector_of(ctx, w, false), (size_t)n_dofs_of(ctx, w) * sizeof(double),
+                                  cudaMemcpyDeviceToHost, ctx->main));
+    PECS_CUDA(cudaStreamSynchronize(ctx->main));
+  });
+}
+
+void* pecs_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void pecs_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 pecs_status pecs_synchronize(pecs_ctx* ctx) {
   return guarded([&] {
     require(ctx != nullptr, "pecs_synchronize: NULL context");

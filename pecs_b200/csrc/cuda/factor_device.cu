@@ -1,16 +1,365 @@
-// factor_device.cu -- see factor_device.cuh.  (device implementation follows; host factorisation until then)
+// factor_device.cu -- numeric multifrontal factorisation on the device (one-time setup, see host/SparseDirect.hpp).
+//
+// Replaces SparseDirectUMFPACK::initialize (reference source/Carrier.cpp:26-32, source/Poisson.cpp:92-96).
+// Level by level from the leaves: assemble every frontal matrix F = [F_PP F_PB; F_BP F_BB] (original entries +
+// the children's Schur complements), then per front
+//     Inv = F_PP^-1,   -H = -Inv F_PB,   G = F_BP Inv,   F_BB <- F_BB - G F_PB  (the Schur complement for the parent)
+// Small fronts (the vast majority) are handled by one thread block each with Gauss-Jordan elimination; large fronts
+// use cuSOLVER getrf/getrs for the inverse and cuBLAS DGEMM for the three products (plain library GEMMs, setup only).
+// All matrices are row-major; a row-major matrix handed to a column-major library is its transpose, and
+// (F_PP^T)^-1 = Inv^T, so the library results land directly in the row-major tables (derivation in the comments).
 #include "factor_device.cuh"
 
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
 #include <cstdlib>
+#include <string>
+#include <vector>
 
 #include "../error.hpp"
+#include "device_util.cuh"
 
 namespace pecs {
 
-bool device_factorization_enabled() { return false; }
+namespace {
 
-void factorize_device(const SolvePlan&, const CsrMatrix&, const DeviceFront*, const int*, const int*, double*, double*) {
-  throw StatusError(PECS_ERR_INTERNAL, "factorize_device: not built");
+constexpr int kSmallFrontMaxNp = 96;
+
+struct FactorFront {
+  int np, nb, p0;
+  int child[2];            // indices into the PREVIOUS level's FactorFront array, -1 if none
+  long long bd_off;        // into bd_index
+  long long F_off;         // into this level's frontal buffer (m x m, row-major)
+  long long fwd_off, bwd_off;
+  long long cl_off[2];     // into the child-local index scratch
+};
+
+__device__ __forceinline__ int local_index(int pos, int p0, int np, const int* bd, int nb) {
+  if (pos < p0 + np) return pos - p0;
+  int lo = 0, hi = nb;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (bd[mid] < pos)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return (lo < nb && bd[lo] == pos) ? np + lo : -1;
+}
+
+// original matrix entries: one block per front
+__global__ void assemble_kernel(const FactorFront* __restrict__ fronts, const int* __restrict__ bd_index,
+                                const int* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ val,
+                                const int* __restrict__ trp, const int* __restrict__ tcol, const double* __restrict__ tval,
+                                double* Fbuf, int* error) {
+  const FactorFront F = fronts[blockIdx.x];
+  const int m = F.np + F.nb;
+  const int* bd = bd_index + F.bd_off;
+  double* M = Fbuf + F.F_off;
+  for (int i = threadIdx.x; i < F.np; i += blockDim.x) {
+    const int r = F.p0 + i;
+    for (int k = rp[r]; k < rp[r + 1]; ++k) {
+      const int q = col[k];
+      if (q < F.p0) continue;
+      const int l = local_index(q, F.p0, F.np, bd, F.nb);
+      if (l < 0) {
+        atomicExch(error, 1);
+        continue;
+      }
+      M[(size_t)i * m + l] = val[k];
+    }
+    for (int k = trp[r]; k < trp[r + 1]; ++k) {
+      const int q = tcol[k];
+      if (q < F.p0 + F.np) continue;
+      const int l = local_index(q, F.p0, F.np, bd, F.nb);
+      if (l < 0) {
+        atomicExch(error, 1);
+        continue;
+      }
+      M[(size_t)l * m + i] = tval[k];
+    }
+  }
+}
+
+// cl[s] = local index in the parent front of the child's boundary slot s
+__global__ void child_local_kernel(const FactorFront* __restrict__ fronts, const FactorFront* __restrict__ child_fronts,
+                                   const int* __restrict__ bd_index, int which, int* cl, int* error) {
+  const FactorFront F = fronts[blockIdx.x];
+  if (F.child[which] < 0) return;
+  const FactorFront C = child_fronts[F.child[which]];
+  const int* cbd = bd_index + C.bd_off;
+  const int* bd = bd_index + F.bd_off;
+  int* out = cl + F.cl_off[which];
+  for (int s = threadIdx.x; s < C.nb; s += blockDim.x) {
+    const int l = local_index(cbd[s], F.p0, F.np, bd, F.nb);
+    if (l < 0) atomicExch(error, 2);
+    out[s] = l;
+  }
+}
+
+// F[cl[s]][cl[t]] += U_child[s][t]; grid.x = front, grid.y = row chunk of the child's Schur complement
+__global__ void extend_add_kernel(const FactorFront* __restrict__ fronts, const FactorFront* __restrict__ child_fronts,
+                                  int which, const int* __restrict__ cl, const double* __restrict__ child_Fbuf, double* Fbuf) {
+  const FactorFront F = fronts[blockIdx.x];
+  if (F.child[which] < 0) return;
+  const FactorFront C = child_fronts[F.child[which]];
+  const int m = F.np + F.nb, mc = C.np + C.nb;
+  const int* map = cl + F.cl_off[which];
+  const double* U = child_Fbuf + C.F_off + (size_t)C.np * mc + C.np;
+  double* M = Fbuf + F.F_off;
+  for (int s = blockIdx.y; s < C.nb; s += gridDim.y) {
+    double* row = M + (size_t)map[s] * m;
+    const double* u = U + (size_t)s * mc;
+    for (int t = threadIdx.x; t < C.nb; t += blockDim.x) row[map[t]] += u[t];
+  }
+}
+
+// One block per small front: Gauss-Jordan inverse of F_PP (partial pivoting) straight into the backward table,
+// then -H, G and the Schur complement.  Everything stays in L1/L2 for these sizes.
+__global__ void __launch_bounds__(256) small_front_kernel(const FactorFront* __restrict__ fronts,
+                                                          const int* __restrict__ small_list, double* Fbuf, double* fwd,
+                                                          double* bwd, int* error) {
+  const FactorFront F = fronts[small_list[blockIdx.x]];
+  const int np = F.np, nb = F.nb, m = np + nb;
+  double* M = Fbuf + F.F_off;   // rows 0..np-1 hold [F_PP | F_PB]
+  double* B = bwd + F.bwd_off;  // [Inv | -H], row stride m
+  double* G = fwd + F.fwd_off;  // nb x np
+  __shared__ int s_piv;
+  __shared__ double s_val[256];
+  __shared__ int s_idx[256];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < np * np; e += nt) B[(size_t)(e / np) * m + (e % np)] = (e / np == e % np) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int k = 0; k < np; ++k) {
+    // pivot search in column k, rows k..np-1
+    double best = -1.0;
+    int bi = k;
+    for (int r = k + tid; r < np; r += nt) {
+      const double a = fabs(M[(size_t)r * m + k]);
+      if (a > best) {
+        best = a;
+        bi = r;
+      }
+    }
+    s_val[tid] = best;
+    s_idx[tid] = bi;
+    __syncthreads();
+    for (int o = nt >> 1; o > 0; o >>= 1) {
+      if (tid < o && (s_val[tid + o] > s_val[tid] || (s_val[tid + o] == s_val[tid] && s_idx[tid + o] < s_idx[tid]))) {
+        s_val[tid] = s_val[tid + o];
+        s_idx[tid] = s_idx[tid + o];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      s_piv = s_idx[0];
+      if (!(s_val[0] > 0.0) || !isfinite(s_val[0])) atomicExch(error, 3);
+    }
+    __syncthreads();
+    const int p = s_piv;
+    if (p != k) {
+      for (int j = tid; j < np; j += nt) {
+        const double a = M[(size_t)k * m + j];
+        M[(size_t)k * m + j] = M[(size_t)p * m + j];
+        M[(size_t)p * m + j] = a;
+        const double b = B[(size_t)k * m + j];
+        B[(size_t)k * m + j] = B[(size_t)p * m + j];
+        B[(size_t)p * m + j] = b;
+      }
+      __syncthreads();
+    }
+    const double inv = 1.0 / M[(size_t)k * m + k];
+    __syncthreads();
+    for (int j = tid; j < np; j += nt) {
+      M[(size_t)k * m + j] *= inv;
+      B[(size_t)k * m + j] *= inv;
+    }
+    __syncthreads();
+    // eliminate column k from every other row; each thread owns (row, column) pairs, column k is read first
+    for (int e = tid; e < np * np; e += nt) {
+      const int r = e / np, j = e % np;
+      if (r == k) continue;
+      const double f = M[(size_t)r * m + k];
+      if (j != k) M[(size_t)r * m + j] -= f * M[(size_t)k * m + j];
+      B[(size_t)r * m + j] -= f * B[(size_t)k * m + j];
+    }
+    __syncthreads();
+    for (int r = tid; r < np; r += nt)
+      if (r != k) M[(size_t)r * m + k] = 0.0;
+    __syncthreads();
+  }
+  // NOTE: row swaps were applied to F_PP only; F_PB rows were not swapped, which is right: P F_PP = LU-like
+  // elimination acts on [F_PP | I], and B now holds F_PP^-1 exactly (no permutation left over).
+  // -H = -Inv * F_PB
+  for (int e = tid; e < np * nb; e += nt) {
+    const int i = e / nb, j = e % nb;
+    double s = 0.0;
+    for (int k = 0; k < np; ++k) s += B[(size_t)i * m + k] * M[(size_t)k * m + np + j];
+    B[(size_t)i * m + np + j] = -s;
+  }
+  // G = F_BP * Inv
+  for (int e = tid; e < nb * np; e += nt) {
+    const int i = e / np, j = e % np;
+    double s = 0.0;
+    for (int k = 0; k < np; ++k) s += M[(size_t)(np + i) * m + k] * B[(size_t)k * m + j];
+    G[(size_t)i * np + j] = s;
+  }
+  __syncthreads();
+  // F_BB -= G * F_PB
+  for (int e = tid; e < nb * nb; e += nt) {
+    const int i = e / nb, j = e % nb;
+    double s = 0.0;
+    for (int k = 0; k < np; ++k) s += G[(size_t)i * np + k] * M[(size_t)k * m + np + j];
+    M[(size_t)(np + i) * m + np + j] -= s;
+  }
+}
+
+__global__ void check_info_kernel(const int* info, int* error) {
+  if (*info != 0) atomicExch(error, 3);
+}
+
+__global__ void set_identity_kernel(double* B, int np, int ld) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < np * np) B[(size_t)(e / np) * ld + (e % np)] = (e / np == e % np) ? 1.0 : 0.0;
+}
+
+void cublas_check(cublasStatus_t s, const char* what) {
+  if (s != CUBLAS_STATUS_SUCCESS) throw StatusError(PECS_ERR_CUDA, std::string(what) + ": cuBLAS status " + std::to_string((int)s));
+}
+void cusolver_check(cusolverStatus_t s, const char* what) {
+  if (s != CUSOLVER_STATUS_SUCCESS)
+    throw StatusError(PECS_ERR_CUDA, std::string(what) + ": cuSOLVER status " + std::to_string((int)s));
+}
+
+struct Handles {
+  cublasHandle_t blas = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  Handles() {
+    cublas_check(cublasCreate(&blas), "cublasCreate");
+    cusolver_check(cusolverDnCreate(&solver), "cusolverDnCreate");
+  }
+  ~Handles() {
+    if (solver) cusolverDnDestroy(solver);
+    if (blas) cublasDestroy(blas);
+  }
+};
+
+} // namespace
+
+bool device_factorization_enabled() {
+  const char* e = std::getenv("PECS_B200_HOST_FACTOR");
+  return !(e && e[0] == '1');
+}
+
+void factorize_device(const SolvePlan& plan, const CsrMatrix& A, const DeviceFront*, const int* d_bd_index, const int*,
+                      double* d_fwd, double* d_bwd) {
+  const CsrMatrix Ap = permute_csr(A, plan.perm, false), Apt = permute_csr(A, plan.perm, true);
+  DeviceBuffer<int> rp, col, trp, tcol, d_error(1);
+  DeviceBuffer<double> val, tval;
+  rp.upload(Ap.row_ptr);
+  col.upload(Ap.col);
+  val.upload(Ap.val);
+  trp.upload(Apt.row_ptr);
+  tcol.upload(Apt.col);
+  tval.upload(Apt.val);
+  d_error.zero();
+  PECS_CUDA(cudaMemset(d_fwd, 0, (size_t)std::max<int64_t>(plan.fwd_entries, 2) * sizeof(double)));
+  PECS_CUDA(cudaMemset(d_bwd, 0, (size_t)std::max<int64_t>(plan.bwd_entries, 2) * sizeof(double)));
+
+  Handles h;
+  DeviceBuffer<double> Fcur, Fchild, work;
+  DeviceBuffer<FactorFront> d_cur, d_child;
+  DeviceBuffer<int> ipiv((size_t)std::max(plan.max_np, 1)), info(1), cl, small_list;
+  std::vector<int> index_in_level(plan.fronts.size(), -1);
+
+  for (int d = (int)plan.levels.size() - 1; d >= 0; --d) {
+    const std::vector<int>& lvl = plan.levels[d];
+    std::vector<FactorFront> ff(lvl.size());
+    std::vector<int> small, large;
+    long long F_total = 0, cl_total = 0;
+    int max_child_nb = 0;
+    for (size_t k = 0; k < lvl.size(); ++k) {
+      const Front& F = plan.fronts[lvl[k]];
+      FactorFront& x = ff[k];
+      x.np = F.np;
+      x.nb = F.nb;
+      x.p0 = F.p0;
+      x.bd_off = F.bd_off;
+      x.fwd_off = F.fwd_off;
+      x.bwd_off = F.bwd_off;
+      x.F_off = F_total;
+      F_total += (long long)(F.np + F.nb) * (F.np + F.nb);
+      for (int c = 0; c < 2; ++c) {
+        x.child[c] = F.child[c] >= 0 ? index_in_level[F.child[c]] : -1;
+        x.cl_off[c] = cl_total;
+        if (F.child[c] >= 0) {
+          cl_total += plan.fronts[F.child[c]].nb;
+          max_child_nb = std::max(max_child_nb, plan.fronts[F.child[c]].nb);
+        }
+      }
+      (F.np <= kSmallFrontMaxNp ? small : large).push_back((int)k);
+    }
+    for (size_t k = 0; k < lvl.size(); ++k) index_in_level[lvl[k]] = (int)k;
+    Fcur.resize((size_t)F_total);
+    Fcur.zero();
+    d_cur.upload(ff);
+    const int nfl = (int)lvl.size();
+    assemble_kernel<<<nfl, 128>>>(d_cur.get(), d_bd_index, rp.get(), col.get(), val.get(), trp.get(), tcol.get(),
+                                  tval.get(), Fcur.get(), d_error.get());
+    if (cl_total > 0) {
+      cl.resize((size_t)cl_total);
+      for (int c = 0; c < 2; ++c) {
+        child_local_kernel<<<nfl, 128>>>(d_cur.get(), d_child.get(), d_bd_index, c, cl.get(), d_error.get());
+        const dim3 grid(nfl, std::max(1, std::min(max_child_nb, 1024)));
+        extend_add_kernel<<<grid, 256>>>(d_cur.get(), d_child.get(), c, cl.get(), Fchild.get(), Fcur.get());
+      }
+    }
+    PECS_CUDA(cudaGetLastError());
+    if (!small.empty()) {
+      small_list.upload(small);
+      small_front_kernel<<<(int)small.size(), 256>>>(d_cur.get(), small_list.get(), Fcur.get(), d_fwd, d_bwd, d_error.get());
+      PECS_CUDA(cudaGetLastError());
+    }
+    for (int k : large) {
+      const FactorFront& x = ff[k];
+      const int np = x.np, nb = x.nb, m = np + nb;
+      double* M = Fcur.get() + x.F_off;
+      double* B = d_bwd + x.bwd_off;
+      double* G = d_fwd + x.fwd_off;
+      // col-major view of the row-major F_PP (ld m) is F_PP^T; getrf/getrs on it give (F_PP^T)^-1 = Inv^T, whose
+      // col-major storage with ld m IS the row-major Inv with row stride m: the result lands in the table directly.
+      int lwork = 0;
+      cusolver_check(cusolverDnDgetrf_bufferSize(h.solver, np, np, M, m, &lwork), "getrf_bufferSize");
+      if ((size_t)lwork > work.size()) work.resize((size_t)lwork);
+      cusolver_check(cusolverDnDgetrf(h.solver, np, np, M, m, work.get(), ipiv.get(), info.get()), "getrf");
+      check_info_kernel<<<1, 1>>>(info.get(), d_error.get());
+      set_identity_kernel<<<(np * np + 255) / 256, 256>>>(B, np, m);
+      cusolver_check(cusolverDnDgetrs(h.solver, CUBLAS_OP_N, np, np, M, m, ipiv.get(), B, m, info.get()), "getrs");
+      if (nb > 0) {
+        const double one = 1.0, zero = 0.0, minus = -1.0;
+        // (-H)^T = -F_PB^T Inv^T : C(nb x np, ld m) = -A(nb x np: F_PB memory, ld m) * B(np x np: Inv memory, ld m)
+        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, np, np, &minus, M + np, m, B, m, &zero, B + np, m),
+                     "dgemm H");
+        // G^T = Inv^T F_BP^T : C(np x nb, ld np) = A(np x np: Inv memory, ld m) * B(np x nb: F_BP memory, ld m)
+        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, np, nb, np, &one, B, m, M + (size_t)np * m, m, &zero, G, np),
+                     "dgemm G");
+        // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * B(np x nb: G memory, ld np)
+        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, nb, np, &minus, M + np, m, G, np, &one,
+                                 M + (size_t)np * m + np, m),
+                     "dgemm U");
+      }
+    }
+    PECS_CUDA(cudaDeviceSynchronize());
+    int herr = 0;
+    PECS_CUDA(cudaMemcpy(&herr, d_error.get(), sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr == 3) throw StatusError(PECS_ERR_SINGULAR, "factorize_device: singular pivot block in a small front");
+    if (herr != 0) throw StatusError(PECS_ERR_INTERNAL, "factorize_device: matrix entry outside the symbolic front structure");
+    // this level becomes the child level of the next one
+    std::swap(Fcur, Fchild);
+    std::swap(d_cur, d_child);
+  }
 }
 
 } // namespace pecs

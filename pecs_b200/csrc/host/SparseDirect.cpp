@@ -294,7 +294,9 @@ bool invert(int n, double* M, bool par) {
   return true;
 }
 
-CsrMatrix permute(const CsrMatrix& A, const std::vector<int>& perm, bool transpose) {
+} // namespace
+
+CsrMatrix permute_csr(const CsrMatrix& A, const std::vector<int>& perm, bool transpose) {
   TripletList tl(A.n);
   tl.reserve(A.nnz());
   for (int i = 0; i < A.n; ++i)
@@ -307,10 +309,8 @@ CsrMatrix permute(const CsrMatrix& A, const std::vector<int>& perm, bool transpo
   return tl.compress();
 }
 
-} // namespace
-
 void factorize_host(const SolvePlan& plan, const CsrMatrix& A, std::vector<double>& fwd, std::vector<double>& bwd) {
-  const CsrMatrix Ap = permute(A, plan.perm, false), Apt = permute(A, plan.perm, true);
+  const CsrMatrix Ap = permute_csr(A, plan.perm, false), Apt = permute_csr(A, plan.perm, true);
   fwd.assign((size_t)plan.fwd_entries, 0.0);
   bwd.assign((size_t)plan.bwd_entries, 0.0);
   const int nf = (int)plan.fronts.size();

@@ -57,6 +57,9 @@ struct SolvePlan {
 SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_dof, const std::vector<double>& node_x,
                            const std::vector<double>& node_y, int leaf_nodes);
 
+// P A P^T (or its transpose) in CSR, P = plan.perm
+CsrMatrix permute_csr(const CsrMatrix& A, const std::vector<int>& perm, bool transpose);
+
 // Host numeric factorisation: fills fwd (all G) and bwd (all [Inv | -H]) tables.  Throws StatusError(PECS_ERR_SINGULAR)
 // when a pivot block cannot be inverted.
 void factorize_host(const SolvePlan& plan, const CsrMatrix& A, std::vector<double>& fwd, std::vector<double>& bwd);

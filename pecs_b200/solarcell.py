@@ -84,6 +84,9 @@ class SolarCellProblem:
                                               C.byref(self._h)))
 
     def close(self):
+        for p in getattr(self, "_pinned", []):
+            self._lib.pecs_host_free(p)
+        self._pinned = []
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.pecs_solarcell_destroy(self._h)
             self._h = C.c_void_p()
@@ -244,6 +247,24 @@ class SolarCellProblem:
 
     def step(self, n_steps=1):
         check(self._lib.pecs_step(self.ctx, int(n_steps)))
+
+    def pinned_states(self):
+        """five page-locked numpy arrays (electrons, holes, reductants, oxidants, Poisson) for step_host()"""
+        out = []
+        for w in range(5):
+            n = self.n_dofs(w)
+            p = self._lib.pecs_host_alloc(8 * max(n, 1))
+            if not p:
+                raise MemoryError("pecs_host_alloc failed")
+            arr = np.ctypeslib.as_array(C.cast(p, _lib.c_double_p), shape=(max(n, 1),))[:n]
+            self._pinned = getattr(self, "_pinned", []) + [p]
+            out.append(arr)
+        return out
+
+    def step_host(self, n_steps, states):
+        """n steps with host-resident state: H2D of the five solutions, the steps, D2H of the five solutions."""
+        ptrs = (_lib.c_double_p * 5)(*[_dp(a) if a.size else None for a in states])
+        check(self._lib.pecs_step_host(self.ctx, int(n_steps), ptrs))
 
     def synchronize(self):
         check(self._lib.pecs_synchronize(self.ctx))
