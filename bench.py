@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py -- IMEX steps/sec of the PECS per-step hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path (oracle port)
+
+A step = one pass of the loop body of the reference's time loop (reference source/SolarCell.cpp:2055-2080): both
+carrier RHS assemblies, the four carrier solves, the Poisson RHS and the Poisson solve, on synthetic input: the
+reference's default geometry refined to ~1 M DoF per carrier (cfg3: global refinements 7, local 1; 983 040 DoF per
+carrier, Poisson 492 800 DoF).  With N > 1 every rank runs its own context at its own applied bias (the I-V sweep
+of BASELINE.json config 5): weak scaling, no data-path collective.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "IMEX steps/sec at ~1M DoF/carrier"
+UNIT = "steps/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.lines, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for line in self.lines:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # samples under load: the upper half of the clock readings
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def workload_name(g, l):
+    return (f"default input_file.prm geometry, global refinements {g}, local refinements {l}, fp64, degree 1" +
+            (" (cfg3: 983040 DoF per carrier, Poisson 492800 DoF)" if (g, l) == (7, 1) else ""))
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_run(g_sample, l, steps, warmup, threads=None):
+    """Times the oracle (CPU restatement of the reference's WorkStream + UMFPACK path) on a bounded sample mesh.
+    Returns (steps_per_s on the sample mesh, cells per subdomain of the sample, threads, section seconds)."""
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pecs_b200 as pecs
+    from helpers import make_oracle
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g_sample, l))
+    prob.setup_full_system_host()  # mesh tables only; no device involved
+    o = make_oracle(prob, True)
+    o.project_initial_conditions()
+    o.assemble_Poisson_rhs()
+    o.solve_Poisson()
+    o.step(warmup)
+    t0 = time.perf_counter()
+    sections = o.step(steps)
+    dt = time.perf_counter() - t0
+    cells = prob.n_cells(0)
+    prob.close()
+    return steps / dt, cells, int(os.environ.get("OMP_NUM_THREADS", os.cpu_count())), [float(s) for s in sections]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0  # only rank 0 runs and prints the CPU arm
+    g_full, l = args.global_refinements, args.local_refinements
+    g_s = min(args.cpu_sample_refinements, g_full)
+    sps, cells, threads, sections = cpu_oracle_run(g_s, l, args.steps, max(args.warmup, 1))
+    cells_full = 4 ** g_full + (4 ** (g_full + l) if l > 0 else 0)
+    scale = cells / cells_full  # linear extrapolation in the number of cells: generous to the CPU (LU fill is superlinear)
+    value = sps * scale * args.gpus  # N replicas of the same CPU job would need N boxes; reported per the contract
+    sample = (f"oracle port (OpenMP cell loops + 4 concurrent sparse LU substitutions + 1) on global refinements {g_s} "
+              f"({cells} cells/subdomain, {12 * cells} DoF/carrier), {args.steps} timed steps; steps/s scaled by "
+              f"cells ratio {scale:.5f} to the cfg workload")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / (sps * scale), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(g_full, l), "sample_global_refinements": g_s},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "section_seconds": dict(zip(["Assemble semiconductor rhs", "Assemble electrolyte rhs",
+                                                          "Solve LDG Systems", "Assemble Poisson rhs",
+                                                          "Solve Poisson system"], sections))},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import numpy as np
+    import pecs_b200 as pecs
+    from pecs_b200 import solarcell as sc, sweep
+
+    rank, local, world, dist = sweep.init_distributed("nccl")
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    device = local
+    if dist is not None:
+        import torch
+        torch.cuda.set_device(device)
+    if pecs.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; pecs_b200 has no CPU fallback")
+    g, l = args.global_refinements, args.local_refinements
+    overrides = {}
+    if world > 1:  # one applied bias per rank; the bias only acts through Dirichlet faces at x == 0 (insulated=false)
+        overrides = {"physical__insulated": False, "physical__applied_bias": sweep.bias_for_rank(rank, world)}
+    t_setup = time.perf_counter()
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **overrides), device=device)
+    prob.setup_full_system()
+    prob.synchronize()
+    t_setup = time.perf_counter() - t_setup
+
+    K, W = args.steps, max(args.warmup, 3)
+    prob.step(W)
+    prob.synchronize()
+    sweep.barrier(dist, device)
+    sampler = ClockSampler(device)
+    sampler.start()
+    ms = prob.step_timed(K)[0]  # CUDA events on the context's stream around K graph replays
+    clocks = sampler.stop()
+    sweep.barrier(dist, device)
+    ms_max = sweep.max_over_ranks(ms, dist, device)
+    value = world * K / (ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer entry point: H2D of the five states, one step, D2H of the five states
+    states = prob.pinned_states()
+    for w in range(5):
+        states[w][:] = prob.get_solution(w)
+    prob.step_host(1, states)  # warm
+    sweep.barrier(dist, device)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        prob.step_host(1, states)
+    e2e_s = time.perf_counter() - t0
+    e2e_s = sweep.max_over_ranks(e2e_s, dist, device)
+    state_bytes = int(sum(a.nbytes for a in states))
+
+    line = None
+    # ---- roofline of the dominant kernels (sectioned run: device time per reference TimerOutput section)
+    sect = prob.step_timed(min(K, 10), sectioned=True) / min(K, 10)
+    factor_bytes = prob.info(sc.INFO_FACTOR_BYTES)
+    solve_ms = sect[3] + sect[5]
+    rhs_ms, rhs_launches = prob.time_kernel(0, 20)
+    rhs_bytes = 368 * (prob.n_cells(0) + prob.n_cells(1))
+    peak, peak_src = measured_peaks()
+    if rank == 0:
+        solve_gbs = factor_bytes / (solve_ms * 1e-3) / 1e9
+        rhs_gbs = rhs_bytes / (rhs_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(g, l), "parallelism": "1 context per GPU, one applied bias per rank"
+                       if world > 1 else "single context",
+                       "l2": "inputs larger than L2: every step streams the factor tables "
+                             f"({factor_bytes / 1e9:.1f} GB) once; the isolated RHS timing flushes L2 (256 MB memset)",
+                       "setup_seconds": t_setup},
+            "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
+                    "d2h_bytes_per_step": state_bytes},
+            "gpu_launches": prob.info(sc.INFO_LAUNCHES_PER_STEP) * K,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "forward/backward level kernels of the five multifrontal solves",
+                         "achieved": solve_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": solve_gbs / peak, "traffic": None,
+                         "algorithmic_bytes_per_step": factor_bytes, "ms_per_step": solve_ms},
+            "rhs_roofline": {"bound": "hbm", "kernel": "carrier_cell_rhs + carrier_boundary_rhs (both subdomains)",
+                             "achieved": rhs_gbs, "peak": peak, "unit": "GB/s", "frac": rhs_gbs / peak,
+                             "algorithmic_bytes_per_launch_group": rhs_bytes, "ms": rhs_ms, "launches": rhs_launches},
+            "section_ms_per_step": dict(zip(["Assemble semiconductor rhs", "Assemble electrolyte rhs",
+                                             "Solve LDG Systems", "Assemble Poisson rhs", "Solve Poisson system"],
+                                            [float(x) for x in sect[1:]])),
+        }
+    prob.close()
+    if rank == 0:
+        # CPU baseline on this box's host cores (rank 0, N = 1 only): bounded sample of the same workload
+        if world == 1 and not args.no_cpu_baseline:
+            g_s = min(args.cpu_sample_refinements, g)
+            sps, cells, threads, _ = cpu_oracle_run(g_s, l, args.cpu_steps, 1)
+            cells_full = prob_cells(g, l)
+            line["cpu_baseline"] = {
+                "value": sps * cells / cells_full, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"oracle port on global refinements {g_s} ({cells} cells/subdomain), {args.cpu_steps} steps, "
+                          f"scaled linearly in cells to the workload (generous to the CPU: LU fill grows faster)"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def prob_cells(g, l):
+    return 4 ** g + (4 ** (g + l) if l > 0 else 0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["pecs_b200", "reference"], default="pecs_b200")
+    ap.add_argument("--global-refinements", type=int, default=7)
+    ap.add_argument("--local-refinements", type=int, default=1)
+    ap.add_argument("--cpu-sample-refinements", type=int, default=5,
+                    help="mesh of the bounded CPU sample (the oracle's sparse LU at refinement 7 does not fit the budget)")
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -268,7 +268,9 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, const DeviceFro
   PECS_CUDA(cudaMemset(d_fwd, 0, (size_t)std::max<int64_t>(plan.fwd_entries, 2) * sizeof(double)));
   PECS_CUDA(cudaMemset(d_bwd, 0, (size_t)std::max<int64_t>(plan.bwd_entries, 2) * sizeof(double)));
 
-  Handles h;
+  // cuSOLVER / cuBLAS initialisation costs about a second: one set of handles per process
+  static Handles* handles = new Handles();
+  Handles& h = *handles;
   DeviceBuffer<double> Fcur, Fchild, work;
   DeviceBuffer<FactorFront> d_cur, d_child;
   DeviceBuffer<int> ipiv((size_t)std::max(plan.max_np, 1)), info(1), cl, small_list;

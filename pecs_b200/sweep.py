@@ -1,0 +1,55 @@
+"""Multi-GPU layout of the benchmark and of I-V sweeps: one context per applied bias, one bias per rank.
+
+The reference has no sweep driver (`applied bias` is one scalar, reference input_file.prm:86); BASELINE.json config 5
+places one applied voltage per GPU.  Contexts of different biases share nothing, so there is no data-path
+collective: torch.distributed is used only for the barrier and for the max-over-ranks of the device time."""
+import os
+
+
+def bias_for_rank(rank, world_size, v_min=0.0, v_step=0.05):
+    """applied bias [V] of a rank: 0, 0.05, 0.10, ... (>= 0: the reference's pattern forbids negative values,
+    reference source/ParameterReader.cpp:66-68)"""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    return v_min + v_step * rank
+
+
+def init_distributed(backend=None):
+    """(rank, local_rank, world_size, dist or None) from the torchrun environment; no process group for 1 rank"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        return rank, local, world, None
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if not dist.is_initialized():
+        dist.init_process_group(backend=backend or "nccl", rank=rank, world_size=world)
+    return rank, local, world, dist
+
+
+def barrier(dist, device=None):
+    if dist is not None:
+        if device is not None:
+            dist.barrier(device_ids=[device])
+        else:
+            dist.barrier()
+
+
+def max_over_ranks(value, dist, device=None):
+    """max of a python float over all ranks (gloo on CPU tensors, nccl on the rank's GPU)"""
+    if dist is None:
+        return float(value)
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=f"cuda:{device}" if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, dist, device=None):
+    if dist is None:
+        return float(value)
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=f"cuda:{device}" if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

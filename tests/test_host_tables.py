@@ -1,0 +1,125 @@
+"""Host logic on CPU: meshes, dof numbering, mappings and the constant matrices built by pecs_b200/csrc/host,
+checked against SURVEY App. D counts, against the independently written oracle, and through structural identities."""
+import os
+
+import numpy as np
+import pytest
+
+import pecs_b200 as pecs
+from helpers import make_oracle
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def default_problem():
+    prob = pecs.SolarCellProblem(pecs.default_input_file(4, 1))
+    prob.setup_full_system_host()
+    return prob, make_oracle(prob, True, factor=False)
+
+
+@pytest.mark.parametrize("g,l,cells,rt,pairs", [(4, 1, 1280, 5280, 32), (3, 1, 320, 1360, 16), (4, 0, 256, None, 16),
+                                                (3, 2, None, None, 32)])
+def test_mesh_counts(g, l, cells, rt, pairs):
+    """cells/subdomain = 4^g + 4^(g+l), RT0 count incl. parent and child edges on hanging lines"""
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l))
+    prob.setup_full_system_host()
+    if cells is not None:
+        assert prob.n_cells(0) == cells and prob.n_cells(1) == cells and prob.n_cells(2) == 2 * cells
+    if rt is not None:
+        assert prob.n_rt == rt
+    assert len(prob.interface_pairs()[0]) == pairs
+    for which in range(3):
+        m = prob.mesh(which)
+        # 2:1 balance (deal.II smoothing): neighbours differ by at most one level
+        for c in range(m["n_cells"]):
+            for f in range(4):
+                k = m["face_kind"][c, f]
+                if k == 0:
+                    assert m["level"][m["neighbor"][c, f]] == m["level"][c]
+                elif k == 2:
+                    assert m["level"][m["neighbor"][c, f]] == m["level"][c] + 1
+                    assert m["level"][m["neighbor2"][c, f]] == m["level"][c] + 1
+                elif k == 3:
+                    assert m["level"][m["neighbor"][c, f]] == m["level"][c] - 1
+        # positive Jacobian at the vertices
+        v = m["vertices"]
+        det = (v[:, 1, 0] - v[:, 0, 0]) * (v[:, 2, 1] - v[:, 0, 1]) - (v[:, 2, 0] - v[:, 0, 0]) * (v[:, 1, 1] - v[:, 0, 1])
+        assert (det > 0).all()
+
+
+def test_boundary_tagging_default_input(default_problem):
+    """reference Grid.cpp:340-461 incl. the radius-one quirk on the bottom edge"""
+    prob, _ = default_problem
+    m = prob.mesh(0)
+    on_bdry = m["face_kind"] == 1
+    ids = m["boundary_id"][on_bdry]
+    assert set(np.unique(ids)) == {0, 1, 2, 3}  # interface, Dirichlet, Neumann, Schottky all present
+    assert (ids == 0).sum() == 32
+    # bottom faces with 0.3 < x < 0.6 are Neumann, x < 0.3 Dirichlet
+    v = m["vertices"]
+    for c in range(m["n_cells"]):
+        if m["face_kind"][c, 2] == 1 and v[c, 0, 1] == 0.0:
+            xc = 0.5 * (v[c, 0, 0] + v[c, 1, 0])
+            assert m["boundary_id"][c, 2] == (2 if xc > 0.3 else 1)
+
+
+def test_dofs_and_maps_match_oracle(default_problem):
+    prob, o = default_problem
+    assert o.n_rt == prob.n_rt
+    assert (o.poisson_face_dofs(prob.n_cells(2)) == prob.poisson_face_dofs()).all()
+    assert (o.cell_map(0, prob.n_cells(0)) == prob.cell_map(0)).all()
+    assert (o.cell_map(1, prob.n_cells(1)) == prob.cell_map(1)).all()
+    dof, master, w = prob.constraints()
+    assert (w[master >= 0] == 0.5).all() and len(dof) > 0
+
+
+@pytest.mark.parametrize("which", range(7))
+def test_matrices_match_oracle(default_problem, which):
+    """block-form host assembly vs the oracle's FEValues loops (hanging faces included: l = 1)"""
+    prob, o = default_problem
+    A, B = prob.matrix(which), o.matrix(which)
+    assert A.nnz == B.nnz
+    assert abs(A - B).max() <= 1e-13 * abs(B).max()
+
+
+def test_carrier_matrix_structure(default_problem):
+    """symmetric part = diag(mu^-1 A, M/dt + penalty); B blocks are skew"""
+    prob, _ = default_problem
+    A = prob.matrix(0).tocsr()
+    n = A.shape[0] // 3
+    S = 0.5 * (A + A.T)
+    off = S[: 2 * n, 2 * n:]
+    assert abs(off).max() <= 1e-13 * abs(A).max()
+    # current-current block is the cell mass matrix / mu: symmetric positive definite, block diagonal
+    JJ = A[: 2 * n, : 2 * n]
+    assert abs(JJ - JJ.T).max() <= 1e-13 * abs(JJ).max()
+    assert JJ.diagonal().min() > 0
+
+
+def test_mass_matrix_row_sums(default_problem):
+    """sum of M = |Omega| / dt (partition of unity)"""
+    prob, _ = default_problem
+    M = prob.matrix(5)
+    area = 0.5 * (0.3 + 0.6) * 1.0  # trapezoid semiconductor
+    assert abs(M.sum() * prob.delta_t - area) <= 1e-12
+
+
+def test_oracle_matches_golden():
+    """the committed fixtures are oracle outputs: this notices any change of the oracle (and of the host tables)"""
+    for name, g, overrides in (("production_g2_l1.npz", 2, {}),
+                               ("production_g3_l1_biased.npz", 3,
+                                {"physical__insulated": False, "physical__applied_bias": 0.1})):
+        gold = np.load(os.path.join(GOLDEN, name))
+        prob = pecs.SolarCellProblem(pecs.default_input_file(g, 1, **overrides))
+        prob.setup_full_system_host()
+        o = make_oracle(prob, True)
+        o.project_initial_conditions()
+        o.assemble_Poisson_rhs()
+        o.solve_Poisson()
+        scale = abs(gold["poisson_solution_initial"]).max()
+        assert abs(o.solution(4) - gold["poisson_solution_initial"]).max() <= 1e-11 * max(scale, 1e-300)
+        o.step(int(gold["n_steps"]))
+        for s in range(5):
+            ref = gold[f"state_after_steps_{s}"]
+            assert abs(o.solution(s) - ref).max() <= 1e-10 * abs(ref).max()

@@ -1,0 +1,65 @@
+"""Host logic on CPU: the nested-dissection plan and the factor tables (host numeric factorisation) solve the
+constant systems; the oracle's own sparse LU is cross-checked with SuperLU (scipy) as a third, unrelated solver."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+import pecs_b200 as pecs
+from helpers import make_oracle
+
+
+@pytest.fixture(scope="module")
+def problem():
+    prob = pecs.SolarCellProblem(pecs.default_input_file(3, 1))
+    prob.setup_full_system_host()
+    return prob
+
+
+@pytest.mark.parametrize("which", [0, 1, 2, 4])
+@pytest.mark.parametrize("leaf", [0, 1, 9])
+def test_plan_and_tables_solve_the_system(problem, which, leaf):
+    A = problem.matrix(which)
+    rng = np.random.default_rng(which)
+    b = rng.standard_normal(A.shape[0])
+    x = problem.selftest_direct_solve(which, b, leaf)
+    assert np.linalg.norm(A @ x - b) <= 1e-10 * np.linalg.norm(b)
+    st = problem.plan_stats(which, leaf)
+    assert st["fwd_entries"] > 0 and st["levels"] >= 3
+
+
+def test_poisson_plan_never_needs_cross_front_pivoting():
+    """the saddle-point matrix has a zero (Phi, Phi) block: pairing each potential with fluxes of its own cell
+    keeps every pivot block invertible (host/SolverSetup.hpp) -- on the hanging-node mesh and on the test grids"""
+    for prm, test_defaults, setup in ((pecs.default_input_file(4, 1), False, None), (None, True, 4)):
+        prob = pecs.SolarCellProblem(prm, test_defaults=test_defaults)
+        if setup is None:
+            prob.setup_full_system_host()
+        else:
+            prob.setup_test_host(pecs.KIND_TEST_DD_POISSON, setup)
+        A = prob.matrix(pecs.POISSON)
+        b = np.ones(A.shape[0])
+        x = prob.selftest_direct_solve(pecs.POISSON, b)
+        assert np.linalg.norm(A @ x - b) <= 1e-9 * np.linalg.norm(b)
+
+
+def test_oracle_lu_against_superlu(problem):
+    o = make_oracle(problem, True)
+    rng = np.random.default_rng(7)
+    for which in (0, 3, 4):
+        A = o.matrix(which).tocsc()
+        b = rng.standard_normal(A.shape[0])
+        o.set_vector(which, 1, b)
+        if which == 4:
+            # PoissonData::solve also distributes the constraints; compare the unconstrained rows
+            o.solve_Poisson()
+        else:
+            o.solve_species(which)
+        x_ref = spla.splu(A).solve(b)
+        x = o.solution(which)
+        if which == 4:
+            dof, _, _ = problem.constraints()
+            keep = np.ones(A.shape[0], bool)
+            keep[dof] = False
+            assert np.abs(x[keep] - x_ref[keep]).max() <= 1e-9 * np.abs(x_ref).max()
+        else:
+            assert np.abs(x - x_ref).max() <= 1e-10 * np.abs(x_ref).max()
