@@ -73,6 +73,9 @@ pecs_status pecs_solarcell_mixed_errors(pecs_solarcell* p, double out[2]);
  * stats[0] fronts, [1] levels, [2] max np, [3] max nb, [4] forward-table entries, [5] backward-table entries,
  * [6] update-buffer entries.  which: 0..3 species, 4 Poisson. */
 pecs_status pecs_solarcell_plan_stats(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, int64_t stats[8]);
+/* per-level breakdown of the same plan: for level d (0 = root) out[6*d..6*d+5] = fronts, forward entries, backward
+ * entries, max np, max nb, sum of np; returns the number of levels (<= max_levels written) */
+int32_t pecs_solarcell_plan_levels(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, int64_t* out, int32_t max_levels);
 /* Additionally runs the HOST numeric factorisation and the host reference of the two solve sweeps on rhs b, so
  * that the CPU test-suite can check plan + factor tables against the matrix (residual) without a GPU. */
 pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,

@@ -33,13 +33,12 @@ namespace pecs {
 struct DeviceSystem {
   int n = 0;
   SolvePlan plan;
-  DeviceBuffer<double> fwd, bwd, upd, w_in, w_fin, x_perm;
-  DeviceBuffer<int> bd_index, child_map, perm, iperm;
+  DeviceBuffer<double> fwd, bwd, cbuf, w_in, w_fin, x_perm;
+  DeviceBuffer<int> bd_index, out_map, perm, iperm;
   DeviceBuffer<DeviceFront> fronts;
   struct Level {
-    DeviceBuffer<SolveTile> fwd_tiles, bwd_tiles;
-    int smem_fwd = 0, smem_bwd = 0;
-    bool vec2_fwd = true, vec2_bwd = true;
+    DeviceBuffer<SolveTile> fwd_row_tiles, fwd_col_tiles, bwd_tiles;
+    int smem_fwd = 0, smem_bwd = 0; // doubles; smem_bwd == 0: gather on the fly
   };
   std::vector<Level> levels;
   int launches_per_solve = 0;
@@ -49,6 +48,14 @@ struct DeviceSystem {
     int m = 0;
     for (const Level& l : levels) m = std::max(m, std::max(l.smem_fwd, l.smem_bwd));
     return m;
+  }
+
+  // rows per tile so that a level offers several CTAs per SM even when it has only a few big fronts
+  static int rows_per_tile(int64_t total_rows) {
+    const int64_t want_tiles = 8 * 148;
+    int64_t r = (total_rows + want_tiles - 1) / want_tiles;
+    r = ((r + 7) / 8) * 8;
+    return (int)std::min<int64_t>(64, std::max<int64_t>(8, r));
   }
 
   void build(const CsrMatrix& A, const NodeLayout& layout, int leaf_nodes, bool factor_on_device) {
@@ -62,30 +69,30 @@ struct DeviceSystem {
       D.np = F.np;
       D.nb = F.nb;
       D.p0 = F.p0;
+      D.ld_fwd = F.ld_fwd;
+      D.ld_bwd = F.ld_bwd;
+      D.fwd_colmajor = F.fwd_colmajor;
       D.bd_off = F.bd_off;
       D.fwd_off = F.fwd_off;
       D.bwd_off = F.bwd_off;
-      D.upd_off = F.upd_off;
-      for (int k = 0; k < 2; ++k) {
-        D.has_child[k] = F.child[k] >= 0;
-        D.cmap_off[k] = F.cmap_off[k];
-        D.child_upd_off[k] = F.child[k] >= 0 ? plan.fronts[F.child[k]].upd_off : 0;
-      }
+      D.cbuf_off[0] = F.cbuf_off[0];
+      D.cbuf_off[1] = F.cbuf_off[1];
+      D.out_off = F.parent >= 0 ? plan.fronts[F.parent].cbuf_off[F.which_child] : -1;
     }
     fronts.upload(df);
     bd_index.upload(plan.bd_index);
-    child_map.upload(plan.child_map);
+    out_map.upload(plan.out_map);
     perm.upload(plan.perm);
     iperm.upload(plan.iperm);
-    upd.resize((size_t)std::max<int64_t>(plan.upd_entries, 1));
-    upd.zero();
+    cbuf.resize((size_t)std::max<int64_t>(plan.upd_entries, 2));
+    cbuf.zero(); // slots no child ever writes must read as zero forever
     w_in.resize(n);
     w_fin.resize(n);
     x_perm.resize(n);
     fwd.resize((size_t)std::max<int64_t>(plan.fwd_entries, 2));
     bwd.resize((size_t)std::max<int64_t>(plan.bwd_entries, 2));
     if (factor_on_device) {
-      factorize_device(plan, A, fronts.get(), bd_index.get(), perm.get(), fwd.get(), bwd.get());
+      factorize_device(plan, A, fwd.get(), bwd.get());
     } else {
       std::vector<double> hf, hb;
       factorize_host(plan, A, hf, hb);
@@ -98,41 +105,55 @@ struct DeviceSystem {
     levels.resize(plan.levels.size());
     launches_per_solve = 2; // the two permutation gathers
     for (size_t d = 0; d < plan.levels.size(); ++d) {
-      std::vector<SolveTile> ft, bt;
+      std::vector<SolveTile> fr, fc, bt;
       Level& L = levels[d];
+      int64_t rows_f = 0, rows_b = 0;
+      int max_m = 0;
       for (int f : plan.levels[d]) {
         const Front& F = plan.fronts[f];
-        const int m = F.np + F.nb;
-        L.smem_fwd = std::max(L.smem_fwd, F.np);
-        L.smem_bwd = std::max(L.smem_bwd, m);
-        if (F.np & 1) L.vec2_fwd = false;
-        if (m & 1) L.vec2_bwd = false;
-        int first = 1;
-        for (int r0 = 0; r0 < std::max(F.nb, 1); r0 += kSolveRowsPerTile) {
-          ft.push_back(SolveTile{f, r0, std::max(0, std::min(kSolveRowsPerTile, F.nb - r0)), first});
-          first = 0;
-        }
-        for (int r0 = 0; r0 < F.np; r0 += kSolveRowsPerTile)
-          bt.push_back(SolveTile{f, r0, std::min(kSolveRowsPerTile, F.np - r0), 0});
+        if (!F.fwd_colmajor) rows_f += F.nb;
+        rows_b += F.np;
+        max_m = std::max(max_m, F.np + F.nb);
       }
-      L.smem_fwd += L.smem_fwd & 1;
-      L.smem_bwd += L.smem_bwd & 1;
-      L.fwd_tiles.upload(ft);
+      const int rf = rows_per_tile(rows_f), rb = rows_per_tile(rows_b);
+      for (int f : plan.levels[d]) {
+        const Front& F = plan.fronts[f];
+        int first = 1;
+        if (F.fwd_colmajor) {
+          for (int r0 = 0; r0 < std::max(F.nb, 1); r0 += kColTileRows) {
+            fc.push_back(SolveTile{f, r0, std::max(0, std::min(kColTileRows, F.nb - r0)), first});
+            first = 0;
+          }
+        } else {
+          L.smem_fwd = std::max(L.smem_fwd, F.np + 2);
+          for (int r0 = 0; r0 < std::max(F.nb, 1); r0 += rf) {
+            fr.push_back(SolveTile{f, r0, std::max(0, std::min(rf, F.nb - r0)), first});
+            first = 0;
+          }
+        }
+        for (int r0 = 0; r0 < F.np; r0 += rb) bt.push_back(SolveTile{f, r0, std::min(rb, F.np - r0), 0});
+      }
+      L.smem_bwd = max_m <= kBackwardStageMax ? max_m + 2 : 0;
+      L.fwd_row_tiles.upload(fr);
+      L.fwd_col_tiles.upload(fc);
       L.bwd_tiles.upload(bt);
-      launches_per_solve += 2;
+      launches_per_solve += (fr.empty() ? 0 : 1) + (fc.empty() ? 0 : 1) + 1;
     }
   }
 
   // solution = A^-1 rhs, all on stream s
   void solve(const double* rhs, double* solution, cudaStream_t s) {
-    const SolveTables t{fronts.get(), bd_index.get(), child_map.get(), fwd.get(), bwd.get()};
+    const SolveTables t{fronts.get(), bd_index.get(), out_map.get(), fwd.get(), bwd.get()};
     launch_gather(n, iperm.get(), rhs, w_in.get(), s);
-    for (int d = (int)levels.size() - 1; d >= 0; --d)
-      launch_forward_level(t, levels[d].fwd_tiles.get(), (int)levels[d].fwd_tiles.size(), levels[d].smem_fwd,
-                           levels[d].vec2_fwd, w_in.get(), w_fin.get(), upd.get(), s);
+    for (int d = (int)levels.size() - 1; d >= 0; --d) {
+      Level& L = levels[d];
+      launch_forward_cols(t, L.fwd_col_tiles.get(), (int)L.fwd_col_tiles.size(), w_in.get(), w_fin.get(), cbuf.get(), s);
+      launch_forward_rows(t, L.fwd_row_tiles.get(), (int)L.fwd_row_tiles.size(), L.smem_fwd, w_in.get(), w_fin.get(),
+                          cbuf.get(), s);
+    }
     for (size_t d = 0; d < levels.size(); ++d)
-      launch_backward_level(t, levels[d].bwd_tiles.get(), (int)levels[d].bwd_tiles.size(), levels[d].smem_bwd,
-                            levels[d].vec2_bwd, w_fin.get(), x_perm.get(), s);
+      launch_backward_rows(t, levels[d].bwd_tiles.get(), (int)levels[d].bwd_tiles.size(), levels[d].smem_bwd, w_fin.get(),
+                           x_perm.get(), s);
     launch_gather(n, perm.get(), x_perm.get(), solution, s);
   }
 };

@@ -25,7 +25,7 @@ namespace pecs {
 
 namespace {
 
-constexpr int kSmallFrontMaxNp = 96;
+constexpr int kSmallFrontMaxNp = kColMajorMaxNp;
 
 struct FactorFront {
   int np, nb, p0;
@@ -34,6 +34,7 @@ struct FactorFront {
   long long F_off;         // into this level's frontal buffer (m x m, row-major)
   long long fwd_off, bwd_off;
   long long cl_off[2];     // into the child-local index scratch
+  int ld_fwd, ld_bwd, fwd_colmajor;
 };
 
 __device__ __forceinline__ int local_index(int pos, int p0, int np, const int* bd, int nb) {
@@ -124,13 +125,15 @@ __global__ void __launch_bounds__(256) small_front_kernel(const FactorFront* __r
   const FactorFront F = fronts[small_list[blockIdx.x]];
   const int np = F.np, nb = F.nb, m = np + nb;
   double* M = Fbuf + F.F_off;   // rows 0..np-1 hold [F_PP | F_PB]
-  double* B = bwd + F.bwd_off;  // [Inv | -H], row stride m
-  double* G = fwd + F.fwd_off;  // nb x np
+  double* B = bwd + F.bwd_off;  // [Inv | -H], row stride ld_bwd
+  double* G = fwd + F.fwd_off;  // nb x np, row- or column-major
+  const int ldb = F.ld_bwd;
+  const size_t g_rs = F.fwd_colmajor ? 1 : (size_t)F.ld_fwd, g_cs = F.fwd_colmajor ? (size_t)F.ld_fwd : 1;
   __shared__ int s_piv;
   __shared__ double s_val[256];
   __shared__ int s_idx[256];
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int e = tid; e < np * np; e += nt) B[(size_t)(e / np) * m + (e % np)] = (e / np == e % np) ? 1.0 : 0.0;
+  for (int e = tid; e < np * np; e += nt) B[(size_t)(e / np) * ldb + (e % np)] = (e / np == e % np) ? 1.0 : 0.0;
   __syncthreads();
   for (int k = 0; k < np; ++k) {
     // pivot search in column k, rows k..np-1
@@ -164,9 +167,9 @@ __global__ void __launch_bounds__(256) small_front_kernel(const FactorFront* __r
         const double a = M[(size_t)k * m + j];
         M[(size_t)k * m + j] = M[(size_t)p * m + j];
         M[(size_t)p * m + j] = a;
-        const double b = B[(size_t)k * m + j];
-        B[(size_t)k * m + j] = B[(size_t)p * m + j];
-        B[(size_t)p * m + j] = b;
+        const double b = B[(size_t)k * ldb + j];
+        B[(size_t)k * ldb + j] = B[(size_t)p * ldb + j];
+        B[(size_t)p * ldb + j] = b;
       }
       __syncthreads();
     }
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(256) small_front_kernel(const FactorFront* __r
     __syncthreads();
     for (int j = tid; j < np; j += nt) {
       M[(size_t)k * m + j] *= inv;
-      B[(size_t)k * m + j] *= inv;
+      B[(size_t)k * ldb + j] *= inv;
     }
     __syncthreads();
     // eliminate column k from every other row; each thread owns (row, column) pairs, column k is read first
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(256) small_front_kernel(const FactorFront* __r
       if (r == k) continue;
       const double f = M[(size_t)r * m + k];
       if (j != k) M[(size_t)r * m + j] -= f * M[(size_t)k * m + j];
-      B[(size_t)r * m + j] -= f * B[(size_t)k * m + j];
+      B[(size_t)r * ldb + j] -= f * B[(size_t)k * ldb + j];
     }
     __syncthreads();
     for (int r = tid; r < np; r += nt)
@@ -196,22 +199,22 @@ __global__ void __launch_bounds__(256) small_front_kernel(const FactorFront* __r
   for (int e = tid; e < np * nb; e += nt) {
     const int i = e / nb, j = e % nb;
     double s = 0.0;
-    for (int k = 0; k < np; ++k) s += B[(size_t)i * m + k] * M[(size_t)k * m + np + j];
-    B[(size_t)i * m + np + j] = -s;
+    for (int k = 0; k < np; ++k) s += B[(size_t)i * ldb + k] * M[(size_t)k * m + np + j];
+    B[(size_t)i * ldb + np + j] = -s;
   }
   // G = F_BP * Inv
   for (int e = tid; e < nb * np; e += nt) {
     const int i = e / np, j = e % np;
     double s = 0.0;
-    for (int k = 0; k < np; ++k) s += M[(size_t)(np + i) * m + k] * B[(size_t)k * m + j];
-    G[(size_t)i * np + j] = s;
+    for (int k = 0; k < np; ++k) s += M[(size_t)(np + i) * m + k] * B[(size_t)k * ldb + j];
+    G[(size_t)i * g_rs + (size_t)j * g_cs] = s;
   }
   __syncthreads();
   // F_BB -= G * F_PB
   for (int e = tid; e < nb * nb; e += nt) {
     const int i = e / nb, j = e % nb;
     double s = 0.0;
-    for (int k = 0; k < np; ++k) s += G[(size_t)i * np + k] * M[(size_t)k * m + np + j];
+    for (int k = 0; k < np; ++k) s += G[(size_t)i * g_rs + (size_t)k * g_cs] * M[(size_t)k * m + np + j];
     M[(size_t)(np + i) * m + np + j] -= s;
   }
 }
@@ -253,8 +256,10 @@ bool device_factorization_enabled() {
   return !(e && e[0] == '1');
 }
 
-void factorize_device(const SolvePlan& plan, const CsrMatrix& A, const DeviceFront*, const int* d_bd_index, const int*,
-                      double* d_fwd, double* d_bwd) {
+void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, double* d_bwd) {
+  DeviceBuffer<int> bd_index_buf;
+  bd_index_buf.upload(plan.bd_index.data(), std::max<size_t>(plan.bd_index.size(), 1));
+  const int* d_bd_index = bd_index_buf.get();
   const CsrMatrix Ap = permute_csr(A, plan.perm, false), Apt = permute_csr(A, plan.perm, true);
   DeviceBuffer<int> rp, col, trp, tcol, d_error(1);
   DeviceBuffer<double> val, tval;
@@ -291,6 +296,9 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, const DeviceFro
       x.bd_off = F.bd_off;
       x.fwd_off = F.fwd_off;
       x.bwd_off = F.bwd_off;
+      x.ld_fwd = F.ld_fwd;
+      x.ld_bwd = F.ld_bwd;
+      x.fwd_colmajor = F.fwd_colmajor;
       x.F_off = F_total;
       F_total += (long long)(F.np + F.nb) * (F.np + F.nb);
       for (int c = 0; c < 2; ++c) {
@@ -331,26 +339,39 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, const DeviceFro
       double* B = d_bwd + x.bwd_off;
       double* G = d_fwd + x.fwd_off;
       // col-major view of the row-major F_PP (ld m) is F_PP^T; getrf/getrs on it give (F_PP^T)^-1 = Inv^T, whose
-      // col-major storage with ld m IS the row-major Inv with row stride m: the result lands in the table directly.
+      // col-major storage with leading dimension ldb IS the row-major Inv with row stride ldb: it lands in the table.
+      const int ldb = x.ld_bwd, ldf = x.ld_fwd;
       int lwork = 0;
       cusolver_check(cusolverDnDgetrf_bufferSize(h.solver, np, np, M, m, &lwork), "getrf_bufferSize");
       if ((size_t)lwork > work.size()) work.resize((size_t)lwork);
       cusolver_check(cusolverDnDgetrf(h.solver, np, np, M, m, work.get(), ipiv.get(), info.get()), "getrf");
       check_info_kernel<<<1, 1>>>(info.get(), d_error.get());
-      set_identity_kernel<<<(np * np + 255) / 256, 256>>>(B, np, m);
-      cusolver_check(cusolverDnDgetrs(h.solver, CUBLAS_OP_N, np, np, M, m, ipiv.get(), B, m, info.get()), "getrs");
+      set_identity_kernel<<<(np * np + 255) / 256, 256>>>(B, np, ldb);
+      cusolver_check(cusolverDnDgetrs(h.solver, CUBLAS_OP_N, np, np, M, m, ipiv.get(), B, ldb, info.get()), "getrs");
       if (nb > 0) {
         const double one = 1.0, zero = 0.0, minus = -1.0;
-        // (-H)^T = -F_PB^T Inv^T : C(nb x np, ld m) = -A(nb x np: F_PB memory, ld m) * B(np x np: Inv memory, ld m)
-        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, np, np, &minus, M + np, m, B, m, &zero, B + np, m),
+        // (-H)^T = -F_PB^T Inv^T : C(nb x np, ld ldb) = -A(nb x np: F_PB memory, ld m) * B(np x np: Inv memory, ld ldb)
+        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, np, np, &minus, M + np, m, B, ldb, &zero, B + np, ldb),
                      "dgemm H");
-        // G^T = Inv^T F_BP^T : C(np x nb, ld np) = A(np x np: Inv memory, ld m) * B(np x nb: F_BP memory, ld m)
-        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, np, nb, np, &one, B, m, M + (size_t)np * m, m, &zero, G, np),
-                     "dgemm G");
-        // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * B(np x nb: G memory, ld np)
-        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, nb, np, &minus, M + np, m, G, np, &one,
-                                 M + (size_t)np * m + np, m),
-                     "dgemm U");
+        if (x.fwd_colmajor) {
+          // G (nb x np) column-major, ld ldf:  G = (F_BP^T)^T (Inv^T)^T with both operands read transposed
+          cublas_check(cublasDgemm(h.blas, CUBLAS_OP_T, CUBLAS_OP_T, nb, np, np, &one, M + (size_t)np * m, m, B, ldb, &zero,
+                                   G, ldf),
+                       "dgemm G (col)");
+          // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * op_T(G: nb x np col-major)
+          cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_T, nb, nb, np, &minus, M + np, m, G, ldf, &one,
+                                   M + (size_t)np * m + np, m),
+                       "dgemm U (col)");
+        } else {
+          // G^T = Inv^T F_BP^T : C(np x nb, ld ldf) = A(np x np: Inv memory, ld ldb) * B(np x nb: F_BP memory, ld m)
+          cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, np, nb, np, &one, B, ldb, M + (size_t)np * m, m, &zero,
+                                   G, ldf),
+                       "dgemm G");
+          // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * B(np x nb: G memory, ld ldf)
+          cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, nb, np, &minus, M + np, m, G, ldf, &one,
+                                   M + (size_t)np * m + np, m),
+                       "dgemm U");
+        }
       }
     }
     PECS_CUDA(cudaDeviceSynchronize());

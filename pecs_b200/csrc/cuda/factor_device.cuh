@@ -11,7 +11,6 @@ namespace pecs {
 bool device_factorization_enabled();
 
 // Fills the forward / backward tables (already allocated on the device, zero-initialised inside) of `plan`.
-void factorize_device(const SolvePlan& plan, const CsrMatrix& A, const DeviceFront* d_fronts, const int* d_bd_index,
-                      const int* d_perm, double* d_fwd, double* d_bwd);
+void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, double* d_bwd);
 
 } // namespace pecs

@@ -173,43 +173,44 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
       for (int k = 0; k < (int)node_dofs[v].size(); ++k) plan.bd_index.push_back(node_first_dofpos[v] + k);
     }
     F.nb = (int)((int64_t)plan.bd_index.size() - F.bd_off);
+    F.fwd_colmajor = F.np <= kColMajorMaxNp;
+    F.ld_fwd = F.fwd_colmajor ? (F.nb + (F.nb & 1)) : (F.np + (F.np & 1));
+    F.ld_bwd = (F.np + F.nb) + ((F.np + F.nb) & 1);
     F.fwd_off = plan.fwd_entries;
-    plan.fwd_entries += (int64_t)F.nb * F.np;
-    plan.fwd_entries += plan.fwd_entries & 1; // keep every table 16-byte aligned for the device's double2 loads
+    plan.fwd_entries += F.fwd_size();
     F.bwd_off = plan.bwd_entries;
-    plan.bwd_entries += (int64_t)F.np * (F.np + F.nb);
-    plan.bwd_entries += plan.bwd_entries & 1;
-    F.upd_off = plan.upd_entries;
-    plan.upd_entries += F.nb;
+    plan.bwd_entries += F.bwd_size();
+    for (int k = 0; k < 2; ++k)
+      if (F.child[k] >= 0) {
+        plan.fronts[F.child[k]].which_child = k;
+        F.cbuf_off[k] = plan.upd_entries;
+        plan.upd_entries += F.np + F.nb;
+        plan.upd_entries += plan.upd_entries & 1;
+      }
     plan.max_np = std::max(plan.max_np, F.np);
     plan.max_nb = std::max(plan.max_nb, F.nb);
   }
-  // inverse child maps
+  // where every boundary unknown of a front lives in its parent's local numbering [pivots | boundary]
+  plan.out_map.assign(plan.bd_index.size(), -1);
   for (int f = 0; f < nf; ++f) {
-    Front& F = plan.fronts[f];
-    const int m = F.np + F.nb;
-    for (int k = 0; k < 2; ++k) {
-      F.cmap_off[k] = (int64_t)plan.child_map.size();
-      if (F.child[k] < 0) continue;
-      plan.child_map.resize(plan.child_map.size() + m, -1);
-      int* cmap = plan.child_map.data() + F.cmap_off[k];
-      const Front& C = plan.fronts[F.child[k]];
-      const int* cbd = plan.bd(C);
-      const int* fbd = plan.bd(F);
-      for (int s = 0; s < C.nb; ++s) {
-        const int pos = cbd[s];
-        int l;
-        if (pos < F.p0 + F.np) {
-          if (pos < F.p0) throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: child boundary below parent pivots");
-          l = pos - F.p0;
-        } else {
-          const int* it = std::lower_bound(fbd, fbd + F.nb, pos);
-          if (it == fbd + F.nb || *it != pos)
-            throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: child boundary not contained in parent front");
-          l = F.np + (int)(it - fbd);
-        }
-        cmap[l] = s;
+    const Front& C = plan.fronts[f];
+    if (C.parent < 0) continue;
+    const Front& F = plan.fronts[C.parent];
+    const int* cbd = plan.bd(C);
+    const int* fbd = plan.bd(F);
+    for (int s = 0; s < C.nb; ++s) {
+      const int pos = cbd[s];
+      int l;
+      if (pos < F.p0 + F.np) {
+        if (pos < F.p0) throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: child boundary below parent pivots");
+        l = pos - F.p0;
+      } else {
+        const int* it = std::lower_bound(fbd, fbd + F.nb, pos);
+        if (it == fbd + F.nb || *it != pos)
+          throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: child boundary not contained in parent front");
+        l = F.np + (int)(it - fbd);
       }
+      plan.out_map[C.bd_off + s] = l;
     }
   }
   int max_depth = 0;
@@ -371,19 +372,21 @@ void factorize_host(const SolvePlan& plan, const CsrMatrix& A, std::vector<doubl
       return;
     }
     // G = Fbp * Inv (stored positively), H = Inv * Fpb (stored negated next to Inv), U = Fbb - G * Fpb
-    double* G = fwd.data() + F.fwd_off;
-    std::vector<double> negG((size_t)nb * np, 0.0);
+    std::vector<double> negG((size_t)nb * np, 0.0), G((size_t)nb * np);
     gemm_sub(nb, np, np, Fbp.data(), np, Fpp.data(), np, negG.data(), np, inner_parallel);
     for (size_t k = 0; k < negG.size(); ++k) G[k] = -negG[k];
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j < np; ++j) fwd[(size_t)F.fwd_index(i, j)] = G[(size_t)i * np + j];
     double* B = bwd.data() + F.bwd_off;
-    for (int i = 0; i < np; ++i) std::copy(Fpp.begin() + (size_t)i * np, Fpp.begin() + (size_t)(i + 1) * np, B + (size_t)i * m);
-    gemm_sub(np, nb, np, Fpp.data(), np, Fpb.data(), nb, B + np, m, inner_parallel); // writes -H
+    const int ldb = F.ld_bwd;
+    for (int i = 0; i < np; ++i) std::copy(Fpp.begin() + (size_t)i * np, Fpp.begin() + (size_t)(i + 1) * np, B + (size_t)i * ldb);
+    gemm_sub(np, nb, np, Fpp.data(), np, Fpb.data(), nb, B + np, ldb, inner_parallel); // writes -H
     if (F.parent >= 0) {
       std::vector<double>& U = update[f];
       U.resize((size_t)nb * nb);
       for (int i = 0; i < nb; ++i)
         std::copy(M.begin() + (size_t)(np + i) * m + np, M.begin() + (size_t)(np + i + 1) * m, U.begin() + (size_t)i * nb);
-      gemm_sub(nb, nb, np, G, np, Fpb.data(), nb, U.data(), nb, inner_parallel);
+      gemm_sub(nb, nb, np, G.data(), np, Fpb.data(), nb, U.data(), nb, inner_parallel);
     }
   };
 
@@ -406,39 +409,39 @@ void factorize_host(const SolvePlan& plan, const CsrMatrix& A, std::vector<doubl
 void solve_host(const SolvePlan& plan, const std::vector<double>& fwd, const std::vector<double>& bwd, const double* b,
                 double* x) {
   const int n = plan.n;
-  std::vector<double> w(n), xp(n), upd((size_t)plan.upd_entries, 0.0);
+  std::vector<double> w(n), xp(n), cbuf((size_t)std::max<int64_t>(plan.upd_entries, 1), 0.0);
   for (int i = 0; i < n; ++i) w[plan.perm[i]] = b[i];
   for (int d = (int)plan.levels.size() - 1; d >= 0; --d)
     for (int f : plan.levels[d]) {
       const Front& F = plan.fronts[f];
       const int np = F.np, nb = F.nb;
-      double* t = upd.data() + F.upd_off;
-      for (int c = 0; c < 2; ++c) {
-        if (F.child[c] < 0) continue;
-        const int* cmap = plan.child_map.data() + F.cmap_off[c];
-        const double* tc = upd.data() + plan.fronts[F.child[c]].upd_off;
-        for (int l = 0; l < np; ++l)
-          if (cmap[l] >= 0) w[F.p0 + l] -= tc[cmap[l]];
-        for (int l = 0; l < nb; ++l)
-          if (cmap[np + l] >= 0) t[l] += tc[cmap[np + l]];
-      }
-      const double* G = fwd.data() + F.fwd_off;
+      // finalise the pivot right-hand side with what the children eliminated into it
+      for (int c = 0; c < 2; ++c)
+        if (F.cbuf_off[c] >= 0)
+          for (int l = 0; l < np; ++l) w[F.p0 + l] -= cbuf[(size_t)F.cbuf_off[c] + l];
+      if (F.parent < 0) continue;
+      const Front& P = plan.fronts[F.parent];
+      double* out = cbuf.data() + P.cbuf_off[F.which_child];
+      const int* omap = plan.out_map.data() + F.bd_off;
       for (int i = 0; i < nb; ++i) {
+        double carry = 0.0;
+        for (int c = 0; c < 2; ++c)
+          if (F.cbuf_off[c] >= 0) carry += cbuf[(size_t)F.cbuf_off[c] + np + i];
         double s = 0;
-        for (int j = 0; j < np; ++j) s += G[(size_t)i * np + j] * w[F.p0 + j];
-        t[i] += s;
+        for (int j = 0; j < np; ++j) s += fwd[(size_t)F.fwd_index(i, j)] * w[F.p0 + j];
+        out[omap[i]] = carry + s;
       }
     }
   for (size_t d = 0; d < plan.levels.size(); ++d)
     for (int f : plan.levels[d]) {
       const Front& F = plan.fronts[f];
-      const int np = F.np, nb = F.nb, m = np + nb;
+      const int np = F.np, nb = F.nb;
       const int* bd = plan.bd(F);
       const double* B = bwd.data() + F.bwd_off;
       for (int i = 0; i < np; ++i) {
         double s = 0;
-        for (int j = 0; j < np; ++j) s += B[(size_t)i * m + j] * w[F.p0 + j];
-        for (int j = 0; j < nb; ++j) s += B[(size_t)i * m + np + j] * xp[bd[j]];
+        for (int j = 0; j < np; ++j) s += B[(size_t)i * F.ld_bwd + j] * w[F.p0 + j];
+        for (int j = 0; j < nb; ++j) s += B[(size_t)i * F.ld_bwd + np + j] * xp[bd[j]];
         xp[F.p0 + i] = s;
       }
     }

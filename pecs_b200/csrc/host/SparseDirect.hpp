@@ -15,6 +15,14 @@
 //         forward  (leaves -> root):  w_P = b_P - children's updates,   t = children's updates on B + G w_P
 //         backward (root -> leaves):  x_P = Inv w_P - H x_B
 //     All fronts of one level are independent: one batched, HBM-streaming kernel per level and sweep.
+//   * a front hands its update t to its parent in the PARENT's local numbering ([pivots | boundary]): every front
+//     owns one dense buffer per child, the child scatters into it through a precomputed map, the parent reads it
+//     with unit stride.  Slots a child never writes stay zero from setup.
+//
+// Table layouts (what the device kernels stream): every row is padded to an even length so that all loads can be
+// 16 bytes wide.  Backward table [Inv | -H]: row-major, np rows, leading dimension ld_bwd = even(np+nb).
+// Forward table G: row-major (nb rows, ld_fwd = even(np)) for large fronts -- one warp per row -- and column-major
+// (np columns of ld_fwd = even(nb) entries) for fronts with np <= kColMajorMaxNp -- one thread per row.
 //
 // This header holds the symbolic part (tree, index maps, level schedule) and the host numeric factorisation used
 // for small problems and as the checker of the device factorisation.
@@ -26,17 +34,25 @@
 
 namespace pecs {
 
+constexpr int kColMajorMaxNp = 128;
+
 struct Front {
   int np = 0, nb = 0;       // pivot / boundary unknowns
   int p0 = 0;               // pivots occupy positions [p0, p0+np) of the permuted vector
   int parent = -1;
   int child[2] = {-1, -1};
+  int which_child = 0;      // this front is child[which_child] of its parent
   int depth = 0;            // root = 0
-  int64_t bd_off = 0;       // offset of this front's boundary index list in SolvePlan::bd_index
-  int64_t fwd_off = 0;      // offset of G            (nb x np, row-major)          in the forward table
-  int64_t bwd_off = 0;      // offset of [Inv | -H]   (np x (np+nb), row-major)     in the backward table
-  int64_t upd_off = 0;      // offset of this front's update vector t (nb entries) in the update buffer
-  int64_t cmap_off[2] = {0, 0}; // per child: for every local index l in [0, np+nb) the child's boundary slot or -1
+  int fwd_colmajor = 0;     // layout of G, see above
+  int ld_fwd = 0, ld_bwd = 0;
+  int64_t bd_off = 0;       // offset of this front's boundary index list in SolvePlan::bd_index (also of its out map)
+  int64_t fwd_off = 0;      // offset of G in the forward table
+  int64_t bwd_off = 0;      // offset of [Inv | -H] in the backward table
+  int64_t cbuf_off[2] = {-1, -1}; // this front's dense update buffers, one per child, np+nb entries each (-1: no child)
+  // G(i, j), i < nb, j < np
+  int64_t fwd_index(int i, int j) const { return fwd_off + (fwd_colmajor ? (int64_t)j * ld_fwd + i : (int64_t)i * ld_fwd + j); }
+  int64_t fwd_size() const { return (int64_t)(fwd_colmajor ? np : nb) * ld_fwd; }
+  int64_t bwd_size() const { return (int64_t)np * ld_bwd; }
 };
 
 struct SolvePlan {
@@ -45,9 +61,9 @@ struct SolvePlan {
   std::vector<int> iperm;    // iperm[position] = dof
   std::vector<Front> fronts; // postorder: children before parents, root last
   std::vector<int> bd_index; // concatenated boundary lists (positions in the permuted vector, ascending)
-  std::vector<int> child_map; // concatenated inverse child maps (see Front::cmap_off)
+  std::vector<int> out_map;  // same layout as bd_index: the parent-local index of every boundary unknown
   std::vector<std::vector<int>> levels; // fronts per depth
-  int64_t fwd_entries = 0, bwd_entries = 0, upd_entries = 0;
+  int64_t fwd_entries = 0, bwd_entries = 0, upd_entries = 0; // upd_entries: total size of all child buffers
   int max_np = 0, max_nb = 0;
   const int* bd(const Front& f) const { return bd_index.data() + f.bd_off; }
 };

@@ -1,4 +1,5 @@
 // capi_host.cpp -- extern "C" bindings of the host classes (include/pecs_b200_host.h).
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -230,6 +231,28 @@ pecs_status pecs_solarcell_plan_stats(pecs_solarcell* p, int32_t which, int32_t 
     stats[6] = plan.upd_entries;
     stats[7] = 0;
   });
+}
+int32_t pecs_solarcell_plan_levels(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, int64_t* out, int32_t max_levels) {
+  try {
+    const pecs::SolvePlan plan = pecs::plan_for_system(*p->problem, which, leaf_nodes);
+    for (int d = 0; d < (int)plan.levels.size() && d < max_levels; ++d) {
+      int64_t* o = out + 6 * d;
+      o[0] = (int64_t)plan.levels[d].size();
+      o[1] = o[2] = o[3] = o[4] = o[5] = 0;
+      for (int f : plan.levels[d]) {
+        const pecs::Front& F = plan.fronts[f];
+        o[1] += F.fwd_size();
+        o[2] += F.bwd_size();
+        o[3] = std::max<int64_t>(o[3], F.np);
+        o[4] = std::max<int64_t>(o[4], F.nb);
+        o[5] += F.np;
+      }
+    }
+    return (int32_t)plan.levels.size();
+  } catch (const std::exception& e) {
+    pecs::set_last_error(e.what());
+    return -1;
+  }
 }
 pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,
                                                  double* x) {

@@ -288,6 +288,11 @@ class SolarCellProblem:
         check(self._lib.pecs_solarcell_plan_stats(self._h, which, leaf_nodes, st.ctypes.data_as(C.POINTER(C.c_int64))))
         return dict(zip(["fronts", "levels", "max_np", "max_nb", "fwd_entries", "bwd_entries", "upd_entries"], st))
 
+    def plan_levels(self, which, leaf_nodes=0):
+        out = np.zeros((64, 6), np.int64)
+        n = self._lib.pecs_solarcell_plan_levels(self._h, which, leaf_nodes, out.ctypes.data_as(C.POINTER(C.c_int64)), 64)
+        return out[:n]
+
     def selftest_direct_solve(self, which, b, leaf_nodes=0):
         b = np.ascontiguousarray(b, np.float64)
         x = np.zeros_like(b)
