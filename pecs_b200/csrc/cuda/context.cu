@@ -24,7 +24,9 @@
 #include "../host/SparseDirect.hpp"
 #include "device_util.cuh"
 #include "factor_device.cuh"
+#include "../host/SchurReduction.hpp"
 #include "rhs_kernels.cuh"
+#include "schur_kernels.cuh"
 #include "solve_kernels.cuh"
 
 namespace pecs {
@@ -165,6 +167,13 @@ struct DeviceDomain {
   DeviceBuffer<int> rt_dof, phi_dof, bcell, bface_id, bnb_cell, bnb_face;
   DeviceBuffer<double> solution[2], rhs[2];
   DeviceSystem system[2];
+  // Schur-reduced carriers (host/SchurReduction.hpp): system[k] then factorises S (4 unknowns per cell)
+  struct Reduced {
+    bool active = false;
+    DeviceEll T1, Ainv, T2;
+    DeviceBuffer<double> rtilde;
+    int64_t bytes() const { return active ? (int64_t)(T1.bytes() + Ainv.bytes() + T2.bytes()) : 0; }
+  } reduced[2];
   DomainView view{};
   RhsParams prm{};
   int n_dofs() const { return 12 * n_cells; }
@@ -305,7 +314,18 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
   for (int k = 0; k < 2; ++k) {
     if (ctx.kind != PECS_KIND_PRODUCTION && k == 1) break; // the manufactured tests only solve carrier_1
     const CsrMatrix A = copy_csr(d.system_matrix[k], 12 * n, "domain: system matrix size");
-    D.system[k].build(A, layout, default_leaf_nodes(false), factor_on_device);
+    SchurReduction R;
+    if (schur_reduction_enabled() && build_schur_reduction(A, n, R)) {
+      DeviceDomain::Reduced& red = D.reduced[k];
+      red.active = true;
+      red.T1.upload(R.T1);
+      red.Ainv.upload(R.Ainv);
+      red.T2.upload(R.T2);
+      red.rtilde.resize(4 * (size_t)n);
+      D.system[k].build(R.S, carrier_density_nodes(d), default_leaf_nodes(false), factor_on_device);
+    } else {
+      D.system[k].build(A, layout, default_leaf_nodes(false), factor_on_device);
+    }
   }
 }
 
@@ -379,8 +399,20 @@ void enqueue_poisson_solve(pecs_ctx* ctx, cudaStream_t s) {
 }
 void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s) {
   DeviceDomain& D = ctx->dom[which / 2];
-  require(D.system[which % 2].n > 0, "this species has no factorised system in this context");
-  D.system[which % 2].solve(D.rhs[which % 2].get(), D.solution[which % 2].get(), s);
+  const int k = which % 2;
+  require(D.system[k].n > 0, "this species has no factorised system in this context");
+  if (!D.reduced[k].active) {
+    D.system[k].solve(D.rhs[k].get(), D.solution[k].get(), s);
+    return;
+  }
+  // S u = r_u - T1 r_q ;  q = Ainv r_q - T2 u
+  DeviceDomain::Reduced& red = D.reduced[k];
+  const int nq = 8 * D.n_cells, nu = 4 * D.n_cells;
+  const double* r = D.rhs[k].get();
+  double* x = D.solution[k].get();
+  launch_ell_combine(nu, r + nq, nullptr, nullptr, red.T1, r, red.rtilde.get(), s);
+  D.system[k].solve(red.rtilde.get(), x + nq, s);
+  launch_ell_combine(nq, nullptr, &red.Ainv, r, red.T2, x + nq, x, s);
 }
 void enqueue_full_solve(pecs_ctx* ctx) {
   // four concurrent solves, reference SolarCell.cpp:1763-1781 (Threads::new_task x4 + join_all)
@@ -404,7 +436,8 @@ int launches_per_step(const pecs_ctx* ctx) {
   for (int w = 0; w < ctx->n_domains(); ++w) {
     n += 2 + 1; // cell + boundary + Poisson cell kernels
     for (int k = 0; k < 2; ++k)
-      if (ctx->dom[w].system[k].n > 0) n += ctx->dom[w].system[k].launches_per_solve;
+      if (ctx->dom[w].system[k].n > 0)
+        n += ctx->dom[w].system[k].launches_per_solve + (ctx->dom[w].reduced[k].active ? 2 : 0);
   }
   n += ctx->p_system.launches_per_solve + (ctx->n_constraints > 0 ? 1 : 0);
   return n;
@@ -731,7 +764,8 @@ pecs_status pecs_time_kernel(pecs_ctx* ctx, int32_t which, int32_t repeats, doub
           n_launch = 0;
           for (int w = 0; w < ctx->n_domains(); ++w)
             for (int k = 0; k < 2; ++k)
-              if (ctx->dom[w].system[k].n > 0) n_launch += ctx->dom[w].system[k].launches_per_solve;
+              if (ctx->dom[w].system[k].n > 0)
+                n_launch += ctx->dom[w].system[k].launches_per_solve + (ctx->dom[w].reduced[k].active ? 2 : 0);
           break;
         case 3:
           enqueue_poisson_solve(ctx, ctx->main);
@@ -761,7 +795,7 @@ int64_t pecs_get_info(const pecs_ctx* ctx, int32_t what) {
   for (int w = 0; w < ctx->n_domains(); ++w) {
     cells += ctx->dom[w].n_cells;
     for (int k = 0; k < 2; ++k) {
-      factor += ctx->dom[w].system[k].factor_bytes();
+      factor += ctx->dom[w].system[k].factor_bytes() + ctx->dom[w].reduced[k].bytes();
       levels = std::max(levels, (int)ctx->dom[w].system[k].levels.size());
     }
   }

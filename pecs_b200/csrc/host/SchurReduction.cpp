@@ -1,0 +1,160 @@
+// SchurReduction.cpp -- see SchurReduction.hpp.
+#include "SchurReduction.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "../error.hpp"
+
+namespace pecs {
+
+namespace {
+
+// dense n x n inverse (row-major, in place) with partial pivoting; false if singular
+bool invert_small(int n, double* M) {
+  std::vector<double> X((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) X[(size_t)i * n + i] = 1.0;
+  for (int k = 0; k < n; ++k) {
+    int p = k;
+    for (int r = k + 1; r < n; ++r)
+      if (std::fabs(M[(size_t)r * n + k]) > std::fabs(M[(size_t)p * n + k])) p = r;
+    if (M[(size_t)p * n + k] == 0.0) return false;
+    if (p != k)
+      for (int j = 0; j < n; ++j) {
+        std::swap(M[(size_t)k * n + j], M[(size_t)p * n + j]);
+        std::swap(X[(size_t)k * n + j], X[(size_t)p * n + j]);
+      }
+    const double inv = 1.0 / M[(size_t)k * n + k];
+    for (int j = 0; j < n; ++j) {
+      M[(size_t)k * n + j] *= inv;
+      X[(size_t)k * n + j] *= inv;
+    }
+    for (int r = 0; r < n; ++r) {
+      if (r == k) continue;
+      const double f = M[(size_t)r * n + k];
+      if (f == 0.0) continue;
+      for (int j = 0; j < n; ++j) {
+        M[(size_t)r * n + j] -= f * M[(size_t)k * n + j];
+        X[(size_t)r * n + j] -= f * X[(size_t)k * n + j];
+      }
+    }
+  }
+  std::copy(X.begin(), X.end(), M);
+  return true;
+}
+
+// sparse row accumulator with a dense value array and a touched list
+struct RowAccumulator {
+  std::vector<double> val;
+  std::vector<char> used;
+  std::vector<int> touched;
+  explicit RowAccumulator(int n) : val(n, 0.0), used(n, 0) {}
+  void add(int j, double v) {
+    if (!used[j]) {
+      used[j] = 1;
+      touched.push_back(j);
+    }
+    val[j] += v;
+  }
+  // appends the row (sorted by column, exact zeros dropped) to a CSR under construction and resets
+  void flush(CsrMatrix& A) {
+    std::sort(touched.begin(), touched.end());
+    for (int j : touched) {
+      if (val[j] != 0.0) {
+        A.col.push_back(j);
+        A.val.push_back(val[j]);
+      }
+      val[j] = 0.0;
+      used[j] = 0;
+    }
+    touched.clear();
+    A.row_ptr.push_back((int)A.col.size());
+  }
+};
+
+} // namespace
+
+bool build_schur_reduction(const CsrMatrix& A, int n_cells, SchurReduction& out) {
+  const int nq = 8 * n_cells, nu = 4 * n_cells;
+  if (A.n != nq + nu) throw StatusError(PECS_ERR_INVALID, "build_schur_reduction: matrix size is not 12 * n_cells");
+  // q unknown i (component i / 4n, node i % 4): its cell and its slot 0..7 inside the cell block
+  auto q_cell = [&](int i) { return (i % (4 * n_cells)) / 4; };
+  auto q_slot = [&](int i) { return 4 * (i / (4 * n_cells)) + (i % 4); };
+  auto q_index = [&](int cell, int slot) { return (slot / 4) * 4 * n_cells + 4 * cell + (slot % 4); };
+
+  // 1. cell blocks of A_qq; refuse if A_qq couples different cells
+  std::vector<double> blocks((size_t)n_cells * 64, 0.0);
+  for (int i = 0; i < nq; ++i)
+    for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k) {
+      const int j = A.col[k];
+      if (j >= nq) continue;
+      if (q_cell(j) != q_cell(i)) {
+        if (A.val[k] != 0.0) return false;
+        continue;
+      }
+      blocks[(size_t)q_cell(i) * 64 + 8 * q_slot(i) + q_slot(j)] = A.val[k];
+    }
+  for (int c = 0; c < n_cells; ++c)
+    if (!invert_small(8, &blocks[(size_t)c * 64]))
+      throw StatusError(PECS_ERR_SINGULAR, "build_schur_reduction: singular current mass block");
+
+  SchurReduction R;
+  R.n_cells = n_cells;
+  // 2. Ainv as CSR
+  R.Ainv.n = nq;
+  R.Ainv.row_ptr.assign(1, 0);
+  {
+    RowAccumulator acc(nq);
+    for (int i = 0; i < nq; ++i) {
+      const int c = q_cell(i), s = q_slot(i);
+      for (int t = 0; t < 8; ++t) acc.add(q_index(c, t), blocks[(size_t)c * 64 + 8 * s + t]);
+      acc.flush(R.Ainv);
+    }
+  }
+  // 3. T2 = Ainv * G_qu   (8n x 4n): row i = sum_t Ainv(i, t) * G_qu(row t of the same cell, :)
+  R.T2.n = nq;
+  R.T2.row_ptr.assign(1, 0);
+  {
+    RowAccumulator acc(nu);
+    for (int i = 0; i < nq; ++i) {
+      const int c = q_cell(i), s = q_slot(i);
+      for (int t = 0; t < 8; ++t) {
+        const double a = blocks[(size_t)c * 64 + 8 * s + t];
+        if (a == 0.0) continue;
+        const int r = q_index(c, t);
+        for (int k = A.row_ptr[r]; k < A.row_ptr[r + 1]; ++k)
+          if (A.col[k] >= nq) acc.add(A.col[k] - nq, a * A.val[k]);
+      }
+      acc.flush(R.T2);
+    }
+  }
+  // 4. T1 = G_uq * Ainv (4n x 8n) and S = S_uu - G_uq * T2 (4n x 4n)
+  R.T1.n = nu;
+  R.T1.row_ptr.assign(1, 0);
+  R.S.n = nu;
+  R.S.row_ptr.assign(1, 0);
+  {
+    RowAccumulator acc1(nq), accS(nu);
+    for (int i = 0; i < nu; ++i) {
+      const int r = nq + i;
+      for (int k = A.row_ptr[r]; k < A.row_ptr[r + 1]; ++k) {
+        const int j = A.col[k];
+        const double v = A.val[k];
+        if (j >= nq) {
+          accS.add(j - nq, v);
+          continue;
+        }
+        const int c = q_cell(j), s = q_slot(j);
+        for (int t = 0; t < 8; ++t) acc1.add(q_index(c, t), v * blocks[(size_t)c * 64 + 8 * s + t]);
+        for (int kk = R.T2.row_ptr[j]; kk < R.T2.row_ptr[j + 1]; ++kk) accS.add(R.T2.col[kk], -v * R.T2.val[kk]);
+      }
+      acc1.flush(R.T1);
+      accS.flush(R.S);
+    }
+  }
+  out = std::move(R);
+  return true;
+}
+
+} // namespace pecs

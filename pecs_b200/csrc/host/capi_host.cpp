@@ -257,10 +257,7 @@ int32_t pecs_solarcell_plan_levels(pecs_solarcell* p, int32_t which, int32_t lea
 pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,
                                                  double* x) {
   return guarded([&] {
-    const pecs::SolvePlan plan = pecs::plan_for_system(*p->problem, which, leaf_nodes);
-    std::vector<double> fwd, bwd;
-    pecs::factorize_host(plan, matrix(p, which), fwd, bwd);
-    pecs::solve_host(plan, fwd, bwd, b, x);
+    pecs::solve_system_host(*p->problem, which, leaf_nodes, b, x);
   });
 }
 
