@@ -1,0 +1,84 @@
+"""More GPU checks through the C ABI: committed golden fixtures, host-buffer stepping, solver variants."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import pecs_b200 as pecs
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.parametrize("name,g,overrides", [
+    ("production_g2_l1.npz", 2, {}),
+    ("production_g3_l1_biased.npz", 3, {"physical__insulated": False, "physical__applied_bias": 0.1})])
+def test_golden_fixtures(name, g, overrides):
+    """fixtures were produced by the oracle in the build container (tests/golden/make_golden.py)"""
+    gold = np.load(os.path.join(GOLDEN, name))
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, 1, **overrides))
+    prob.setup_full_system()
+    assert rel_err(prob.get_rhs(pecs.POISSON), gold["poisson_rhs_initial"]) <= 1e-12
+    assert rel_err(prob.get_solution(pecs.POISSON), gold["poisson_solution_initial"]) <= 1e-9
+    prob.step(int(gold["n_steps"]))
+    for s in range(5):
+        ref = gold[f"state_after_steps_{s}"]
+        got = prob.get_solution(s)
+        if s < 4:
+            nc = got.size // 12
+            assert rel_err(got[8 * nc:], ref[8 * nc:]) <= 1e-9
+        else:
+            n_rt = prob.n_rt
+            assert rel_err(got[n_rt:], ref[n_rt:]) <= 1e-9 and rel_err(got[:n_rt], ref[:n_rt]) <= 1e-9
+    prob.close()
+
+
+def test_step_host_equals_step():
+    """the host-buffer entry point (H2D, step, D2H) is the same arithmetic as the resident path"""
+    prob = pecs.SolarCellProblem(pecs.default_input_file(3, 1))
+    prob.setup_full_system()
+    start = [prob.get_solution(s) for s in range(5)]
+    prob.step(3)
+    resident = [prob.get_solution(s) for s in range(5)]
+    states = prob.pinned_states()
+    for s in range(5):
+        states[s][:] = start[s]
+    for _ in range(3):
+        prob.step_host(1, states)
+    for s in range(5):
+        assert np.array_equal(states[s], resident[s])
+    assert prob.info(0) > 0 and prob.info(1) > 0
+    ms = prob.step_timed(2, sectioned=True)
+    assert ms[0] > 0 and abs(ms[1:].sum() - ms[0]) < 1e-6 * ms[0] + 1e-9
+    prob.close()
+
+
+VARIANT = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+import pecs_b200 as pecs
+prob = pecs.SolarCellProblem(pecs.default_input_file(3, 1))
+prob.setup_full_system()
+prob.step(4)
+np.save(sys.argv[1], np.concatenate([prob.get_solution(s) for s in range(5)]))
+"""
+
+
+def test_solver_variants_agree(tmp_path):
+    """Schur-reduced device factorisation (default) vs full 12-unknown systems vs host factorisation"""
+    script = tmp_path / "variant.py"
+    script.write_text(VARIANT % ROOT)
+    results = []
+    for env in ({}, {"PECS_B200_NO_SCHUR": "1"}, {"PECS_B200_HOST_FACTOR": "1"}, {"PECS_B200_LEAF_NODES": "3"}):
+        out = tmp_path / ("out_" + "_".join(env) + ".npy")
+        r = subprocess.run([sys.executable, str(script), str(out)], env=dict(os.environ, **env), capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        results.append(np.load(out))
+    for other in results[1:]:
+        assert rel_err(other, results[0]) <= 1e-9
