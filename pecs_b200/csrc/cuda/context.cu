@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -35,34 +36,56 @@ namespace pecs {
 struct DeviceSystem {
   int n = 0;
   SolvePlan plan;
-  DeviceBuffer<double> fwd, bwd, cbuf, w_in, w_fin, x_perm;
-  DeviceBuffer<int> bd_index, out_map, perm, iperm;
+  DeviceBuffer<double> fwd, bwd, cbuf, w_fin, x_perm;
+  DeviceBuffer<int> bd_index, out_map, iperm;
   DeviceBuffer<DeviceFront> fronts;
   struct Level {
-    DeviceBuffer<SolveTile> fwd_row_tiles, fwd_col_tiles, bwd_tiles;
-    int smem_fwd = 0, smem_bwd = 0; // doubles; smem_bwd == 0: gather on the fly
+    DeviceBuffer<SolveTile> fwd_tiles, bwd_tiles;
+    int vec_fwd = 0, vec_bwd = 0;       // doubles of the staged vector
+    int stages_fwd = 0, stages_bwd = 0; // depth of the per-warp bulk-copy rings
   };
   std::vector<Level> levels;
   int launches_per_solve = 0;
 
   int64_t factor_bytes() const { return (int64_t)(fwd.bytes() + bwd.bytes()); }
-  int max_smem_doubles() const {
-    int m = 0;
-    for (const Level& l : levels) m = std::max(m, std::max(l.smem_fwd, l.smem_bwd));
+  int64_t logical_bytes() const { return plan.logical_entries() * (int64_t)sizeof(double); }
+  size_t max_smem_bytes() const {
+    size_t m = 0;
+    for (const Level& l : levels)
+      m = std::max(m, std::max(solve_smem_bytes(l.vec_fwd, kSolveWarps, l.stages_fwd),
+                               solve_smem_bytes(l.vec_bwd, kSolveWarps, l.stages_bwd)));
     return m;
   }
 
-  // rows per tile so that a level offers several CTAs per SM even when it has only a few big fronts
-  static int rows_per_tile(int64_t total_rows) {
-    const int64_t want_tiles = 8 * 148;
-    int64_t r = (total_rows + want_tiles - 1) / want_tiles;
-    r = ((r + 7) / 8) * 8;
-    return (int)std::min<int64_t>(64, std::max<int64_t>(8, r));
+  static int env_int(const char* name, int fallback) {
+    const char* e = std::getenv(name);
+    return e && std::atoi(e) > 0 ? std::atoi(e) : fallback;
+  }
+  // ring depth: deep enough to cover the HBM latency with the resident warps, shallow enough that two thread blocks
+  // share an SM whenever the staged vector allows it (one block stages its vector while the other one streams)
+  static int pick_stages(int vec_doubles) {
+    const int forced = env_int("PECS_B200_SOLVE_STAGES", 0);
+    if (forced) return forced;
+    const size_t budget = 227 * 1024 - 2048;
+    for (int st : {4, 3})
+      if (2 * (solve_smem_bytes(vec_doubles, kSolveWarps, st) + 1024) <= budget) return st;
+    return 6;
+  }
+  // panels per tile (thread block): at least one per warp, more when the level is so large that whole waves of blocks
+  // would otherwise stage the same vector over and over
+  static int panels_per_tile(int64_t level_panels) {
+    const int forced = env_int("PECS_B200_SOLVE_PANELS_PER_TILE", 0);
+    if (forced) return forced;
+    const int64_t want_tiles = 148 * 8;
+    return (int)std::min<int64_t>(64, std::max<int64_t>(kSolveWarps, (level_panels + want_tiles - 1) / want_tiles));
   }
 
   void build(const CsrMatrix& A, const NodeLayout& layout, int leaf_nodes, bool factor_on_device) {
+    build(A, plan_from_layout(A, layout, leaf_nodes), factor_on_device);
+  }
+  void build(const CsrMatrix& A, SolvePlan&& ready_plan, bool factor_on_device) {
     n = A.n;
-    plan = build_solve_plan(A, layout.node_of_dof, layout.x, layout.y, leaf_nodes);
+    plan = std::move(ready_plan);
     const int nf = (int)plan.fronts.size();
     std::vector<DeviceFront> df(nf);
     for (int f = 0; f < nf; ++f) {
@@ -71,24 +94,23 @@ struct DeviceSystem {
       D.np = F.np;
       D.nb = F.nb;
       D.p0 = F.p0;
-      D.ld_fwd = F.ld_fwd;
-      D.ld_bwd = F.ld_bwd;
-      D.fwd_colmajor = F.fwd_colmajor;
+      D.fwd_log2P = F.fwd.log2P;
+      D.fwd_cols_pad = F.fwd.cols_pad;
+      D.bwd_log2P = F.bwd.log2P;
+      D.bwd_cols_pad = F.bwd.cols_pad;
       D.bd_off = F.bd_off;
-      D.fwd_off = F.fwd_off;
-      D.bwd_off = F.bwd_off;
+      D.fwd_off = F.fwd.off;
+      D.bwd_off = F.bwd.off;
       D.cbuf_off[0] = F.cbuf_off[0];
       D.cbuf_off[1] = F.cbuf_off[1];
       D.out_off = F.parent >= 0 ? plan.fronts[F.parent].cbuf_off[F.which_child] : -1;
     }
     fronts.upload(df);
-    bd_index.upload(plan.bd_index);
-    out_map.upload(plan.out_map);
-    perm.upload(plan.perm);
+    bd_index.upload(plan.bd_index.data(), std::max<size_t>(plan.bd_index.size(), 1));
+    out_map.upload(plan.out_map.data(), std::max<size_t>(plan.out_map.size(), 1));
     iperm.upload(plan.iperm);
     cbuf.resize((size_t)std::max<int64_t>(plan.upd_entries, 2));
     cbuf.zero(); // slots no child ever writes must read as zero forever
-    w_in.resize(n);
     w_fin.resize(n);
     x_perm.resize(n);
     fwd.resize((size_t)std::max<int64_t>(plan.fwd_entries, 2));
@@ -105,58 +127,49 @@ struct DeviceSystem {
     }
     // tile lists per level
     levels.resize(plan.levels.size());
-    launches_per_solve = 2; // the two permutation gathers
+    launches_per_solve = 0;
     for (size_t d = 0; d < plan.levels.size(); ++d) {
-      std::vector<SolveTile> fr, fc, bt;
+      std::vector<SolveTile> ft, bt;
       Level& L = levels[d];
-      int64_t rows_f = 0, rows_b = 0;
-      int max_m = 0;
+      int64_t panels_f = 0, panels_b = 0;
       for (int f : plan.levels[d]) {
         const Front& F = plan.fronts[f];
-        if (!F.fwd_colmajor) rows_f += F.nb;
-        rows_b += F.np;
-        max_m = std::max(max_m, F.np + F.nb);
+        panels_f += F.fwd.n_panels();
+        panels_b += F.bwd.n_panels();
+        L.vec_fwd = std::max(L.vec_fwd, F.fwd.cols_pad);
+        L.vec_bwd = std::max(L.vec_bwd, F.bwd.cols_pad);
       }
-      const int rf = rows_per_tile(rows_f), rb = rows_per_tile(rows_b);
+      const int pf = panels_per_tile(panels_f), pb = panels_per_tile(panels_b);
       for (int f : plan.levels[d]) {
         const Front& F = plan.fronts[f];
         int first = 1;
-        if (F.fwd_colmajor) {
-          for (int r0 = 0; r0 < std::max(F.nb, 1); r0 += kColTileRows) {
-            fc.push_back(SolveTile{f, r0, std::max(0, std::min(kColTileRows, F.nb - r0)), first});
-            first = 0;
-          }
-        } else {
-          L.smem_fwd = std::max(L.smem_fwd, F.np + 2);
-          for (int r0 = 0; r0 < std::max(F.nb, 1); r0 += rf) {
-            fr.push_back(SolveTile{f, r0, std::max(0, std::min(rf, F.nb - r0)), first});
-            first = 0;
-          }
+        for (int p0 = 0; p0 < std::max(F.fwd.n_panels(), 1); p0 += pf) {
+          ft.push_back(SolveTile{f, p0, std::max(0, std::min(pf, F.fwd.n_panels() - p0)), first});
+          first = 0;
         }
-        for (int r0 = 0; r0 < F.np; r0 += rb) bt.push_back(SolveTile{f, r0, std::min(rb, F.np - r0), 0});
+        for (int p0 = 0; p0 < F.bwd.n_panels(); p0 += pb) bt.push_back(SolveTile{f, p0, std::min(pb, F.bwd.n_panels() - p0), 0});
       }
-      L.smem_bwd = max_m <= kBackwardStageMax ? max_m + 2 : 0;
-      L.fwd_row_tiles.upload(fr);
-      L.fwd_col_tiles.upload(fc);
+      L.stages_fwd = pick_stages(L.vec_fwd);
+      L.stages_bwd = pick_stages(L.vec_bwd);
+      L.fwd_tiles.upload(ft);
       L.bwd_tiles.upload(bt);
-      launches_per_solve += (fr.empty() ? 0 : 1) + (fc.empty() ? 0 : 1) + 1;
+      launches_per_solve += 2;
     }
   }
 
   // solution = A^-1 rhs, all on stream s
   void solve(const double* rhs, double* solution, cudaStream_t s) {
-    const SolveTables t{fronts.get(), bd_index.get(), out_map.get(), fwd.get(), bwd.get()};
-    launch_gather(n, iperm.get(), rhs, w_in.get(), s);
+    const SolveTables t{fronts.get(), bd_index.get(), out_map.get(), iperm.get(), fwd.get(), bwd.get()};
     for (int d = (int)levels.size() - 1; d >= 0; --d) {
       Level& L = levels[d];
-      launch_forward_cols(t, L.fwd_col_tiles.get(), (int)L.fwd_col_tiles.size(), w_in.get(), w_fin.get(), cbuf.get(), s);
-      launch_forward_rows(t, L.fwd_row_tiles.get(), (int)L.fwd_row_tiles.size(), L.smem_fwd, w_in.get(), w_fin.get(),
-                          cbuf.get(), s);
+      launch_forward_level(t, L.fwd_tiles.get(), (int)L.fwd_tiles.size(), L.vec_fwd, kSolveWarps, L.stages_fwd, rhs,
+                           w_fin.get(), cbuf.get(), s);
     }
-    for (size_t d = 0; d < levels.size(); ++d)
-      launch_backward_rows(t, levels[d].bwd_tiles.get(), (int)levels[d].bwd_tiles.size(), levels[d].smem_bwd, w_fin.get(),
-                           x_perm.get(), s);
-    launch_gather(n, perm.get(), x_perm.get(), solution, s);
+    for (size_t d = 0; d < levels.size(); ++d) {
+      Level& L = levels[d];
+      launch_backward_level(t, L.bwd_tiles.get(), (int)L.bwd_tiles.size(), L.vec_bwd, kSolveWarps, L.stages_bwd, w_fin.get(),
+                            x_perm.get(), solution, s);
+    }
   }
 };
 
@@ -558,14 +571,14 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     }
     {
       const CsrMatrix A = copy_csr(P.system_matrix, np, "poisson: system matrix size");
-      ctx->p_system.build(A, poisson_nodes(P), default_leaf_nodes(true), factor_on_device);
+      ctx->p_system.build(A, poisson_plan(A, P, default_leaf_nodes(true)), factor_on_device);
     }
-    int smem = ctx->p_system.max_smem_doubles();
+    size_t smem = ctx->p_system.max_smem_bytes();
     for (int w = 0; w < ctx->n_domains(); ++w)
-      for (int k = 0; k < 2; ++k) smem = std::max(smem, ctx->dom[w].system[k].max_smem_doubles());
+      for (int k = 0; k < 2; ++k) smem = std::max(smem, ctx->dom[w].system[k].max_smem_bytes());
     int max_optin = 0;
     PECS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    if ((size_t)smem * sizeof(double) > (size_t)max_optin)
+    if (smem > (size_t)max_optin)
       throw StatusError(PECS_ERR_INTERNAL, "a front's vector does not fit into shared memory");
     configure_solve_kernels(max_optin);
     PECS_CUDA(cudaDeviceSynchronize());
@@ -789,20 +802,21 @@ pecs_status pecs_time_kernel(pecs_ctx* ctx, int32_t which, int32_t repeats, doub
 
 int64_t pecs_get_info(const pecs_ctx* ctx, int32_t what) {
   if (!ctx) return -1;
-  int64_t factor = ctx->p_system.factor_bytes();
+  int64_t factor = ctx->p_system.factor_bytes(), logical = ctx->p_system.logical_bytes();
   int levels = (int)ctx->p_system.levels.size();
   int64_t cells = 0;
   for (int w = 0; w < ctx->n_domains(); ++w) {
     cells += ctx->dom[w].n_cells;
     for (int k = 0; k < 2; ++k) {
       factor += ctx->dom[w].system[k].factor_bytes() + ctx->dom[w].reduced[k].bytes();
+      logical += ctx->dom[w].system[k].logical_bytes() + ctx->dom[w].reduced[k].bytes();
       levels = std::max(levels, (int)ctx->dom[w].system[k].levels.size());
     }
   }
   switch (what) {
     case PECS_INFO_LAUNCHES_PER_STEP: return launches_per_step(ctx);
     case PECS_INFO_FACTOR_BYTES: return factor;
-    case PECS_INFO_SOLVE_BYTES_PER_STEP: return factor; // every factor entry is streamed exactly once per step
+    case PECS_INFO_SOLVE_BYTES_PER_STEP: return logical; // every factor entry is streamed exactly once per step (padding not counted)
     case PECS_INFO_TREE_LEVELS_MAX: return levels;
     case PECS_INFO_RHS_BYTES_PER_STEP: return cells * (kCarrierRhsBytesPerCell + kPoissonRhsBytesPerCell);
   }

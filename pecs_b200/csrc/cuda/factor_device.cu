@@ -7,7 +7,8 @@
 // Small fronts (the vast majority) are handled by one thread block each with Gauss-Jordan elimination; large fronts
 // use cuSOLVER getrf/getrs for the inverse and cuBLAS DGEMM for the three products (plain library GEMMs, setup only).
 // All matrices are row-major; a row-major matrix handed to a column-major library is its transpose, and
-// (F_PP^T)^-1 = Inv^T, so the library results land directly in the row-major tables (derivation in the comments).
+// (F_PP^T)^-1 = Inv^T, so the library results land directly in row-major scratch operators (derivation in the
+// comments); a last kernel per level packs them into the panel layout the solve kernels stream.
 #include "factor_device.cuh"
 
 #include <cublas_v2.h>
@@ -25,16 +26,16 @@ namespace pecs {
 
 namespace {
 
-constexpr int kSmallFrontMaxNp = kColMajorMaxNp;
-
 struct FactorFront {
   int np, nb, p0;
   int child[2];            // indices into the PREVIOUS level's FactorFront array, -1 if none
   long long bd_off;        // into bd_index
   long long F_off;         // into this level's frontal buffer (m x m, row-major)
-  long long fwd_off, bwd_off;
+  long long Gs_off, Bs_off; // into this level's scratch operators: G (nb x np) and [Inv | -H] (np x m), row-major
   long long cl_off[2];     // into the child-local index scratch
-  int ld_fwd, ld_bwd, fwd_colmajor;
+  // destination panels (host/SparseDirect.hpp PanelTable)
+  long long fwd_off, bwd_off;
+  int fwd_log2P, fwd_cols_pad, bwd_log2P, bwd_cols_pad;
 };
 
 __device__ __forceinline__ int local_index(int pos, int p0, int np, const int* bd, int nb) {
@@ -120,15 +121,15 @@ __global__ void extend_add_kernel(const FactorFront* __restrict__ fronts, const 
 // One block per small front: Gauss-Jordan inverse of F_PP (partial pivoting) straight into the backward table,
 // then -H, G and the Schur complement.  Everything stays in L1/L2 for these sizes.
 __global__ void __launch_bounds__(256) small_front_kernel(const FactorFront* __restrict__ fronts,
-                                                          const int* __restrict__ small_list, double* Fbuf, double* fwd,
-                                                          double* bwd, int* error) {
+                                                          const int* __restrict__ small_list, double* Fbuf, double* Gs,
+                                                          double* Bs, int* error) {
   const FactorFront F = fronts[small_list[blockIdx.x]];
   const int np = F.np, nb = F.nb, m = np + nb;
   double* M = Fbuf + F.F_off;   // rows 0..np-1 hold [F_PP | F_PB]
-  double* B = bwd + F.bwd_off;  // [Inv | -H], row stride ld_bwd
-  double* G = fwd + F.fwd_off;  // nb x np, row- or column-major
-  const int ldb = F.ld_bwd;
-  const size_t g_rs = F.fwd_colmajor ? 1 : (size_t)F.ld_fwd, g_cs = F.fwd_colmajor ? (size_t)F.ld_fwd : 1;
+  double* B = Bs + F.Bs_off;    // [Inv | -H], row stride m
+  double* G = Gs + F.Gs_off;    // nb x np, row-major
+  const int ldb = m;
+  const size_t g_rs = (size_t)np, g_cs = 1;
   __shared__ int s_piv;
   __shared__ double s_val[256];
   __shared__ int s_idx[256];
@@ -219,6 +220,33 @@ __global__ void __launch_bounds__(256) small_front_kernel(const FactorFront* __r
   }
 }
 
+// row-major scratch operators -> panels; grid.x = front, grid.y strides over the entries
+__global__ void pack_kernel(const FactorFront* __restrict__ fronts, const double* __restrict__ Gs, const double* __restrict__ Bs,
+                            double* __restrict__ fwd, double* __restrict__ bwd) {
+  const FactorFront F = fronts[blockIdx.x];
+  const int np = F.np, nb = F.nb, m = np + nb;
+  const long long stride = (long long)gridDim.y * blockDim.x;
+  const long long first = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+  {
+    const double* G = Gs + F.Gs_off;
+    const int P = 1 << F.fwd_log2P;
+    const long long ps = (long long)F.fwd_cols_pad << F.fwd_log2P;
+    for (long long e = first; e < (long long)nb * np; e += stride) {
+      const int i = (int)(e / np), j = (int)(e % np);
+      fwd[F.fwd_off + (long long)(i >> F.fwd_log2P) * ps + ((long long)j << F.fwd_log2P) + (i & (P - 1))] = G[e];
+    }
+  }
+  {
+    const double* B = Bs + F.Bs_off;
+    const int P = 1 << F.bwd_log2P;
+    const long long ps = (long long)F.bwd_cols_pad << F.bwd_log2P;
+    for (long long e = first; e < (long long)np * m; e += stride) {
+      const int i = (int)(e / m), j = (int)(e % m);
+      bwd[F.bwd_off + (long long)(i >> F.bwd_log2P) * ps + ((long long)j << F.bwd_log2P) + (i & (P - 1))] = B[e];
+    }
+  }
+}
+
 __global__ void check_info_kernel(const int* info, int* error) {
   if (*info != 0) atomicExch(error, 3);
 }
@@ -276,7 +304,7 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, 
   // cuSOLVER / cuBLAS initialisation costs about a second: one set of handles per process
   static Handles* handles = new Handles();
   Handles& h = *handles;
-  DeviceBuffer<double> Fcur, Fchild, work;
+  DeviceBuffer<double> Fcur, Fchild, work, Gs, Bs;
   DeviceBuffer<FactorFront> d_cur, d_child;
   DeviceBuffer<int> ipiv((size_t)std::max(plan.max_np, 1)), info(1), cl, small_list;
   std::vector<int> index_in_level(plan.fronts.size(), -1);
@@ -285,7 +313,7 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, 
     const std::vector<int>& lvl = plan.levels[d];
     std::vector<FactorFront> ff(lvl.size());
     std::vector<int> small, large;
-    long long F_total = 0, cl_total = 0;
+    long long F_total = 0, cl_total = 0, Gs_total = 0, Bs_total = 0;
     int max_child_nb = 0;
     for (size_t k = 0; k < lvl.size(); ++k) {
       const Front& F = plan.fronts[lvl[k]];
@@ -294,11 +322,16 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, 
       x.nb = F.nb;
       x.p0 = F.p0;
       x.bd_off = F.bd_off;
-      x.fwd_off = F.fwd_off;
-      x.bwd_off = F.bwd_off;
-      x.ld_fwd = F.ld_fwd;
-      x.ld_bwd = F.ld_bwd;
-      x.fwd_colmajor = F.fwd_colmajor;
+      x.fwd_off = F.fwd.off;
+      x.bwd_off = F.bwd.off;
+      x.fwd_log2P = F.fwd.log2P;
+      x.fwd_cols_pad = F.fwd.cols_pad;
+      x.bwd_log2P = F.bwd.log2P;
+      x.bwd_cols_pad = F.bwd.cols_pad;
+      x.Gs_off = Gs_total;
+      Gs_total += (long long)F.nb * F.np;
+      x.Bs_off = Bs_total;
+      Bs_total += (long long)F.np * (F.np + F.nb);
       x.F_off = F_total;
       F_total += (long long)(F.np + F.nb) * (F.np + F.nb);
       for (int c = 0; c < 2; ++c) {
@@ -314,6 +347,8 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, 
     for (size_t k = 0; k < lvl.size(); ++k) index_in_level[lvl[k]] = (int)k;
     Fcur.resize((size_t)F_total);
     Fcur.zero();
+    if ((size_t)Gs_total > Gs.size()) Gs.resize((size_t)Gs_total);
+    if ((size_t)Bs_total > Bs.size()) Bs.resize((size_t)Bs_total);
     d_cur.upload(ff);
     const int nfl = (int)lvl.size();
     assemble_kernel<<<nfl, 128>>>(d_cur.get(), d_bd_index, rp.get(), col.get(), val.get(), trp.get(), tcol.get(),
@@ -329,18 +364,19 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, 
     PECS_CUDA(cudaGetLastError());
     if (!small.empty()) {
       small_list.upload(small);
-      small_front_kernel<<<(int)small.size(), 256>>>(d_cur.get(), small_list.get(), Fcur.get(), d_fwd, d_bwd, d_error.get());
+      small_front_kernel<<<(int)small.size(), 256>>>(d_cur.get(), small_list.get(), Fcur.get(), Gs.get(), Bs.get(),
+                                                     d_error.get());
       PECS_CUDA(cudaGetLastError());
     }
     for (int k : large) {
       const FactorFront& x = ff[k];
       const int np = x.np, nb = x.nb, m = np + nb;
       double* M = Fcur.get() + x.F_off;
-      double* B = d_bwd + x.bwd_off;
-      double* G = d_fwd + x.fwd_off;
+      double* B = Bs.get() + x.Bs_off;
+      double* G = Gs.get() + x.Gs_off;
       // col-major view of the row-major F_PP (ld m) is F_PP^T; getrf/getrs on it give (F_PP^T)^-1 = Inv^T, whose
       // col-major storage with leading dimension ldb IS the row-major Inv with row stride ldb: it lands in the table.
-      const int ldb = x.ld_bwd, ldf = x.ld_fwd;
+      const int ldb = m, ldf = np;
       int lwork = 0;
       cusolver_check(cusolverDnDgetrf_bufferSize(h.solver, np, np, M, m, &lwork), "getrf_bufferSize");
       if ((size_t)lwork > work.size()) work.resize((size_t)lwork);
@@ -353,26 +389,21 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, 
         // (-H)^T = -F_PB^T Inv^T : C(nb x np, ld ldb) = -A(nb x np: F_PB memory, ld m) * B(np x np: Inv memory, ld ldb)
         cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, np, np, &minus, M + np, m, B, ldb, &zero, B + np, ldb),
                      "dgemm H");
-        if (x.fwd_colmajor) {
-          // G (nb x np) column-major, ld ldf:  G = (F_BP^T)^T (Inv^T)^T with both operands read transposed
-          cublas_check(cublasDgemm(h.blas, CUBLAS_OP_T, CUBLAS_OP_T, nb, np, np, &one, M + (size_t)np * m, m, B, ldb, &zero,
-                                   G, ldf),
-                       "dgemm G (col)");
-          // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * op_T(G: nb x np col-major)
-          cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_T, nb, nb, np, &minus, M + np, m, G, ldf, &one,
-                                   M + (size_t)np * m + np, m),
-                       "dgemm U (col)");
-        } else {
-          // G^T = Inv^T F_BP^T : C(np x nb, ld ldf) = A(np x np: Inv memory, ld ldb) * B(np x nb: F_BP memory, ld m)
-          cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, np, nb, np, &one, B, ldb, M + (size_t)np * m, m, &zero,
-                                   G, ldf),
-                       "dgemm G");
-          // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * B(np x nb: G memory, ld ldf)
-          cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, nb, np, &minus, M + np, m, G, ldf, &one,
-                                   M + (size_t)np * m + np, m),
-                       "dgemm U");
-        }
+        // G^T = Inv^T F_BP^T : C(np x nb, ld ldf) = A(np x np: Inv memory, ld ldb) * B(np x nb: F_BP memory, ld m)
+        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, np, nb, np, &one, B, ldb, M + (size_t)np * m, m, &zero,
+                                 G, ldf),
+                     "dgemm G");
+        // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * B(np x nb: G memory, ld ldf)
+        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, nb, np, &minus, M + np, m, G, ldf, &one,
+                                 M + (size_t)np * m + np, m),
+                     "dgemm U");
       }
+    }
+    {
+      long long max_entries = 1;
+      for (const FactorFront& x : ff) max_entries = std::max(max_entries, (long long)x.np * (x.np + x.nb));
+      const dim3 grid(nfl, (unsigned)std::max<long long>(1, std::min<long long>(512, max_entries / 1024)));
+      pack_kernel<<<grid, 256>>>(d_cur.get(), Gs.get(), Bs.get(), d_fwd, d_bwd);
     }
     PECS_CUDA(cudaDeviceSynchronize());
     int herr = 0;

@@ -6,216 +6,240 @@
 //     forward level kernels  (deepest level -> root):  w_P = b_P - children,  t = children + G w_P  -> parent
 //     backward level kernels (root -> deepest level):  x_P = [Inv | -H] [w_P ; x_B]
 // The only traffic that matters is the factor tables: every entry is streamed from HBM exactly once per solve
-// (8 B per stored entry).  Layout and mapping are chosen for that stream:
-//   * rows padded to even length, 16-byte streaming loads (ld.global.cs), 8 independent loads in flight per lane;
-//   * large fronts: row-major tables, one warp owns two rows at a time, the front's small input vector sits in
-//     shared memory (or is gathered on the fly for the few root-level fronts whose vector would cost occupancy);
-//   * small fronts (np <= 128, the vast majority): column-major forward table, one THREAD owns two rows, no
-//     shuffles at all, a warp still reads 512 contiguous bytes per instruction;
+// (8 B per stored entry, nothing is re-read).  The kernels are built around that stream:
+//   * tables are stored as contiguous PANELS (P rows, column-major, host/SparseDirect.hpp); one warp owns a panel;
+//   * every warp runs its own pipeline of bulk asynchronous copies (cp.async.bulk global -> shared, completion on an
+//     mbarrier): lane 0 keeps `stages` 2 KB chunks of the warp's panels in flight, independent of what the warp's
+//     arithmetic is doing, so the bytes in flight per SM are set by shared memory, not by registers or occupancy;
+//   * 32 consecutive doubles of a chunk are 32/P columns of the panel's P rows: lane l multiplies entry 32 s + l with
+//     vector element (column) and accumulates for row l % P -- no shuffles until the end of the panel;
+//   * the front's input vector is staged once per thread block in shared memory while the first chunks are in flight;
 //   * a front's update goes to a dense buffer in its parent's local numbering: the parent reads it with unit stride;
-//   * every output row has exactly one owner: no atomics, fixed summation order, bit-reproducible solves.
+//   * the permutations in and out of the elimination order are fused into the staging / the final store;
+//   * every output row has exactly one owner and a fixed summation order: no atomics, bit-reproducible solves.
 #include "solve_kernels.cuh"
 
 namespace pecs {
 
 namespace {
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t a = smem_addr(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP); the table is read once per solve: L2 evict-first
+__device__ __forceinline__ void bulk_copy(double* dst, const double* src, uint32_t bytes, unsigned long long* bar,
+                                          unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_addr(dst)),
+      "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long evict_first_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 
-// dot products of TWO table rows (n2 double2 each) with a vector delivered by vec(j) -> double2
-template <class VecFn>
-__device__ __forceinline__ void dot2(const double2* __restrict__ A, const double2* __restrict__ B, int n2, int lane,
-                                     VecFn vec, double& outA, double& outB) {
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-  int j = lane;
-  for (; j + 96 < n2; j += 128) {
-    const double2 xa0 = __ldcs(A + j), xa1 = __ldcs(A + j + 32), xa2 = __ldcs(A + j + 64), xa3 = __ldcs(A + j + 96);
-    const double2 xb0 = __ldcs(B + j), xb1 = __ldcs(B + j + 32), xb2 = __ldcs(B + j + 64), xb3 = __ldcs(B + j + 96);
-    const double2 s0 = vec(j), s1 = vec(j + 32), s2 = vec(j + 64), s3 = vec(j + 96);
-    a0 += xa0.x * s0.x;
-    a1 += xa0.y * s0.y;
-    a2 += xa1.x * s1.x;
-    a3 += xa1.y * s1.y;
-    a0 += xa2.x * s2.x;
-    a1 += xa2.y * s2.y;
-    a2 += xa3.x * s3.x;
-    a3 += xa3.y * s3.y;
-    b0 += xb0.x * s0.x;
-    b1 += xb0.y * s0.y;
-    b2 += xb1.x * s1.x;
-    b3 += xb1.y * s1.y;
-    b0 += xb2.x * s2.x;
-    b1 += xb2.y * s2.y;
-    b2 += xb3.x * s3.x;
-    b3 += xb3.y * s3.y;
-  }
-  for (; j < n2; j += 32) {
-    const double2 xa = __ldcs(A + j), xb = __ldcs(B + j), s0 = vec(j);
-    a0 += xa.x * s0.x;
-    a1 += xa.y * s0.y;
-    b0 += xb.x * s0.x;
-    b1 += xb.y * s0.y;
-  }
-  outA = warp_sum((a0 + a1) + (a2 + a3));
-  outB = warp_sum((b0 + b1) + (b2 + b3));
-}
-
-// finalised pivot right-hand side of a front into shared memory (and, once per front, into w_fin)
-__device__ __forceinline__ void stage_pivot_rhs(const DeviceFront& F, bool publish, const double* __restrict__ w_in,
-                                                double* __restrict__ w_fin, const double* cbuf, double* sv) {
-  const double* c0 = F.cbuf_off[0] >= 0 ? cbuf + F.cbuf_off[0] : nullptr;
-  const double* c1 = F.cbuf_off[1] >= 0 ? cbuf + F.cbuf_off[1] : nullptr;
-  for (int l = threadIdx.x; l < F.np; l += blockDim.x) {
-    double v = w_in[F.p0 + l];
-    if (c0) v -= c0[l];
-    if (c1) v -= c1[l];
-    sv[l] = v;
-    if (publish) w_fin[F.p0 + l] = v;
-  }
-  if (threadIdx.x == 0 && (F.np & 1)) sv[F.np] = 0.0;
-}
-
-// t[row] = (children's updates on row) + dot ; scattered into the parent's buffer in the parent's numbering
-__device__ __forceinline__ void emit_update(const DeviceFront& F, const SolveTables& t, double* cbuf, int row, double dot) {
-  double carry = 0.0;
-  if (F.cbuf_off[0] >= 0) carry += cbuf[F.cbuf_off[0] + F.np + row];
-  if (F.cbuf_off[1] >= 0) carry += cbuf[F.cbuf_off[1] + F.np + row];
-  cbuf[F.out_off + t.out_map[F.bd_off + row]] = carry + dot;
-}
-
-__global__ void __launch_bounds__(kSolveThreads) forward_rows_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
-                                                                     const double* __restrict__ w_in,
-                                                                     double* __restrict__ w_fin, double* cbuf) {
-  extern __shared__ __align__(16) double sv[];
-  const SolveTile tile = tiles[blockIdx.x];
-  const DeviceFront F = t.fronts[tile.front];
-  stage_pivot_rhs(F, tile.first != 0, w_in, w_fin, cbuf, sv);
-  __syncthreads();
+// One warp streams its share of the tile's panels (panel0 + warp, + n_warps, ...) through its private ring and hands
+// every finished row to emit(row, value).  sv: the front's vector in shared memory, zero beyond the logical columns.
+template <class Emit>
+__device__ __forceinline__ void stream_panels(const double* __restrict__ table, int log2P, int cols_pad, int rows,
+                                              const SolveTile& tile, const double* sv, double* ring,
+                                              unsigned long long* bars, int stages, Emit emit) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  const int n2 = F.ld_fwd >> 1;
-  const double2* G = reinterpret_cast<const double2*>(t.fwd + F.fwd_off);
-  const double2* S2 = reinterpret_cast<const double2*>(sv);
-  for (int r = 2 * warp; r < tile.nrows; r += 2 * n_warps) {
-    const int rowA = tile.row0 + r;
-    const bool hasB = r + 1 < tile.nrows;
-    const int rowB = hasB ? rowA + 1 : rowA;
-    double dA, dB;
-    dot2(G + (size_t)rowA * n2, G + (size_t)rowB * n2, n2, lane, [&](int j) { return S2[j]; }, dA, dB);
-    if (lane == 0) emit_update(F, t, cbuf, rowA, dA);
-    if (lane == 1 && hasB) emit_update(F, t, cbuf, rowB, dB);
+  const int P = 1 << log2P;
+  const int cg = 32 >> log2P;                               // columns covered by 32 consecutive doubles
+  const int panel_doubles = cols_pad << log2P;
+  const int cpp = (panel_doubles + kChunkDoubles - 1) / kChunkDoubles; // chunks per panel
+  const int n_my = warp < tile.npanels ? (tile.npanels - warp + n_warps - 1) / n_warps : 0;
+  const int total = n_my * cpp;
+  double* my_ring = ring + (size_t)warp * stages * kChunkDoubles;
+  unsigned long long* my_bars = bars + warp * stages;
+  const unsigned long long policy = evict_first_policy();
+
+  // producer state (lane 0 only): next chunk to issue
+  int ik = 0, ic = 0, issued = 0, islot = 0;
+  auto issue = [&]() {
+    const int panel = tile.panel0 + warp + ik * n_warps;
+    const int e0 = ic * kChunkDoubles;
+    const int elems = min(kChunkDoubles, panel_doubles - e0);
+    mbar_expect_tx(my_bars + islot, (uint32_t)elems * 8u);
+    bulk_copy(my_ring + islot * kChunkDoubles, table + (size_t)panel * panel_doubles + e0, (uint32_t)elems * 8u,
+              my_bars + islot, policy);
+    ++issued;
+    if (++islot == stages) islot = 0;
+    if (++ic == cpp) {
+      ic = 0;
+      ++ik;
+    }
+  };
+  if (lane == 0)
+    for (int q = 0; q < stages && q < total; ++q) issue();
+
+  // the vector is staged by the whole block while the first chunks fly
+  __syncthreads();
+
+  const int row_in_panel = lane & (P - 1);
+  const int col_of_lane = lane >> log2P;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int k = 0; k < n_my; ++k) {
+    const int panel = tile.panel0 + warp + k * n_warps;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int c = 0; c < cpp; ++c) {
+      mbar_wait(my_bars + slot, phase);
+      const double* ch = my_ring + slot * kChunkDoubles + lane;
+      const int e0 = c * kChunkDoubles;
+      const int elems = min(kChunkDoubles, panel_doubles - e0);
+      const double* v = sv + (e0 >> log2P) + col_of_lane;
+      if (elems == kChunkDoubles) {
+        a0 += ch[0] * v[0];
+        a1 += ch[32] * v[cg];
+        a2 += ch[64] * v[2 * cg];
+        a3 += ch[96] * v[3 * cg];
+        a0 += ch[128] * v[4 * cg];
+        a1 += ch[160] * v[5 * cg];
+        a2 += ch[192] * v[6 * cg];
+        a3 += ch[224] * v[7 * cg];
+      } else {
+        for (int s = 0; s < elems; s += 32) a0 += ch[s] * v[(s >> 5) * cg];
+      }
+      __syncwarp();
+      if (lane == 0 && issued < total) issue();
+      if (++slot == stages) {
+        slot = 0;
+        phase ^= 1u;
+      }
+    }
+    double sum = (a0 + a1) + (a2 + a3);
+    for (int o = P; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const int row = (panel << log2P) + row_in_panel;
+    if (lane < P && row < rows) emit(row, sum);
   }
 }
 
-__global__ void __launch_bounds__(kSolveThreads) forward_cols_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
-                                                                     const double* __restrict__ w_in,
-                                                                     double* __restrict__ w_fin, double* cbuf) {
-  __shared__ __align__(16) double sv[130];
+__device__ __forceinline__ void init_pipeline(unsigned long long* bars, int stages) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    for (int q = 0; q < stages; ++q) mbar_init(bars + warp * stages + q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
+                                                                        int vec_doubles, int stages,
+                                                                        const double* __restrict__ rhs,
+                                                                        double* __restrict__ w_fin, double* cbuf) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sv = reinterpret_cast<double*>(smem_raw);
+  double* ring = sv + vec_doubles;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)(blockDim.x >> 5) * stages * kChunkDoubles);
   const SolveTile tile = tiles[blockIdx.x];
   const DeviceFront F = t.fronts[tile.front];
-  stage_pivot_rhs(F, tile.first != 0, w_in, w_fin, cbuf, sv);
-  __syncthreads();
-  const int r = 2 * threadIdx.x;
-  if (r >= tile.nrows) return;
-  const int row = tile.row0 + r;
-  const int ld2 = F.ld_fwd >> 1;
-  const double2* G = reinterpret_cast<const double2*>(t.fwd + F.fwd_off + row);
-  double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-  int j = 0;
-  for (; j + 8 <= F.np; j += 8) {
-    double2 g[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) g[u] = __ldcs(G + (size_t)(j + u) * ld2);
-#pragma unroll
-    for (int u = 0; u < 8; u += 2) {
-      a0 += g[u].x * sv[j + u];
-      b0 += g[u].y * sv[j + u];
-      a1 += g[u + 1].x * sv[j + u + 1];
-      b1 += g[u + 1].y * sv[j + u + 1];
+  init_pipeline(bars, stages);
+  // finalised pivot right-hand side: w_P = b_P - what the children eliminated into it
+  {
+    const double* c0 = F.cbuf_off[0] >= 0 ? cbuf + F.cbuf_off[0] : nullptr;
+    const double* c1 = F.cbuf_off[1] >= 0 ? cbuf + F.cbuf_off[1] : nullptr;
+    const int count = max(F.np, F.fwd_cols_pad);
+    for (int l = threadIdx.x; l < count; l += blockDim.x) {
+      double v = 0.0;
+      if (l < F.np) {
+        v = rhs[t.iperm[F.p0 + l]];
+        if (c0) v -= c0[l];
+        if (c1) v -= c1[l];
+        if (tile.first) w_fin[F.p0 + l] = v;
+      }
+      if (l < F.fwd_cols_pad) sv[l] = v;
     }
   }
-  for (; j < F.np; ++j) {
-    const double2 g = __ldcs(G + (size_t)j * ld2);
-    a0 += g.x * sv[j];
-    b0 += g.y * sv[j];
+  const double* carry0 = F.cbuf_off[0] >= 0 ? cbuf + F.cbuf_off[0] + F.np : nullptr;
+  const double* carry1 = F.cbuf_off[1] >= 0 ? cbuf + F.cbuf_off[1] + F.np : nullptr;
+  const int* omap = t.out_map + F.bd_off;
+  double* out = cbuf + F.out_off;
+  if (F.np == 0) {
+    // a front without pivots (its region fell apart into unconnected pieces) only hands its children's updates on
+    for (int row = threadIdx.x; row < F.nb; row += blockDim.x) {
+      double carry = 0.0;
+      if (carry0) carry += carry0[row];
+      if (carry1) carry += carry1[row];
+      out[omap[row]] = carry;
+    }
   }
-  emit_update(F, t, cbuf, row, a0 + a1);
-  if (row + 1 < F.nb) emit_update(F, t, cbuf, row + 1, b0 + b1);
+  stream_panels(t.fwd + F.fwd_off, F.fwd_log2P, F.fwd_cols_pad, F.nb, tile, sv, ring, bars, stages, [&](int row, double dot) {
+    double carry = 0.0;
+    if (carry0) carry += carry0[row];
+    if (carry1) carry += carry1[row];
+    out[omap[row]] = carry + dot;
+  });
 }
 
-template <bool STAGED>
-__global__ void __launch_bounds__(kSolveThreads) backward_rows_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
-                                                                      const double* __restrict__ w_fin, double* x_perm) {
-  extern __shared__ __align__(16) double sv[];
+__global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
+                                                                         int vec_doubles, int stages,
+                                                                         const double* __restrict__ w_fin, double* x_perm,
+                                                                         double* __restrict__ solution) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sv = reinterpret_cast<double*>(smem_raw);
+  double* ring = sv + vec_doubles;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)(blockDim.x >> 5) * stages * kChunkDoubles);
   const SolveTile tile = tiles[blockIdx.x];
   const DeviceFront F = t.fronts[tile.front];
-  const int np = F.np, m = F.np + F.nb;
-  const int* bd = t.bd_index + F.bd_off;
-  const double* wp = w_fin + F.p0;
-  if (STAGED) {
-    for (int l = threadIdx.x; l < m; l += blockDim.x) sv[l] = l < np ? wp[l] : x_perm[bd[l - np]];
-    if (threadIdx.x == 0 && (m & 1)) sv[m] = 0.0;
-    __syncthreads();
+  init_pipeline(bars, stages);
+  {
+    const int np = F.np, m = F.np + F.nb;
+    const int* bd = t.bd_index + F.bd_off;
+    const double* wp = w_fin + F.p0;
+    for (int l = threadIdx.x; l < F.bwd_cols_pad; l += blockDim.x) sv[l] = l < np ? wp[l] : (l < m ? x_perm[bd[l - np]] : 0.0);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  const int n2 = F.ld_bwd >> 1;
-  const double2* B = reinterpret_cast<const double2*>(t.bwd + F.bwd_off);
-  const double2* S2 = reinterpret_cast<const double2*>(sv);
-  auto element = [&](int e) -> double { return e < np ? wp[e] : (e < m ? x_perm[bd[e - np]] : 0.0); };
-  for (int r = 2 * warp; r < tile.nrows; r += 2 * n_warps) {
-    const int rowA = tile.row0 + r;
-    const bool hasB = r + 1 < tile.nrows;
-    const int rowB = hasB ? rowA + 1 : rowA;
-    double dA, dB;
-    if (STAGED)
-      dot2(B + (size_t)rowA * n2, B + (size_t)rowB * n2, n2, lane, [&](int j) { return S2[j]; }, dA, dB);
-    else
-      dot2(B + (size_t)rowA * n2, B + (size_t)rowB * n2, n2, lane,
-           [&](int j) { return make_double2(element(2 * j), element(2 * j + 1)); }, dA, dB);
-    if (lane == 0) x_perm[F.p0 + rowA] = dA;
-    if (lane == 1 && hasB) x_perm[F.p0 + rowB] = dB;
-  }
-}
-
-__global__ void gather_kernel(int n, const int* __restrict__ index, const double* __restrict__ in, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[index[i]];
+  stream_panels(t.bwd + F.bwd_off, F.bwd_log2P, F.bwd_cols_pad, F.np, tile, sv, ring, bars, stages, [&](int row, double x) {
+    x_perm[F.p0 + row] = x;
+    solution[t.iperm[F.p0 + row]] = x;
+  });
 }
 
 } // namespace
 
 void configure_solve_kernels(int max_smem_bytes) {
-  cudaFuncSetAttribute(forward_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
-  cudaFuncSetAttribute(backward_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  cudaFuncSetAttribute(forward_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  cudaFuncSetAttribute(backward_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
 }
 
-void launch_forward_rows(const SolveTables& t, const SolveTile* tiles, int n_tiles, int smem_doubles, const double* w_in,
-                         double* w_fin, double* cbuf, cudaStream_t s) {
+void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int vec_doubles, int warps, int stages,
+                          const double* rhs, double* w_fin, double* cbuf, cudaStream_t s) {
   if (n_tiles == 0) return;
-  forward_rows_kernel<<<n_tiles, kSolveThreads, (size_t)smem_doubles * sizeof(double), s>>>(t, tiles, w_in, w_fin, cbuf);
+  const int vec = (vec_doubles + 15) / 16 * 16;
+  forward_level_kernel<<<n_tiles, warps * 32, solve_smem_bytes(vec_doubles, warps, stages), s>>>(t, tiles, vec, stages, rhs,
+                                                                                                w_fin, cbuf);
 }
 
-void launch_forward_cols(const SolveTables& t, const SolveTile* tiles, int n_tiles, const double* w_in, double* w_fin,
-                         double* cbuf, cudaStream_t s) {
+void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int vec_doubles, int warps, int stages,
+                           const double* w_fin, double* x_perm, double* solution, cudaStream_t s) {
   if (n_tiles == 0) return;
-  forward_cols_kernel<<<n_tiles, kSolveThreads, 0, s>>>(t, tiles, w_in, w_fin, cbuf);
-}
-
-void launch_backward_rows(const SolveTables& t, const SolveTile* tiles, int n_tiles, int smem_doubles, const double* w_fin,
-                          double* x_perm, cudaStream_t s) {
-  if (n_tiles == 0) return;
-  if (smem_doubles > 0)
-    backward_rows_kernel<true><<<n_tiles, kSolveThreads, (size_t)smem_doubles * sizeof(double), s>>>(t, tiles, w_fin, x_perm);
-  else
-    backward_rows_kernel<false><<<n_tiles, kSolveThreads, 0, s>>>(t, tiles, w_fin, x_perm);
-}
-
-void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s) {
-  if (n == 0) return;
-  gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, index, in, out);
+  const int vec = (vec_doubles + 15) / 16 * 16;
+  backward_level_kernel<<<n_tiles, warps * 32, solve_smem_bytes(vec_doubles, warps, stages), s>>>(t, tiles, vec, stages, w_fin,
+                                                                                                 x_perm, solution);
 }
 
 } // namespace pecs

@@ -1,6 +1,9 @@
 // SchurReduction.cpp -- see SchurReduction.hpp.
 #include "SchurReduction.hpp"
 
+#include <cmath>
+#include <cstdlib>
+
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -57,11 +60,17 @@ struct RowAccumulator {
     }
     val[j] += v;
   }
-  // appends the row (sorted by column, exact zeros dropped) to a CSR under construction and resets
-  void flush(CsrMatrix& A) {
+  // appends the row (sorted by column; exact zeros and entries not above rel_drop * max|row| dropped) to a CSR under
+  // construction and resets
+  void flush(CsrMatrix& A, double rel_drop = 0.0) {
     std::sort(touched.begin(), touched.end());
+    double cut = 0.0;
+    if (rel_drop > 0.0) {
+      for (int j : touched) cut = std::max(cut, std::fabs(val[j]));
+      cut *= rel_drop;
+    }
     for (int j : touched) {
-      if (val[j] != 0.0) {
+      if (val[j] != 0.0 && std::fabs(val[j]) > cut) {
         A.col.push_back(j);
         A.val.push_back(val[j]);
       }
@@ -74,6 +83,11 @@ struct RowAccumulator {
 };
 
 } // namespace
+
+double schur_drop_tolerance() {
+  if (const char* e = std::getenv("PECS_B200_SCHUR_DROP")) return std::atof(e);
+  return 1e-13;
+}
 
 bool build_schur_reduction(const CsrMatrix& A, int n_cells, SchurReduction& out) {
   const int nq = 8 * n_cells, nu = 4 * n_cells;
@@ -150,7 +164,11 @@ bool build_schur_reduction(const CsrMatrix& A, int n_cells, SchurReduction& out)
         for (int kk = R.T2.row_ptr[j]; kk < R.T2.row_ptr[j + 1]; ++kk) accS.add(R.T2.col[kk], -v * R.T2.val[kk]);
       }
       acc1.flush(R.T1);
-      accS.flush(R.S);
+      // The LDG fluxes make S compact: the couplings of a cell with the cells two faces away cancel exactly.  In
+      // floating point the cancellation leaves entries of the order of 1e-17 of the row, far below the rounding error
+      // of the large entries of the same product; they are removed so that they do not widen the separators
+      // (there is nothing between 1e-16 and 1e-6 of the row maximum; PECS_B200_SCHUR_DROP overrides the threshold).
+      accS.flush(R.S, schur_drop_tolerance());
     }
   }
   out = std::move(R);

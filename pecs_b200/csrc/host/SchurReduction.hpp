@@ -30,6 +30,9 @@ struct SchurReduction {
   CsrMatrix T2;       // 8n x 4n   q = Ainv r_q - T2 u
 };
 
+// entries of S not above this fraction of their row's largest entry are rounding residue of exact cancellations
+double schur_drop_tolerance();
+
 // A: full carrier matrix (12 n_cells rows).  Returns false (and leaves out untouched) when A_qq couples cells.
 bool build_schur_reduction(const CsrMatrix& A, int n_cells, SchurReduction& out);
 

@@ -1,6 +1,7 @@
 // SolverSetup.cpp -- see SolverSetup.hpp.
 #include "SolverSetup.hpp"
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "../error.hpp"
@@ -47,19 +48,194 @@ NodeLayout poisson_nodes(const pecs_poisson_desc& d) {
   return L;
 }
 
+namespace {
+
+struct PoissonNd {
+  const std::vector<std::vector<int>>& adj; // on unknowns
+  const pecs_poisson_desc& d;
+  std::vector<double> cx, cy;
+  int leaf_cells;
+  std::vector<char> assigned;  // per unknown
+  std::vector<int> side;       // per cell: 0 outside the current region, 1 / 2
+  std::vector<int> comp;       // per cell: component id inside the current region (valid while stamp matches)
+  std::vector<int> comp_stamp; // per cell
+  int stamp = 0;
+  EliminationTree out;
+
+  int phi(int cell) const { return d.n_rt + cell; }
+
+  // connected components of the region's cells through edge fluxes no ancestor has taken; returns their number
+  int components(const std::vector<int>& cells) {
+    ++stamp;
+    for (int c : cells) comp_stamp[c] = -stamp; // in region, not visited
+    int n_comp = 0;
+    std::vector<int> stack;
+    for (int c0 : cells) {
+      if (comp_stamp[c0] == stamp) continue;
+      comp_stamp[c0] = stamp;
+      comp[c0] = n_comp;
+      stack.push_back(c0);
+      while (!stack.empty()) {
+        const int c = stack.back();
+        stack.pop_back();
+        for (int e : adj[phi(c)]) {
+          if (e >= d.n_rt || assigned[e]) continue;
+          for (int w : adj[e]) {
+            if (w < d.n_rt) continue;
+            const int c2 = w - d.n_rt;
+            if (comp_stamp[c2] == -stamp) {
+              comp_stamp[c2] = stamp;
+              comp[c2] = n_comp;
+              stack.push_back(c2);
+            }
+          }
+        }
+      }
+      ++n_comp;
+    }
+    return n_comp;
+  }
+
+  // returns the tree index; `delayed` receives the potentials (as cells) this region passes up, one per component
+  int build(std::vector<int>& cells, std::vector<int>& delayed) {
+    if ((int)cells.size() <= leaf_cells) {
+      const int n_comp = components(cells);
+      std::vector<char> has(n_comp, 0);
+      EliminationTree::Node t;
+      for (int c : cells) {
+        if (!has[comp[c]]) {
+          has[comp[c]] = 1;
+          delayed.push_back(c);
+        } else {
+          t.nodes.push_back(phi(c));
+        }
+        for (int e : adj[phi(c)])
+          if (e < d.n_rt && !assigned[e]) {
+            assigned[e] = 1;
+            t.nodes.push_back(e);
+          }
+        for (int f = 0; f < 4; ++f) { // decoupled rows (hanging children, Neumann edges) go with their first cell
+          const int e = d.face_dof[4 * (size_t)c + f];
+          if (!assigned[e] && adj[e].empty()) {
+            assigned[e] = 1;
+            t.nodes.push_back(e);
+          }
+        }
+      }
+      std::sort(t.nodes.begin(), t.nodes.end());
+      out.tree.push_back(std::move(t));
+      return (int)out.tree.size() - 1;
+    }
+    std::vector<int> bestS, bestA, bestB;
+    for (int dir = 0; dir < 2; ++dir) {
+      const std::vector<double>& c = dir == 0 ? cx : cy;
+      std::vector<int> sorted = cells;
+      const size_t half = sorted.size() / 2;
+      std::nth_element(sorted.begin(), sorted.begin() + half, sorted.end(),
+                       [&](int a, int b) { return c[a] < c[b] || (c[a] == c[b] && a < b); });
+      for (size_t k = 0; k < sorted.size(); ++k) side[sorted[k]] = k < half ? 1 : 2;
+      std::vector<int> S;
+      for (size_t k = 0; k < half; ++k)
+        for (int e : adj[phi(sorted[k])]) {
+          if (e >= d.n_rt || assigned[e]) continue;
+          bool other = false;
+          for (int w : adj[e])
+            if (w >= d.n_rt && side[w - d.n_rt] == 2) other = true;
+          if (other) S.push_back(e);
+        }
+      std::sort(S.begin(), S.end());
+      S.erase(std::unique(S.begin(), S.end()), S.end());
+      for (int v : sorted) side[v] = 0;
+      if (dir == 0 || S.size() < bestS.size()) {
+        bestS.swap(S);
+        bestA.assign(sorted.begin(), sorted.begin() + half);
+        bestB.assign(sorted.begin() + half, sorted.end());
+      }
+    }
+    // components of this region are defined BEFORE its own separator is taken out
+    const int n_comp = components(cells);
+    std::vector<int> comp_of_cell_local;
+    std::vector<int> region_cells = cells; // keep for the component lookup of the delayed potentials
+    std::vector<int> region_comp(region_cells.size());
+    for (size_t k = 0; k < region_cells.size(); ++k) region_comp[k] = comp[region_cells[k]];
+    for (int e : bestS) assigned[e] = 1;
+    cells.clear();
+    cells.shrink_to_fit();
+    EliminationTree::Node t;
+    std::vector<int> from_children;
+    t.child[0] = build(bestA, from_children);
+    t.child[1] = build(bestB, from_children);
+    // the recursion overwrote comp[]: restore this region's numbering
+    for (size_t k = 0; k < region_cells.size(); ++k) comp[region_cells[k]] = region_comp[k];
+    std::vector<char> has(n_comp, 0);
+    t.nodes = bestS;
+    for (int c : from_children) {
+      if (!has[comp[c]]) {
+        has[comp[c]] = 1;
+        delayed.push_back(c);
+      } else {
+        t.nodes.push_back(phi(c));
+      }
+    }
+    std::sort(t.nodes.begin(), t.nodes.end());
+    out.tree.push_back(std::move(t));
+    return (int)out.tree.size() - 1;
+  }
+};
+
+} // namespace
+
+SolvePlan poisson_plan(const CsrMatrix& A, const pecs_poisson_desc& d, int leaf_cells) {
+  if (std::getenv("PECS_B200_POISSON_CELL_NODES") != nullptr) return plan_from_layout(A, poisson_nodes(d), leaf_cells);
+  const int n = d.n_rt + d.n_cells;
+  if (A.n != n) throw StatusError(PECS_ERR_INVALID, "poisson_plan: matrix size");
+  std::vector<int> identity(n);
+  for (int i = 0; i < n; ++i) identity[i] = i;
+  const std::vector<std::vector<int>> adj = node_adjacency(A, identity, n);
+  PoissonNd nd{adj, d, {}, {}, std::max(1, leaf_cells), std::vector<char>(n, 0), std::vector<int>(d.n_cells, 0),
+               std::vector<int>(d.n_cells, 0), std::vector<int>(d.n_cells, 0), 0, {}};
+  nd.cx.resize(d.n_cells);
+  nd.cy.resize(d.n_cells);
+  for (int c = 0; c < d.n_cells; ++c) {
+    const double* v = d.vertices + 8 * (size_t)c;
+    nd.cx[c] = 0.25 * (v[0] + v[2] + v[4] + v[6]);
+    nd.cy[c] = 0.25 * (v[1] + v[3] + v[5] + v[7]);
+  }
+  std::vector<int> all(d.n_cells), rest;
+  for (int c = 0; c < d.n_cells; ++c) all[c] = c;
+  nd.build(all, rest);
+  // the root eliminates the potentials that are still delayed, and anything the tables never mentioned
+  EliminationTree::Node& root = nd.out.tree.back();
+  for (int c : rest) root.nodes.push_back(nd.phi(c));
+  for (int e = 0; e < d.n_rt; ++e)
+    if (!nd.assigned[e]) root.nodes.push_back(e);
+  std::sort(root.nodes.begin(), root.nodes.end());
+  return build_solve_plan(A, identity, n, adj, nd.out);
+}
+
 NodeLayout carrier_density_nodes(const pecs_domain_desc& d) {
   NodeLayout L;
   const int n = d.n_cells;
   L.node_of_dof.resize(4 * (size_t)n);
+  L.group_of_node.resize(4 * (size_t)n);
   L.x.resize(n);
   L.y.resize(n);
+  const bool per_cell = std::getenv("PECS_B200_CELL_SEPARATORS") != nullptr; // comparison: whole cells as graph nodes
   for (int c = 0; c < n; ++c) {
     const double* v = d.vertices + 8 * (size_t)c;
     L.x[c] = 0.25 * (v[0] + v[2] + v[4] + v[6]);
     L.y[c] = 0.25 * (v[1] + v[3] + v[5] + v[7]);
-    for (int a = 0; a < 4; ++a) L.node_of_dof[4 * (size_t)c + a] = c;
+    for (int a = 0; a < 4; ++a) {
+      L.node_of_dof[4 * (size_t)c + a] = per_cell ? c : 4 * c + a;
+      L.group_of_node[4 * (size_t)c + a] = c;
+    }
   }
+  if (per_cell) L.group_of_node.clear();
   return L;
+}
+
+SolvePlan plan_from_layout(const CsrMatrix& A, const NodeLayout& L, int leaf_groups) {
+  return build_solve_plan(A, L.node_of_dof, L.group_of_node, L.x, L.y, leaf_groups);
 }
 
 bool schur_reduction_enabled() {
@@ -72,7 +248,7 @@ int default_leaf_nodes(bool poisson) {
     const int v = std::atoi(e);
     if (v > 0) return v;
   }
-  return poisson ? 16 : 8;
+  return 16;
 }
 
 namespace {
@@ -106,7 +282,7 @@ void solve_system_host(SOLARCELL::SolarCellProblem& s, int which, int leaf_nodes
   d.n_cells = n;
   d.vertices = ref.mesh->vertices.data();
   const NodeLayout L = carrier_density_nodes(d);
-  const SolvePlan plan = build_solve_plan(R.S, L.node_of_dof, L.x, L.y, leaf_nodes > 0 ? leaf_nodes : default_leaf_nodes(false));
+  const SolvePlan plan = plan_from_layout(R.S, L, leaf_nodes > 0 ? leaf_nodes : default_leaf_nodes(false));
   factorize_host(plan, R.S, fwd, bwd);
   std::vector<double> t(nu), rt(nu), q1(nq), q2(nq);
   R.T1.vmult(t.data(), b);                       // T1 r_q
@@ -125,9 +301,7 @@ SolvePlan plan_for_system(SOLARCELL::SolarCellProblem& s, int which, int leaf_no
     d.vertices = P.vertices.data();
     d.n_rt = s.Poisson_object.dofs.n_rt;
     d.face_dof = s.Poisson_object.dofs.face_dof.data();
-    const NodeLayout L = poisson_nodes(d);
-    return build_solve_plan(s.Poisson_object.system_matrix, L.node_of_dof, L.x, L.y,
-                            leaf_nodes > 0 ? leaf_nodes : default_leaf_nodes(true));
+    return poisson_plan(s.Poisson_object.system_matrix, d, leaf_nodes > 0 ? leaf_nodes : default_leaf_nodes(true));
   }
   if (which < 0 || which > 3) throw StatusError(PECS_ERR_INVALID, "plan_for_system: which must be 0..4");
   const bool semi = which <= 1;
@@ -141,11 +315,11 @@ SolvePlan plan_for_system(SOLARCELL::SolarCellProblem& s, int which, int leaf_no
     SchurReduction R;
     if (build_schur_reduction(A, M.n_cells, R)) {
       const NodeLayout L = carrier_density_nodes(d);
-      return build_solve_plan(R.S, L.node_of_dof, L.x, L.y, leaf_nodes > 0 ? leaf_nodes : default_leaf_nodes(false));
+      return plan_from_layout(R.S, L, leaf_nodes > 0 ? leaf_nodes : default_leaf_nodes(false));
     }
   }
   const NodeLayout L = carrier_nodes(d);
-  return build_solve_plan(A, L.node_of_dof, L.x, L.y, leaf_nodes > 0 ? leaf_nodes : default_leaf_nodes(false));
+  return plan_from_layout(A, L, leaf_nodes > 0 ? leaf_nodes : default_leaf_nodes(false));
 }
 
 } // namespace pecs

@@ -20,16 +20,29 @@ namespace pecs {
 
 struct NodeLayout {
   std::vector<int> node_of_dof;
-  std::vector<double> x, y;
+  std::vector<int> group_of_node; // the mesh cell a graph node is bisected with; empty: node == group
+  std::vector<double> x, y;       // per group
 };
 
 // from the C-ABI tables (this is what pecs_ctx_create uses)
 NodeLayout carrier_nodes(const pecs_domain_desc& d);
-// one node per cell with only its 4 density unknowns (the Schur-reduced carrier system, host/SchurReduction.hpp)
+// the Schur-reduced carrier system (host/SchurReduction.hpp): every density unknown is its own graph node, bisected
+// through its cell -- separators are then sets of unknowns (6 per cell row), not of whole cells (8 per cell row)
 NodeLayout carrier_density_nodes(const pecs_domain_desc& d);
+SolvePlan plan_from_layout(const CsrMatrix& A, const NodeLayout& L, int leaf_groups);
 // PECS_B200_NO_SCHUR=1 factorises the full 12-unknowns-per-cell systems instead (debugging / comparison)
 bool schur_reduction_enabled();
 NodeLayout poisson_nodes(const pecs_poisson_desc& d);
+// Plan of the saddle-point Poisson matrix [A  -B^T; -lambda^2 B  0] (RT0 fluxes on edges, one potential per cell).
+// Default: EDGE separators.  The cells of a region are bisected geometrically and the separator is the set of edge
+// fluxes shared by the two halves -- one unknown per cell row instead of the three of a whole cell.  A region whose
+// boundary fluxes all belong to ancestors is a pure Neumann problem: its leading block is singular by the constant
+// potential.  Therefore every region passes ONE potential per connected component up to its parent instead of
+// eliminating it (a delayed pivot chosen symbolically): with it pinned the divergence block has full row rank and every
+// pivot block is invertible without pivoting across fronts; the parent eliminates all but one of the potentials it
+// receives per component of its own region, the root eliminates the rest.
+// PECS_B200_POISSON_CELL_NODES=1 selects the older vertex-separator plan on poisson_nodes() (comparison).
+SolvePlan poisson_plan(const CsrMatrix& A, const pecs_poisson_desc& d, int leaf_cells);
 // recursion stops at this many nodes per leaf; PECS_B200_LEAF_NODES overrides (tuning)
 int default_leaf_nodes(bool poisson);
 

@@ -16,82 +16,118 @@ namespace pecs {
 
 namespace {
 
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
 struct NdBuilder {
   const std::vector<std::vector<int>>& adj;
-  const std::vector<double>&x, &y;
-  int leaf_nodes;
-  std::vector<int> side; // scratch: 0 = outside, 1 = A, 2 = B
-  struct TreeNode {
-    std::vector<int> nodes;
-    int child[2] = {-1, -1};
-  };
-  std::vector<TreeNode> tree; // postorder
+  const std::vector<int>& group_of; // empty: every node is its own group
+  const std::vector<double>&x, &y;  // per group
+  int leaf_groups;
+  std::vector<int> side;   // per node: 0 = outside the current region, 1 = A, 2 = B
+  std::vector<int> gside;  // per group, scratch
+  std::vector<int> gstamp; // per group: last region that counted it
+  int stamp = 0;
+  EliminationTree out;
+
+  int group(int v) const { return group_of.empty() ? v : group_of[v]; }
 
   int leaf(std::vector<int>& nodes) {
-    TreeNode t;
+    EliminationTree::Node t;
+    std::sort(nodes.begin(), nodes.end());
     t.nodes.swap(nodes);
-    tree.push_back(std::move(t));
-    return (int)tree.size() - 1;
+    out.tree.push_back(std::move(t));
+    return (int)out.tree.size() - 1;
   }
 
   int build(std::vector<int>& nodes) {
-    if ((int)nodes.size() <= leaf_nodes) return leaf(nodes);
+    std::vector<int> groups;
+    ++stamp;
+    for (int v : nodes) {
+      const int g = group(v);
+      if (gstamp[g] != stamp) {
+        gstamp[g] = stamp;
+        groups.push_back(g);
+      }
+    }
+    if ((int)groups.size() <= leaf_groups) return leaf(nodes);
     std::vector<int> bestA, bestB, bestS;
     bool have = false;
+    long long best_imbalance = 0;
     for (int dir = 0; dir < 2; ++dir) {
       const std::vector<double>& c = dir == 0 ? x : y;
-      std::vector<int> sorted = nodes;
+      std::vector<int> sorted = groups;
       const size_t half = sorted.size() / 2;
       std::nth_element(sorted.begin(), sorted.begin() + half, sorted.end(),
                        [&](int a, int b) { return c[a] < c[b] || (c[a] == c[b] && a < b); });
-      for (size_t k = 0; k < sorted.size(); ++k) side[sorted[k]] = k < half ? 1 : 2;
-      std::vector<int> A, B, S;
-      for (size_t k = 0; k < sorted.size(); ++k) {
-        const int v = sorted[k];
-        if (k >= half) {
-          B.push_back(v);
-          continue;
-        }
-        bool touches = false;
-        for (int w : adj[v])
-          if (side[w] == 2) {
-            touches = true;
-            break;
+      for (size_t k = 0; k < sorted.size(); ++k) gside[sorted[k]] = k < half ? 1 : 2;
+      for (int v : nodes) side[v] = gside[group(v)];
+      for (int from = 1; from <= 2; ++from) {
+        // separator = nodes of side `from` that touch the other side
+        std::vector<int> A, B, S;
+        for (int v : nodes) {
+          if (side[v] != from) {
+            (side[v] == 1 ? A : B).push_back(v);
+            continue;
           }
-        (touches ? S : A).push_back(v);
+          bool touches = false;
+          for (int w : adj[v])
+            if (side[w] == 3 - from) {
+              touches = true;
+              break;
+            }
+          (touches ? S : (from == 1 ? A : B)).push_back(v);
+        }
+        if (A.empty() || B.empty() || S.empty()) continue;
+        const long long imbalance = std::llabs((long long)A.size() - (long long)B.size());
+        if (!have || S.size() < bestS.size() || (S.size() == bestS.size() && imbalance < best_imbalance)) {
+          bestA.swap(A);
+          bestB.swap(B);
+          bestS.swap(S);
+          best_imbalance = imbalance;
+          have = true;
+        }
       }
-      for (int v : sorted) side[v] = 0;
-      if (A.empty() || B.empty() || S.empty()) continue;
-      if (!have || S.size() < bestS.size()) {
-        bestA.swap(A);
-        bestB.swap(B);
-        bestS.swap(S);
-        have = true;
-      }
+      for (int v : nodes) side[v] = 0;
     }
     if (!have) return leaf(nodes);
     nodes.clear();
     nodes.shrink_to_fit();
-    TreeNode t;
+    EliminationTree::Node t;
     t.child[0] = build(bestA);
     t.child[1] = build(bestB);
     std::sort(bestS.begin(), bestS.end());
     t.nodes.swap(bestS);
-    tree.push_back(std::move(t));
-    return (int)tree.size() - 1;
+    out.tree.push_back(std::move(t));
+    return (int)out.tree.size() - 1;
   }
 };
 
+// largest power of two <= 32 that divides v (v a positive multiple of 4)
+int max_panel_log2(int v) {
+  int l = 0;
+  while (l < 5 && v % (2 << l) == 0) ++l;
+  return l;
+}
+
+void shape_table(PanelTable& t, int rows, int cols, int log2_cap) {
+  t.rows = rows;
+  t.cols = cols;
+  if (rows == 0 || cols == 0) {
+    t.rows = t.cols = t.rows_pad = t.cols_pad = t.log2P = 0;
+    return;
+  }
+  t.rows_pad = round_up(rows, 4);
+  t.log2P = std::min(log2_cap, max_panel_log2(t.rows_pad));
+  // a front is streamed by the kWarpsPerFront warps of one thread block: give every warp a panel when the front allows it
+  while (t.log2P > 0 && (t.rows_pad >> t.log2P) < kWarpsPerFront) --t.log2P;
+  t.cols_pad = round_up(cols, 32 >> t.log2P);
+}
+
 } // namespace
 
-SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_dof, const std::vector<double>& node_x,
-                           const std::vector<double>& node_y, int leaf_nodes) {
-  const int n = A.n;
-  const int n_nodes = (int)node_x.size();
-  if ((int)node_of_dof.size() != n) throw StatusError(PECS_ERR_INVALID, "build_solve_plan: node_of_dof size");
-  std::vector<std::vector<int>> node_dofs(n_nodes), adj(n_nodes);
-  for (int i = 0; i < n; ++i) node_dofs[node_of_dof[i]].push_back(i);
-  for (int i = 0; i < n; ++i)
+std::vector<std::vector<int>> node_adjacency(const CsrMatrix& A, const std::vector<int>& node_of_dof, int n_nodes) {
+  std::vector<std::vector<int>> adj(n_nodes);
+  for (int i = 0; i < A.n; ++i)
     for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k) {
       const int a = node_of_dof[i], b = node_of_dof[A.col[k]];
       if (a != b) {
@@ -103,15 +139,41 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
     std::sort(a.begin(), a.end());
     a.erase(std::unique(a.begin(), a.end()), a.end());
   }
+  return adj;
+}
 
-  NdBuilder nd{adj, node_x, node_y, std::max(1, leaf_nodes), std::vector<int>(n_nodes, 0), {}};
-  {
-    std::vector<int> all;
-    for (int v = 0; v < n_nodes; ++v)
-      if (!node_dofs[v].empty()) all.push_back(v);
-    nd.build(all);
-  }
-  const int nf = (int)nd.tree.size();
+EliminationTree nested_dissection(const std::vector<std::vector<int>>& adj, const std::vector<int>& group_of_node,
+                                  const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups) {
+  const int n_nodes = (int)adj.size();
+  const int n_groups = (int)group_x.size();
+  if (!group_of_node.empty() && (int)group_of_node.size() != n_nodes)
+    throw StatusError(PECS_ERR_INVALID, "nested_dissection: group_of_node size");
+  if (group_of_node.empty() && n_groups != n_nodes) throw StatusError(PECS_ERR_INVALID, "nested_dissection: coordinates size");
+  NdBuilder nd{adj, group_of_node, group_x, group_y, std::max(1, leaf_groups), std::vector<int>(n_nodes, 0),
+               std::vector<int>(n_groups, 0), std::vector<int>(n_groups, 0), 0, {}};
+  std::vector<int> all(n_nodes);
+  std::iota(all.begin(), all.end(), 0);
+  nd.build(all);
+  return std::move(nd.out);
+}
+
+SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_dof, const std::vector<int>& group_of_node,
+                           const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups) {
+  if ((int)node_of_dof.size() != A.n) throw StatusError(PECS_ERR_INVALID, "build_solve_plan: node_of_dof size");
+  const int n_nodes = group_of_node.empty() ? (int)group_x.size() : (int)group_of_node.size();
+  const std::vector<std::vector<int>> adj = node_adjacency(A, node_of_dof, n_nodes);
+  const EliminationTree tree = nested_dissection(adj, group_of_node, group_x, group_y, leaf_groups);
+  return build_solve_plan(A, node_of_dof, n_nodes, adj, tree);
+}
+
+SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_dof, int n_nodes,
+                           const std::vector<std::vector<int>>& adj, const EliminationTree& etree) {
+  const int n = A.n;
+  if ((int)node_of_dof.size() != n) throw StatusError(PECS_ERR_INVALID, "build_solve_plan: node_of_dof size");
+  std::vector<std::vector<int>> node_dofs(n_nodes);
+  for (int i = 0; i < n; ++i) node_dofs[node_of_dof[i]].push_back(i);
+  const std::vector<EliminationTree::Node>& tree = etree.tree;
+  const int nf = (int)tree.size();
 
   SolvePlan plan;
   plan.n = n;
@@ -125,7 +187,8 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
   for (int f = 0; f < nf; ++f) {
     Front& F = plan.fronts[f];
     F.p0 = next_dof;
-    for (int v : nd.tree[f].nodes) {
+    for (int v : tree[f].nodes) {
+      if (node_pos[v] >= 0) throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: a node is eliminated twice");
       node_pos[v] = next_node++;
       node_first_dofpos[v] = next_dof;
       for (int d : node_dofs[v]) {
@@ -137,7 +200,7 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
     F.np = next_dof - F.p0;
     last_node_pos[f] = next_node - 1;
     for (int k = 0; k < 2; ++k) {
-      F.child[k] = nd.tree[f].child[k];
+      F.child[k] = tree[f].child[k];
       if (F.child[k] >= 0) plan.fronts[F.child[k]].parent = f;
     }
   }
@@ -152,7 +215,7 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
   std::vector<std::vector<int>> bd_nodes(nf);
   for (int f = 0; f < nf; ++f) {
     std::vector<int> s;
-    for (int v : nd.tree[f].nodes)
+    for (int v : tree[f].nodes)
       for (int w : adj[v])
         if (node_pos[w] > last_node_pos[f]) s.push_back(node_pos[w]);
     for (int k = 0; k < 2; ++k)
@@ -164,7 +227,7 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
     s.erase(std::unique(s.begin(), s.end()), s.end());
     bd_nodes[f].swap(s);
   }
-  // expand to unknowns, lay out tables
+  // expand to unknowns
   for (int f = 0; f < nf; ++f) {
     Front& F = plan.fronts[f];
     F.bd_off = (int64_t)plan.bd_index.size();
@@ -173,13 +236,41 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
       for (int k = 0; k < (int)node_dofs[v].size(); ++k) plan.bd_index.push_back(node_first_dofpos[v] + k);
     }
     F.nb = (int)((int64_t)plan.bd_index.size() - F.bd_off);
-    F.fwd_colmajor = F.np <= kColMajorMaxNp;
-    F.ld_fwd = F.fwd_colmajor ? (F.nb + (F.nb & 1)) : (F.np + (F.np & 1));
-    F.ld_bwd = (F.np + F.nb) + ((F.np + F.nb) & 1);
-    F.fwd_off = plan.fwd_entries;
-    plan.fwd_entries += F.fwd_size();
-    F.bwd_off = plan.bwd_entries;
-    plan.bwd_entries += F.bwd_size();
+    std::vector<int>().swap(bd_nodes[f]);
+  }
+  int max_depth = 0;
+  for (const Front& F : plan.fronts) max_depth = std::max(max_depth, F.depth);
+  plan.levels.assign(max_depth + 1, {});
+  for (int f = 0; f < nf; ++f) plan.levels[plan.fronts[f].depth].push_back(f);
+  // panel heights: as tall as possible, capped per level so that the level offers enough panels for the whole GPU
+  for (const std::vector<int>& lvl : plan.levels)
+    for (int which = 0; which < 2; ++which) {
+      int cap = 5;
+      for (; cap > 0; --cap) {
+        int64_t panels = 0;
+        for (int f : lvl) {
+          const Front& F = plan.fronts[f];
+          PanelTable t;
+          shape_table(t, which == 0 ? F.nb : F.np, which == 0 ? F.np : F.np + F.nb, cap);
+          panels += t.n_panels();
+        }
+        if (panels >= kTargetPanelsPerLevel) break;
+      }
+      for (int f : lvl) {
+        Front& F = plan.fronts[f];
+        if (which == 0)
+          shape_table(F.fwd, F.nb, F.np, cap);
+        else
+          shape_table(F.bwd, F.np, F.np + F.nb, cap);
+      }
+    }
+  // lay out tables and child buffers
+  for (int f = 0; f < nf; ++f) {
+    Front& F = plan.fronts[f];
+    F.fwd.off = plan.fwd_entries;
+    plan.fwd_entries += F.fwd.size();
+    F.bwd.off = plan.bwd_entries;
+    plan.bwd_entries += F.bwd.size();
     for (int k = 0; k < 2; ++k)
       if (F.child[k] >= 0) {
         plan.fronts[F.child[k]].which_child = k;
@@ -213,10 +304,6 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
       plan.out_map[C.bd_off + s] = l;
     }
   }
-  int max_depth = 0;
-  for (const Front& F : plan.fronts) max_depth = std::max(max_depth, F.depth);
-  plan.levels.assign(max_depth + 1, {});
-  for (int f = 0; f < nf; ++f) plan.levels[plan.fronts[f].depth].push_back(f);
   return plan;
 }
 
@@ -376,11 +463,13 @@ void factorize_host(const SolvePlan& plan, const CsrMatrix& A, std::vector<doubl
     gemm_sub(nb, np, np, Fbp.data(), np, Fpp.data(), np, negG.data(), np, inner_parallel);
     for (size_t k = 0; k < negG.size(); ++k) G[k] = -negG[k];
     for (int i = 0; i < nb; ++i)
-      for (int j = 0; j < np; ++j) fwd[(size_t)F.fwd_index(i, j)] = G[(size_t)i * np + j];
-    double* B = bwd.data() + F.bwd_off;
-    const int ldb = F.ld_bwd;
-    for (int i = 0; i < np; ++i) std::copy(Fpp.begin() + (size_t)i * np, Fpp.begin() + (size_t)(i + 1) * np, B + (size_t)i * ldb);
-    gemm_sub(np, nb, np, Fpp.data(), np, Fpb.data(), nb, B + np, ldb, inner_parallel); // writes -H
+      for (int j = 0; j < np; ++j) fwd[(size_t)F.fwd.index(i, j)] = G[(size_t)i * np + j];
+    std::vector<double> negH((size_t)np * nb, 0.0);
+    gemm_sub(np, nb, np, Fpp.data(), np, Fpb.data(), nb, negH.data(), nb, inner_parallel); // -H = -Inv F_PB
+    for (int i = 0; i < np; ++i) {
+      for (int j = 0; j < np; ++j) bwd[(size_t)F.bwd.index(i, j)] = Fpp[(size_t)i * np + j];
+      for (int j = 0; j < nb; ++j) bwd[(size_t)F.bwd.index(i, np + j)] = negH[(size_t)i * nb + j];
+    }
     if (F.parent >= 0) {
       std::vector<double>& U = update[f];
       U.resize((size_t)nb * nb);
@@ -428,7 +517,7 @@ void solve_host(const SolvePlan& plan, const std::vector<double>& fwd, const std
         for (int c = 0; c < 2; ++c)
           if (F.cbuf_off[c] >= 0) carry += cbuf[(size_t)F.cbuf_off[c] + np + i];
         double s = 0;
-        for (int j = 0; j < np; ++j) s += fwd[(size_t)F.fwd_index(i, j)] * w[F.p0 + j];
+        for (int j = 0; j < np; ++j) s += fwd[(size_t)F.fwd.index(i, j)] * w[F.p0 + j];
         out[omap[i]] = carry + s;
       }
     }
@@ -437,11 +526,10 @@ void solve_host(const SolvePlan& plan, const std::vector<double>& fwd, const std
       const Front& F = plan.fronts[f];
       const int np = F.np, nb = F.nb;
       const int* bd = plan.bd(F);
-      const double* B = bwd.data() + F.bwd_off;
       for (int i = 0; i < np; ++i) {
         double s = 0;
-        for (int j = 0; j < np; ++j) s += B[(size_t)i * F.ld_bwd + j] * w[F.p0 + j];
-        for (int j = 0; j < nb; ++j) s += B[(size_t)i * F.ld_bwd + np + j] * xp[bd[j]];
+        for (int j = 0; j < np; ++j) s += bwd[(size_t)F.bwd.index(i, j)] * w[F.p0 + j];
+        for (int j = 0; j < nb; ++j) s += bwd[(size_t)F.bwd.index(i, np + j)] * xp[bd[j]];
         xp[F.p0 + i] = s;
       }
     }

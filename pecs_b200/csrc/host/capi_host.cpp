@@ -241,8 +241,8 @@ int32_t pecs_solarcell_plan_levels(pecs_solarcell* p, int32_t which, int32_t lea
       o[1] = o[2] = o[3] = o[4] = o[5] = 0;
       for (int f : plan.levels[d]) {
         const pecs::Front& F = plan.fronts[f];
-        o[1] += F.fwd_size();
-        o[2] += F.bwd_size();
+        o[1] += F.fwd.size();
+        o[2] += F.bwd.size();
         o[3] = std::max<int64_t>(o[3], F.np);
         o[4] = std::max<int64_t>(o[4], F.nb);
         o[5] += F.np;

@@ -70,11 +70,14 @@ np.save(sys.argv[1], np.concatenate([prob.get_solution(s) for s in range(5)]))
 
 
 def test_solver_variants_agree(tmp_path):
-    """Schur-reduced device factorisation (default) vs full 12-unknown systems vs host factorisation"""
+    """default plan (Schur reduction, unknown-level separators, Poisson edge separators, device factorisation) vs
+    full 12-unknown systems, host factorisation, other leaf sizes, cell separators, other pipeline shapes"""
     script = tmp_path / "variant.py"
     script.write_text(VARIANT % ROOT)
     results = []
-    for env in ({}, {"PECS_B200_NO_SCHUR": "1"}, {"PECS_B200_HOST_FACTOR": "1"}, {"PECS_B200_LEAF_NODES": "3"}):
+    for env in ({}, {"PECS_B200_NO_SCHUR": "1"}, {"PECS_B200_HOST_FACTOR": "1"}, {"PECS_B200_LEAF_NODES": "3"},
+                {"PECS_B200_CELL_SEPARATORS": "1", "PECS_B200_SCHUR_DROP": "0", "PECS_B200_POISSON_CELL_NODES": "1"},
+                {"PECS_B200_SOLVE_STAGES": "2", "PECS_B200_SOLVE_PANELS_PER_TILE": "3"}):
         out = tmp_path / ("out_" + "_".join(env) + ".npy")
         r = subprocess.run([sys.executable, str(script), str(out)], env=dict(os.environ, **env), capture_output=True,
                            text=True, timeout=600)
