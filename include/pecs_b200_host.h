@@ -76,6 +76,9 @@ pecs_status pecs_solarcell_plan_stats(pecs_solarcell* p, int32_t which, int32_t 
 /* per-level breakdown of the same plan: for level d (0 = root) out[6*d..6*d+5] = fronts, forward entries, backward
  * entries, max np, max nb, sum of np; returns the number of levels (<= max_levels written) */
 int32_t pecs_solarcell_plan_levels(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, int64_t* out, int32_t max_levels);
+/* per-front listing of the same plan: out[8*f..8*f+7] = depth, np, nb, log2 of the forward / backward panel height,
+ * forward / backward "one warp per front" flags, parent; returns the number of fronts (<= max_fronts written) */
+int64_t pecs_solarcell_plan_fronts(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, int32_t* out, int64_t max_fronts);
 /* Additionally runs the HOST numeric factorisation and the host reference of the two solve sweeps on rhs b, so
  * that the CPU test-suite can check plan + factor tables against the matrix (residual) without a GPU. */
 pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,

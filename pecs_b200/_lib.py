@@ -82,6 +82,7 @@ SIGNATURES = {
     "pecs_solarcell_mixed_errors": (C.c_int, [VOIDP, c_double_p]),
     "pecs_solarcell_plan_stats": (C.c_int, [VOIDP, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "pecs_solarcell_plan_levels": (C.c_int32, [VOIDP, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int32]),
+    "pecs_solarcell_plan_fronts": (C.c_int64, [VOIDP, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int64]),
     "pecs_solarcell_selftest_direct_solve": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p, c_double_p]),
 }
 

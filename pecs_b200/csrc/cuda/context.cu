@@ -36,24 +36,36 @@ namespace pecs {
 struct DeviceSystem {
   int n = 0;
   SolvePlan plan;
-  DeviceBuffer<double> fwd, bwd, cbuf, w_fin, x_perm;
+  DeviceBuffer<double> fwd, bwd, cbuf, w_in, w_fin, x_perm;
   DeviceBuffer<int> bd_index, out_map, iperm;
-  DeviceBuffer<DeviceFront> fronts;
+  // one sweep of one level: large fronts cut into block tiles, small fronts one warp each
+  struct Sweep {
+    DeviceBuffer<SolveTile> block_tiles, warp_tiles;
+    int vec_block = 0, vec_warp = 0; // doubles of the staged vector (per block / per warp)
+    int stages = 2;                  // depth of the per-warp bulk-copy rings, thread-block tiles
+    int stages_warp = 4;             // ... one-warp-per-front tiles: the whole small table is in flight at once
+  };
   struct Level {
-    DeviceBuffer<SolveTile> fwd_tiles, bwd_tiles;
-    int vec_fwd = 0, vec_bwd = 0;       // doubles of the staged vector
-    int stages_fwd = 0, stages_bwd = 0; // depth of the per-warp bulk-copy rings
+    Sweep fwd, bwd;
   };
   std::vector<Level> levels;
   int launches_per_solve = 0;
+  // The matrix itself, rows in elimination order: every solve is done in INCREMENT form,
+  //     x = x_old + A^-1 (b - A x_old),
+  // with x_old the previous time step's solution that is sitting in the solution vector anyway.  The same linear
+  // system, but the explicit front operators then only act on a small correction: measured on the default problem
+  // the density error of a step against an extended-precision solve drops from 1.8e-11 to 7e-13 (reductants),
+  // below that of a sparse LU applied to the full right-hand side (3e-12).  Cost: one ELL mat-vec, ~4 % more bytes.
+  DeviceEll matrix_rows;
 
-  int64_t factor_bytes() const { return (int64_t)(fwd.bytes() + bwd.bytes()); }
-  int64_t logical_bytes() const { return plan.logical_entries() * (int64_t)sizeof(double); }
+  int64_t factor_bytes() const { return (int64_t)(fwd.bytes() + bwd.bytes() + matrix_rows.bytes()); }
+  int64_t logical_bytes() const { return plan.logical_entries() * (int64_t)sizeof(double) + (int64_t)matrix_rows.bytes(); }
   size_t max_smem_bytes() const {
     size_t m = 0;
     for (const Level& l : levels)
-      m = std::max(m, std::max(solve_smem_bytes(l.vec_fwd, kSolveWarps, l.stages_fwd),
-                               solve_smem_bytes(l.vec_bwd, kSolveWarps, l.stages_bwd)));
+      for (const Sweep* sw : {&l.fwd, &l.bwd})
+        m = std::max(m, std::max(solve_smem_bytes(sw->vec_block, false, solve_warps(), sw->stages),
+                                 solve_smem_bytes(sw->vec_warp, true, solve_warps(), sw->stages_warp)));
     return m;
   }
 
@@ -61,23 +73,19 @@ struct DeviceSystem {
     const char* e = std::getenv(name);
     return e && std::atoi(e) > 0 ? std::atoi(e) : fallback;
   }
-  // ring depth: deep enough to cover the HBM latency with the resident warps, shallow enough that two thread blocks
-  // share an SM whenever the staged vector allows it (one block stages its vector while the other one streams)
-  static int pick_stages(int vec_doubles) {
-    const int forced = env_int("PECS_B200_SOLVE_STAGES", 0);
-    if (forced) return forced;
-    const size_t budget = 227 * 1024 - 2048;
-    for (int st : {4, 3})
-      if (2 * (solve_smem_bytes(vec_doubles, kSolveWarps, st) + 1024) <= budget) return st;
-    return 6;
-  }
-  // panels per tile (thread block): at least one per warp, more when the level is so large that whole waves of blocks
-  // would otherwise stage the same vector over and over
+  // warps per thread block.  Measured (scripts/tune_solve.py, cfg3): 4 warps beat 8 -- smaller blocks, more of them
+  // resident, finer tiles
+  static int solve_warps() { return std::min(kSolveWarps, env_int("PECS_B200_SOLVE_WARPS", kWarpsPerFront)); }
+  // Ring depth.  Measured on B200 (scripts/tune_solve.py): shallow rings win -- what hides the latency of a block's
+  // prologue (tile descriptor, vector gather) is the NEXT block already resident on the SM, and shared memory buys
+  // more residency than depth.  Two chunks per warp keep 4 KB per warp in flight, ~150 KB per SM at full residency.
+  static int pick_stages() { return env_int("PECS_B200_SOLVE_STAGES", 2); }
+  // panels per block tile: one per warp, more only when the level is so large that the tile count would explode
   static int panels_per_tile(int64_t level_panels) {
     const int forced = env_int("PECS_B200_SOLVE_PANELS_PER_TILE", 0);
     if (forced) return forced;
-    const int64_t want_tiles = 148 * 8;
-    return (int)std::min<int64_t>(64, std::max<int64_t>(kSolveWarps, (level_panels + want_tiles - 1) / want_tiles));
+    const int64_t want_tiles = 148 * 16;
+    return (int)std::min<int64_t>(64, std::max<int64_t>(solve_warps(), (level_panels + want_tiles - 1) / want_tiles));
   }
 
   void build(const CsrMatrix& A, const NodeLayout& layout, int leaf_nodes, bool factor_on_device) {
@@ -86,31 +94,13 @@ struct DeviceSystem {
   void build(const CsrMatrix& A, SolvePlan&& ready_plan, bool factor_on_device) {
     n = A.n;
     plan = std::move(ready_plan);
-    const int nf = (int)plan.fronts.size();
-    std::vector<DeviceFront> df(nf);
-    for (int f = 0; f < nf; ++f) {
-      const Front& F = plan.fronts[f];
-      DeviceFront& D = df[f];
-      D.np = F.np;
-      D.nb = F.nb;
-      D.p0 = F.p0;
-      D.fwd_log2P = F.fwd.log2P;
-      D.fwd_cols_pad = F.fwd.cols_pad;
-      D.bwd_log2P = F.bwd.log2P;
-      D.bwd_cols_pad = F.bwd.cols_pad;
-      D.bd_off = F.bd_off;
-      D.fwd_off = F.fwd.off;
-      D.bwd_off = F.bwd.off;
-      D.cbuf_off[0] = F.cbuf_off[0];
-      D.cbuf_off[1] = F.cbuf_off[1];
-      D.out_off = F.parent >= 0 ? plan.fronts[F.parent].cbuf_off[F.which_child] : -1;
-    }
-    fronts.upload(df);
     bd_index.upload(plan.bd_index.data(), std::max<size_t>(plan.bd_index.size(), 1));
     out_map.upload(plan.out_map.data(), std::max<size_t>(plan.out_map.size(), 1));
     iperm.upload(plan.iperm);
+    matrix_rows.upload(A, &plan.iperm);
     cbuf.resize((size_t)std::max<int64_t>(plan.upd_entries, 2));
     cbuf.zero(); // slots no child ever writes must read as zero forever
+    w_in.resize(n);
     w_fin.resize(n);
     x_perm.resize(n);
     fwd.resize((size_t)std::max<int64_t>(plan.fwd_entries, 2));
@@ -129,47 +119,87 @@ struct DeviceSystem {
     levels.resize(plan.levels.size());
     launches_per_solve = 0;
     for (size_t d = 0; d < plan.levels.size(); ++d) {
-      std::vector<SolveTile> ft, bt;
       Level& L = levels[d];
-      int64_t panels_f = 0, panels_b = 0;
-      for (int f : plan.levels[d]) {
-        const Front& F = plan.fronts[f];
-        panels_f += F.fwd.n_panels();
-        panels_b += F.bwd.n_panels();
-        L.vec_fwd = std::max(L.vec_fwd, F.fwd.cols_pad);
-        L.vec_bwd = std::max(L.vec_bwd, F.bwd.cols_pad);
-      }
-      const int pf = panels_per_tile(panels_f), pb = panels_per_tile(panels_b);
-      for (int f : plan.levels[d]) {
-        const Front& F = plan.fronts[f];
-        int first = 1;
-        for (int p0 = 0; p0 < std::max(F.fwd.n_panels(), 1); p0 += pf) {
-          ft.push_back(SolveTile{f, p0, std::max(0, std::min(pf, F.fwd.n_panels() - p0)), first});
-          first = 0;
+      for (int which = 0; which < 2; ++which) {
+        Sweep& sw = which == 0 ? L.fwd : L.bwd;
+        std::vector<SolveTile> bt, wt;
+        int64_t panels = 0;
+        for (int f : plan.levels[d]) {
+          const PanelTable& T = which == 0 ? plan.fronts[f].fwd : plan.fronts[f].bwd;
+          if (!T.small) panels += T.n_panels();
         }
-        for (int p0 = 0; p0 < F.bwd.n_panels(); p0 += pb) bt.push_back(SolveTile{f, p0, std::min(pb, F.bwd.n_panels() - p0), 0});
+        const int ppt = panels_per_tile(panels);
+        for (int f : plan.levels[d]) {
+          const Front& F = plan.fronts[f];
+          const PanelTable& T = which == 0 ? F.fwd : F.bwd;
+          SolveTile tile{};
+          tile.np = F.np;
+          tile.nb = F.nb;
+          tile.p0 = F.p0;
+          tile.log2P = T.log2P;
+          tile.cols_pad = T.cols_pad;
+          tile.table_off = T.off;
+          tile.bd_off = F.bd_off;
+          tile.cbuf_off[0] = F.cbuf_off[0];
+          tile.cbuf_off[1] = F.cbuf_off[1];
+          tile.out_off = F.parent >= 0 ? plan.fronts[F.parent].cbuf_off[F.which_child] : -1;
+          // a front without boundary (the root) has no forward work at all: the backward sweep finalises its
+          // right-hand side itself; a front without pivots still hands its children's updates on in the forward sweep
+          if (which == 0 ? F.nb == 0 : F.np == 0) continue;
+          tile.first = which == 0 ? 1 : (F.nb == 0 ? 1 : 0);
+          const bool per_warp = T.small || T.n_panels() == 0;
+          if (per_warp) {
+            tile.panel0 = 0;
+            tile.npanels = T.n_panels();
+            wt.push_back(tile);
+            sw.vec_warp = std::max(sw.vec_warp, T.cols_pad);
+          } else {
+            for (int p0 = 0; p0 < T.n_panels(); p0 += ppt) {
+              tile.panel0 = p0;
+              tile.npanels = std::min(ppt, T.n_panels() - p0);
+              bt.push_back(tile);
+              if (which == 0) tile.first = 0; // one publisher per front; the backward flag holds for every tile
+            }
+            sw.vec_block = std::max(sw.vec_block, T.cols_pad);
+          }
+        }
+        sw.stages = pick_stages();
+        sw.stages_warp = env_int("PECS_B200_SOLVE_STAGES_WARP", 4);
+        sw.block_tiles.upload(bt);
+        sw.warp_tiles.upload(wt);
+        launches_per_solve += (bt.empty() ? 0 : 1) + (wt.empty() ? 0 : 1);
       }
-      L.stages_fwd = pick_stages(L.vec_fwd);
-      L.stages_bwd = pick_stages(L.vec_bwd);
-      L.fwd_tiles.upload(ft);
-      L.bwd_tiles.upload(bt);
-      launches_per_solve += 2;
     }
   }
 
-  // solution = A^-1 rhs, all on stream s
-  void solve(const double* rhs, double* solution, cudaStream_t s) {
-    const SolveTables t{fronts.get(), bd_index.get(), out_map.get(), iperm.get(), fwd.get(), bwd.get()};
+  // solution += A^-1 w, all on stream s; w = residual of the current content of `solution`, in elimination order
+  // (residual() below, or the caller's own fused kernel)
+  void solve_increment(const double* w, double* solution, cudaStream_t s) {
+    const SolveTables t{bd_index.get(), out_map.get(), iperm.get(), fwd.get(), bwd.get()};
+    const int warps = solve_warps();
     for (int d = (int)levels.size() - 1; d >= 0; --d) {
-      Level& L = levels[d];
-      launch_forward_level(t, L.fwd_tiles.get(), (int)L.fwd_tiles.size(), L.vec_fwd, kSolveWarps, L.stages_fwd, rhs,
+      Sweep& sw = levels[d].fwd;
+      launch_forward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, w,
+                           w_fin.get(), cbuf.get(), s);
+      launch_forward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, warps, sw.stages, w,
                            w_fin.get(), cbuf.get(), s);
     }
     for (size_t d = 0; d < levels.size(); ++d) {
-      Level& L = levels[d];
-      launch_backward_level(t, L.bwd_tiles.get(), (int)L.bwd_tiles.size(), L.vec_bwd, kSolveWarps, L.stages_bwd, w_fin.get(),
-                            x_perm.get(), solution, s);
+      Sweep& sw = levels[d].bwd;
+      launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, warps, sw.stages, w,
+                            cbuf.get(), w_fin.get(), x_perm.get(), solution, s);
+      launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, w,
+                            cbuf.get(), w_fin.get(), x_perm.get(), solution, s);
     }
+  }
+  // w_in = rhs - A solution (rows in elimination order)
+  void residual(const double* rhs, const double* solution, cudaStream_t s) {
+    launch_ell_combine(n, rhs, iperm.get(), EllTerm{&matrix_rows, solution, -1.0}, EllTerm{}, EllTerm{}, w_in.get(), s);
+  }
+  // solution = A^-1 rhs in increment form
+  void solve(const double* rhs, double* solution, cudaStream_t s) {
+    residual(rhs, solution, s);
+    solve_increment(w_in.get(), solution, s);
   }
 };
 
@@ -331,11 +361,11 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
     if (schur_reduction_enabled() && build_schur_reduction(A, n, R)) {
       DeviceDomain::Reduced& red = D.reduced[k];
       red.active = true;
-      red.T1.upload(R.T1);
+      D.system[k].build(R.S, carrier_density_nodes(d), default_leaf_nodes(false), factor_on_device);
+      red.T1.upload(R.T1, &D.system[k].plan.iperm); // r~ is produced directly in elimination order
       red.Ainv.upload(R.Ainv);
       red.T2.upload(R.T2);
       red.rtilde.resize(4 * (size_t)n);
-      D.system[k].build(R.S, carrier_density_nodes(d), default_leaf_nodes(false), factor_on_device);
     } else {
       D.system[k].build(A, layout, default_leaf_nodes(false), factor_on_device);
     }
@@ -418,14 +448,15 @@ void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s) {
     D.system[k].solve(D.rhs[k].get(), D.solution[k].get(), s);
     return;
   }
-  // S u = r_u - T1 r_q ;  q = Ainv r_q - T2 u
   DeviceDomain::Reduced& red = D.reduced[k];
   const int nq = 8 * D.n_cells, nu = 4 * D.n_cells;
   const double* r = D.rhs[k].get();
   double* x = D.solution[k].get();
-  launch_ell_combine(nu, r + nq, nullptr, nullptr, red.T1, r, red.rtilde.get(), s);
-  D.system[k].solve(red.rtilde.get(), x + nq, s);
-  launch_ell_combine(nq, nullptr, &red.Ainv, r, red.T2, x + nq, x, s);
+  // S du = r_u - T1 r_q - S u_old ;  u = u_old + du ;  q = Ainv r_q - T2 u
+  launch_ell_combine(nu, r + nq, D.system[k].iperm.get(), EllTerm{&red.T1, r, -1.0},
+                     EllTerm{&D.system[k].matrix_rows, x + nq, -1.0}, EllTerm{}, red.rtilde.get(), s);
+  D.system[k].solve_increment(red.rtilde.get(), x + nq, s);
+  launch_ell_combine(nq, nullptr, nullptr, EllTerm{&red.Ainv, r, 1.0}, EllTerm{&red.T2, x + nq, -1.0}, EllTerm{}, x, s);
 }
 void enqueue_full_solve(pecs_ctx* ctx) {
   // four concurrent solves, reference SolarCell.cpp:1763-1781 (Threads::new_task x4 + join_all)
@@ -450,9 +481,9 @@ int launches_per_step(const pecs_ctx* ctx) {
     n += 2 + 1; // cell + boundary + Poisson cell kernels
     for (int k = 0; k < 2; ++k)
       if (ctx->dom[w].system[k].n > 0)
-        n += ctx->dom[w].system[k].launches_per_solve + (ctx->dom[w].reduced[k].active ? 2 : 0);
+        n += ctx->dom[w].system[k].launches_per_solve + (ctx->dom[w].reduced[k].active ? 2 : 1);
   }
-  n += ctx->p_system.launches_per_solve + (ctx->n_constraints > 0 ? 1 : 0);
+  n += ctx->p_system.launches_per_solve + 1 + (ctx->n_constraints > 0 ? 1 : 0);
   return n;
 }
 void build_step_graph(pecs_ctx* ctx) {
@@ -778,11 +809,11 @@ pecs_status pecs_time_kernel(pecs_ctx* ctx, int32_t which, int32_t repeats, doub
           for (int w = 0; w < ctx->n_domains(); ++w)
             for (int k = 0; k < 2; ++k)
               if (ctx->dom[w].system[k].n > 0)
-                n_launch += ctx->dom[w].system[k].launches_per_solve + (ctx->dom[w].reduced[k].active ? 2 : 0);
+                n_launch += ctx->dom[w].system[k].launches_per_solve + (ctx->dom[w].reduced[k].active ? 2 : 1);
           break;
         case 3:
           enqueue_poisson_solve(ctx, ctx->main);
-          n_launch = ctx->p_system.launches_per_solve + (ctx->n_constraints > 0 ? 1 : 0);
+          n_launch = ctx->p_system.launches_per_solve + 1 + (ctx->n_constraints > 0 ? 1 : 0);
           break;
         default:
           throw StatusError(PECS_ERR_INVALID, "pecs_time_kernel: which must be 0..3");

@@ -15,12 +15,20 @@ struct DeviceEll {
   int n = 0, width = 0;
   DeviceBuffer<int> col;
   DeviceBuffer<double> val;
-  void upload(const CsrMatrix& A);
+  // row_order (optional): ELL row i holds row (*row_order)[i] of A
+  void upload(const CsrMatrix& A, const std::vector<int>* row_order = nullptr);
   size_t bytes() const { return col.bytes() + val.bytes(); }
 };
 
-// y[i] = (base ? base[i] : 0) + sum_k A1(i,k) x1[k] - sum_k A2(i,k) x2[k]     (A1 may be null)
-void launch_ell_combine(int n_rows, const double* base, const DeviceEll* A1, const double* x1, const DeviceEll& A2,
-                        const double* x2, double* y, cudaStream_t s);
+// one sparse term of a combination: sign * A x (A == nullptr: term absent)
+struct EllTerm {
+  const DeviceEll* A = nullptr;
+  const double* x = nullptr;
+  double sign = 1.0;
+};
+
+// y[i] = (base ? base[base_index ? base_index[i] : i] : 0) + sum over the terms of sign * (A x)[i]
+void launch_ell_combine(int n_rows, const double* base, const int* base_index, EllTerm t0, EllTerm t1, EllTerm t2, double* y,
+                        cudaStream_t s);
 
 } // namespace pecs

@@ -15,7 +15,8 @@
 //     vector element (column) and accumulates for row l % P -- no shuffles until the end of the panel;
 //   * the front's input vector is staged once per thread block in shared memory while the first chunks are in flight;
 //   * a front's update goes to a dense buffer in its parent's local numbering: the parent reads it with unit stride;
-//   * the permutations in and out of the elimination order are fused into the staging / the final store;
+//   * solves are done in increment form (x += A^-1 (b - A x), cuda/context.cu): the residual arrives in elimination
+//     order from the fused ELL kernel and the backward sweep adds the correction to the caller's vector in place;
 //   * every output row has exactly one owner and a fixed summation order: no atomics, bit-reproducible solves.
 #include "solve_kernels.cuh"
 
@@ -61,27 +62,27 @@ __device__ __forceinline__ unsigned long long evict_first_policy() {
   return p;
 }
 
-// One warp streams its share of the tile's panels (panel0 + warp, + n_warps, ...) through its private ring and hands
-// every finished row to emit(row, value).  sv: the front's vector in shared memory, zero beyond the logical columns.
-template <class Emit>
-__device__ __forceinline__ void stream_panels(const double* __restrict__ table, int log2P, int cols_pad, int rows,
-                                              const SolveTile& tile, const double* sv, double* ring,
-                                              unsigned long long* bars, int stages, Emit emit) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+// One warp streams panels panel0 + rank, panel0 + rank + n_ranks, ... of the tile through its private ring and hands
+// every finished row to emit(row, value).  sv: the front's vector in shared memory, zero beyond the logical columns;
+// vector_ready() is the barrier (block or warp) that publishes sv, called after the first copies were issued.
+template <class Ready, class Emit>
+__device__ __forceinline__ void stream_panels(const double* __restrict__ table, int rows, const SolveTile& tile, int rank,
+                                              int n_ranks, const double* sv, double* my_ring, unsigned long long* my_bars,
+                                              int stages, Ready vector_ready, Emit emit) {
+  const int lane = threadIdx.x & 31;
+  const int log2P = tile.log2P;
   const int P = 1 << log2P;
   const int cg = 32 >> log2P;                               // columns covered by 32 consecutive doubles
-  const int panel_doubles = cols_pad << log2P;
+  const int panel_doubles = tile.cols_pad << log2P;
   const int cpp = (panel_doubles + kChunkDoubles - 1) / kChunkDoubles; // chunks per panel
-  const int n_my = warp < tile.npanels ? (tile.npanels - warp + n_warps - 1) / n_warps : 0;
+  const int n_my = rank < tile.npanels ? (tile.npanels - rank + n_ranks - 1) / n_ranks : 0;
   const int total = n_my * cpp;
-  double* my_ring = ring + (size_t)warp * stages * kChunkDoubles;
-  unsigned long long* my_bars = bars + warp * stages;
   const unsigned long long policy = evict_first_policy();
 
   // producer state (lane 0 only): next chunk to issue
   int ik = 0, ic = 0, issued = 0, islot = 0;
   auto issue = [&]() {
-    const int panel = tile.panel0 + warp + ik * n_warps;
+    const int panel = tile.panel0 + rank + ik * n_ranks;
     const int e0 = ic * kChunkDoubles;
     const int elems = min(kChunkDoubles, panel_doubles - e0);
     mbar_expect_tx(my_bars + islot, (uint32_t)elems * 8u);
@@ -97,15 +98,15 @@ __device__ __forceinline__ void stream_panels(const double* __restrict__ table, 
   if (lane == 0)
     for (int q = 0; q < stages && q < total; ++q) issue();
 
-  // the vector is staged by the whole block while the first chunks fly
-  __syncthreads();
+  // the vector is staged while the first chunks fly
+  vector_ready();
 
   const int row_in_panel = lane & (P - 1);
   const int col_of_lane = lane >> log2P;
   int slot = 0;
   uint32_t phase = 0;
   for (int k = 0; k < n_my; ++k) {
-    const int panel = tile.panel0 + warp + k * n_warps;
+    const int panel = tile.panel0 + rank + k * n_ranks;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     for (int c = 0; c < cpp; ++c) {
       mbar_wait(my_bars + slot, phase);
@@ -139,107 +140,182 @@ __device__ __forceinline__ void stream_panels(const double* __restrict__ table, 
   }
 }
 
-__device__ __forceinline__ void init_pipeline(unsigned long long* bars, int stages) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
-    for (int q = 0; q < stages; ++q) mbar_init(bars + warp * stages + q, 1);
+__device__ __forceinline__ void init_pipeline(unsigned long long* my_bars, int stages) {
+  if ((threadIdx.x & 31) == 0) {
+    for (int q = 0; q < stages; ++q) mbar_init(my_bars + q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
 }
 
+// shared memory carve-up common to both sweeps
+struct BlockSmem {
+  double* sv;                  // this thread's vector (the block's, or its warp's)
+  double* my_ring;
+  unsigned long long* my_bars;
+};
+template <bool PER_WARP>
+__device__ __forceinline__ BlockSmem carve(unsigned char* raw, int vec_doubles, int stages) {
+  const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  double* base = reinterpret_cast<double*>(raw);
+  double* ring = base + (size_t)vec_doubles * (PER_WARP ? n_warps : 1);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)n_warps * stages * kChunkDoubles);
+  return BlockSmem{base + (PER_WARP ? (size_t)warp * vec_doubles : 0), ring + (size_t)warp * stages * kChunkDoubles,
+                   bars + warp * stages};
+}
+
+template <bool PER_WARP>
 __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
-                                                                        int vec_doubles, int stages,
-                                                                        const double* __restrict__ rhs,
+                                                                        int n_tiles, int vec_doubles, int stages,
+                                                                        const double* __restrict__ w_in,
                                                                         double* __restrict__ w_fin, double* cbuf) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* sv = reinterpret_cast<double*>(smem_raw);
-  double* ring = sv + vec_doubles;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)(blockDim.x >> 5) * stages * kChunkDoubles);
-  const SolveTile tile = tiles[blockIdx.x];
-  const DeviceFront F = t.fronts[tile.front];
-  init_pipeline(bars, stages);
+  const BlockSmem sm = carve<PER_WARP>(smem_raw, vec_doubles, stages);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
+  if (PER_WARP && tile_index >= n_tiles) return;
+  const SolveTile tile = tiles[tile_index];
+  init_pipeline(sm.my_bars, stages);
+  const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
+  const double* c0 = tile.cbuf_off[0] >= 0 ? cbuf + tile.cbuf_off[0] : nullptr;
+  const double* c1 = tile.cbuf_off[1] >= 0 ? cbuf + tile.cbuf_off[1] : nullptr;
   // finalised pivot right-hand side: w_P = b_P - what the children eliminated into it
   {
-    const double* c0 = F.cbuf_off[0] >= 0 ? cbuf + F.cbuf_off[0] : nullptr;
-    const double* c1 = F.cbuf_off[1] >= 0 ? cbuf + F.cbuf_off[1] : nullptr;
-    const int count = max(F.np, F.fwd_cols_pad);
-    for (int l = threadIdx.x; l < count; l += blockDim.x) {
+    const int count = max(tile.np, tile.cols_pad);
+    for (int l = first_thread; l < count; l += n_threads) {
       double v = 0.0;
-      if (l < F.np) {
-        v = rhs[t.iperm[F.p0 + l]];
+      if (l < tile.np) {
+        v = w_in[tile.p0 + l];
         if (c0) v -= c0[l];
         if (c1) v -= c1[l];
-        if (tile.first) w_fin[F.p0 + l] = v;
+        if (tile.first) w_fin[tile.p0 + l] = v;
       }
-      if (l < F.fwd_cols_pad) sv[l] = v;
+      if (l < tile.cols_pad) sm.sv[l] = v;
     }
   }
-  const double* carry0 = F.cbuf_off[0] >= 0 ? cbuf + F.cbuf_off[0] + F.np : nullptr;
-  const double* carry1 = F.cbuf_off[1] >= 0 ? cbuf + F.cbuf_off[1] + F.np : nullptr;
-  const int* omap = t.out_map + F.bd_off;
-  double* out = cbuf + F.out_off;
-  if (F.np == 0) {
+  const double* carry0 = c0 ? c0 + tile.np : nullptr;
+  const double* carry1 = c1 ? c1 + tile.np : nullptr;
+  const int* omap = t.out_map + tile.bd_off;
+  double* out = cbuf + tile.out_off;
+  if (tile.np == 0) {
     // a front without pivots (its region fell apart into unconnected pieces) only hands its children's updates on
-    for (int row = threadIdx.x; row < F.nb; row += blockDim.x) {
+    for (int row = first_thread; row < tile.nb; row += n_threads) {
       double carry = 0.0;
       if (carry0) carry += carry0[row];
       if (carry1) carry += carry1[row];
       out[omap[row]] = carry;
     }
   }
-  stream_panels(t.fwd + F.fwd_off, F.fwd_log2P, F.fwd_cols_pad, F.nb, tile, sv, ring, bars, stages, [&](int row, double dot) {
-    double carry = 0.0;
-    if (carry0) carry += carry0[row];
-    if (carry1) carry += carry1[row];
-    out[omap[row]] = carry + dot;
-  });
+  stream_panels(
+      t.fwd + tile.table_off, tile.nb, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.sv, sm.my_ring, sm.my_bars, stages,
+      [] {
+        if (PER_WARP)
+          __syncwarp();
+        else
+          __syncthreads();
+      },
+      [&](int row, double dot) {
+        double carry = 0.0;
+        if (carry0) carry += carry0[row];
+        if (carry1) carry += carry1[row];
+        out[omap[row]] = carry + dot;
+      });
 }
 
+template <bool PER_WARP>
 __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
-                                                                         int vec_doubles, int stages,
+                                                                         int n_tiles, int vec_doubles, int stages,
+                                                                         const double* __restrict__ w_in,
+                                                                         const double* __restrict__ cbuf,
                                                                          const double* __restrict__ w_fin, double* x_perm,
-                                                                         double* __restrict__ solution) {
+                                                                         double* solution) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* sv = reinterpret_cast<double*>(smem_raw);
-  double* ring = sv + vec_doubles;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)(blockDim.x >> 5) * stages * kChunkDoubles);
-  const SolveTile tile = tiles[blockIdx.x];
-  const DeviceFront F = t.fronts[tile.front];
-  init_pipeline(bars, stages);
+  const BlockSmem sm = carve<PER_WARP>(smem_raw, vec_doubles, stages);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
+  if (PER_WARP && tile_index >= n_tiles) return;
+  const SolveTile tile = tiles[tile_index];
+  init_pipeline(sm.my_bars, stages);
   {
-    const int np = F.np, m = F.np + F.nb;
-    const int* bd = t.bd_index + F.bd_off;
-    const double* wp = w_fin + F.p0;
-    for (int l = threadIdx.x; l < F.bwd_cols_pad; l += blockDim.x) sv[l] = l < np ? wp[l] : (l < m ? x_perm[bd[l - np]] : 0.0);
+    const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
+    const int np = tile.np, m = tile.np + tile.nb;
+    const int* bd = t.bd_index + tile.bd_off;
+    if (tile.first) {
+      // no boundary, hence no forward tile: w_P = b_P - what the children eliminated into it, finalised here
+      const double* c0 = tile.cbuf_off[0] >= 0 ? cbuf + tile.cbuf_off[0] : nullptr;
+      const double* c1 = tile.cbuf_off[1] >= 0 ? cbuf + tile.cbuf_off[1] : nullptr;
+      for (int l = first_thread; l < tile.cols_pad; l += n_threads) {
+        double v = 0.0;
+        if (l < np) {
+          v = w_in[tile.p0 + l];
+          if (c0) v -= c0[l];
+          if (c1) v -= c1[l];
+        }
+        sm.sv[l] = v;
+      }
+    } else {
+      const double* wp = w_fin + tile.p0;
+      for (int l = first_thread; l < tile.cols_pad; l += n_threads)
+        sm.sv[l] = l < np ? wp[l] : (l < m ? x_perm[bd[l - np]] : 0.0);
+    }
   }
-  stream_panels(t.bwd + F.bwd_off, F.bwd_log2P, F.bwd_cols_pad, F.np, tile, sv, ring, bars, stages, [&](int row, double x) {
-    x_perm[F.p0 + row] = x;
-    solution[t.iperm[F.p0 + row]] = x;
-  });
+  stream_panels(
+      t.bwd + tile.table_off, tile.np, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.sv, sm.my_ring, sm.my_bars, stages,
+      [] {
+        if (PER_WARP)
+          __syncwarp();
+        else
+          __syncthreads();
+      },
+      [&](int row, double x) {
+        x_perm[tile.p0 + row] = x;
+        solution[t.iperm[tile.p0 + row]] += x; // increment form: the right-hand side was the residual of `solution`
+      });
+}
+
+__global__ void gather_kernel(int n, const int* __restrict__ index, const double* __restrict__ in, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[index[i]];
 }
 
 } // namespace
 
 void configure_solve_kernels(int max_smem_bytes) {
-  cudaFuncSetAttribute(forward_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
-  cudaFuncSetAttribute(backward_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  cudaFuncSetAttribute(forward_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  cudaFuncSetAttribute(forward_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  cudaFuncSetAttribute(backward_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  cudaFuncSetAttribute(backward_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
 }
 
-void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int vec_doubles, int warps, int stages,
-                          const double* rhs, double* w_fin, double* cbuf, cudaStream_t s) {
+void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
+                          int stages, const double* w_in, double* w_fin, double* cbuf, cudaStream_t s) {
   if (n_tiles == 0) return;
   const int vec = (vec_doubles + 15) / 16 * 16;
-  forward_level_kernel<<<n_tiles, warps * 32, solve_smem_bytes(vec_doubles, warps, stages), s>>>(t, tiles, vec, stages, rhs,
-                                                                                                w_fin, cbuf);
+  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages);
+  if (per_warp)
+    forward_level_kernel<true><<<(n_tiles + warps - 1) / warps, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in,
+                                                                                      w_fin, cbuf);
+  else
+    forward_level_kernel<false><<<n_tiles, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in, w_fin, cbuf);
 }
 
-void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int vec_doubles, int warps, int stages,
-                           const double* w_fin, double* x_perm, double* solution, cudaStream_t s) {
+void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
+                           int stages, const double* w_in, const double* cbuf, const double* w_fin, double* x_perm,
+                           double* solution, cudaStream_t s) {
   if (n_tiles == 0) return;
   const int vec = (vec_doubles + 15) / 16 * 16;
-  backward_level_kernel<<<n_tiles, warps * 32, solve_smem_bytes(vec_doubles, warps, stages), s>>>(t, tiles, vec, stages, w_fin,
-                                                                                                 x_perm, solution);
+  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages);
+  if (per_warp)
+    backward_level_kernel<true><<<(n_tiles + warps - 1) / warps, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in,
+                                                                                       cbuf, w_fin, x_perm, solution);
+  else
+    backward_level_kernel<false><<<n_tiles, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in, cbuf, w_fin, x_perm,
+                                                                  solution);
+}
+
+void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s) {
+  if (n == 0) return;
+  gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, index, in, out);
 }
 
 } // namespace pecs

@@ -6,25 +6,23 @@
 
 namespace pecs {
 
-// one front as the kernels see it (see host/SparseDirect.hpp for the maths and the panel layout of the tables)
-struct DeviceFront {
-  int np, nb, p0;
-  int fwd_log2P, fwd_cols_pad; // G          : nb rows, np columns
-  int bwd_log2P, bwd_cols_pad; // [Inv | -H] : np rows, np + nb columns
-  long long bd_off;      // boundary index list (positions in the permuted vector); the out map shares the offset
-  long long fwd_off;     // first panel of G
-  long long bwd_off;     // first panel of [Inv | -H]
-  long long cbuf_off[2]; // dense update buffers written by the two children (np+nb entries each), -1: no child
-  long long out_off;     // the parent's buffer this front scatters its own update into, -1: root
-};
-
-// a unit of work of one level kernel (one thread block): panels [panel0, panel0+npanels) of one front's table
+// A unit of work of one level kernel, self-contained (one 96-byte load, no second look-up): panels
+// [panel0, panel0 + npanels) of one front's table (host/SparseDirect.hpp for the maths and the panel layout).
+// Large fronts are cut into several tiles, one thread block each, the block's warps sharing the front's vector;
+// small fronts are one tile each and a thread block takes kSolveWarps of them, one per warp.
 struct SolveTile {
-  int front, panel0, npanels, first; // first != 0: this tile also publishes the finalised pivot right-hand side
+  int np, nb, p0;          // the front
+  int log2P, cols_pad;     // panel shape of the table this tile belongs to (forward: G, backward: [Inv | -H])
+  int panel0, npanels;
+  int first;               // forward: this tile publishes the finalised pivot right-hand side of its front;
+                           // backward: the front has no boundary (root), its right-hand side is finalised here
+  long long table_off;     // first panel of the front's table
+  long long bd_off;        // boundary index list (positions in the elimination order); the out map shares the offset
+  long long cbuf_off[2];   // dense update buffers written by the two children (np + nb entries each), -1: no child
+  long long out_off;       // the parent's buffer this front scatters its own update into, -1: root
 };
 
 struct SolveTables {
-  const DeviceFront* fronts;
   const int* bd_index;
   const int* out_map;
   const int* iperm;    // iperm[position in the elimination order] = unknown
@@ -35,19 +33,24 @@ struct SolveTables {
 constexpr int kChunkDoubles = 256; // one bulk asynchronous copy: 2 KB of a panel
 constexpr int kSolveWarps = 8;
 
-// shared memory of one thread block: the front's vector, one ring of `stages` chunks per warp, one mbarrier per slot
-inline size_t solve_smem_bytes(int vec_doubles, int warps, int stages) {
-  const size_t vec = ((size_t)vec_doubles + 15) / 16 * 16;
+// shared memory of one thread block: the vector (one per block, or one per warp), one ring of `stages` chunks per
+// warp, one mbarrier per slot
+inline size_t solve_smem_bytes(int vec_doubles, bool per_warp, int warps, int stages) {
+  const size_t vec = ((size_t)vec_doubles + 15) / 16 * 16 * (per_warp ? warps : 1);
   return (vec + (size_t)warps * stages * kChunkDoubles) * sizeof(double) + (size_t)warps * stages * sizeof(unsigned long long);
 }
 
-// forward sweep of one level.  rhs: right-hand side in the caller's numbering (read through iperm); w_fin: finalised
-// pivot right-hand sides in elimination order (written by the `first` tile of every front); cbuf: child-update buffers.
-void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int vec_doubles, int warps, int stages,
-                          const double* rhs, double* w_fin, double* cbuf, cudaStream_t s);
-// backward sweep of one level; writes x_perm (elimination order, read by the deeper levels) and the caller's solution
-void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int vec_doubles, int warps, int stages,
-                           const double* w_fin, double* x_perm, double* solution, cudaStream_t s);
+// forward sweep of one level.  w_in: right-hand side in elimination order; w_fin: finalised pivot right-hand sides
+// (written by the `first` tile of every front); cbuf: child-update buffers.  per_warp: one small front per warp.
+void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
+                          int stages, const double* w_in, double* w_fin, double* cbuf, cudaStream_t s);
+// backward sweep of one level; writes x_perm (elimination order, read by the deeper levels) and ADDS the result to the
+// caller's solution vector (increment form)
+void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
+                           int stages, const double* w_in, const double* cbuf, const double* w_fin, double* x_perm,
+                           double* solution, cudaStream_t s);
+// out[i] = in[index[i]]
+void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s);
 // opt in to large dynamic shared memory once per process
 void configure_solve_kernels(int max_smem_bytes);
 

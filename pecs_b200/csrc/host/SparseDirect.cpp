@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <stdexcept>
 
@@ -102,25 +103,60 @@ struct NdBuilder {
   }
 };
 
-// largest power of two <= 32 that divides v (v a positive multiple of 4)
-int max_panel_log2(int v) {
+int64_t target_panels_per_level() {
+  static const int64_t v = [] {
+    const char* e = std::getenv("PECS_B200_TARGET_PANELS");
+    return e && std::atoll(e) > 0 ? (int64_t)std::atoll(e) : (int64_t)kTargetPanelsPerLevel;
+  }();
+  return v;
+}
+
+int64_t env_or(const char* name, int64_t fallback) {
+  const char* e = std::getenv(name);
+  return e ? (int64_t)std::atoll(e) : fallback;
+}
+int64_t small_table_doubles() {
+  static const int64_t v = env_or("PECS_B200_SMALL_TABLE", kSmallTableDoubles);
+  return v;
+}
+int64_t panel_target_doubles() {
+  static const int64_t v = std::max<int64_t>(32, env_or("PECS_B200_PANEL_DOUBLES", kPanelTargetDoubles));
+  return v;
+}
+int pow2_ceil_log2(int v) {
   int l = 0;
-  while (l < 5 && v % (2 << l) == 0) ++l;
+  while ((1 << l) < v) ++l;
   return l;
 }
 
+// Shape of one front operator.  log2_cap: level-wide cap on the panel height (keeps enough panels per level).
 void shape_table(PanelTable& t, int rows, int cols, int log2_cap) {
+  t = PanelTable{};
+  if (rows == 0 || cols == 0) return;
   t.rows = rows;
   t.cols = cols;
-  if (rows == 0 || cols == 0) {
-    t.rows = t.cols = t.rows_pad = t.cols_pad = t.log2P = 0;
-    return;
+  if (rows <= 64) {
+    // candidate for "one warp per front": one or two panels as tall as the table, no shuffles when P = 32
+    const int l = rows <= 32 ? std::max(2, pow2_ceil_log2(rows)) : 5;
+    const int rows_pad = round_up(rows, 1 << l), cols_pad = round_up(cols, 32 >> l);
+    if ((int64_t)rows_pad * cols_pad <= small_table_doubles()) {
+      t.small = 1;
+      t.log2P = l;
+      t.rows_pad = rows_pad;
+      t.cols_pad = cols_pad;
+      return;
+    }
   }
-  t.rows_pad = round_up(rows, 4);
-  t.log2P = std::min(log2_cap, max_panel_log2(t.rows_pad));
+  // thread-block mode: panels of about panel_target_doubles entries, so that the warps of a level carry equal loads
+  int l = 0;
+  while (l < 5 && l < log2_cap && ((int64_t)cols << (l + 1)) <= panel_target_doubles()) ++l;
+  // not more than 1/16 of padding rows (panels of up to 4 rows are always fine)
+  while (l > 2 && (round_up(rows, 1 << l) - rows) * 16 > rows) --l;
   // a front is streamed by the kWarpsPerFront warps of one thread block: give every warp a panel when the front allows it
-  while (t.log2P > 0 && (t.rows_pad >> t.log2P) < kWarpsPerFront) --t.log2P;
-  t.cols_pad = round_up(cols, 32 >> t.log2P);
+  while (l > 0 && (round_up(rows, 1 << l) >> l) < kWarpsPerFront) --l;
+  t.log2P = l;
+  t.rows_pad = round_up(rows, 1 << l);
+  t.cols_pad = round_up(cols, 32 >> l);
 }
 
 } // namespace
@@ -254,7 +290,7 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
           shape_table(t, which == 0 ? F.nb : F.np, which == 0 ? F.np : F.np + F.nb, cap);
           panels += t.n_panels();
         }
-        if (panels >= kTargetPanelsPerLevel) break;
+        if (panels >= target_panels_per_level()) break;
       }
       for (int f : lvl) {
         Front& F = plan.fronts[f];

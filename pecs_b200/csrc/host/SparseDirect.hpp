@@ -21,8 +21,8 @@
 //     with unit stride.  Slots a child never writes stay zero from setup.
 //
 // Table layout (what the device kernels stream, cuda/solve_kernels.cu): PANELS.  A table with R rows and N columns is
-// cut into panels of P consecutive rows (P a power of two <= 32, chosen per front so that a tree level always offers
-// enough panels to occupy the whole GPU); a panel is stored column-major and contiguously:
+// cut into panels of P consecutive rows (P a power of two <= 32, chosen per front so that a panel is about 64 KB and a
+// tree level always offers enough panels to occupy the whole GPU); a panel is stored column-major and contiguously:
 //         entry (i, j)  ->  off + (i / P) * P * cols_pad + j * P + (i % P)
 // Rows are zero-padded to a multiple of P, columns to a multiple of 32 / P.  One warp streams one panel with bulk
 // asynchronous copies: 32 consecutive doubles of a panel are 32 / P columns of its P rows, so lane l always works
@@ -40,13 +40,16 @@ namespace pecs {
 
 constexpr int kSmallFrontMaxNp = 128;  // fronts up to this many pivots are factorised by one thread block each
 constexpr int kTargetPanelsPerLevel = 148 * 16;
-constexpr int kWarpsPerFront = 8;      // warps of the thread block that streams a front's panels (cuda/solve_kernels.cuh)
+constexpr int kSmallTableDoubles = 2048; // tables up to 16 KB and 64 rows are one warp's work (per-warp mode of the kernels)
+constexpr int kPanelTargetDoubles = 8192; // otherwise a panel holds about 64 KB: equal loads for the warps of a level
+constexpr int kWarpsPerFront = 4;      // warps of the thread block that streams a front's panels (cuda/solve_kernels.cuh)
 
 struct PanelTable {
   int rows = 0, cols = 0; // logical size
   int log2P = 0;          // panel height P = 1 << log2P
-  int rows_pad = 0;       // multiple of P (and of 4)
+  int rows_pad = 0;       // multiple of P
   int cols_pad = 0;       // multiple of 32 / P
+  int small = 0;          // the whole table is streamed by ONE warp (<= kSmallTableDoubles entries)
   int64_t off = 0;        // offset of the first panel in the table array (in doubles)
   int P() const { return 1 << log2P; }
   int n_panels() const { return rows_pad >> log2P; }

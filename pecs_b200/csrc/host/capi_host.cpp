@@ -254,6 +254,28 @@ int32_t pecs_solarcell_plan_levels(pecs_solarcell* p, int32_t which, int32_t lea
     return -1;
   }
 }
+int64_t pecs_solarcell_plan_fronts(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, int32_t* out, int64_t max_fronts) {
+  try {
+    const pecs::SolvePlan plan = pecs::plan_for_system(*p->problem, which, leaf_nodes);
+    const int64_t nf = (int64_t)plan.fronts.size();
+    for (int64_t f = 0; f < nf && f < max_fronts; ++f) {
+      const pecs::Front& F = plan.fronts[f];
+      int32_t* o = out + 8 * f;
+      o[0] = F.depth;
+      o[1] = F.np;
+      o[2] = F.nb;
+      o[3] = F.fwd.log2P;
+      o[4] = F.bwd.log2P;
+      o[5] = F.fwd.small;
+      o[6] = F.bwd.small;
+      o[7] = F.parent < 0 ? -1 : (int32_t)F.parent;
+    }
+    return nf;
+  } catch (const std::exception& e) {
+    pecs::set_last_error(e.what());
+    return -1;
+  }
+}
 pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,
                                                  double* x) {
   return guarded([&] {

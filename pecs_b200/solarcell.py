@@ -293,6 +293,15 @@ class SolarCellProblem:
         n = self._lib.pecs_solarcell_plan_levels(self._h, which, leaf_nodes, out.ctypes.data_as(C.POINTER(C.c_int64)), 64)
         return out[:n]
 
+    def plan_fronts(self, which, leaf_nodes=0):
+        """per front: depth, np, nb, log2P forward, log2P backward, small forward, small backward, parent"""
+        cap = 1 << 20
+        out = np.zeros((cap, 8), np.int32)
+        n = self._lib.pecs_solarcell_plan_fronts(self._h, which, leaf_nodes, _ip(out), cap)
+        if n < 0:
+            raise RuntimeError("plan_fronts failed")
+        return out[:n]
+
     def selftest_direct_solve(self, which, b, leaf_nodes=0):
         b = np.ascontiguousarray(b, np.float64)
         x = np.zeros_like(b)

@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 
 RHS_TOL = 1e-12
 STATE_TOL = 1e-9
+CURRENT_TOL = 1e-7  # LDG currents: derived quantities, see test_rhs_vectors_perturbed_state
 
 
 @pytest.fixture(scope="module")
@@ -63,8 +64,15 @@ def test_rhs_vectors_perturbed_state(production):
         prob.solve_Poisson()
         o.solve_full_system()
         o.solve_Poisson()
+        # Densities and potential carry the north_star tolerance.  The currents of this deliberately rough state are
+        # small differences of large terms (q = A^-1 (r_q - G u)): a density error is amplified ~150x for the redox
+        # species (mobility 2.6e-6).  Against an extended-precision refinement of the same system the oracle's LU is
+        # itself 5e-10 off in that block, SuperLU 2e-10, the Schur-reduced solve 2.6e-9 -- hence CURRENT_TOL there.
         for s in SPECIES:
-            assert block_rel_err(prob.get_solution(s), o.solution(s)) <= STATE_TOL, f"species {s}"
+            ug, uo = prob.get_solution(s), o.solution(s)
+            nc = ug.size // 12
+            assert rel_err(ug[8 * nc:], uo[8 * nc:]) <= STATE_TOL, f"density of species {s}"
+            assert block_rel_err(ug, uo) <= CURRENT_TOL, f"currents of species {s}"
         n_rt = prob.n_rt
         xg, xo = prob.get_solution(pecs.POISSON), o.solution(4)
         assert rel_err(xg[:n_rt], xo[:n_rt]) <= STATE_TOL and rel_err(xg[n_rt:], xo[n_rt:]) <= STATE_TOL
@@ -84,7 +92,7 @@ def test_states_after_n_steps(production):
         ug, uo = prob.get_solution(s), o.solution(s)
         nc = ug.size // 12
         assert rel_err(ug[8 * nc:], uo[8 * nc:]) <= STATE_TOL, f"density of species {s}"
-        assert block_rel_err(ug, uo) <= 1e-7, f"currents of species {s}"
+        assert block_rel_err(ug, uo) <= CURRENT_TOL, f"currents of species {s}"
     n_rt = prob.n_rt
     xg, xo = prob.get_solution(pecs.POISSON), o.solution(4)
     assert rel_err(xg[n_rt:], xo[n_rt:]) <= STATE_TOL
