@@ -26,6 +26,15 @@ METRIC = "IMEX steps/sec at ~1M DoF/carrier"
 UNIT = "steps/s"
 
 
+def measured_traffic():
+    """DRAM bytes per step of the solve kernels from the committed ncu pass (profiles/r01_solve_traffic.json), or None"""
+    path = os.path.join(ROOT, "profiles", "r01_solve_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_step")
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -185,18 +194,22 @@ def run_gpu_arm(args):
         prob.step_host(1, states)
     e2e_s = time.perf_counter() - t0
     e2e_s = sweep.max_over_ranks(e2e_s, dist, device)
-    state_bytes = int(sum(a.nbytes for a in states))
+    h2d_bytes, d2h_bytes = prob.info(sc.INFO_HOST_STEP_H2D_BYTES), prob.info(sc.INFO_HOST_STEP_D2H_BYTES)
 
     line = None
-    # ---- roofline of the dominant kernels (sectioned run: device time per reference TimerOutput section)
+    # ---- roofline of the dominant kernels: K replays of a graph that holds only the five solves (the level kernels of
+    # the four concurrent carrier solves + Poisson), CUDA events on the launching stream; the sectioned run (one
+    # launch at a time, includes launch gaps) only reports the reference's five TimerOutput sections
+    solve_ms = sweep.max_over_ranks(prob.step_timed(K, sectioned=2)[0] / K, dist, device)
     sect = prob.step_timed(min(K, 10), sectioned=True) / min(K, 10)
     factor_bytes = prob.info(sc.INFO_FACTOR_BYTES)
-    solve_ms = sect[3] + sect[5]
+    solve_bytes = prob.info(sc.INFO_SOLVE_BYTES_PER_STEP)
+    n_solve_launches = prob.info(sc.INFO_LAUNCHES_PER_STEP) - 6
     rhs_ms, rhs_launches = prob.time_kernel(0, 20)
     rhs_bytes = 368 * (prob.n_cells(0) + prob.n_cells(1))
     peak, peak_src = measured_peaks()
     if rank == 0:
-        solve_gbs = factor_bytes / (solve_ms * 1e-3) / 1e9
+        solve_gbs = solve_bytes / (solve_ms * 1e-3) / 1e9
         rhs_gbs = rhs_bytes / (rhs_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -207,14 +220,21 @@ def run_gpu_arm(args):
                        "l2": "inputs larger than L2: every step streams the factor tables "
                              f"({factor_bytes / 1e9:.1f} GB) once; the isolated RHS timing flushes L2 (256 MB memset)",
                        "setup_seconds": t_setup},
-            "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
-                    "d2h_bytes_per_step": state_bytes},
+            "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes,
+                    "what": "pecs_step_host on pinned host states: upload of what a step reads (4 density blocks + "
+                            "Poisson vector), one step, download of all five state vectors (overlapped per species)"},
             "gpu_launches": prob.info(sc.INFO_LAUNCHES_PER_STEP) * K,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "forward/backward level kernels of the five multifrontal solves",
+            "roofline": {"bound": "hbm", "kernel": "forward/backward level kernels (+ residual/recover ELL kernels) of "
+                                                   "the five multifrontal solves of one step",
                          "achieved": solve_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": solve_gbs / peak, "traffic": None,
-                         "algorithmic_bytes_per_step": factor_bytes, "ms_per_step": solve_ms},
+                         "frac": solve_gbs / peak, "traffic": measured_traffic(),
+                         "algorithmic_bytes_per_step": solve_bytes, "launches_per_step": n_solve_launches,
+                         "ms_per_step": solve_ms,
+                         "note": "achieved = algorithmic bytes of one step's solves (8 B per front-operator entry, 12 B per "
+                                 "ELL entry, each read once) / device time of the solve-only graph; traffic = DRAM bytes "
+                                 "read+written by the same kernels in the committed ncu pass (profiles/)"},
             "rhs_roofline": {"bound": "hbm", "kernel": "carrier_cell_rhs + carrier_boundary_rhs (both subdomains)",
                              "achieved": rhs_gbs, "peak": peak, "unit": "GB/s", "frac": rhs_gbs / peak,
                              "algorithmic_bytes_per_launch_group": rhs_bytes, "ms": rhs_ms, "launches": rhs_launches},

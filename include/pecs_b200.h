@@ -166,17 +166,22 @@ pecs_status pecs_step(pecs_ctx* ctx, int32_t n_steps);
 pecs_status pecs_synchronize(pecs_ctx* ctx);
 
 /* The same n_steps with HOST-resident state, as a host that keeps Carrier::solution / PoissonData::solution in its
- * own memory would call it: uploads the five solution vectors (states[PECS_ELECTRONS..PECS_POISSON], NULL entries
- * are skipped), runs the steps, downloads the five vectors back and waits.  Pinned buffers (pecs_host_alloc) make
- * the copies asynchronous DMA transfers. */
+ * own memory would call it (states[PECS_ELECTRONS..PECS_POISSON], NULL entries are skipped).  Uploads what a step
+ * reads of the caller's state -- the density block of every carrier and the Poisson vector; the LDG currents are
+ * outputs only (the assembly reads densities, reference source/SolarCell.cpp:1146-1193; Carrier::solve overwrites the
+ * whole solution, source/Carrier.cpp:34-40) -- runs the steps, downloads all five vectors and waits.  With pinned
+ * buffers (pecs_host_alloc) every species is downloaded on its own stream as soon as its solve has finished, while the
+ * other solves and the Poisson part still run; pageable buffers are copied after the last step. */
 pecs_status pecs_step_host(pecs_ctx* ctx, int32_t n_steps, double* const states[5]);
 /* page-locked host memory for the above */
 void* pecs_host_alloc(uint64_t bytes);
 void pecs_host_free(void* p);
 
 /* measurement support for bench.py: run n_steps and report device times measured with CUDA events on the
- * context's own streams.  ms[0] = whole region, ms[1..5] = the reference's five TimerOutput sections
- *  summed over the steps when sectioned != 0 (sections are then serialised), else 0. */
+ * context's own streams.  ms[0] = whole region.  sectioned == 0: n_steps replays of the step graph; sectioned == 1:
+ * ms[1..5] = the reference's five TimerOutput sections summed over the steps, launched one by one
+ * (serialised, includes launch gaps); sectioned == 2: n_steps replays of a graph that holds only the five solves
+ * (four concurrent carrier solves, then Poisson) -- the denominator of the solve roofline. */
 pecs_status pecs_step_timed(pecs_ctx* ctx, int32_t n_steps, int32_t sectioned, double ms[6]);
 /* repeat one kernel class in isolation: which = 0 carrier RHS (both subdomains), 1 Poisson RHS, 2 carrier solves,
  * 3 Poisson solve; returns average ms per launch group and the number of kernel launches in one group */
@@ -188,7 +193,9 @@ enum {
   PECS_INFO_FACTOR_BYTES = 1,      /* bytes of all factor tables resident in HBM */
   PECS_INFO_SOLVE_BYTES_PER_STEP = 2, /* factor bytes streamed by the five solves of one step */
   PECS_INFO_TREE_LEVELS_MAX = 3,
-  PECS_INFO_RHS_BYTES_PER_STEP = 4 /* algorithmic bytes of the carrier + Poisson RHS kernels of one step */
+  PECS_INFO_RHS_BYTES_PER_STEP = 4, /* algorithmic bytes of the carrier + Poisson RHS kernels of one step */
+  PECS_INFO_HOST_STEP_H2D_BYTES = 5, /* bytes pecs_step_host uploads per call */
+  PECS_INFO_HOST_STEP_D2H_BYTES = 6  /* bytes pecs_step_host downloads per call */
 };
 int64_t pecs_get_info(const pecs_ctx* ctx, int32_t what);
 

@@ -207,7 +207,7 @@ struct DeviceSystem {
 struct DeviceDomain {
   int n_cells = 0, n_bcells = 0;
   DeviceBuffer<double> vx, vy;
-  DeviceBuffer<int> rt_dof, phi_dof, bcell, bface_id, bnb_cell, bnb_face;
+  DeviceBuffer<int> rt_dof, phi_dof, bcell, bface_id, bnb_cell, bnb_face, brecord;
   DeviceBuffer<double> solution[2], rhs[2];
   DeviceSystem system[2];
   // Schur-reduced carriers (host/SchurReduction.hpp): system[k] then factorises S (4 unknowns per cell)
@@ -240,7 +240,11 @@ struct pecs_ctx {
   // streams / graph
   cudaStream_t main = nullptr, side[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr}; // host-buffer step: a species' download has finished
   cudaGraphExec_t step_graph = nullptr;
+  cudaGraphExec_t solve_graph = nullptr;     // the five solves only (measurement, pecs_step_timed mode 2)
+  cudaGraphExec_t host_step_graph = nullptr; // one step + overlapped downloads into host_key[]
+  double* host_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   DeviceBuffer<char> l2_flush;
 
   int n_pdofs() const { return n_rt + n_pcells; }
@@ -249,7 +253,11 @@ struct pecs_ctx {
   ~pecs_ctx() {
     cudaSetDevice(device);
     if (step_graph) cudaGraphExecDestroy(step_graph);
+    if (solve_graph) cudaGraphExecDestroy(solve_graph);
+    if (host_step_graph) cudaGraphExecDestroy(host_step_graph);
     for (cudaEvent_t e : join)
+      if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : copied)
       if (e) cudaEventDestroy(e);
     if (fork) cudaEventDestroy(fork);
     for (cudaStream_t s : side)
@@ -344,6 +352,11 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
   D.bface_id.upload(bid);
   D.bnb_cell.upload(nbc);
   D.bnb_face.upload(nbf);
+  {
+    std::vector<int> rec(n, -1);
+    for (size_t r = 0; r < bcell.size(); ++r) rec[bcell[r]] = (int)r;
+    D.brecord.upload(rec);
+  }
   for (int k = 0; k < 2; ++k) {
     D.solution[k].resize((size_t)D.n_dofs());
     D.solution[k].zero();
@@ -351,7 +364,7 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
     D.rhs[k].zero();
   }
   D.view = DomainView{n,          D.vx.get(),       D.vy.get(),       D.rt_dof.get(),  D.phi_dof.get(),
-                      D.n_bcells, D.bcell.get(), D.bface_id.get(), D.bnb_cell.get(), D.bnb_face.get()};
+                      D.n_bcells, D.bcell.get(), D.bface_id.get(), D.bnb_cell.get(), D.bnb_face.get(), D.brecord.get()};
   // factorise the two fixed carrier matrices
   const NodeLayout layout = carrier_nodes(d);
   for (int k = 0; k < 2; ++k) {
@@ -419,21 +432,34 @@ int n_dofs_of(const pecs_ctx* ctx, int which) {
 }
 
 // ---- enqueue helpers (no synchronisation) ----
-void enqueue_carrier_rhs(pecs_ctx* ctx, int w, cudaStream_t s) {
+CarrierPass carrier_pass(pecs_ctx* ctx, int w) {
   DeviceDomain& D = ctx->dom[w];
   DeviceDomain& O = ctx->dom[1 - w];
-  launch_carrier_cell_rhs(D.view, D.prm, D.solution[0].get(), D.solution[1].get(), ctx->p_solution.get(), D.rhs[0].get(),
-                          D.rhs[1].get(), s);
-  launch_carrier_boundary_rhs(D.view, O.view, D.prm, D.solution[0].get(), D.solution[1].get(), O.solution[0].get(),
-                              O.solution[1].get(), D.rhs[0].get(), D.rhs[1].get(), s);
+  CarrierPass p{};
+  p.d = D.view;
+  p.p = D.prm;
+  p.other_n_cells = O.n_cells;
+  p.u1 = D.solution[0].get();
+  p.u2 = D.solution[1].get();
+  p.o1 = O.solution[0].get();
+  p.o2 = O.solution[1].get();
+  p.rhs1 = D.rhs[0].get();
+  p.rhs2 = D.rhs[1].get();
+  return p;
+}
+// which: 0 / 1 one subdomain (the reference-named calls), 2 both subdomains in ONE launch (the step)
+void enqueue_carrier_rhs(pecs_ctx* ctx, int which, cudaStream_t s) {
+  const CarrierPass none{};
+  if (which == 2 && ctx->full)
+    launch_carrier_rhs(carrier_pass(ctx, 0), carrier_pass(ctx, 1), ctx->kind, ctx->p_solution.get(), s);
+  else
+    launch_carrier_rhs(carrier_pass(ctx, which == 2 ? 0 : which), none, ctx->kind, ctx->p_solution.get(), s);
 }
 void enqueue_poisson_rhs(pecs_ctx* ctx, cudaStream_t s) {
-  // flux rows: the static Dirichlet data; potential rows: the charge integrals
+  // flux rows: the static Dirichlet data; potential rows: the charge integrals of both subdomains, one launch
   PECS_CUDA(cudaMemcpyAsync(ctx->p_rhs.get(), ctx->p_static.get(), ctx->p_rhs.bytes(), cudaMemcpyDeviceToDevice, s));
-  for (int w = 0; w < ctx->n_domains(); ++w) {
-    DeviceDomain& D = ctx->dom[w];
-    launch_poisson_cell_rhs(D.view, D.prm, D.solution[0].get(), D.solution[1].get(), ctx->p_rhs.get(), s);
-  }
+  const CarrierPass none{};
+  launch_poisson_cell_rhs(carrier_pass(ctx, 0), ctx->full ? carrier_pass(ctx, 1) : none, ctx->kind, ctx->p_rhs.get(), s);
 }
 void enqueue_poisson_solve(pecs_ctx* ctx, cudaStream_t s) {
   ctx->p_system.solve(ctx->p_rhs.get(), ctx->p_solution.get(), s);
@@ -458,7 +484,9 @@ void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s) {
   D.system[k].solve_increment(red.rtilde.get(), x + nq, s);
   launch_ell_combine(nq, nullptr, nullptr, EllTerm{&red.Ainv, r, 1.0}, EllTerm{&red.T2, x + nq, -1.0}, EllTerm{}, x, s);
 }
-void enqueue_full_solve(pecs_ctx* ctx) {
+// host != nullptr: every species' solution is downloaded into host[k] on its own stream as soon as its solve is done
+// (the copy engine works while the other solves and the Poisson part still run); *n_copies counts them
+void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_copies = nullptr) {
   // four concurrent solves, reference SolarCell.cpp:1763-1781 (Threads::new_task x4 + join_all)
   const int n_species = ctx->full ? 4 : (ctx->kind == PECS_KIND_PRODUCTION ? 2 : 1);
   PECS_CUDA(cudaEventRecord(ctx->fork, ctx->main));
@@ -467,18 +495,32 @@ void enqueue_full_solve(pecs_ctx* ctx) {
     enqueue_species_solve(ctx, k, ctx->side[k]);
     PECS_CUDA(cudaEventRecord(ctx->join[k], ctx->side[k]));
     PECS_CUDA(cudaStreamWaitEvent(ctx->main, ctx->join[k], 0));
+    if (host && host[k]) {
+      PECS_CUDA(cudaMemcpyAsync(host[k], vector_of(ctx, k, false), (size_t)n_dofs_of(ctx, k) * sizeof(double),
+                                cudaMemcpyDeviceToHost, ctx->side[k]));
+      PECS_CUDA(cudaEventRecord(ctx->copied[k], ctx->side[k]));
+      if (n_copies) ++*n_copies;
+    }
   }
 }
-void enqueue_step(pecs_ctx* ctx) {
-  for (int w = 0; w < ctx->n_domains(); ++w) enqueue_carrier_rhs(ctx, w, ctx->main);
-  enqueue_full_solve(ctx);
+void enqueue_step(pecs_ctx* ctx, double* const* host = nullptr) {
+  enqueue_carrier_rhs(ctx, 2, ctx->main);
+  int n_copies = 0;
+  enqueue_full_solve(ctx, host, &n_copies);
   enqueue_poisson_rhs(ctx, ctx->main);
   enqueue_poisson_solve(ctx, ctx->main);
+  if (host) {
+    if (host[PECS_POISSON])
+      PECS_CUDA(cudaMemcpyAsync(host[PECS_POISSON], ctx->p_solution.get(), ctx->p_solution.bytes(), cudaMemcpyDeviceToHost,
+                                ctx->main));
+    for (int k = 0; k < 4; ++k)
+      if (host[k] && n_dofs_of(ctx, k) > 0) PECS_CUDA(cudaStreamWaitEvent(ctx->main, ctx->copied[k], 0));
+  }
 }
 int launches_per_step(const pecs_ctx* ctx) {
   int n = 0;
+  n += 1 + 1; // the fused carrier RHS kernel + the Poisson cell kernel
   for (int w = 0; w < ctx->n_domains(); ++w) {
-    n += 2 + 1; // cell + boundary + Poisson cell kernels
     for (int k = 0; k < 2; ++k)
       if (ctx->dom[w].system[k].n > 0)
         n += ctx->dom[w].system[k].launches_per_solve + (ctx->dom[w].reduced[k].active ? 2 : 1);
@@ -486,19 +528,55 @@ int launches_per_step(const pecs_ctx* ctx) {
   n += ctx->p_system.launches_per_solve + 1 + (ctx->n_constraints > 0 ? 1 : 0);
   return n;
 }
-void build_step_graph(pecs_ctx* ctx) {
+template <class Enqueue>
+cudaGraphExec_t capture_graph(pecs_ctx* ctx, Enqueue&& enqueue) {
   cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
   PECS_CUDA(cudaStreamBeginCapture(ctx->main, cudaStreamCaptureModeThreadLocal));
   try {
-    enqueue_step(ctx);
+    enqueue();
   } catch (...) {
     cudaStreamEndCapture(ctx->main, &graph);
     if (graph) cudaGraphDestroy(graph);
     throw;
   }
   PECS_CUDA(cudaStreamEndCapture(ctx->main, &graph));
-  PECS_CUDA(cudaGraphInstantiate(&ctx->step_graph, graph, 0));
+  PECS_CUDA(cudaGraphInstantiate(&exec, graph, 0));
   PECS_CUDA(cudaGraphDestroy(graph));
+  return exec;
+}
+void build_step_graph(pecs_ctx* ctx) {
+  ctx->step_graph = capture_graph(ctx, [&] { enqueue_step(ctx); });
+}
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+// what one step reads of the caller's state: the density block of every carrier (the LDG currents are outputs only:
+// the assembly reads densities, reference source/SolarCell.cpp:1146-1193, and Carrier::solve overwrites the whole
+// solution vector) and the complete Poisson vector
+size_t upload_step_inputs(pecs_ctx* ctx, double* const states[5], bool enqueue) {
+  size_t bytes = 0;
+  for (int w = 0; w < 4; ++w) {
+    const int n = n_dofs_of(ctx, w);
+    if (!states[w] || n == 0) continue;
+    const size_t off = (size_t)n / 12 * 8, cnt = (size_t)n / 12 * 4;
+    if (enqueue)
+      PECS_CUDA(cudaMemcpyAsync(vector_of(ctx, w, false) + off, states[w] + off, cnt * sizeof(double), cudaMemcpyHostToDevice,
+                                ctx->main));
+    bytes += cnt * sizeof(double);
+  }
+  if (states[PECS_POISSON]) {
+    if (enqueue)
+      PECS_CUDA(cudaMemcpyAsync(ctx->p_solution.get(), states[PECS_POISSON], ctx->p_solution.bytes(), cudaMemcpyHostToDevice,
+                                ctx->main));
+    bytes += ctx->p_solution.bytes();
+  }
+  return bytes;
 }
 
 } // namespace
@@ -537,6 +615,7 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     for (int k = 0; k < 4; ++k) {
       PECS_CUDA(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
       PECS_CUDA(cudaEventCreateWithFlags(&ctx->join[k], cudaEventDisableTiming));
+      PECS_CUDA(cudaEventCreateWithFlags(&ctx->copied[k], cudaEventDisableTiming));
     }
     PECS_CUDA(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
 
@@ -702,15 +781,30 @@ pecs_status pecs_step_host(pecs_ctx* ctx, int32_t n_steps, double* const states[
     require(ctx != nullptr && n_steps >= 0 && states, "pecs_step_host: bad argument");
     require(ctx->step_graph != nullptr, "pecs_step_host: only the production problem has a step graph");
     PECS_CUDA(cudaSetDevice(ctx->device));
+    if (n_steps == 0) return;
+    bool pinned = true;
     for (int w = 0; w < 5; ++w)
-      if (states[w] && n_dofs_of(ctx, w) > 0)
-        PECS_CUDA(cudaMemcpyAsync(vector_of(ctx, w, false), states[w], (size_t)n_dofs_of(ctx, w) * sizeof(double),
-                                  cudaMemcpyHostToDevice, ctx->main));
-    for (int s = 0; s < n_steps; ++s) PECS_CUDA(cudaGraphLaunch(ctx->step_graph, ctx->main));
-    for (int w = 0; w < 5; ++w)
-      if (states[w] && n_dofs_of(ctx, w) > 0)
-        PECS_CUDA(cudaMemcpyAsync(states[w], vector_of(ctx, w, false), (size_t)n_dofs_of(ctx, w) * sizeof(double),
-                                  cudaMemcpyDeviceToHost, ctx->main));
+      if (states[w] && n_dofs_of(ctx, w) > 0 && !is_pinned(states[w])) pinned = false;
+    upload_step_inputs(ctx, states, true);
+    for (int s = 0; s + 1 < n_steps; ++s) PECS_CUDA(cudaGraphLaunch(ctx->step_graph, ctx->main));
+    if (pinned) {
+      // last step + downloads overlapped with the solves still running: a graph per set of host buffers
+      bool same = ctx->host_step_graph != nullptr;
+      for (int w = 0; w < 5; ++w) same = same && ctx->host_key[w] == states[w];
+      if (!same) {
+        if (ctx->host_step_graph) PECS_CUDA(cudaGraphExecDestroy(ctx->host_step_graph));
+        ctx->host_step_graph = nullptr;
+        ctx->host_step_graph = capture_graph(ctx, [&] { enqueue_step(ctx, states); });
+        for (int w = 0; w < 5; ++w) ctx->host_key[w] = states[w];
+      }
+      PECS_CUDA(cudaGraphLaunch(ctx->host_step_graph, ctx->main));
+    } else {
+      PECS_CUDA(cudaGraphLaunch(ctx->step_graph, ctx->main));
+      for (int w = 0; w < 5; ++w)
+        if (states[w] && n_dofs_of(ctx, w) > 0)
+          PECS_CUDA(cudaMemcpyAsync(states[w], vector_of(ctx, w, false), (size_t)n_dofs_of(ctx, w) * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ctx->main));
+    }
     PECS_CUDA(cudaStreamSynchronize(ctx->main));
   });
 }
@@ -744,9 +838,15 @@ pecs_status pecs_step_timed(pecs_ctx* ctx, int32_t n_steps, int32_t sectioned, d
     sync_all(ctx);
     cudaEvent_t ev[6];
     for (cudaEvent_t& e : ev) PECS_CUDA(cudaEventCreate(&e));
-    if (!sectioned) {
+    if (sectioned == 2 && !ctx->solve_graph)
+      ctx->solve_graph = capture_graph(ctx, [&] {
+        enqueue_full_solve(ctx);
+        enqueue_poisson_solve(ctx, ctx->main);
+      });
+    if (sectioned == 0 || sectioned == 2) {
+      cudaGraphExec_t g = sectioned == 2 ? ctx->solve_graph : ctx->step_graph;
       PECS_CUDA(cudaEventRecord(ev[0], ctx->main));
-      for (int s = 0; s < n_steps; ++s) PECS_CUDA(cudaGraphLaunch(ctx->step_graph, ctx->main));
+      for (int s = 0; s < n_steps; ++s) PECS_CUDA(cudaGraphLaunch(g, ctx->main));
       PECS_CUDA(cudaEventRecord(ev[1], ctx->main));
       PECS_CUDA(cudaEventSynchronize(ev[1]));
       float t = 0;
@@ -795,12 +895,12 @@ pecs_status pecs_time_kernel(pecs_ctx* ctx, int32_t which, int32_t repeats, doub
       PECS_CUDA(cudaEventRecord(a, ctx->main));
       switch (which) {
         case 0:
-          for (int w = 0; w < ctx->n_domains(); ++w) enqueue_carrier_rhs(ctx, w, ctx->main);
-          n_launch = 2 * ctx->n_domains();
+          enqueue_carrier_rhs(ctx, 2, ctx->main);
+          n_launch = 1;
           break;
         case 1:
           enqueue_poisson_rhs(ctx, ctx->main);
-          n_launch = ctx->n_domains();
+          n_launch = 1;
           break;
         case 2:
           // solves overwrite the states; their cost does not depend on the values
@@ -850,6 +950,9 @@ int64_t pecs_get_info(const pecs_ctx* ctx, int32_t what) {
     case PECS_INFO_SOLVE_BYTES_PER_STEP: return logical; // every factor entry is streamed exactly once per step (padding not counted)
     case PECS_INFO_TREE_LEVELS_MAX: return levels;
     case PECS_INFO_RHS_BYTES_PER_STEP: return cells * (kCarrierRhsBytesPerCell + kPoissonRhsBytesPerCell);
+    // two carriers per subdomain; up: their density blocks (4 of 12 unknowns per cell) + Poisson, down: everything
+    case PECS_INFO_HOST_STEP_H2D_BYTES: return (int64_t)(2 * 4 * sizeof(double)) * cells + (int64_t)ctx->p_solution.bytes();
+    case PECS_INFO_HOST_STEP_D2H_BYTES: return (int64_t)(2 * 12 * sizeof(double)) * cells + (int64_t)ctx->p_solution.bytes();
   }
   return -1;
 }

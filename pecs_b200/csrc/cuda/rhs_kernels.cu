@@ -1,10 +1,11 @@
 // rhs_kernels.cu -- per-step right-hand-side assembly on the device (sm_100a).
 //
 // Replaces the WorkStream passes of the reference's time loop:
-//   carrier_cell_rhs      <- mass_matrix.vmult x2 + the cell q-loop of assemble_local_{semiconductor,electrolyte}_rhs
+//   carrier_rhs           <- ONE launch for both subdomains:
+//       cell terms        <- mass_matrix.vmult x2 + the cell q-loop of assemble_local_{semiconductor,electrolyte}_rhs
 //                            (reference source/SolarCell.cpp:1043-1047, 1146-1193, 1423-1427, 1519-1553)
-//   carrier_boundary_rhs  <- the boundary-face branches Dirichlet / Interface / Schottky
-//                            (reference source/SolarCell.cpp:1197-1412, 1557-1725)
+//       boundary terms    <- the boundary-face branches Dirichlet / Interface / Schottky
+//                            (reference source/SolarCell.cpp:1197-1412, 1557-1725), by the thread that owns the cell
 //   poisson_cell_rhs      <- the cell loops of assemble_local_Poisson_rhs_for_{semiconductor,electrolyte}
 //                            (reference source/SolarCell.cpp:551-578, 741-762)
 //   poisson_face_rhs      <- their Dirichlet / Schottky face loops (reference source/SolarCell.cpp:583-683, 768-814),
@@ -29,6 +30,10 @@ namespace pecs {
 namespace {
 
 constexpr int kThreads = 128;
+
+struct CarrierPassPair {
+  CarrierPass pass[2];
+};
 
 __device__ __forceinline__ fe::CellVerts load_verts(const DomainView& d, int c) {
   fe::CellVerts v;
@@ -60,14 +65,12 @@ __device__ __forceinline__ void add4(double* p, const double v[4]) {
   store4(p, t);
 }
 
-// ------------------------------------------------------------------------------------------ carrier cell kernel
+// ------------------------------------------------------------------------------------------ carrier cell terms
 template <int KIND>
-__global__ void __launch_bounds__(kThreads) carrier_cell_rhs_kernel(DomainView d, RhsParams p, const double* __restrict__ u1,
-                                                                    const double* __restrict__ u2,
-                                                                    const double* __restrict__ X, double* __restrict__ rhs1,
-                                                                    double* __restrict__ rhs2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d.n_cells) return;
+__device__ __forceinline__ void carrier_cell_terms(const DomainView& d, const RhsParams& p, int c,
+                                                   const double* __restrict__ u1, const double* __restrict__ u2,
+                                                   const double* __restrict__ X, double* __restrict__ rhs1,
+                                                   double* __restrict__ rhs2) {
   const size_t n = (size_t)d.n_cells;
   constexpr bool kProduction = KIND == PECS_KIND_PRODUCTION;
   constexpr bool kDrift = KIND != PECS_KIND_TEST_STEADY;
@@ -173,15 +176,13 @@ __device__ __forceinline__ double trace(const double N[4], const double r[4]) {
   return N[0] * r[0] + N[1] * r[1] + N[2] * r[2] + N[3] * r[3];
 }
 
+// Face terms of boundary cell record r, added to what the cell terms of the same thread have just stored.  Kept out
+// of line: 1.5 % of the cells take this path and its registers must not burden the other 98.5 %.
 template <int KIND>
-__global__ void __launch_bounds__(kThreads) carrier_boundary_rhs_kernel(DomainView d, DomainView other, RhsParams p,
-                                                                        const double* __restrict__ u1,
-                                                                        const double* __restrict__ u2,
-                                                                        const double* __restrict__ o1,
-                                                                        const double* __restrict__ o2, double* rhs1,
-                                                                        double* rhs2) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= d.n_bcells) return;
+__device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int other_n_cells, const RhsParams& p, int r,
+                                                    const double* __restrict__ u1, const double* __restrict__ u2,
+                                                    const double* __restrict__ o1, const double* __restrict__ o2, double* rhs1,
+                                                    double* rhs2) {
   constexpr bool kProduction = KIND == PECS_KIND_PRODUCTION;
   const int c = d.bcell[r];
   const size_t n = (size_t)d.n_cells;
@@ -203,8 +204,8 @@ __global__ void __launch_bounds__(kThreads) carrier_boundary_rhs_kernel(DomainVi
     if (kProduction && id == PECS_INTERFACE) {
       const int nc = d.bnb_cell[r];
       nb_face = d.bnb_face[r];
-      load4(o1 + 8 * (size_t)other.n_cells + 4 * (size_t)nc, q1);
-      load4(o2 + 8 * (size_t)other.n_cells + 4 * (size_t)nc, q2);
+      load4(o1 + 8 * (size_t)other_n_cells + 4 * (size_t)nc, q1);
+      load4(o2 + 8 * (size_t)other_n_cells + 4 * (size_t)nc, q2);
     }
     for (int q = 0; q < 3; ++q) {
       const double t = fe::gauss_x(q);
@@ -291,12 +292,32 @@ __global__ void __launch_bounds__(kThreads) carrier_boundary_rhs_kernel(DomainVi
   }
 }
 
+// ONE launch assembles the carrier right-hand sides of BOTH subdomains: blocks [0, blocks_a) work on pass a, the rest
+// on pass b (a pass with n_cells == 0 is absent); every thread does the cell terms of its cell and, if the cell has
+// boundary faces, their terms right after.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 4) carrier_rhs_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a,
+                                                               const double* __restrict__ X) {
+  const bool first = (int)blockIdx.x < blocks_a;
+  const CarrierPass& w = pp.pass[first ? 0 : 1]; // stays in the constant bank: no local copy
+  const int c = ((int)blockIdx.x - (first ? 0 : blocks_a)) * blockDim.x + threadIdx.x;
+  if (c >= w.d.n_cells) return;
+  carrier_cell_terms<KIND>(w.d, w.p, c, w.u1, w.u2, X, w.rhs1, w.rhs2);
+  const int r = w.d.brecord ? w.d.brecord[c] : -1;
+  if (r >= 0) carrier_boundary_terms<KIND>(w.d, w.other_n_cells, w.p, r, w.u1, w.u2, w.o1, w.o2, w.rhs1, w.rhs2);
+}
+
 // ------------------------------------------------------------------------------------------ Poisson cells
 template <int KIND>
-__global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(DomainView d, RhsParams p, const double* __restrict__ u1,
-                                                                    const double* __restrict__ u2,
+__global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a,
                                                                     double* __restrict__ poisson_rhs) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool first = (int)blockIdx.x < blocks_a;
+  const CarrierPass& w = pp.pass[first ? 0 : 1];
+  const DomainView& d = w.d;
+  const RhsParams& p = w.p;
+  const double* __restrict__ u1 = w.u1;
+  const double* __restrict__ u2 = w.u2;
+  const int c = ((int)blockIdx.x - (first ? 0 : blocks_a)) * blockDim.x + threadIdx.x;
   if (c >= d.n_cells) return;
   const size_t n = (size_t)d.n_cells;
   const fe::CellVerts v = load_verts(d, c);
@@ -394,29 +415,21 @@ inline int blocks_for(int n) { return (n + kThreads - 1) / kThreads; }
     default: { CALL(PECS_KIND_TEST_DD_POISSON); break; }                 \
   }
 
-void launch_carrier_cell_rhs(const DomainView& d, const RhsParams& p, const double* u1, const double* u2,
-                             const double* X, double* rhs1, double* rhs2, cudaStream_t s) {
-  if (d.n_cells == 0) return;
-#define CALL(K) carrier_cell_rhs_kernel<K><<<blocks_for(d.n_cells), kThreads, 0, s>>>(d, p, u1, u2, X, rhs1, rhs2)
-  PECS_DISPATCH_KIND(p.kind, CALL)
+void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, const double* X, cudaStream_t s) {
+  const int blocks_a = blocks_for(a.d.n_cells), blocks_b = blocks_for(b.d.n_cells);
+  if (blocks_a + blocks_b == 0) return;
+  const CarrierPassPair pp{{a, b}};
+#define CALL(K) carrier_rhs_kernel<K><<<blocks_a + blocks_b, kThreads, 0, s>>>(pp, blocks_a, X)
+  PECS_DISPATCH_KIND(kind, CALL)
 #undef CALL
 }
 
-void launch_carrier_boundary_rhs(const DomainView& d, const DomainView& other, const RhsParams& p, const double* u1,
-                                 const double* u2, const double* o1, const double* o2, double* rhs1, double* rhs2,
-                                 cudaStream_t s) {
-  if (d.n_bcells == 0) return;
-#define CALL(K) \
-  carrier_boundary_rhs_kernel<K><<<blocks_for(d.n_bcells), kThreads, 0, s>>>(d, other, p, u1, u2, o1, o2, rhs1, rhs2)
-  PECS_DISPATCH_KIND(p.kind, CALL)
-#undef CALL
-}
-
-void launch_poisson_cell_rhs(const DomainView& d, const RhsParams& p, const double* u1, const double* u2,
-                             double* poisson_rhs, cudaStream_t s) {
-  if (d.n_cells == 0) return;
-#define CALL(K) poisson_cell_rhs_kernel<K><<<blocks_for(d.n_cells), kThreads, 0, s>>>(d, p, u1, u2, poisson_rhs)
-  PECS_DISPATCH_KIND(p.kind, CALL)
+void launch_poisson_cell_rhs(const CarrierPass& a, const CarrierPass& b, int kind, double* poisson_rhs, cudaStream_t s) {
+  const int blocks_a = blocks_for(a.d.n_cells), blocks_b = blocks_for(b.d.n_cells);
+  if (blocks_a + blocks_b == 0) return;
+  const CarrierPassPair pp{{a, b}};
+#define CALL(K) poisson_cell_rhs_kernel<K><<<blocks_a + blocks_b, kThreads, 0, s>>>(pp, blocks_a, poisson_rhs)
+  PECS_DISPATCH_KIND(kind, CALL)
 #undef CALL
 }
 

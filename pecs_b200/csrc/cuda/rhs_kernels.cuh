@@ -19,6 +19,7 @@ struct DomainView {
   const int* bface_id;   // [n_bcells][4] boundary id of face f, -1 if the face is interior
   const int* bnb_cell;   // [n_bcells] matched cell of the other subdomain across the interface (or -1)
   const int* bnb_face;   // [n_bcells] its face number
+  const int* brecord;    // [n_cells] index of the cell's boundary record, -1 for interior cells
 };
 
 // scalars of one subdomain pass (see include/pecs_b200.h PECS_P_*)
@@ -37,16 +38,21 @@ struct RhsParams {
   double time;         // manufactured right-hand sides
 };
 
-// rhs_c = M u_c + cell terms for both carriers of the subdomain
-void launch_carrier_cell_rhs(const DomainView& d, const RhsParams& p, const double* u1, const double* u2,
-                             const double* poisson_solution, double* rhs1, double* rhs2, cudaStream_t s);
-// boundary / interface / Schottky face terms added into rhs; o1, o2 = the other subdomain's carriers
-void launch_carrier_boundary_rhs(const DomainView& d, const DomainView& other, const RhsParams& p, const double* u1,
-                                 const double* u2, const double* o1, const double* o2, double* rhs1, double* rhs2,
-                                 cudaStream_t s);
-// potential rows of the Poisson rhs: -int (doping + z1 rho1 + z2 rho2) per matched cell
-void launch_poisson_cell_rhs(const DomainView& d, const RhsParams& p, const double* u1, const double* u2,
-                             double* poisson_rhs, cudaStream_t s);
+// everything one subdomain contributes to a fused launch; n_cells == 0: pass absent
+struct CarrierPass {
+  DomainView d;
+  RhsParams p;
+  int other_n_cells;       // cells of the other subdomain (offset of its density block)
+  const double *u1, *u2;   // this subdomain's carriers (state)
+  const double *o1, *o2;   // the other subdomain's carriers: traces across the interface
+  double *rhs1, *rhs2;
+};
+
+// rhs_c = M u_c + cell terms + boundary / interface / Schottky face terms for both carriers of both passes, one launch
+// (SURVEY K1-K3); X = Poisson solution (electric field)
+void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, const double* X, cudaStream_t s);
+// potential rows of the Poisson rhs: -int (doping + z1 rho1 + z2 rho2) per matched cell, both passes, one launch
+void launch_poisson_cell_rhs(const CarrierPass& a, const CarrierPass& b, int kind, double* poisson_rhs, cudaStream_t s);
 
 // Poisson boundary faces: time-independent, evaluated once into a static vector
 struct PoissonFaceView {

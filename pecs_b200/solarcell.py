@@ -20,7 +20,8 @@ PARAM_NAMES = ["delta_t", "penalty", "mu_n", "mu_p", "mu_r", "mu_o", "eps_s", "e
                "v_n", "v_p", "gen_flux", "gen_alpha", "gen_location", "rho_n_e", "rho_p_e", "rho_r_e", "rho_o_e",
                "phi_bi", "phi_app", "phi_sch", "sch_location", "transient"]
 
-INFO_LAUNCHES_PER_STEP, INFO_FACTOR_BYTES, INFO_SOLVE_BYTES_PER_STEP, INFO_TREE_LEVELS_MAX, INFO_RHS_BYTES_PER_STEP = range(5)
+(INFO_LAUNCHES_PER_STEP, INFO_FACTOR_BYTES, INFO_SOLVE_BYTES_PER_STEP, INFO_TREE_LEVELS_MAX, INFO_RHS_BYTES_PER_STEP,
+ INFO_HOST_STEP_H2D_BYTES, INFO_HOST_STEP_D2H_BYTES) = range(7)
 
 
 def device_count():

@@ -24,7 +24,7 @@ WORKER = textwrap.dedent("""
     t = sweep.max_over_ranks(1.0 + rank, dist)
     total = sweep.sum_over_ranks(prob.n_cells(0), dist)
     assert t == 2.0 and total == 2 * prob.n_cells(0)
-    sys.stdout.write(f"rank {rank} bias {bias} ok\n")  # one write per rank: the two ranks share the pipe
+    sys.stdout.write("rank " + str(rank) + " bias " + str(bias) + " ok" + chr(10))  # ONE write: the ranks share the pipe
     sys.stdout.flush()
 """) % ROOT
 
