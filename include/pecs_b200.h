@@ -120,7 +120,10 @@ typedef struct {
   int32_t kind;         /* PECS_KIND_* */
   int32_t full_system;  /* 0: semiconductor + Poisson only (the manufactured tests), 1: both subdomains */
   int32_t device;       /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t owned_species; /* bit k set: carrier k (PECS_ELECTRONS..PECS_OXIDANTS) is factorised and solved by this
+                          * context; 0 = all four.  A context that owns a subset is one shard of a step spread over
+                          * several GPUs (pecs_step_local / pecs_step_finish below); the others' densities arrive from
+                          * their owners through pecs_density_block */
   double params[32];    /* PECS_P_* */
   pecs_domain_desc semiconductor;
   pecs_domain_desc electrolyte; /* ignored unless full_system */
@@ -162,7 +165,19 @@ pecs_status pecs_assemble_poisson_rhs(pecs_ctx* ctx);
 pecs_status pecs_solve_poisson(pecs_ctx* ctx);
 /* n_steps iterations of the body of the time loop (reference source/SolarCell.cpp:2055-2080), captured in a CUDA graph */
 pecs_status pecs_step(pecs_ctx* ctx, int32_t n_steps);
-/* all five calls above return after enqueueing; this waits for the context's streams */
+/* One step cut at its only exchange point, for contexts that own a subset of the carriers (owned_species):
+ *   pecs_step_local : both RHS assemblies of the subdomains with owned carriers + the owned solves   (graph replay)
+ *   -- the caller exchanges the density blocks (pecs_density_block) between the owners, on pecs_stream --
+ *   pecs_step_finish: Poisson RHS + Poisson solve (every shard keeps its own copy of the potential)   (graph replay)
+ * The reference's decomposition is the same: separate triangulations and CarrierPairs per subdomain
+ * (include/SolarCell.hpp:351-367), four independent solve tasks (source/SolarCell.cpp:1763-1781). */
+pecs_status pecs_step_local(pecs_ctx* ctx);
+pecs_status pecs_step_finish(pecs_ctx* ctx);
+/* device pointer to the density block of carrier `which` (4 * n_cells doubles, *n_doubles receives the count) */
+double* pecs_density_block(pecs_ctx* ctx, int32_t which, int64_t* n_doubles);
+/* the context's main CUDA stream (cudaStream_t): everything above is enqueued on it */
+void* pecs_stream(pecs_ctx* ctx);
+/* all calls above return after enqueueing; this waits for the context's streams */
 pecs_status pecs_synchronize(pecs_ctx* ctx);
 
 /* The same n_steps with HOST-resident state, as a host that keeps Carrier::solution / PoissonData::solution in its

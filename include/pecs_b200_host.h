@@ -22,6 +22,8 @@ typedef struct pecs_solarcell pecs_solarcell;
  * test_file.prm defaults instead (reference source/ParameterReader.cpp:209-392). */
 pecs_status pecs_solarcell_create(const char* prm_text, int32_t test_defaults, int32_t device, pecs_solarcell** out);
 void pecs_solarcell_destroy(pecs_solarcell* p);
+/* before setup_*: which carriers this process' context factorises and solves (pecs_problem_desc::owned_species) */
+pecs_status pecs_solarcell_set_owned_species(pecs_solarcell* p, int32_t mask);
 
 /* staged setup: *_host builds grids, dofs, mappings and the constant matrices on the host (no device needed);
  * the variants without _host additionally create the device context (set_solvers), upload the initial state and,

@@ -44,6 +44,10 @@ SIGNATURES = {
     "pecs_assemble_poisson_rhs": (C.c_int, [VOIDP]),
     "pecs_solve_poisson": (C.c_int, [VOIDP]),
     "pecs_step": (C.c_int, [VOIDP, C.c_int32]),
+    "pecs_step_local": (C.c_int, [VOIDP]),
+    "pecs_step_finish": (C.c_int, [VOIDP]),
+    "pecs_density_block": (VOIDP, [VOIDP, C.c_int32, C.POINTER(C.c_int64)]),
+    "pecs_stream": (VOIDP, [VOIDP]),
     "pecs_synchronize": (C.c_int, [VOIDP]),
     "pecs_step_host": (C.c_int, [VOIDP, C.c_int32, C.POINTER(c_double_p)]),
     "pecs_host_alloc": (VOIDP, [C.c_uint64]),
@@ -54,6 +58,7 @@ SIGNATURES = {
     # ---- include/pecs_b200_host.h ----
     "pecs_solarcell_create": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(VOIDP)]),
     "pecs_solarcell_destroy": (None, [VOIDP]),
+    "pecs_solarcell_set_owned_species": (C.c_int, [VOIDP, C.c_int32]),
     "pecs_solarcell_setup_full_system_host": (C.c_int, [VOIDP]),
     "pecs_solarcell_setup_full_system": (C.c_int, [VOIDP]),
     "pecs_solarcell_setup_test_host": (C.c_int, [VOIDP, C.c_int32, C.c_int32]),

@@ -229,6 +229,7 @@ using namespace pecs;
 struct pecs_ctx {
   int device = 0, kind = 0;
   bool full = true;
+  int owned = 0xF; // carriers factorised and solved here
   double params[32] = {};
   DeviceDomain dom[2];
   // Poisson
@@ -243,6 +244,8 @@ struct pecs_ctx {
   cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr}; // host-buffer step: a species' download has finished
   cudaGraphExec_t step_graph = nullptr;
   cudaGraphExec_t solve_graph = nullptr;     // the five solves only (measurement, pecs_step_timed mode 2)
+  cudaGraphExec_t local_graph = nullptr;     // sharded step, part 1: RHS + owned solves
+  cudaGraphExec_t finish_graph = nullptr;    // sharded step, part 2: Poisson RHS + Poisson solve
   cudaGraphExec_t host_step_graph = nullptr; // one step + overlapped downloads into host_key[]
   double* host_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   DeviceBuffer<char> l2_flush;
@@ -254,6 +257,8 @@ struct pecs_ctx {
     cudaSetDevice(device);
     if (step_graph) cudaGraphExecDestroy(step_graph);
     if (solve_graph) cudaGraphExecDestroy(solve_graph);
+    if (local_graph) cudaGraphExecDestroy(local_graph);
+    if (finish_graph) cudaGraphExecDestroy(finish_graph);
     if (host_step_graph) cudaGraphExecDestroy(host_step_graph);
     for (cudaEvent_t e : join)
       if (e) cudaEventDestroy(e);
@@ -369,6 +374,7 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
   const NodeLayout layout = carrier_nodes(d);
   for (int k = 0; k < 2; ++k) {
     if (ctx.kind != PECS_KIND_PRODUCTION && k == 1) break; // the manufactured tests only solve carrier_1
+    if (!(ctx.owned >> (2 * which + k) & 1)) continue;       // another shard owns this carrier
     const CsrMatrix A = copy_csr(d.system_matrix[k], 12 * n, "domain: system matrix size");
     SchurReduction R;
     if (schur_reduction_enabled() && build_schur_reduction(A, n, R)) {
@@ -447,9 +453,12 @@ CarrierPass carrier_pass(pecs_ctx* ctx, int w) {
   p.rhs2 = D.rhs[1].get();
   return p;
 }
-// which: 0 / 1 one subdomain (the reference-named calls), 2 both subdomains in ONE launch (the step)
+// which: 0 / 1 one subdomain (the reference-named calls), 2 both subdomains in ONE launch (the step); a shard only
+// assembles the subdomains it owns a carrier of
 void enqueue_carrier_rhs(pecs_ctx* ctx, int which, cudaStream_t s) {
   const CarrierPass none{};
+  if (which == 2 && ctx->full && !(ctx->owned & 0x3)) which = 1;
+  if (which == 2 && ctx->full && !(ctx->owned & 0xC)) which = 0;
   if (which == 2 && ctx->full)
     launch_carrier_rhs(carrier_pass(ctx, 0), carrier_pass(ctx, 1), ctx->kind, ctx->p_solution.get(), s);
   else
@@ -491,6 +500,7 @@ void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_cop
   const int n_species = ctx->full ? 4 : (ctx->kind == PECS_KIND_PRODUCTION ? 2 : 1);
   PECS_CUDA(cudaEventRecord(ctx->fork, ctx->main));
   for (int k = 0; k < n_species; ++k) {
+    if (!(ctx->owned >> k & 1)) continue;
     PECS_CUDA(cudaStreamWaitEvent(ctx->side[k], ctx->fork, 0));
     enqueue_species_solve(ctx, k, ctx->side[k]);
     PECS_CUDA(cudaEventRecord(ctx->join[k], ctx->side[k]));
@@ -610,6 +620,7 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     ctx->device = desc->device;
     ctx->kind = desc->kind;
     ctx->full = desc->full_system != 0;
+    ctx->owned = desc->owned_species ? (desc->owned_species & 0xF) : 0xF;
     std::memcpy(ctx->params, desc->params, sizeof(ctx->params));
     PECS_CUDA(cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking));
     for (int k = 0; k < 4; ++k) {
@@ -766,6 +777,38 @@ pecs_status pecs_solve_species(pecs_ctx* ctx, int32_t which) {
     PECS_CUDA(cudaGetLastError());
   });
 }
+
+pecs_status pecs_step_local(pecs_ctx* ctx) {
+  return guarded([&] {
+    require(ctx != nullptr && ctx->kind == PECS_KIND_PRODUCTION, "pecs_step_local: production contexts only");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->local_graph)
+      ctx->local_graph = capture_graph(ctx, [&] {
+        enqueue_carrier_rhs(ctx, 2, ctx->main);
+        enqueue_full_solve(ctx);
+      });
+    PECS_CUDA(cudaGraphLaunch(ctx->local_graph, ctx->main));
+  });
+}
+pecs_status pecs_step_finish(pecs_ctx* ctx) {
+  return guarded([&] {
+    require(ctx != nullptr && ctx->kind == PECS_KIND_PRODUCTION, "pecs_step_finish: production contexts only");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->finish_graph)
+      ctx->finish_graph = capture_graph(ctx, [&] {
+        enqueue_poisson_rhs(ctx, ctx->main);
+        enqueue_poisson_solve(ctx, ctx->main);
+      });
+    PECS_CUDA(cudaGraphLaunch(ctx->finish_graph, ctx->main));
+  });
+}
+double* pecs_density_block(pecs_ctx* ctx, int32_t which, int64_t* n_doubles) {
+  if (!ctx || which < 0 || which > 3 || (which >= 2 && !ctx->full)) return nullptr;
+  DeviceDomain& D = ctx->dom[which / 2];
+  if (n_doubles) *n_doubles = 4 * (int64_t)D.n_cells;
+  return D.solution[which % 2].get() + 8 * (size_t)D.n_cells;
+}
+void* pecs_stream(pecs_ctx* ctx) { return ctx ? (void*)ctx->main : nullptr; }
 
 pecs_status pecs_step(pecs_ctx* ctx, int32_t n_steps) {
   return guarded([&] {

@@ -235,6 +235,7 @@ void SolarCellProblem::set_solvers() {
   d.kind = kind;
   d.full_system = full_system ? 1 : 0;
   d.device = device;
+  d.owned_species = owned_species;
   fill_params(d.params);
 
   const pecs::MeshTables& S = semiconductor_triangulation.tables();

@@ -84,6 +84,7 @@ public:
   bool full_system = true;
   int kind = PECS_KIND_PRODUCTION;
   int device = 0;
+  int owned_species = 0; // bit k: carrier k is solved by this process' context; 0 = all (pecs_problem_desc::owned_species)
   double delta_t = 0.0;
   bool verbose = false;
 

@@ -78,6 +78,12 @@ pecs_status pecs_solarcell_create(const char* prm_text, int32_t test_defaults, i
   });
 }
 void pecs_solarcell_destroy(pecs_solarcell* p) { delete p; }
+pecs_status pecs_solarcell_set_owned_species(pecs_solarcell* p, int32_t mask) {
+  return guarded([&] {
+    if (mask < 0 || mask > 0xF) throw pecs::StatusError(PECS_ERR_INVALID, "owned species mask must be 0..15");
+    p->problem->owned_species = mask;
+  });
+}
 
 #define PECS_FORWARD(name, expr) \
   pecs_status name(pecs_solarcell* p) { return guarded([&] { expr; }); }

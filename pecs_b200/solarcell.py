@@ -249,6 +249,30 @@ class SolarCellProblem:
     def step(self, n_steps=1):
         check(self._lib.pecs_step(self.ctx, int(n_steps)))
 
+    # ---- one step cut at its exchange point (pecs_b200/shard.py drives these over several GPUs) ----
+    def set_owned_species(self, mask):
+        """before setup_*: bit k set = carrier k is factorised and solved by this process"""
+        check(self._lib.pecs_solarcell_set_owned_species(self._h, int(mask)))
+
+    def step_local(self):
+        check(self._lib.pecs_step_local(self.ctx))
+
+    def step_finish(self):
+        check(self._lib.pecs_step_finish(self.ctx))
+
+    def density_block(self, which):
+        """(device pointer, number of doubles) of the density block of carrier `which`"""
+        n = C.c_int64(0)
+        ptr = self._lib.pecs_density_block(self.ctx, int(which), C.byref(n))
+        if not ptr:
+            raise ValueError("no such carrier in this context")
+        return int(ptr), int(n.value)
+
+    @property
+    def stream(self):
+        """the context's main cudaStream_t as an integer handle"""
+        return int(self._lib.pecs_stream(self.ctx) or 0)
+
     def pinned_states(self):
         """five page-locked numpy arrays (electrons, holes, reductants, oxidants, Poisson) for step_host()"""
         out = []
