@@ -42,8 +42,10 @@ struct DeviceSystem {
   struct Sweep {
     DeviceBuffer<SolveTile> block_tiles, warp_tiles;
     int vec_block = 0, vec_warp = 0; // doubles of the staged vector (per block / per warp)
+    int warps = 4;                   // warps per thread block of the block-tile launch
     int stages = 2;                  // depth of the per-warp bulk-copy rings, thread-block tiles
     int stages_warp = 4;             // ... one-warp-per-front tiles: the whole small table is in flight at once
+    int chunk = kChunkDoubles;       // doubles per bulk copy (256 or 512)
   };
   struct Level {
     Sweep fwd, bwd;
@@ -64,7 +66,7 @@ struct DeviceSystem {
     size_t m = 0;
     for (const Level& l : levels)
       for (const Sweep* sw : {&l.fwd, &l.bwd})
-        m = std::max(m, std::max(solve_smem_bytes(sw->vec_block, false, solve_warps(), sw->stages),
+        m = std::max(m, std::max(solve_smem_bytes(sw->vec_block, false, sw->warps, sw->stages, sw->chunk),
                                  solve_smem_bytes(sw->vec_warp, true, solve_warps(), sw->stages_warp)));
     return m;
   }
@@ -76,16 +78,44 @@ struct DeviceSystem {
   // warps per thread block.  Measured (scripts/tune_solve.py, cfg3): 4 warps beat 8 -- smaller blocks, more of them
   // resident, finer tiles
   static int solve_warps() { return std::min(kSolveWarps, env_int("PECS_B200_SOLVE_WARPS", kWarpsPerFront)); }
-  // Ring depth.  Measured on B200 (scripts/tune_solve.py): shallow rings win -- what hides the latency of a block's
-  // prologue (tile descriptor, vector gather) is the NEXT block already resident on the SM, and shared memory buys
-  // more residency than depth.  Two chunks per warp keep 4 KB per warp in flight, ~150 KB per SM at full residency.
-  static int pick_stages() { return env_int("PECS_B200_SOLVE_STAGES", 2); }
+  // Shape of the block-tile launch of one level: warps per block and ring depth.  What counts is the number of bytes
+  // in flight per SM (ncu: a bulk copy takes 2-4 us under load, so ~44 GB/s per SM needs > 128 KB in flight) and that at
+  // least two blocks are resident (one stages its vector while the other streams).  Levels with small vectors reach
+  // that with 4 warps and 2-deep rings at 10+ blocks per SM -- measured best (scripts/tune_solve.py: 6 stages 2 889
+  // GB/s, 4: 3 757, 2: 4 505; 4 warps beat 8); levels whose vector eats the shared memory (top of the tree, 30-45 KB)
+  // get 8 warps per block, which share one vector, and deeper rings.
+  static void pick_shape(int vec_doubles, int& warps, int& stages, int& chunk) {
+    chunk = env_int("PECS_B200_CHUNK", kChunkDoubles) == 512 ? 512 : 256;
+    const int forced_stages = env_int("PECS_B200_SOLVE_STAGES", 0), forced_warps = env_int("PECS_B200_SOLVE_WARPS", 0);
+    const size_t sm_bytes = 227 * 1024, target = (size_t)env_int("PECS_B200_INFLIGHT_KB", 160) * 1024;
+    size_t best_inflight = 0;
+    int best_blocks = 0;
+    warps = forced_warps ? std::min(forced_warps, kSolveWarps) : kWarpsPerFront;
+    stages = forced_stages ? forced_stages : 2;
+    for (int w : {4, 8}) {
+      if (forced_warps && w != warps) continue;
+      for (int st : {2, 3, 4}) {
+        if (forced_stages && st != stages) continue;
+        const size_t smem = solve_smem_bytes(vec_doubles, false, w, st, chunk) + 1024;
+        const int blocks = (int)std::min<size_t>(std::min<size_t>(sm_bytes / smem, 64 / w), 32);
+        if (blocks < 2 && best_blocks >= 2) continue;
+        const size_t inflight = std::min(target, (size_t)blocks * w * st * chunk * sizeof(double));
+        // more bytes in flight up to the target; then more resident blocks; then shallower rings
+        if (inflight > best_inflight || (inflight == best_inflight && blocks > best_blocks)) {
+          best_inflight = inflight;
+          best_blocks = blocks;
+          warps = w;
+          stages = st;
+        }
+      }
+    }
+  }
   // panels per block tile: one per warp, more only when the level is so large that the tile count would explode
-  static int panels_per_tile(int64_t level_panels) {
+  static int panels_per_tile(int64_t level_panels, int warps) {
     const int forced = env_int("PECS_B200_SOLVE_PANELS_PER_TILE", 0);
     if (forced) return forced;
     const int64_t want_tiles = 148 * 16;
-    return (int)std::min<int64_t>(64, std::max<int64_t>(solve_warps(), (level_panels + want_tiles - 1) / want_tiles));
+    return (int)std::min<int64_t>(64, std::max<int64_t>(warps, (level_panels + want_tiles - 1) / want_tiles));
   }
 
   void build(const CsrMatrix& A, const NodeLayout& layout, int leaf_nodes, bool factor_on_device) {
@@ -124,11 +154,16 @@ struct DeviceSystem {
         Sweep& sw = which == 0 ? L.fwd : L.bwd;
         std::vector<SolveTile> bt, wt;
         int64_t panels = 0;
+        int vec_block = 0;
         for (int f : plan.levels[d]) {
           const PanelTable& T = which == 0 ? plan.fronts[f].fwd : plan.fronts[f].bwd;
-          if (!T.small) panels += T.n_panels();
+          if (!T.small && T.n_panels() > 0) {
+            panels += T.n_panels();
+            vec_block = std::max(vec_block, T.cols_pad);
+          }
         }
-        const int ppt = panels_per_tile(panels);
+        pick_shape(vec_block, sw.warps, sw.stages, sw.chunk);
+        const int ppt = panels_per_tile(panels, sw.warps);
         for (int f : plan.levels[d]) {
           const Front& F = plan.fronts[f];
           const PanelTable& T = which == 0 ? F.fwd : F.bwd;
@@ -163,7 +198,6 @@ struct DeviceSystem {
             sw.vec_block = std::max(sw.vec_block, T.cols_pad);
           }
         }
-        sw.stages = pick_stages();
         sw.stages_warp = env_int("PECS_B200_SOLVE_STAGES_WARP", 4);
         sw.block_tiles.upload(bt);
         sw.warp_tiles.upload(wt);
@@ -179,17 +213,17 @@ struct DeviceSystem {
     const int warps = solve_warps();
     for (int d = (int)levels.size() - 1; d >= 0; --d) {
       Sweep& sw = levels[d].fwd;
-      launch_forward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, w,
-                           w_fin.get(), cbuf.get(), s);
-      launch_forward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, warps, sw.stages, w,
-                           w_fin.get(), cbuf.get(), s);
+      launch_forward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, kChunkDoubles,
+                           w, w_fin.get(), cbuf.get(), s);
+      launch_forward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages, sw.chunk,
+                           w, w_fin.get(), cbuf.get(), s);
     }
     for (size_t d = 0; d < levels.size(); ++d) {
       Sweep& sw = levels[d].bwd;
-      launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, warps, sw.stages, w,
-                            cbuf.get(), w_fin.get(), x_perm.get(), solution, s);
-      launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, w,
-                            cbuf.get(), w_fin.get(), x_perm.get(), solution, s);
+      launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages,
+                            sw.chunk, w, cbuf.get(), w_fin.get(), x_perm.get(), solution, s);
+      launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp,
+                            kChunkDoubles, w, cbuf.get(), w_fin.get(), x_perm.get(), solution, s);
     }
   }
   // w_in = rhs - A solution (rows in elimination order)

@@ -65,7 +65,7 @@ __device__ __forceinline__ unsigned long long evict_first_policy() {
 // One warp streams panels panel0 + rank, panel0 + rank + n_ranks, ... of the tile through its private ring and hands
 // every finished row to emit(row, value).  sv: the front's vector in shared memory, zero beyond the logical columns;
 // vector_ready() is the barrier (block or warp) that publishes sv, called after the first copies were issued.
-template <class Ready, class Emit>
+template <int CHUNK, class Ready, class Emit>
 __device__ __forceinline__ void stream_panels(const double* __restrict__ table, int rows, const SolveTile& tile, int rank,
                                               int n_ranks, const double* sv, double* my_ring, unsigned long long* my_bars,
                                               int stages, Ready vector_ready, Emit emit) {
@@ -74,7 +74,7 @@ __device__ __forceinline__ void stream_panels(const double* __restrict__ table, 
   const int P = 1 << log2P;
   const int cg = 32 >> log2P;                               // columns covered by 32 consecutive doubles
   const int panel_doubles = tile.cols_pad << log2P;
-  const int cpp = (panel_doubles + kChunkDoubles - 1) / kChunkDoubles; // chunks per panel
+  const int cpp = (panel_doubles + CHUNK - 1) / CHUNK; // chunks per panel
   const int n_my = rank < tile.npanels ? (tile.npanels - rank + n_ranks - 1) / n_ranks : 0;
   const int total = n_my * cpp;
   const unsigned long long policy = evict_first_policy();
@@ -83,10 +83,10 @@ __device__ __forceinline__ void stream_panels(const double* __restrict__ table, 
   int ik = 0, ic = 0, issued = 0, islot = 0;
   auto issue = [&]() {
     const int panel = tile.panel0 + rank + ik * n_ranks;
-    const int e0 = ic * kChunkDoubles;
-    const int elems = min(kChunkDoubles, panel_doubles - e0);
+    const int e0 = ic * CHUNK;
+    const int elems = min(CHUNK, panel_doubles - e0);
     mbar_expect_tx(my_bars + islot, (uint32_t)elems * 8u);
-    bulk_copy(my_ring + islot * kChunkDoubles, table + (size_t)panel * panel_doubles + e0, (uint32_t)elems * 8u,
+    bulk_copy(my_ring + islot * CHUNK, table + (size_t)panel * panel_doubles + e0, (uint32_t)elems * 8u,
               my_bars + islot, policy);
     ++issued;
     if (++islot == stages) islot = 0;
@@ -110,19 +110,18 @@ __device__ __forceinline__ void stream_panels(const double* __restrict__ table, 
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     for (int c = 0; c < cpp; ++c) {
       mbar_wait(my_bars + slot, phase);
-      const double* ch = my_ring + slot * kChunkDoubles + lane;
-      const int e0 = c * kChunkDoubles;
-      const int elems = min(kChunkDoubles, panel_doubles - e0);
+      const double* ch = my_ring + slot * CHUNK + lane;
+      const int e0 = c * CHUNK;
+      const int elems = min(CHUNK, panel_doubles - e0);
       const double* v = sv + (e0 >> log2P) + col_of_lane;
-      if (elems == kChunkDoubles) {
-        a0 += ch[0] * v[0];
-        a1 += ch[32] * v[cg];
-        a2 += ch[64] * v[2 * cg];
-        a3 += ch[96] * v[3 * cg];
-        a0 += ch[128] * v[4 * cg];
-        a1 += ch[160] * v[5 * cg];
-        a2 += ch[192] * v[6 * cg];
-        a3 += ch[224] * v[7 * cg];
+      if (elems == CHUNK) {
+#pragma unroll
+        for (int s = 0; s < CHUNK / 32; s += 4) {
+          a0 += ch[32 * s] * v[s * cg];
+          a1 += ch[32 * s + 32] * v[(s + 1) * cg];
+          a2 += ch[32 * s + 64] * v[(s + 2) * cg];
+          a3 += ch[32 * s + 96] * v[(s + 3) * cg];
+        }
       } else {
         for (int s = 0; s < elems; s += 32) a0 += ch[s] * v[(s >> 5) * cg];
       }
@@ -154,23 +153,23 @@ struct BlockSmem {
   double* my_ring;
   unsigned long long* my_bars;
 };
-template <bool PER_WARP>
+template <bool PER_WARP, int CHUNK>
 __device__ __forceinline__ BlockSmem carve(unsigned char* raw, int vec_doubles, int stages) {
   const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   double* base = reinterpret_cast<double*>(raw);
   double* ring = base + (size_t)vec_doubles * (PER_WARP ? n_warps : 1);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)n_warps * stages * kChunkDoubles);
-  return BlockSmem{base + (PER_WARP ? (size_t)warp * vec_doubles : 0), ring + (size_t)warp * stages * kChunkDoubles,
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)n_warps * stages * CHUNK);
+  return BlockSmem{base + (PER_WARP ? (size_t)warp * vec_doubles : 0), ring + (size_t)warp * stages * CHUNK,
                    bars + warp * stages};
 }
 
-template <bool PER_WARP>
+template <bool PER_WARP, int CHUNK>
 __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
                                                                         int n_tiles, int vec_doubles, int stages,
                                                                         const double* __restrict__ w_in,
                                                                         double* __restrict__ w_fin, double* cbuf) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const BlockSmem sm = carve<PER_WARP>(smem_raw, vec_doubles, stages);
+  const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles, stages);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
   if (PER_WARP && tile_index >= n_tiles) return;
@@ -206,7 +205,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
       out[omap[row]] = carry;
     }
   }
-  stream_panels(
+  stream_panels<CHUNK>(
       t.fwd + tile.table_off, tile.nb, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.sv, sm.my_ring, sm.my_bars, stages,
       [] {
         if (PER_WARP)
@@ -222,7 +221,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
       });
 }
 
-template <bool PER_WARP>
+template <bool PER_WARP, int CHUNK>
 __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
                                                                          int n_tiles, int vec_doubles, int stages,
                                                                          const double* __restrict__ w_in,
@@ -230,7 +229,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
                                                                          const double* __restrict__ w_fin, double* x_perm,
                                                                          double* solution) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const BlockSmem sm = carve<PER_WARP>(smem_raw, vec_doubles, stages);
+  const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles, stages);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
   if (PER_WARP && tile_index >= n_tiles) return;
@@ -259,7 +258,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
         sm.sv[l] = l < np ? wp[l] : (l < m ? x_perm[bd[l - np]] : 0.0);
     }
   }
-  stream_panels(
+  stream_panels<CHUNK>(
       t.bwd + tile.table_off, tile.np, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.sv, sm.my_ring, sm.my_bars, stages,
       [] {
         if (PER_WARP)
@@ -280,37 +279,50 @@ __global__ void gather_kernel(int n, const int* __restrict__ index, const double
 
 } // namespace
 
+template <bool PER_WARP, int CHUNK>
+void configure_one(int max_smem_bytes) {
+  cudaFuncSetAttribute(forward_level_kernel<PER_WARP, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  cudaFuncSetAttribute(backward_level_kernel<PER_WARP, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+}
 void configure_solve_kernels(int max_smem_bytes) {
-  cudaFuncSetAttribute(forward_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
-  cudaFuncSetAttribute(forward_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
-  cudaFuncSetAttribute(backward_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
-  cudaFuncSetAttribute(backward_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  configure_one<false, 256>(max_smem_bytes);
+  configure_one<true, 256>(max_smem_bytes);
+  configure_one<false, 512>(max_smem_bytes);
+  configure_one<true, 512>(max_smem_bytes);
 }
 
 void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                          int stages, const double* w_in, double* w_fin, double* cbuf, cudaStream_t s) {
+                          int stages, int chunk, const double* w_in, double* w_fin, double* cbuf, cudaStream_t s) {
   if (n_tiles == 0) return;
   const int vec = (vec_doubles + 15) / 16 * 16;
-  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages);
-  if (per_warp)
-    forward_level_kernel<true><<<(n_tiles + warps - 1) / warps, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in,
-                                                                                      w_fin, cbuf);
-  else
-    forward_level_kernel<false><<<n_tiles, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in, w_fin, cbuf);
+  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, chunk);
+  const int grid = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
+#define PECS_LAUNCH(PW, CH) \
+  forward_level_kernel<PW, CH><<<grid, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in, w_fin, cbuf)
+  if (chunk == 512) {
+    if (per_warp) PECS_LAUNCH(true, 512); else PECS_LAUNCH(false, 512);
+  } else {
+    if (per_warp) PECS_LAUNCH(true, 256); else PECS_LAUNCH(false, 256);
+  }
+#undef PECS_LAUNCH
 }
 
 void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                           int stages, const double* w_in, const double* cbuf, const double* w_fin, double* x_perm,
+                           int stages, int chunk, const double* w_in, const double* cbuf, const double* w_fin, double* x_perm,
                            double* solution, cudaStream_t s) {
   if (n_tiles == 0) return;
   const int vec = (vec_doubles + 15) / 16 * 16;
-  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages);
-  if (per_warp)
-    backward_level_kernel<true><<<(n_tiles + warps - 1) / warps, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in,
-                                                                                       cbuf, w_fin, x_perm, solution);
-  else
-    backward_level_kernel<false><<<n_tiles, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in, cbuf, w_fin, x_perm,
-                                                                  solution);
+  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, chunk);
+  const int grid = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
+#define PECS_LAUNCH(PW, CH)                                                                                             \
+  backward_level_kernel<PW, CH><<<grid, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in, cbuf, w_fin, x_perm, \
+                                                               solution)
+  if (chunk == 512) {
+    if (per_warp) PECS_LAUNCH(true, 512); else PECS_LAUNCH(false, 512);
+  } else {
+    if (per_warp) PECS_LAUNCH(true, 256); else PECS_LAUNCH(false, 256);
+  }
+#undef PECS_LAUNCH
 }
 
 void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s) {

@@ -30,24 +30,24 @@ struct SolveTables {
   const double* bwd;
 };
 
-constexpr int kChunkDoubles = 256; // one bulk asynchronous copy: 2 KB of a panel
+constexpr int kChunkDoubles = 256; // one bulk asynchronous copy: 2 KB of a panel (512 = 4 KB is the other compiled variant)
 constexpr int kSolveWarps = 8;
 
 // shared memory of one thread block: the vector (one per block, or one per warp), one ring of `stages` chunks per
 // warp, one mbarrier per slot
-inline size_t solve_smem_bytes(int vec_doubles, bool per_warp, int warps, int stages) {
+inline size_t solve_smem_bytes(int vec_doubles, bool per_warp, int warps, int stages, int chunk = kChunkDoubles) {
   const size_t vec = ((size_t)vec_doubles + 15) / 16 * 16 * (per_warp ? warps : 1);
-  return (vec + (size_t)warps * stages * kChunkDoubles) * sizeof(double) + (size_t)warps * stages * sizeof(unsigned long long);
+  return (vec + (size_t)warps * stages * chunk) * sizeof(double) + (size_t)warps * stages * sizeof(unsigned long long);
 }
 
 // forward sweep of one level.  w_in: right-hand side in elimination order; w_fin: finalised pivot right-hand sides
 // (written by the `first` tile of every front); cbuf: child-update buffers.  per_warp: one small front per warp.
 void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                          int stages, const double* w_in, double* w_fin, double* cbuf, cudaStream_t s);
+                          int stages, int chunk, const double* w_in, double* w_fin, double* cbuf, cudaStream_t s);
 // backward sweep of one level; writes x_perm (elimination order, read by the deeper levels) and ADDS the result to the
 // caller's solution vector (increment form)
 void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                           int stages, const double* w_in, const double* cbuf, const double* w_fin, double* x_perm,
+                           int stages, int chunk, const double* w_in, const double* cbuf, const double* w_fin, double* x_perm,
                            double* solution, cudaStream_t s);
 // out[i] = in[index[i]]
 void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s);

@@ -85,3 +85,49 @@ def test_solver_variants_agree(tmp_path):
         results.append(np.load(out))
     for other in results[1:]:
         assert rel_err(other, results[0]) <= 1e-9
+
+
+CASES = {
+    # BASELINE.json config 4: strongly non-affine conic wire, two levels of interface refinement (2:1 smoothing layer)
+    "conic_l2": (3, 2, {"mesh__radius_one": 0.2, "mesh__radius_two": 0.6}),
+    # no local refinement: no hanging faces, no Poisson constraints besides the Neumann edges
+    "uniform_l0": (3, 0, {}),
+    # dark, no Schottky contact, not insulated with an applied bias: every boundary branch the default input skips
+    "dark_biased": (2, 1, {"physical__illumination_status": False, "physical__schottky_status": False,
+                           "physical__insulated": False, "physical__applied_bias": 0.2}),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_other_configurations_match_oracle(case):
+    """RHS vectors (1e-12) and densities / potential after 10 steps (1e-9) against the oracle on the meshes and
+    switches of the other BASELINE configurations"""
+    from helpers import SPECIES, block_rel_err, make_oracle
+    g, l, overrides = CASES[case]
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **overrides))
+    prob.setup_full_system()
+    o = make_oracle(prob, True)
+    o.project_initial_conditions()
+    o.assemble_Poisson_rhs()
+    o.solve_Poisson()
+    assert rel_err(prob.get_solution(pecs.POISSON), o.solution(4)) <= 1e-9
+    prob.step(3)
+    o.step(3)
+    prob.assemble_semiconductor_rhs()
+    prob.assemble_electrolyte_rhs()
+    o.assemble_semiconductor_rhs()
+    o.assemble_electrolyte_rhs()
+    for s in SPECIES:
+        # both sides assemble from their own (1e-12-close) states: the RHS tolerance is that of the states here
+        assert block_rel_err(prob.get_rhs(s), o.rhs(s)) <= 1e-9, f"rhs of species {s}"
+    prob.step(7)
+    o.step(7)
+    for s in SPECIES:
+        ug, uo = prob.get_solution(s), o.solution(s)
+        nc = ug.size // 12
+        assert rel_err(ug[8 * nc:], uo[8 * nc:]) <= 1e-9, f"density of species {s}"
+        assert block_rel_err(ug, uo) <= 1e-7, f"currents of species {s}"
+    n_rt = prob.n_rt
+    xg, xo = prob.get_solution(pecs.POISSON), o.solution(4)
+    assert rel_err(xg[n_rt:], xo[n_rt:]) <= 1e-9 and rel_err(xg[:n_rt], xo[:n_rt]) <= 1e-9
+    prob.close()

@@ -63,3 +63,21 @@ def test_oracle_lu_against_superlu(problem):
             assert np.abs(x[keep] - x_ref[keep]).max() <= 1e-9 * np.abs(x_ref).max()
         else:
             assert np.abs(x - x_ref).max() <= 1e-10 * np.abs(x_ref).max()
+
+
+@pytest.mark.parametrize("g,l,overrides", [
+    (3, 2, {"mesh__radius_one": 0.2, "mesh__radius_two": 0.6}),   # conic wire, two interface refinements (2:1 smoothing)
+    (3, 0, {}),                                                   # no hanging faces
+    (2, 1, {"physical__insulated": False, "physical__applied_bias": 0.2, "physical__schottky_status": False})])
+def test_plans_on_the_other_configurations(g, l, overrides):
+    """unknown-level separators (carriers) and edge-flux separators with delayed potentials (Poisson) on the meshes of
+    the other BASELINE configurations: plan + host factor tables solve every constant system"""
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **overrides))
+    prob.setup_full_system_host()
+    for which in range(5):
+        A = prob.matrix(which)
+        b = np.random.default_rng(which).standard_normal(A.shape[0])
+        x = prob.selftest_direct_solve(which, b)
+        assert np.linalg.norm(A @ x - b) <= 1e-9 * np.linalg.norm(b)
+    fronts = prob.plan_fronts(pecs.POISSON)
+    assert (fronts[:, 1] >= 0).all() and fronts[:, 1].sum() == prob.matrix(pecs.POISSON).shape[0]
