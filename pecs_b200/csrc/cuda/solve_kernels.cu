@@ -20,6 +20,8 @@
 //   * every output row has exactly one owner and a fixed summation order: no atomics, bit-reproducible solves.
 #include "solve_kernels.cuh"
 
+#include <cstdlib>
+
 namespace pecs {
 
 namespace {
@@ -62,81 +64,95 @@ __device__ __forceinline__ unsigned long long evict_first_policy() {
   return p;
 }
 
-// One warp streams panels panel0 + rank, panel0 + rank + n_ranks, ... of the tile through its private ring and hands
-// every finished row to emit(row, value).  sv: the front's vector in shared memory, zero beyond the logical columns;
-// vector_ready() is the barrier (block or warp) that publishes sv, called after the first copies were issued.
-template <int CHUNK, class Ready, class Emit>
-__device__ __forceinline__ void stream_panels(const double* __restrict__ table, int rows, const SolveTile& tile, int rank,
-                                              int n_ranks, const double* sv, double* my_ring, unsigned long long* my_bars,
-                                              int stages, Ready vector_ready, Emit emit) {
-  const int lane = threadIdx.x & 31;
-  const int log2P = tile.log2P;
-  const int P = 1 << log2P;
-  const int cg = 32 >> log2P;                               // columns covered by 32 consecutive doubles
-  const int panel_doubles = tile.cols_pad << log2P;
-  const int cpp = (panel_doubles + CHUNK - 1) / CHUNK; // chunks per panel
-  const int n_my = rank < tile.npanels ? (tile.npanels - rank + n_ranks - 1) / n_ranks : 0;
-  const int total = n_my * cpp;
-  const unsigned long long policy = evict_first_policy();
+// One warp streams panels panel0 + rank, panel0 + rank + n_ranks, ... of a tile through its private ring of bulk
+// copies.  start() puts the first chunks in flight -- it touches only the static table, so it runs BEFORE the kernel
+// waits for its predecessor (programmatic dependent launch) and before the vector is staged; run() consumes the
+// chunks against the vector sv in shared memory (zero beyond the logical columns), keeps the ring full and hands
+// every finished row to emit(row, value).
+template <int CHUNK>
+struct PanelStream {
+  const double* table;
+  double* ring;
+  unsigned long long* bars;
+  unsigned long long policy;
+  int lane, log2P, panel_doubles, cpp, n_my, total, stages;
+  int panel0, rank, n_ranks;
+  int ik = 0, ic = 0, issued = 0, islot = 0; // producer state (lane 0 only): next chunk to issue
 
-  // producer state (lane 0 only): next chunk to issue
-  int ik = 0, ic = 0, issued = 0, islot = 0;
-  auto issue = [&]() {
-    const int panel = tile.panel0 + rank + ik * n_ranks;
+  __device__ __forceinline__ PanelStream(const double* table_, const SolveTile& tile, int rank_, int n_ranks_, double* my_ring,
+                                         unsigned long long* my_bars, int stages_)
+      : table(table_), ring(my_ring), bars(my_bars), policy(evict_first_policy()), lane(threadIdx.x & 31), log2P(tile.log2P),
+        panel_doubles(tile.cols_pad << tile.log2P), stages(stages_), panel0(tile.panel0), rank(rank_), n_ranks(n_ranks_) {
+    cpp = (panel_doubles + CHUNK - 1) / CHUNK; // chunks per panel
+    n_my = rank < tile.npanels ? (tile.npanels - rank + n_ranks - 1) / n_ranks : 0;
+    total = n_my * cpp;
+  }
+  __device__ __forceinline__ void issue() {
+    const int panel = panel0 + rank + ik * n_ranks;
     const int e0 = ic * CHUNK;
     const int elems = min(CHUNK, panel_doubles - e0);
-    mbar_expect_tx(my_bars + islot, (uint32_t)elems * 8u);
-    bulk_copy(my_ring + islot * CHUNK, table + (size_t)panel * panel_doubles + e0, (uint32_t)elems * 8u,
-              my_bars + islot, policy);
+    mbar_expect_tx(bars + islot, (uint32_t)elems * 8u);
+    bulk_copy(ring + islot * CHUNK, table + (size_t)panel * panel_doubles + e0, (uint32_t)elems * 8u, bars + islot, policy);
     ++issued;
     if (++islot == stages) islot = 0;
     if (++ic == cpp) {
       ic = 0;
       ++ik;
     }
-  };
-  if (lane == 0)
-    for (int q = 0; q < stages && q < total; ++q) issue();
-
-  // the vector is staged while the first chunks fly
-  vector_ready();
-
-  const int row_in_panel = lane & (P - 1);
-  const int col_of_lane = lane >> log2P;
-  int slot = 0;
-  uint32_t phase = 0;
-  for (int k = 0; k < n_my; ++k) {
-    const int panel = tile.panel0 + rank + k * n_ranks;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    for (int c = 0; c < cpp; ++c) {
-      mbar_wait(my_bars + slot, phase);
-      const double* ch = my_ring + slot * CHUNK + lane;
-      const int e0 = c * CHUNK;
-      const int elems = min(CHUNK, panel_doubles - e0);
-      const double* v = sv + (e0 >> log2P) + col_of_lane;
-      if (elems == CHUNK) {
-#pragma unroll
-        for (int s = 0; s < CHUNK / 32; s += 4) {
-          a0 += ch[32 * s] * v[s * cg];
-          a1 += ch[32 * s + 32] * v[(s + 1) * cg];
-          a2 += ch[32 * s + 64] * v[(s + 2) * cg];
-          a3 += ch[32 * s + 96] * v[(s + 3) * cg];
-        }
-      } else {
-        for (int s = 0; s < elems; s += 32) a0 += ch[s] * v[(s >> 5) * cg];
-      }
-      __syncwarp();
-      if (lane == 0 && issued < total) issue();
-      if (++slot == stages) {
-        slot = 0;
-        phase ^= 1u;
-      }
-    }
-    double sum = (a0 + a1) + (a2 + a3);
-    for (int o = P; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const int row = (panel << log2P) + row_in_panel;
-    if (lane < P && row < rows) emit(row, sum);
   }
+  __device__ __forceinline__ void start() {
+    if (lane == 0)
+      for (int q = 0; q < stages && q < total; ++q) issue();
+  }
+  template <class Emit>
+  __device__ __forceinline__ void run(const double* sv, int rows, Emit emit) {
+    const int P = 1 << log2P;
+    const int cg = 32 >> log2P; // columns covered by 32 consecutive doubles
+    const int row_in_panel = lane & (P - 1);
+    const int col_of_lane = lane >> log2P;
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < n_my; ++k) {
+      const int panel = panel0 + rank + k * n_ranks;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for (int c = 0; c < cpp; ++c) {
+        mbar_wait(bars + slot, phase);
+        const double* ch = ring + slot * CHUNK + lane;
+        const int e0 = c * CHUNK;
+        const int elems = min(CHUNK, panel_doubles - e0);
+        const double* v = sv + (e0 >> log2P) + col_of_lane;
+        if (elems == CHUNK) {
+#pragma unroll
+          for (int s = 0; s < CHUNK / 32; s += 4) {
+            a0 += ch[32 * s] * v[s * cg];
+            a1 += ch[32 * s + 32] * v[(s + 1) * cg];
+            a2 += ch[32 * s + 64] * v[(s + 2) * cg];
+            a3 += ch[32 * s + 96] * v[(s + 3) * cg];
+          }
+        } else {
+          for (int s = 0; s < elems; s += 32) a0 += ch[s] * v[(s >> 5) * cg];
+        }
+        __syncwarp();
+        if (lane == 0 && issued < total) issue();
+        if (++slot == stages) {
+          slot = 0;
+          phase ^= 1u;
+        }
+      }
+      double sum = (a0 + a1) + (a2 + a3);
+      for (int o = P; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const int row = (panel << log2P) + row_in_panel;
+      if (lane < P && row < rows) emit(row, sum);
+    }
+  }
+};
+
+// Programmatic dependent launch: everything before this point overlaps the tail of the previous kernel in the stream
+// (launch latency, tile descriptor, barrier set-up, first table chunks); after it the predecessor's results are visible.
+// The successor is released right away: it may start ITS prologue while this kernel computes.
+__device__ __forceinline__ void wait_for_predecessor() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __device__ __forceinline__ void init_pipeline(unsigned long long* my_bars, int stages) {
@@ -175,6 +191,10 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
   if (PER_WARP && tile_index >= n_tiles) return;
   const SolveTile tile = tiles[tile_index];
   init_pipeline(sm.my_bars, stages);
+  PanelStream<CHUNK> stream(t.fwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.my_ring, sm.my_bars,
+                            stages);
+  stream.start();
+  wait_for_predecessor();
   const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
   const double* c0 = tile.cbuf_off[0] >= 0 ? cbuf + tile.cbuf_off[0] : nullptr;
   const double* c1 = tile.cbuf_off[1] >= 0 ? cbuf + tile.cbuf_off[1] : nullptr;
@@ -205,20 +225,16 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
       out[omap[row]] = carry;
     }
   }
-  stream_panels<CHUNK>(
-      t.fwd + tile.table_off, tile.nb, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.sv, sm.my_ring, sm.my_bars, stages,
-      [] {
-        if (PER_WARP)
-          __syncwarp();
-        else
-          __syncthreads();
-      },
-      [&](int row, double dot) {
-        double carry = 0.0;
-        if (carry0) carry += carry0[row];
-        if (carry1) carry += carry1[row];
-        out[omap[row]] = carry + dot;
-      });
+  if (PER_WARP)
+    __syncwarp();
+  else
+    __syncthreads();
+  stream.run(sm.sv, tile.nb, [&](int row, double dot) {
+    double carry = 0.0;
+    if (carry0) carry += carry0[row];
+    if (carry1) carry += carry1[row];
+    out[omap[row]] = carry + dot;
+  });
 }
 
 template <bool PER_WARP, int CHUNK>
@@ -235,6 +251,10 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
   if (PER_WARP && tile_index >= n_tiles) return;
   const SolveTile tile = tiles[tile_index];
   init_pipeline(sm.my_bars, stages);
+  PanelStream<CHUNK> stream(t.bwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.my_ring, sm.my_bars,
+                            stages);
+  stream.start();
+  wait_for_predecessor();
   {
     const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
     const int np = tile.np, m = tile.np + tile.nb;
@@ -258,18 +278,14 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
         sm.sv[l] = l < np ? wp[l] : (l < m ? x_perm[bd[l - np]] : 0.0);
     }
   }
-  stream_panels<CHUNK>(
-      t.bwd + tile.table_off, tile.np, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.sv, sm.my_ring, sm.my_bars, stages,
-      [] {
-        if (PER_WARP)
-          __syncwarp();
-        else
-          __syncthreads();
-      },
-      [&](int row, double x) {
-        x_perm[tile.p0 + row] = x;
-        solution[t.iperm[tile.p0 + row]] += x; // increment form: the right-hand side was the residual of `solution`
-      });
+  if (PER_WARP)
+    __syncwarp();
+  else
+    __syncthreads();
+  stream.run(sm.sv, tile.np, [&](int row, double x) {
+    x_perm[tile.p0 + row] = x;
+    solution[t.iperm[tile.p0 + row]] += x; // increment form: the right-hand side was the residual of `solution`
+  });
 }
 
 __global__ void gather_kernel(int n, const int* __restrict__ index, const double* __restrict__ in, double* __restrict__ out) {
@@ -278,6 +294,27 @@ __global__ void gather_kernel(int n, const int* __restrict__ index, const double
 }
 
 } // namespace
+
+// Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream is still
+// running and synchronises itself with griddepcontrol.wait (wait_for_predecessor).  PECS_B200_PDL=0 launches plainly.
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+  static const bool pdl = [] {
+    const char* e = std::getenv("PECS_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 template <bool PER_WARP, int CHUNK>
 void configure_one(int max_smem_bytes) {
@@ -298,7 +335,7 @@ void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_ti
   const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, chunk);
   const int grid = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
 #define PECS_LAUNCH(PW, CH) \
-  forward_level_kernel<PW, CH><<<grid, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in, w_fin, cbuf)
+  launch_pdl(forward_level_kernel<PW, CH>, grid, warps * 32, smem, s, t, tiles, n_tiles, vec, stages, w_in, w_fin, cbuf)
   if (chunk == 512) {
     if (per_warp) PECS_LAUNCH(true, 512); else PECS_LAUNCH(false, 512);
   } else {
@@ -314,9 +351,9 @@ void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_t
   const int vec = (vec_doubles + 15) / 16 * 16;
   const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, chunk);
   const int grid = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
-#define PECS_LAUNCH(PW, CH)                                                                                             \
-  backward_level_kernel<PW, CH><<<grid, warps * 32, smem, s>>>(t, tiles, n_tiles, vec, stages, w_in, cbuf, w_fin, x_perm, \
-                                                               solution)
+#define PECS_LAUNCH(PW, CH)                                                                                           \
+  launch_pdl(backward_level_kernel<PW, CH>, grid, warps * 32, smem, s, t, tiles, n_tiles, vec, stages, w_in, cbuf, w_fin, \
+             x_perm, solution)
   if (chunk == 512) {
     if (per_warp) PECS_LAUNCH(true, 512); else PECS_LAUNCH(false, 512);
   } else {
