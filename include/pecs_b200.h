@@ -196,7 +196,10 @@ void pecs_host_free(void* p);
  * context's own streams.  ms[0] = whole region.  sectioned == 0: n_steps replays of the step graph; sectioned == 1:
  * ms[1..5] = the reference's five TimerOutput sections summed over the steps, launched one by one
  * (serialised, includes launch gaps); sectioned == 2: n_steps replays of a graph that holds only the five solves
- * (four concurrent carrier solves, then Poisson) -- the denominator of the solve roofline. */
+ * (four concurrent carrier solves, then Poisson); sectioned == 3: n_steps replays of a graph that holds only the
+ * assembly passes (fused carrier RHS, Poisson RHS).  In the step graph the assembly passes run strictly before / between
+ * the solves, so (mode 0) - (mode 3) is the device time of the solves inside a real step: the denominator of the solve
+ * roofline. */
 pecs_status pecs_step_timed(pecs_ctx* ctx, int32_t n_steps, int32_t sectioned, double ms[6]);
 /* repeat one kernel class in isolation: which = 0 carrier RHS (both subdomains), 1 Poisson RHS, 2 carrier solves,
  * 3 Poisson solve; returns average ms per launch group and the number of kernel launches in one group */

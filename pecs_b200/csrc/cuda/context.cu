@@ -278,6 +278,7 @@ struct pecs_ctx {
   cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr}; // host-buffer step: a species' download has finished
   cudaGraphExec_t step_graph = nullptr;
   cudaGraphExec_t solve_graph = nullptr;     // the five solves only (measurement, pecs_step_timed mode 2)
+  cudaGraphExec_t rhs_graph = nullptr;       // the three assembly passes only (measurement, pecs_step_timed mode 3)
   cudaGraphExec_t local_graph = nullptr;     // sharded step, part 1: RHS + owned solves
   cudaGraphExec_t finish_graph = nullptr;    // sharded step, part 2: Poisson RHS + Poisson solve
   cudaGraphExec_t host_step_graph = nullptr; // one step + overlapped downloads into host_key[]
@@ -291,6 +292,7 @@ struct pecs_ctx {
     cudaSetDevice(device);
     if (step_graph) cudaGraphExecDestroy(step_graph);
     if (solve_graph) cudaGraphExecDestroy(solve_graph);
+    if (rhs_graph) cudaGraphExecDestroy(rhs_graph);
     if (local_graph) cudaGraphExecDestroy(local_graph);
     if (finish_graph) cudaGraphExecDestroy(finish_graph);
     if (host_step_graph) cudaGraphExecDestroy(host_step_graph);
@@ -920,8 +922,13 @@ pecs_status pecs_step_timed(pecs_ctx* ctx, int32_t n_steps, int32_t sectioned, d
         enqueue_full_solve(ctx);
         enqueue_poisson_solve(ctx, ctx->main);
       });
-    if (sectioned == 0 || sectioned == 2) {
-      cudaGraphExec_t g = sectioned == 2 ? ctx->solve_graph : ctx->step_graph;
+    if (sectioned == 3 && !ctx->rhs_graph)
+      ctx->rhs_graph = capture_graph(ctx, [&] {
+        enqueue_carrier_rhs(ctx, 2, ctx->main);
+        enqueue_poisson_rhs(ctx, ctx->main);
+      });
+    if (sectioned == 0 || sectioned == 2 || sectioned == 3) {
+      cudaGraphExec_t g = sectioned == 2 ? ctx->solve_graph : (sectioned == 3 ? ctx->rhs_graph : ctx->step_graph);
       PECS_CUDA(cudaEventRecord(ev[0], ctx->main));
       for (int s = 0; s < n_steps; ++s) PECS_CUDA(cudaGraphLaunch(g, ctx->main));
       PECS_CUDA(cudaEventRecord(ev[1], ctx->main));

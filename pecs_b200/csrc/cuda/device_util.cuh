@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -62,5 +63,37 @@ private:
   T* p_ = nullptr;
   size_t n_ = 0;
 };
+
+#ifdef __CUDACC__
+// Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream is still
+// running and synchronises itself with griddepcontrol.wait (wait_for_predecessor).  PECS_B200_PDL=0 launches plainly.
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+  static const bool pdl = [] {
+    const char* e = std::getenv("PECS_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+
+// Device side of a programmatic dependent launch: everything before this call overlaps the tail of the previous
+// kernel in the stream (launch latency, descriptor loads, prefetches of static tables); after it the predecessor's
+// results are visible.  The successor is released right away: it may start ITS prologue while this kernel computes.
+__device__ __forceinline__ void wait_for_predecessor() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
 
 } // namespace pecs

@@ -7,21 +7,47 @@
 #include "schur_kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace pecs {
 
 void DeviceEll::upload(const CsrMatrix& A, const std::vector<int>* row_order) {
   n = A.n;
-  width = 0;
-  for (int i = 0; i < n; ++i) width = std::max(width, A.row_ptr[i + 1] - A.row_ptr[i]);
+  // slots per row in both formats
+  int w1 = 0, w4 = 0;
+  for (int i = 0; i < n; ++i) {
+    w1 = std::max(w1, A.row_ptr[i + 1] - A.row_ptr[i]);
+    int groups = 0, last = -1;
+    for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k)
+      if (A.col[k] / 4 != last) {
+        last = A.col[k] / 4;
+        ++groups;
+      }
+    w4 = std::max(w4, groups);
+  }
+  const bool forced_scalar = std::getenv("PECS_B200_ELL_SCALAR") != nullptr;
+  block = (!forced_scalar && A.n % 4 == 0 && (size_t)w4 * 36 < (size_t)w1 * 12) ? 4 : 1;
+  width = block == 4 ? w4 : w1;
   std::vector<int> c((size_t)n * width, 0);
-  std::vector<double> v((size_t)n * width, 0.0);
+  std::vector<double> v((size_t)n * width * block, 0.0);
   for (int i = 0; i < n; ++i) {
     const int r = row_order ? (*row_order)[i] : i;
-    for (int k = A.row_ptr[r]; k < A.row_ptr[r + 1]; ++k) {
-      const size_t slot = (size_t)(k - A.row_ptr[r]) * n + i;
-      c[slot] = A.col[k];
-      v[slot] = A.val[k];
+    if (block == 1) {
+      for (int k = A.row_ptr[r]; k < A.row_ptr[r + 1]; ++k) {
+        const size_t slot = (size_t)(k - A.row_ptr[r]) * n + i;
+        c[slot] = A.col[k];
+        v[slot] = A.val[k];
+      }
+    } else {
+      int g = -1, last = -1;
+      for (int k = A.row_ptr[r]; k < A.row_ptr[r + 1]; ++k) { // columns are sorted within a row
+        if (A.col[k] / 4 != last) {
+          last = A.col[k] / 4;
+          ++g;
+          c[(size_t)g * n + i] = 4 * last;
+        }
+        v[((size_t)g * 4 + A.col[k] % 4) * n + i] = A.val[k];
+      }
     }
   }
   col.upload(c);
@@ -30,7 +56,7 @@ void DeviceEll::upload(const CsrMatrix& A, const std::vector<int>* row_order) {
 
 namespace {
 struct EllView {
-  int width;
+  int width, block;
   const int* col;
   const double* val;
   const double* x;
@@ -38,6 +64,18 @@ struct EllView {
 };
 __device__ __forceinline__ double ell_row(const EllView& t, int n, int i) {
   double acc = 0.0;
+  if (t.block == 4) {
+#pragma unroll 2
+    for (int k = 0; k < t.width; ++k) {
+      const int j = __ldcs(t.col + (size_t)k * n + i);
+      const double* v = t.val + (size_t)4 * k * n + i;
+      const double a0 = __ldcs(v), a1 = __ldcs(v + n), a2 = __ldcs(v + 2 * (size_t)n), a3 = __ldcs(v + 3 * (size_t)n);
+      const double2 x01 = __ldg(reinterpret_cast<const double2*>(t.x + j));
+      const double2 x23 = __ldg(reinterpret_cast<const double2*>(t.x + j + 2));
+      acc += (a0 * x01.x + a1 * x01.y) + (a2 * x23.x + a3 * x23.y);
+    }
+    return t.sign * acc;
+  }
 #pragma unroll 4
   for (int k = 0; k < t.width; ++k) {
     const double a = __ldcs(t.val + (size_t)k * n + i);
@@ -50,6 +88,7 @@ __global__ void __launch_bounds__(256) ell_combine_kernel(int n, const double* _
                                                           const int* __restrict__ base_index, EllView t0, EllView t1, EllView t2,
                                                           double* __restrict__ y) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  wait_for_predecessor(); // launched programmatically: the launch latency overlaps the previous kernel's tail
   if (i >= n) return;
   double acc = base ? base[base_index ? base_index[i] : i] : 0.0;
   acc += ell_row(t0, n, i);
@@ -58,15 +97,15 @@ __global__ void __launch_bounds__(256) ell_combine_kernel(int n, const double* _
   y[i] = acc;
 }
 EllView view(const EllTerm& t) {
-  if (!t.A) return EllView{0, nullptr, nullptr, nullptr, 0.0};
-  return EllView{t.A->width, t.A->col.get(), t.A->val.get(), t.x, t.sign};
+  if (!t.A) return EllView{0, 1, nullptr, nullptr, nullptr, 0.0};
+  return EllView{t.A->width, t.A->block, t.A->col.get(), t.A->val.get(), t.x, t.sign};
 }
 } // namespace
 
 void launch_ell_combine(int n_rows, const double* base, const int* base_index, EllTerm t0, EllTerm t1, EllTerm t2, double* y,
                         cudaStream_t s) {
   if (n_rows == 0) return;
-  ell_combine_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(n_rows, base, base_index, view(t0), view(t1), view(t2), y);
+  launch_pdl(ell_combine_kernel, (n_rows + 255) / 256, 256, 0, s, n_rows, base, base_index, view(t0), view(t1), view(t2), y);
 }
 
 } // namespace pecs

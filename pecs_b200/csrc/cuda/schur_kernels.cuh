@@ -9,10 +9,14 @@
 
 namespace pecs {
 
-// ELLPACK copy of a CSR matrix: `width` entries per row, stored column-major (entry k of row i at k*n + i) so that
+// ELLPACK copy of a CSR matrix: `width` slots per row, stored column-major (slot k of row i at k*n + i) so that
 // one thread per row reads with unit stride across the warp.  Padding entries have value 0 and column 0.
+// block == 1: a slot is one entry (8 B value + 4 B column).  block == 4: a slot is four entries in four consecutive,
+// 4-aligned columns (32 B of values + ONE 4 B column): the LDG matrices couple whole cells (4 nodal values), so their
+// entries come in such groups and the column indices shrink to a quarter -- 9 instead of 12 B per entry.  upload()
+// picks whichever is smaller for the matrix at hand.
 struct DeviceEll {
-  int n = 0, width = 0;
+  int n = 0, width = 0, block = 1;
   DeviceBuffer<int> col;
   DeviceBuffer<double> val;
   // row_order (optional): ELL row i holds row (*row_order)[i] of A

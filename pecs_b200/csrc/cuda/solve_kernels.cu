@@ -20,7 +20,7 @@
 //   * every output row has exactly one owner and a fixed summation order: no atomics, bit-reproducible solves.
 #include "solve_kernels.cuh"
 
-#include <cstdlib>
+#include "device_util.cuh"
 
 namespace pecs {
 
@@ -146,14 +146,6 @@ struct PanelStream {
     }
   }
 };
-
-// Programmatic dependent launch: everything before this point overlaps the tail of the previous kernel in the stream
-// (launch latency, tile descriptor, barrier set-up, first table chunks); after it the predecessor's results are visible.
-// The successor is released right away: it may start ITS prologue while this kernel computes.
-__device__ __forceinline__ void wait_for_predecessor() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
 
 __device__ __forceinline__ void init_pipeline(unsigned long long* my_bars, int stages) {
   if ((threadIdx.x & 31) == 0) {
@@ -294,27 +286,6 @@ __global__ void gather_kernel(int n, const int* __restrict__ index, const double
 }
 
 } // namespace
-
-// Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream is still
-// running and synchronises itself with griddepcontrol.wait (wait_for_predecessor).  PECS_B200_PDL=0 launches plainly.
-template <class... KArgs, class... Args>
-void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
-  static const bool pdl = [] {
-    const char* e = std::getenv("PECS_B200_PDL");
-    return !(e && e[0] == '0');
-  }();
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
 
 template <bool PER_WARP, int CHUNK>
 void configure_one(int max_smem_bytes) {

@@ -296,7 +296,7 @@ class SolarCellProblem:
 
     def step_timed(self, n_steps, sectioned=False):
         ms = np.zeros(6)
-        check(self._lib.pecs_step_timed(self.ctx, int(n_steps), int(bool(sectioned)), _dp(ms)))
+        check(self._lib.pecs_step_timed(self.ctx, int(n_steps), int(sectioned), _dp(ms)))
         return ms
 
     def time_kernel(self, which, repeats):

@@ -178,3 +178,22 @@ def test_convergence_order_on_gpu():
     for a, b in zip(errs[:-1], errs[1:]):
         assert np.log2(a["u"] / b["u"]) >= 1.9
         assert np.log2(a["Phi"] / b["Phi"]) >= 0.95
+
+
+@pytest.mark.parametrize("kind,levels,what", [
+    (pecs.KIND_TEST_STEADY, (4, 5, 6, 7), ("u", "Phi")),      # Poisson_test: LDG Poisson + mixed FEM, steady
+    (pecs.KIND_TEST_TRANSIENT, (4, 5, 6), ("u",)),            # IMEX_LDG_test: dt = h^2, T = 1
+    (pecs.KIND_TEST_DD_POISSON, (4, 5, 6), ("u", "Phi"))])    # DD_Poisson_test: the coupled problem
+def test_convergence_gate_refinements_4_to_7(kind, levels, what):
+    """BASELINE config 2: the reference's manufactured-solution programs at the refinements it runs them on, on the
+    GPU path, against the analytic solutions: L2 order k+1 = 2 for the density, 1 for the DG0 potential
+    (reference include/SolarCell.hpp:179-181, 229-235; dt = h^(k+1) makes the transient levels 4x longer each)"""
+    errs = []
+    for level in levels:
+        prob = pecs.SolarCellProblem(None, test_defaults=True)
+        errs.append(prob.run_test(kind, level))
+        prob.close()
+    for a, b in zip(errs[:-1], errs[1:]):
+        assert np.log2(a["u"] / b["u"]) >= 1.9
+        if "Phi" in what:
+            assert np.log2(a["Phi"] / b["Phi"]) >= 0.95
