@@ -286,6 +286,8 @@ def run_sharded_arm(args):
     prob.synchronize()
     t_setup = time.perf_counter() - t_setup
     engine = shard.GpuEngine(prob, device)
+    if args.exchange == "p2p":
+        engine.connect_p2p(dist, rank, world)
     stepper = shard.ShardedStepper(engine, dist, rank, world)
     K, W = args.steps, max(args.warmup, 3)
     stepper.step(W)
@@ -313,8 +315,11 @@ def run_sharded_arm(args):
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": workload_name(g, l), "parallelism": shard.mode_name(world),
-                           "exchange": f"NCCL broadcast of the four density blocks per step ({exchanged} B), "
-                                       "Poisson solved redundantly on every rank",
+                           "exchange": (f"NCCL broadcast of the four density blocks per step ({exchanged} B)"
+                                        if args.exchange == "nccl" else
+                                        f"fused into the backward sweeps: peer-memory stores over NVLink ({exchanged} B per "
+                                        "step and peer), flag kernels, no collective") +
+                                       "; Poisson solved redundantly on every rank",
                            "l2": "inputs larger than L2: every step streams the factor tables once",
                            "setup_seconds": t_setup},
                 "e2e": None, "gpu_launches": int(launches) * K, "clocks": clocks,
@@ -346,6 +351,9 @@ def main():
                     help="mesh of the bounded CPU sample (the oracle's sparse LU at refinement 7 does not fit the budget)")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", choices=["nccl", "p2p"], default="p2p",
+                    help="sharded step: 'p2p' = density exchange fused into the solves over peer memory (default), "
+                         "'nccl' = broadcasts between the two halves of the step")
     ap.add_argument("--parallelism", choices=["sweep", "subdomain", "species"], default="sweep",
                     help="N > 1: 'sweep' = one applied bias per rank (weak scaling, default); 'subdomain' (2 ranks) / "
                          "'species' (4 ranks) = one step sharded over the ranks with an NCCL density exchange (strong)")

@@ -173,6 +173,17 @@ pecs_status pecs_step(pecs_ctx* ctx, int32_t n_steps);
  * (include/SolarCell.hpp:351-367), four independent solve tasks (source/SolarCell.cpp:1763-1781). */
 pecs_status pecs_step_local(pecs_ctx* ctx);
 pecs_status pecs_step_finish(pecs_ctx* ctx);
+/* The same exchange WITHOUT a collective: fused into the solves over peer memory (NVLink / NVSwitch).
+ *   pecs_p2p_export : fills `blob` with CUDA IPC handles of this context's state vectors and flag block; returns the
+ *                     number of bytes written (-1 on error).  Every rank passes its blob to every other rank
+ *                     (any transport; pecs_b200/shard.py uses torch.distributed.all_gather_object, once, at setup).
+ *   pecs_p2p_connect: blobs = the `world` blobs in rank order.  From then on the backward sweep of every owned
+ *                     carrier stores each finished density straight into the other ranks' vectors while it runs,
+ *                     single-thread flag kernels order it against the peers' assembly ("rank r no longer reads the old
+ *                     densities" before the first remote store, "carrier s is complete" before the Poisson assembly),
+ *                     and pecs_step_local / pecs_step_finish need nothing in between.  Ranks must step in lockstep. */
+int64_t pecs_p2p_export(pecs_ctx* ctx, void* blob, int64_t capacity);
+pecs_status pecs_p2p_connect(pecs_ctx* ctx, int32_t rank, int32_t world, const void* blobs);
 /* device pointer to the density block of carrier `which` (4 * n_cells doubles, *n_doubles receives the count) */
 double* pecs_density_block(pecs_ctx* ctx, int32_t which, int64_t* n_doubles);
 /* the context's main CUDA stream (cudaStream_t): everything above is enqueued on it */

@@ -46,6 +46,8 @@ SIGNATURES = {
     "pecs_step": (C.c_int, [VOIDP, C.c_int32]),
     "pecs_step_local": (C.c_int, [VOIDP]),
     "pecs_step_finish": (C.c_int, [VOIDP]),
+    "pecs_p2p_export": (C.c_int64, [VOIDP, VOIDP, C.c_int64]),
+    "pecs_p2p_connect": (C.c_int, [VOIDP, C.c_int32, C.c_int32, VOIDP]),
     "pecs_density_block": (VOIDP, [VOIDP, C.c_int32, C.POINTER(C.c_int64)]),
     "pecs_stream": (VOIDP, [VOIDP]),
     "pecs_synchronize": (C.c_int, [VOIDP]),

@@ -59,6 +59,8 @@ struct DeviceSystem {
   // the density error of a step against an extended-precision solve drops from 1.8e-11 to 7e-13 (reductants),
   // below that of a sparse LU applied to the full right-hand side (3e-12).  Cost: one ELL mat-vec, ~4 % more bytes.
   DeviceEll matrix_rows;
+  double* mirror[3] = {nullptr, nullptr, nullptr}; // peer copies of the solution vector (sharded step, pecs_p2p_connect)
+  int n_mirror = 0;
 
   int64_t factor_bytes() const { return (int64_t)(fwd.bytes() + bwd.bytes() + matrix_rows.bytes()); }
   int64_t logical_bytes() const { return plan.logical_entries() * (int64_t)sizeof(double) + (int64_t)matrix_rows.bytes(); }
@@ -207,9 +209,14 @@ struct DeviceSystem {
   }
 
   // solution += A^-1 w, all on stream s; w = residual of the current content of `solution`, in elimination order
-  // (residual() below, or the caller's own fused kernel)
-  void solve_increment(const double* w, double* solution, cudaStream_t s) {
-    const SolveTables t{bd_index.get(), out_map.get(), iperm.get(), fwd.get(), bwd.get()};
+  // (residual() below, or the caller's own fused kernel).  The two sweeps can be enqueued separately: the sharded step
+  // puts a cross-GPU wait between them.
+  SolveTables tables() const {
+    SolveTables t{bd_index.get(), out_map.get(), iperm.get(), fwd.get(), bwd.get(), {mirror[0], mirror[1], mirror[2]}, n_mirror};
+    return t;
+  }
+  void forward_sweep(const double* w, cudaStream_t s) {
+    const SolveTables t = tables();
     const int warps = solve_warps();
     for (int d = (int)levels.size() - 1; d >= 0; --d) {
       Sweep& sw = levels[d].fwd;
@@ -218,6 +225,10 @@ struct DeviceSystem {
       launch_forward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages, sw.chunk,
                            w, w_fin.get(), cbuf.get(), s);
     }
+  }
+  void backward_sweep(const double* w, double* solution, cudaStream_t s) {
+    const SolveTables t = tables();
+    const int warps = solve_warps();
     for (size_t d = 0; d < levels.size(); ++d) {
       Sweep& sw = levels[d].bwd;
       launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages,
@@ -225,6 +236,10 @@ struct DeviceSystem {
       launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp,
                             kChunkDoubles, w, cbuf.get(), w_fin.get(), x_perm.get(), solution, s);
     }
+  }
+  void solve_increment(const double* w, double* solution, cudaStream_t s) {
+    forward_sweep(w, s);
+    backward_sweep(w, solution, s);
   }
   // w_in = rhs - A solution (rows in elimination order)
   void residual(const double* rhs, const double* solution, cudaStream_t s) {
@@ -279,6 +294,15 @@ struct pecs_ctx {
   cudaGraphExec_t step_graph = nullptr;
   cudaGraphExec_t solve_graph = nullptr;     // the five solves only (measurement, pecs_step_timed mode 2)
   cudaGraphExec_t rhs_graph = nullptr;       // the three assembly passes only (measurement, pecs_step_timed mode 3)
+  // sharded step with the exchange fused into the solves (pecs_p2p_connect): flags[0..7] = "rank r has finished the
+  // assembly of step n", flags[8..11] = "carrier s of step n is complete in this rank's memory", flags[16] = n
+  struct P2P {
+    bool active = false;
+    int rank = 0, world = 1;
+    DeviceBuffer<unsigned long long> flags;
+    DeviceBuffer<unsigned long long*> all_flags; // device array: every rank's flag block (own included)
+    std::vector<void*> opened;                   // cudaIpcOpenMemHandle results
+  } p2p;
   cudaGraphExec_t local_graph = nullptr;     // sharded step, part 1: RHS + owned solves
   cudaGraphExec_t finish_graph = nullptr;    // sharded step, part 2: Poisson RHS + Poisson solve
   cudaGraphExec_t host_step_graph = nullptr; // one step + overlapped downloads into host_key[]
@@ -293,6 +317,7 @@ struct pecs_ctx {
     if (step_graph) cudaGraphExecDestroy(step_graph);
     if (solve_graph) cudaGraphExecDestroy(solve_graph);
     if (rhs_graph) cudaGraphExecDestroy(rhs_graph);
+    for (void* q : p2p.opened) cudaIpcCloseMemHandle(q);
     if (local_graph) cudaGraphExecDestroy(local_graph);
     if (finish_graph) cudaGraphExecDestroy(finish_graph);
     if (host_step_graph) cudaGraphExecDestroy(host_step_graph);
@@ -511,6 +536,38 @@ void enqueue_poisson_solve(pecs_ctx* ctx, cudaStream_t s) {
   launch_distribute(ctx->n_constraints, ctx->c_dof.get(), ctx->c_master.get(), ctx->c_weight.get(),
                     ctx->p_solution.get(), s);
 }
+// ---- cross-GPU flags of the sharded step (single-thread kernels, all on the context's streams) ----
+constexpr int kFlagPublished = 8, kFlagStep = 16, kFlagWords = 32;
+// after the assembly kernel: open step n and tell every rank that this rank no longer reads the old densities
+__global__ void p2p_begin_step_kernel(unsigned long long* mine, unsigned long long* const* all, int world, int rank) {
+  const unsigned long long n = mine[kFlagStep] + 1;
+  mine[kFlagStep] = n;
+  __threadfence_system();
+  for (int r = 0; r < world; ++r) *(volatile unsigned long long*)(all[r] + rank) = n;
+}
+// before a backward sweep writes new densities into the other ranks' memory: all of them have finished assembling
+__global__ void p2p_wait_assembled_kernel(const unsigned long long* mine, int world) {
+  const unsigned long long n = mine[kFlagStep];
+  for (int r = 0; r < world; ++r)
+    while (*(const volatile unsigned long long*)(mine + r) < n) {
+    }
+  __threadfence_system();
+}
+// after an owned solve: its backward kernels have completed (stream order), make their peer stores visible, then flag
+__global__ void p2p_publish_kernel(const unsigned long long* mine, unsigned long long* const* all, int world, int species) {
+  __threadfence_system();
+  const unsigned long long n = mine[kFlagStep];
+  for (int r = 0; r < world; ++r) *(volatile unsigned long long*)(all[r] + kFlagPublished + species) = n;
+}
+// before the Poisson assembly reads all four densities
+__global__ void p2p_wait_published_kernel(const unsigned long long* mine) {
+  const unsigned long long n = mine[kFlagStep];
+  for (int s = 0; s < 4; ++s)
+    while (*(const volatile unsigned long long*)(mine + kFlagPublished + s) < n) {
+    }
+  __threadfence_system();
+}
+
 void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s) {
   DeviceDomain& D = ctx->dom[which / 2];
   const int k = which % 2;
@@ -526,8 +583,12 @@ void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s) {
   // S du = r_u - T1 r_q - S u_old ;  u = u_old + du ;  q = Ainv r_q - T2 u
   launch_ell_combine(nu, r + nq, D.system[k].iperm.get(), EllTerm{&red.T1, r, -1.0},
                      EllTerm{&D.system[k].matrix_rows, x + nq, -1.0}, EllTerm{}, red.rtilde.get(), s);
-  D.system[k].solve_increment(red.rtilde.get(), x + nq, s);
+  D.system[k].forward_sweep(red.rtilde.get(), s);
+  if (ctx->p2p.active) p2p_wait_assembled_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.world);
+  D.system[k].backward_sweep(red.rtilde.get(), x + nq, s);
   launch_ell_combine(nq, nullptr, nullptr, EllTerm{&red.Ainv, r, 1.0}, EllTerm{&red.T2, x + nq, -1.0}, EllTerm{}, x, s);
+  if (ctx->p2p.active)
+    p2p_publish_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.all_flags.get(), ctx->p2p.world, which);
 }
 // host != nullptr: every species' solution is downloaded into host[k] on its own stream as soon as its solve is done
 // (the copy engine works while the other solves and the Poisson part still run); *n_copies counts them
@@ -821,6 +882,9 @@ pecs_status pecs_step_local(pecs_ctx* ctx) {
     if (!ctx->local_graph)
       ctx->local_graph = capture_graph(ctx, [&] {
         enqueue_carrier_rhs(ctx, 2, ctx->main);
+        if (ctx->p2p.active)
+          p2p_begin_step_kernel<<<1, 1, 0, ctx->main>>>(ctx->p2p.flags.get(), ctx->p2p.all_flags.get(), ctx->p2p.world,
+                                                        ctx->p2p.rank);
         enqueue_full_solve(ctx);
       });
     PECS_CUDA(cudaGraphLaunch(ctx->local_graph, ctx->main));
@@ -832,10 +896,69 @@ pecs_status pecs_step_finish(pecs_ctx* ctx) {
     PECS_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->finish_graph)
       ctx->finish_graph = capture_graph(ctx, [&] {
+        if (ctx->p2p.active) p2p_wait_published_kernel<<<1, 1, 0, ctx->main>>>(ctx->p2p.flags.get());
         enqueue_poisson_rhs(ctx, ctx->main);
         enqueue_poisson_solve(ctx, ctx->main);
       });
     PECS_CUDA(cudaGraphLaunch(ctx->finish_graph, ctx->main));
+  });
+}
+int64_t pecs_p2p_export(pecs_ctx* ctx, void* blob, int64_t capacity) {
+  const int64_t need = 5 * (int64_t)sizeof(cudaIpcMemHandle_t);
+  if (!ctx || !blob || capacity < need || !ctx->full) return -1;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+  try {
+    if (ctx->p2p.flags.size() == 0) {
+      ctx->p2p.flags.resize(kFlagWords);
+      ctx->p2p.flags.zero();
+    }
+    cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(blob);
+    for (int s = 0; s < 4; ++s) PECS_CUDA(cudaIpcGetMemHandle(&h[s], vector_of(ctx, s, false)));
+    PECS_CUDA(cudaIpcGetMemHandle(&h[4], ctx->p2p.flags.get()));
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return -1;
+  }
+  return need;
+}
+pecs_status pecs_p2p_connect(pecs_ctx* ctx, int32_t rank, int32_t world, const void* blobs) {
+  return guarded([&] {
+    require(ctx != nullptr && blobs != nullptr && ctx->full, "pecs_p2p_connect: bad argument");
+    require((world == 2 || world == 4) && rank >= 0 && rank < world, "pecs_p2p_connect: 2 or 4 ranks");
+    require(ctx->p2p.flags.size() > 0, "pecs_p2p_connect: call pecs_p2p_export first");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    sync_all(ctx);
+    const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(blobs);
+    std::vector<unsigned long long*> flags(world, nullptr);
+    for (DeviceDomain& D : ctx->dom)
+      for (DeviceSystem& S : D.system) S.n_mirror = 0;
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) {
+        flags[r] = ctx->p2p.flags.get();
+        continue;
+      }
+      void* q = nullptr;
+      PECS_CUDA(cudaIpcOpenMemHandle(&q, h[5 * r + 4], cudaIpcMemLazyEnablePeerAccess));
+      ctx->p2p.opened.push_back(q);
+      flags[r] = static_cast<unsigned long long*>(q);
+      for (int s = 0; s < 4; ++s) {
+        if (!(ctx->owned >> s & 1)) continue; // only owners write
+        PECS_CUDA(cudaIpcOpenMemHandle(&q, h[5 * r + s], cudaIpcMemLazyEnablePeerAccess));
+        ctx->p2p.opened.push_back(q);
+        DeviceDomain& D = ctx->dom[s / 2];
+        DeviceSystem& S = D.system[s % 2];
+        require(D.reduced[s % 2].active, "pecs_p2p_connect: needs the Schur-reduced (density) systems");
+        S.mirror[S.n_mirror++] = static_cast<double*>(q) + 8 * (size_t)D.n_cells; // the peer's density block
+      }
+    }
+    ctx->p2p.all_flags.upload(flags);
+    ctx->p2p.rank = rank;
+    ctx->p2p.world = world;
+    ctx->p2p.active = true;
+    // the two halves of the sharded step are re-captured with the flag kernels and the mirrored stores
+    if (ctx->local_graph) PECS_CUDA(cudaGraphExecDestroy(ctx->local_graph));
+    if (ctx->finish_graph) PECS_CUDA(cudaGraphExecDestroy(ctx->finish_graph));
+    ctx->local_graph = ctx->finish_graph = nullptr;
   });
 }
 double* pecs_density_block(pecs_ctx* ctx, int32_t which, int64_t* n_doubles) {

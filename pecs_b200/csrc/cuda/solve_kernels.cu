@@ -276,7 +276,10 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
     __syncthreads();
   stream.run(sm.sv, tile.np, [&](int row, double x) {
     x_perm[tile.p0 + row] = x;
-    solution[t.iperm[tile.p0 + row]] += x; // increment form: the right-hand side was the residual of `solution`
+    const int i = t.iperm[tile.p0 + row];
+    const double v = solution[i] + x; // increment form: the right-hand side was the residual of `solution`
+    solution[i] = v;
+    for (int m = 0; m < t.n_mirror; ++m) t.mirror[m][i] = v; // peer copies (sharded step)
   });
 }
 

@@ -28,6 +28,10 @@ struct SolveTables {
   const int* iperm;    // iperm[position in the elimination order] = unknown
   const double* fwd;
   const double* bwd;
+  // sharded step over several GPUs: the backward sweep also stores every finished solution entry into the other
+  // ranks' copies of the vector (peer memory over NVLink), so the exchange rides on the solve itself
+  double* mirror[3];
+  int n_mirror;
 };
 
 constexpr int kChunkDoubles = 256; // one bulk asynchronous copy: 2 KB of a panel (512 = 4 KB is the other compiled variant)

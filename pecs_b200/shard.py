@@ -11,7 +11,9 @@ Per step every rank assembles the right-hand sides of the subdomains it owns a c
 with their owner), and every rank forms the Poisson right-hand side and solves the Poisson system itself
 (pecs_step_finish): the potential is needed everywhere and a redundant solve is cheaper than a second exchange.
 That broadcast is the only data-path collective: NCCL over NVLink on the context's own stream, so the step stays
-asynchronous.  Strong scaling: the work of ONE step is divided.
+asynchronous.  Strong scaling: the work of ONE step is divided.  GpuEngine.connect_p2p() removes even that
+collective: the backward sweeps then store every finished density straight into the peers' vectors (CUDA IPC peer
+memory over NVLink) while they run, ordered by single-thread flag kernels -- compute and exchange are one kernel.
 
 The driver only needs an ENGINE with step_local(), step_finish(), density(s) -> 1-D torch tensor and
 store_density(s, tensor); GpuEngine wraps a SolarCellProblem (tensors alias the context's device memory),
@@ -66,6 +68,14 @@ class GpuEngine:
     def exchange_context(self):
         return self.torch.cuda.stream(self.stream)  # collectives are ordered on the context's stream
 
+    def connect_p2p(self, dist, rank, world):
+        """replace the NCCL broadcasts by stores into the peers' memory fused into the backward sweeps
+        (pecs_p2p_export / pecs_p2p_connect); one all_gather_object of the IPC handles at setup"""
+        blobs = [None] * world
+        dist.all_gather_object(blobs, self.prob.p2p_export())
+        self.prob.p2p_connect(rank, world, blobs)
+        self.fused_exchange = True
+
 
 class ShardedStepper:
     def __init__(self, engine, dist, rank, world_size):
@@ -73,8 +83,8 @@ class ShardedStepper:
         self.owner = [owner_of(s, world_size) for s in range(N_SPECIES)]
 
     def exchange(self):
-        if self.world == 1:
-            return
+        if self.world == 1 or getattr(self.engine, "fused_exchange", False):
+            return  # nothing to do between the two halves: the solves have already written into the peers' memory
         ctx = self.engine.exchange_context() if hasattr(self.engine, "exchange_context") else _Null()
         with ctx:
             for s in range(N_SPECIES):

@@ -260,6 +260,19 @@ class SolarCellProblem:
     def step_finish(self):
         check(self._lib.pecs_step_finish(self.ctx))
 
+    def p2p_export(self):
+        """CUDA IPC handles of this context's state vectors and flag block (bytes), for the other ranks"""
+        buf = C.create_string_buffer(1024)
+        n = self._lib.pecs_p2p_export(self.ctx, buf, 1024)
+        if n < 0:
+            raise RuntimeError("pecs_p2p_export failed")
+        return buf.raw[:n]
+
+    def p2p_connect(self, rank, world, blobs):
+        """blobs: the p2p_export() bytes of all ranks in rank order; fuses the density exchange into the solves"""
+        joined = b"".join(blobs)
+        check(self._lib.pecs_p2p_connect(self.ctx, int(rank), int(world), C.create_string_buffer(joined, len(joined))))
+
     def density_block(self, which):
         """(device pointer, number of doubles) of the density block of carrier `which`"""
         n = C.c_int64(0)

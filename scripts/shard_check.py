@@ -20,6 +20,9 @@ prob = pecs.SolarCellProblem(pecs.default_input_file(g, 1), device=local)
 prob.set_owned_species(shard.owned_mask(rank, world))
 prob.setup_full_system()
 engine = shard.GpuEngine(prob, local)
+exchange = sys.argv[2] if len(sys.argv) > 2 else "nccl"
+if exchange == "p2p":
+    engine.connect_p2p(dist, rank, world)
 stepper = shard.ShardedStepper(engine, dist, rank, world)
 stepper.step(steps)
 prob.synchronize()
@@ -32,7 +35,8 @@ if rank == 0:
     for s in range(5):
         ref = single.get_solution(s)
         worst = max(worst, np.abs(full[s] - ref).max() / np.abs(ref).max())
-    print(f"world {world} g {g}: sharded vs single-context after {steps} steps: max rel diff {worst:.3e}", flush=True)
+    print(f"world {world} g {g} exchange {exchange}: sharded vs single-context after {steps} steps: max rel diff {worst:.3e}",
+          flush=True)
     assert worst <= 1e-12
     single.close()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,6 +49,6 @@ with torch.cuda.stream(engine.stream):
 b.synchronize()
 ms = sweep.max_over_ranks(a.elapsed_time(b) / 20, dist, local)
 if rank == 0:
-    print(f"world {world} g {g}: {ms:.3f} ms/step sharded ({shard.mode_name(world)})", flush=True)
+    print(f"world {world} g {g} exchange {exchange}: {ms:.3f} ms/step sharded ({shard.mode_name(world)})", flush=True)
 prob.close()
 dist.destroy_process_group()
