@@ -208,6 +208,13 @@ def run_gpu_arm(args):
     solve_bytes = prob.info(sc.INFO_SOLVE_BYTES_PER_STEP)
     n_solve_launches = prob.info(sc.INFO_LAUNCHES_PER_STEP) - 6
     rhs_ms, rhs_launches = prob.time_kernel(0, 20)
+    # the production carrier kernels side by side (0 point-by-point, 1 sum-factorised, 2 streaming = default)
+    rhs_variants = {}
+    for v in ("0", "1", "2"):
+        os.environ["PECS_B200_RHS_KERNEL"] = v
+        rhs_variants[v] = prob.time_kernel(0, 20)[0]
+    del os.environ["PECS_B200_RHS_KERNEL"]
+    prhs_ms = prob.time_kernel(1, 20)[0]
     rhs_bytes = 368 * (prob.n_cells(0) + prob.n_cells(1))
     peak, peak_src = measured_peaks()
     if rank == 0:
@@ -238,9 +245,13 @@ def run_gpu_arm(args):
                                  "ELL entry, each read once) / device time of the solves inside the step graph (step graph "
                                  "minus assembly-only graph, CUDA events); traffic = DRAM bytes read+written by the same "
                                  "kernels in the committed ncu pass (profiles/)"},
-            "rhs_roofline": {"bound": "hbm", "kernel": "carrier_cell_rhs + carrier_boundary_rhs (both subdomains)",
+            "rhs_roofline": {"bound": "hbm", "kernel": "carrier_rhs_stream_kernel: cell + boundary terms of all four "
+                                                       "carriers, both subdomains, one launch, L2 flushed before it",
                              "achieved": rhs_gbs, "peak": peak, "unit": "GB/s", "frac": rhs_gbs / peak,
-                             "algorithmic_bytes_per_launch_group": rhs_bytes, "ms": rhs_ms, "launches": rhs_launches},
+                             "algorithmic_bytes_per_launch_group": rhs_bytes, "ms": rhs_ms, "launches": rhs_launches,
+                             "variants_ms": rhs_variants,
+                             "poisson_rhs_ms": prhs_ms,
+                             "poisson_rhs_gbs": 140 * (prob.n_cells(0) + prob.n_cells(1)) / (prhs_ms * 1e-3) / 1e9},
             "section_ms_per_step": dict(zip(["Assemble semiconductor rhs", "Assemble electrolyte rhs",
                                              "Solve LDG Systems", "Assemble Poisson rhs", "Solve Poisson system"],
                                             [float(x) for x in sect[1:]])),

@@ -257,6 +257,7 @@ struct DeviceDomain {
   int n_cells = 0, n_bcells = 0;
   DeviceBuffer<double> vx, vy;
   DeviceBuffer<int> rt_dof, phi_dof, bcell, bface_id, bnb_cell, bnb_face, brecord;
+  DeviceBuffer<double> nodal_int, gen_int; // static cell integrals of the production kernels
   DeviceBuffer<double> solution[2], rhs[2];
   DeviceSystem system[2];
   // Schur-reduced carriers (host/SchurReduction.hpp): system[k] then factorises S (4 unknowns per cell)
@@ -430,7 +431,17 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
     D.rhs[k].zero();
   }
   D.view = DomainView{n,          D.vx.get(),       D.vy.get(),       D.rt_dof.get(),  D.phi_dof.get(),
-                      D.n_bcells, D.bcell.get(), D.bface_id.get(), D.bnb_cell.get(), D.bnb_face.get(), D.brecord.get()};
+                      D.n_bcells, D.bcell.get(), D.bface_id.get(), D.bnb_cell.get(), D.bnb_face.get(), D.brecord.get(),
+                      nullptr,    nullptr};
+  if (ctx.kind == PECS_KIND_PRODUCTION) {
+    // time-independent cell integrals: int N_a (Poisson charge rows) and int N_a G (illumination, semiconductor only)
+    D.nodal_int.resize(4 * (size_t)n);
+    if (D.prm.gen_scale != 0.0) D.gen_int.resize(4 * (size_t)n);
+    launch_static_cell_integrals(D.view, D.prm, D.nodal_int.get(), D.gen_int.get(), ctx.main);
+    PECS_CUDA(cudaStreamSynchronize(ctx.main));
+    D.view.nodal_int = D.nodal_int.get();
+    D.view.gen_int = D.gen_int.get();
+  }
   // factorise the two fixed carrier matrices
   const NodeLayout layout = carrier_nodes(d);
   for (int k = 0; k < 2; ++k) {

@@ -21,6 +21,10 @@
 // Algorithmic traffic 368 B per cell (both carriers); the kernel is HBM-bound.
 #include "rhs_kernels.cuh"
 
+#include <cstdlib>
+
+#include "device_util.cuh"
+
 #include "../../../include/pecs_b200.h"
 #include "../fe.hpp"
 #include "../test_functions.hpp"
@@ -307,6 +311,298 @@ __global__ void __launch_bounds__(kThreads, 4) carrier_rhs_kernel(const __grid_c
   if (r >= 0) carrier_boundary_terms<KIND>(w.d, w.other_n_cells, w.p, r, w.u1, w.u2, w.o1, w.o2, w.rhs1, w.rhs2);
 }
 
+// ------------------------------------------------------------------------------------------ static cell integrals
+// Time-independent per-cell tables, evaluated once at context creation (launch_static_cell_integrals):
+//   nodal_int[c][a] = sum_q N_a(x_q) JxW_q               (the Poisson charge integral becomes a 4-term dot product)
+//   gen_int[c][a]   = sum_q N_a(x_q) G(x_q) JxW_q        (Generation::value, reference Generation.cpp:29-44: the nine
+//                                                          exp() per cell and step of SolarCell.cpp:1160-1165 leave the
+//                                                          hot loop; same quadrature, summed ahead of time)
+__global__ void static_cell_integrals_kernel(DomainView d, RhsParams p, double* __restrict__ nodal_int,
+                                             double* __restrict__ gen_int) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.n_cells) return;
+  const fe::CellVerts v = load_verts(d, c);
+  double m[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int qy = 0; qy < 3; ++qy)
+#pragma unroll
+    for (int qx = 0; qx < 3; ++qx) {
+      const double xi = fe::gauss_x(qx), eta = fe::gauss_x(qy), w = fe::gauss_w(qx) * fe::gauss_w(qy);
+      const fe::Jac j = fe::jacobian(v, xi, eta);
+      double N[4];
+      fe::shape(xi, eta, N);
+      const double JxW = j.det * w;
+      double gen = 0.0;
+      if (gen_int) {
+        const double y = v.y[0] * N[0] + v.y[1] * N[1] + v.y[2] * N[2] + v.y[3] * N[3];
+        gen = p.gen_scale * exp(p.gen_alpha * (y - p.gen_location));
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        m[a] += N[a] * JxW;
+        g[a] += N[a] * (gen * JxW);
+      }
+    }
+  store4(nodal_int + 4 * (size_t)c, m);
+  if (gen_int) store4(gen_int + 4 * (size_t)c, g);
+}
+
+// ------------------------------------------------------------------------------------------ production carrier kernel
+// 256-bit global accesses (sm_100a): one instruction per 4-vector of nodal values
+__device__ __forceinline__ void store4_256(double* p, const double v[4]) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ void load4_256(const double* p, double v[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Cell terms of both carriers of one production cell from values in registers, sum-factorised over the 3 x 3 tensor
+// Gauss rule: with N_a = L_ax(xi) L_ay(eta), XA_j = w_j x_xi(eta_j), XB_i = w_i x_eta(xi_i), HX_i = w_i Dhat_x(xi_i),
+// HY_j = w_j Dhat_y(eta_j) (and Y likewise)
+//     JxW_ij = XA_j YB_i - XB_i YA_j,   JxW_ij eps E_x = XA_j HX_i + XB_i HY_j,   JxW_ij eps E_y = YA_j HX_i + YB_i HY_j
+// are shared by both carriers; per carrier the three integrands rho {JxW, Ex, Ey} are contracted first along xi, then
+// along eta: ~420 fp64 operations per cell instead of ~800 for the point-by-point form, no division, no exp.
+__device__ __forceinline__ void production_cell_terms(const double vx[4], const double vy[4], const double r1[4],
+                                                      const double r2[4], const double Xf[4], const double gen[4],
+                                                      double inv_dt, double s1, double s2, double jx1[4], double jy1[4],
+                                                      double rh1[4], double jx2[4], double jy2[4], double rh2[4]) {
+  const double ax = vx[1] - vx[0], bx = vx[3] - vx[2], cx = vx[2] - vx[0], dx = vx[3] - vx[1];
+  const double ay = vy[1] - vy[0], by = vy[3] - vy[2], cy = vy[2] - vy[0], dy = vy[3] - vy[1];
+  double XA[3], YA[3], XB[3], YB[3], HX[3], HY[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double l0w = (1.0 - fe::gauss_x(k)) * fe::gauss_w(k), l1w = fe::gauss_x(k) * fe::gauss_w(k);
+    XA[k] = ax * l0w + bx * l1w;
+    YA[k] = ay * l0w + by * l1w;
+    XB[k] = cx * l0w + dx * l1w;
+    YB[k] = cy * l0w + dy * l1w;
+    HX[k] = Xf[0] * l0w + Xf[1] * l1w;
+    HY[k] = Xf[2] * l0w + Xf[3] * l1w;
+  }
+  double JxW[3][3], Ex[3][3], Ey[3][3]; // [j][i]
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      JxW[j][i] = XA[j] * YB[i] - XB[i] * YA[j];
+      Ex[j][i] = XA[j] * HX[i] + XB[i] * HY[j];
+      Ey[j][i] = YA[j] * HX[i] + YB[i] * HY[j];
+    }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double* r = k == 0 ? r1 : r2;
+    double* jx = k == 0 ? jx1 : jx2;
+    double* jy = k == 0 ? jy1 : jy2;
+    double* rh = k == 0 ? rh1 : rh2;
+    const double s = k == 0 ? s1 : s2;
+    double bot[3], top[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double l0 = 1.0 - fe::gauss_x(i), l1 = fe::gauss_x(i);
+      bot[i] = r[0] * l0 + r[1] * l1;
+      top[i] = r[2] * l0 + r[3] * l1;
+    }
+    double ax_[4] = {0, 0, 0, 0}, ay_[4] = {0, 0, 0, 0}, am[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double m0 = 1.0 - fe::gauss_x(j), m1 = fe::gauss_x(j);
+      double sm0 = 0, sm1 = 0, sx0 = 0, sx1 = 0, sy0 = 0, sy1 = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double rho = bot[i] * m0 + top[i] * m1;
+        const double rho0 = rho * (1.0 - fe::gauss_x(i)), rho1 = rho * fe::gauss_x(i);
+        sm0 += rho0 * JxW[j][i];
+        sm1 += rho1 * JxW[j][i];
+        sx0 += rho0 * Ex[j][i];
+        sx1 += rho1 * Ex[j][i];
+        sy0 += rho0 * Ey[j][i];
+        sy1 += rho1 * Ey[j][i];
+      }
+      am[0] += m0 * sm0;
+      am[1] += m0 * sm1;
+      am[2] += m1 * sm0;
+      am[3] += m1 * sm1;
+      ax_[0] += m0 * sx0;
+      ax_[1] += m0 * sx1;
+      ax_[2] += m1 * sx0;
+      ax_[3] += m1 * sx1;
+      ay_[0] += m0 * sy0;
+      ay_[1] += m0 * sy1;
+      ay_[2] += m1 * sy0;
+      ay_[3] += m1 * sy1;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      rh[a] = am[a] * inv_dt + gen[a];
+      jx[a] = s * ax_[a];
+      jy[a] = s * ay_[a];
+    }
+  }
+}
+
+// Streaming production kernel.  A block owns tiles of kThreads consecutive cells (both subdomains form one tile
+// sequence) and walks them with stride gridDim.x; the grid is one resident wave.  Every thread keeps the inputs of
+// its NEXT cell in flight while it computes the current one: vertices, the two density 4-vectors, the generation
+// integrals and the four gathered Poisson fluxes go global -> shared with cp.async (LDGSTS) into the thread's own slot
+// of a two-stage ring, so no barrier is needed and the prefetch costs no registers.  The flux indices of the cell
+// after next are fetched one iteration earlier with ordinary loads, which removes the dependent gather from the
+// critical path.  Output: six 256-bit stores per cell.
+constexpr int kStageDoubles = 24; // per thread and stage: 8 vertices + 8 densities + 4 generation + 4 fluxes
+constexpr int kStreamSmemBytes = 2 * kStageDoubles * kThreads * (int)sizeof(double);
+
+struct TileCell {
+  int sel; // pass
+  int c;   // cell, -1: none
+};
+__device__ __forceinline__ TileCell locate(const CarrierPassPair& pp, int tile, int tiles_a, int tiles_total) {
+  TileCell t;
+  t.sel = tile < tiles_a ? 0 : 1;
+  const int c = (tile - (t.sel ? tiles_a : 0)) * kThreads + (int)threadIdx.x;
+  t.c = (tile < tiles_total && c < pp.pass[t.sel].d.n_cells) ? c : -1;
+  return t;
+}
+__device__ __forceinline__ void load_flux_index(const CarrierPassPair& pp, TileCell t, int idx[4]) {
+  if (t.c < 0) return;
+  const DomainView& d = pp.pass[t.sel].d;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) idx[f] = __ldg(d.rt_dof + (size_t)f * d.n_cells + t.c);
+}
+// stage layout (doubles, T = kThreads): [0,8T) vertices SoA | [8T,16T) densities as 16-byte pieces [4][T] |
+// [16T,20T) generation [2][T] 16-byte pieces | [20T,24T) fluxes SoA
+__device__ __forceinline__ void issue_cell(const CarrierPassPair& pp, TileCell t, const int idx[4], const double* X,
+                                           double* stage) {
+  if (t.c < 0) return;
+  const CarrierPass& w = pp.pass[t.sel];
+  const size_t n = (size_t)w.d.n_cells;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    cp_async8(stage + a * kThreads + tid, w.d.vx + (size_t)a * n + t.c);
+    cp_async8(stage + (4 + a) * kThreads + tid, w.d.vy + (size_t)a * n + t.c);
+  }
+  const double* u1 = w.u1 + 8 * n + 4 * (size_t)t.c;
+  const double* u2 = w.u2 + 8 * n + 4 * (size_t)t.c;
+  double* rs = stage + 8 * kThreads;
+  cp_async16(rs + 2 * (0 * kThreads + tid), u1);
+  cp_async16(rs + 2 * (1 * kThreads + tid), u1 + 2);
+  cp_async16(rs + 2 * (2 * kThreads + tid), u2);
+  cp_async16(rs + 2 * (3 * kThreads + tid), u2 + 2);
+  if (w.d.gen_int) {
+    double* gs = stage + 16 * kThreads;
+    cp_async16(gs + 2 * (0 * kThreads + tid), w.d.gen_int + 4 * (size_t)t.c);
+    cp_async16(gs + 2 * (1 * kThreads + tid), w.d.gen_int + 4 * (size_t)t.c + 2);
+  }
+#pragma unroll
+  for (int f = 0; f < 4; ++f) cp_async8(stage + (20 + f) * kThreads + tid, X + idx[f]);
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+    carrier_rhs_stream_kernel(const __grid_constant__ CarrierPassPair pp, int tiles_a, int tiles_total,
+                              const double* __restrict__ X) {
+  extern __shared__ __align__(16) double ring[];
+  const int tid = threadIdx.x;
+  int tile = blockIdx.x;
+  TileCell cur = locate(pp, tile, tiles_a, tiles_total);
+  TileCell nxt = locate(pp, tile + (int)gridDim.x, tiles_a, tiles_total);
+  int idx[4] = {0, 0, 0, 0}, nidx[4] = {0, 0, 0, 0};
+  load_flux_index(pp, cur, idx);
+  load_flux_index(pp, nxt, nidx);
+  issue_cell(pp, cur, idx, X, ring);
+  cp_async_commit();
+  int s = 0;
+  for (; tile < tiles_total; tile += (int)gridDim.x) {
+    double* stage = ring + s * kStageDoubles * kThreads;
+    issue_cell(pp, nxt, nidx, X, ring + (s ^ 1) * kStageDoubles * kThreads);
+    cp_async_commit();
+    const TileCell after = locate(pp, tile + 2 * (int)gridDim.x, tiles_a, tiles_total);
+    load_flux_index(pp, after, nidx); // consumed by the next iteration's issue_cell
+    int record = -1;
+    if (cur.c >= 0 && pp.pass[cur.sel].d.brecord) record = __ldg(pp.pass[cur.sel].d.brecord + cur.c);
+    cp_async_wait<1>(); // everything but the group just committed has landed: the current cell is in shared memory
+    if (cur.c >= 0) {
+      const CarrierPass& w = pp.pass[cur.sel];
+      const size_t n = (size_t)w.d.n_cells;
+      double vx[4], vy[4], r1[4], r2[4], Xf[4], gen[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        vx[a] = stage[a * kThreads + tid];
+        vy[a] = stage[(4 + a) * kThreads + tid];
+        Xf[a] = stage[(20 + a) * kThreads + tid];
+      }
+      const double2* rs = reinterpret_cast<const double2*>(stage + 8 * kThreads);
+      const double2 p0 = rs[0 * kThreads + tid], p1 = rs[1 * kThreads + tid], p2 = rs[2 * kThreads + tid],
+                    p3 = rs[3 * kThreads + tid];
+      r1[0] = p0.x, r1[1] = p0.y, r1[2] = p1.x, r1[3] = p1.y;
+      r2[0] = p2.x, r2[1] = p2.y, r2[2] = p3.x, r2[3] = p3.y;
+      if (w.d.gen_int) {
+        const double2* gs = reinterpret_cast<const double2*>(stage + 16 * kThreads);
+        const double2 g0 = gs[0 * kThreads + tid], g1 = gs[1 * kThreads + tid];
+        gen[0] = g0.x, gen[1] = g0.y, gen[2] = g1.x, gen[3] = g1.y;
+      }
+      double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
+      production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps,
+                            jx1, jy1, rh1, jx2, jy2, rh2);
+      const size_t o = 4 * (size_t)cur.c;
+      store4_256(w.rhs1 + o, jx1);
+      store4_256(w.rhs1 + 4 * n + o, jy1);
+      store4_256(w.rhs1 + 8 * n + o, rh1);
+      store4_256(w.rhs2 + o, jx2);
+      store4_256(w.rhs2 + 4 * n + o, jy2);
+      store4_256(w.rhs2 + 8 * n + o, rh2);
+      if (record >= 0)
+        carrier_boundary_terms<PECS_KIND_PRODUCTION>(w.d, w.other_n_cells, w.p, record, w.u1, w.u2, w.o1, w.o2, w.rhs1,
+                                                     w.rhs2);
+    }
+    cur = nxt;
+    nxt = after;
+    s ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
+// One-thread-per-cell production kernel on the sum-factorised cell terms (no staging): the variant for meshes too
+// small to fill a resident wave, and the A/B partner of the streaming kernel (PECS_B200_RHS_KERNEL=1).
+__global__ void __launch_bounds__(kThreads, 4)
+    carrier_rhs_direct_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a, const double* __restrict__ X) {
+  const bool first = (int)blockIdx.x < blocks_a;
+  const CarrierPass& w = pp.pass[first ? 0 : 1];
+  const int c = ((int)blockIdx.x - (first ? 0 : blocks_a)) * blockDim.x + threadIdx.x;
+  if (c >= w.d.n_cells) return;
+  const size_t n = (size_t)w.d.n_cells;
+  double vx[4], vy[4], r1[4], r2[4], Xf[4], gen[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    vx[a] = __ldg(w.d.vx + (size_t)a * n + c);
+    vy[a] = __ldg(w.d.vy + (size_t)a * n + c);
+    Xf[a] = __ldg(X + __ldg(w.d.rt_dof + (size_t)a * n + c));
+  }
+  load4_256(w.u1 + 8 * n + 4 * (size_t)c, r1);
+  load4_256(w.u2 + 8 * n + 4 * (size_t)c, r2);
+  if (w.d.gen_int) load4_256(w.d.gen_int + 4 * (size_t)c, gen);
+  double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
+  production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
+                        jy1, rh1, jx2, jy2, rh2);
+  const size_t o = 4 * (size_t)c;
+  store4_256(w.rhs1 + o, jx1);
+  store4_256(w.rhs1 + 4 * n + o, jy1);
+  store4_256(w.rhs1 + 8 * n + o, rh1);
+  store4_256(w.rhs2 + o, jx2);
+  store4_256(w.rhs2 + 4 * n + o, jy2);
+  store4_256(w.rhs2 + 8 * n + o, rh2);
+  const int r = w.d.brecord ? w.d.brecord[c] : -1;
+  if (r >= 0)
+    carrier_boundary_terms<PECS_KIND_PRODUCTION>(w.d, w.other_n_cells, w.p, r, w.u1, w.u2, w.o1, w.o2, w.rhs1, w.rhs2);
+}
+
 // ------------------------------------------------------------------------------------------ Poisson cells
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a,
@@ -320,6 +616,19 @@ __global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(const __grid
   const int c = ((int)blockIdx.x - (first ? 0 : blocks_a)) * blockDim.x + threadIdx.x;
   if (c >= d.n_cells) return;
   const size_t n = (size_t)d.n_cells;
+  if (KIND == PECS_KIND_PRODUCTION && d.nodal_int) {
+    // -int (doping + z1 rho1 + z2 rho2) = -sum_a m_a (doping + z1 r1_a + z2 r2_a) with the static m_a = int N_a:
+    // the same quadrature sum, reordered; 108 B per cell
+    double r1[4], r2[4], m[4];
+    load4_256(u1 + 8 * n + 4 * (size_t)c, r1);
+    load4_256(u2 + 8 * n + 4 * (size_t)c, r2);
+    load4_256(d.nodal_int + 4 * (size_t)c, m);
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) acc -= m[a] * (p.doping + (p.charge1 * r1[a] + p.charge2 * r2[a]));
+    poisson_rhs[d.phi_dof[c]] = acc;
+    return;
+  }
   const fe::CellVerts v = load_verts(d, c);
   double r1[4] = {0, 0, 0, 0}, r2[4] = {0, 0, 0, 0};
   if (KIND != PECS_KIND_TEST_STEADY) load4(u1 + 8 * n + 4 * (size_t)c, r1);
@@ -415,10 +724,48 @@ inline int blocks_for(int n) { return (n + kThreads - 1) / kThreads; }
     default: { CALL(PECS_KIND_TEST_DD_POISSON); break; }                 \
   }
 
+void launch_static_cell_integrals(const DomainView& d, const RhsParams& p, double* nodal_int, double* gen_int,
+                                  cudaStream_t s) {
+  if (d.n_cells == 0) return;
+  static_cell_integrals_kernel<<<blocks_for(d.n_cells), kThreads, 0, s>>>(d, p, nodal_int, gen_int);
+}
+
+int carrier_rhs_variant() {
+  // read at every launch (a graph freezes the choice at capture): tests flip it between calls of one process
+  const char* e = std::getenv("PECS_B200_RHS_KERNEL");
+  return e && *e ? std::atoi(e) : 2;
+}
+
 void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, const double* X, cudaStream_t s) {
   const int blocks_a = blocks_for(a.d.n_cells), blocks_b = blocks_for(b.d.n_cells);
   if (blocks_a + blocks_b == 0) return;
   const CarrierPassPair pp{{a, b}};
+  // production: the sum-factorised kernels on the static cell tables (variant 0 keeps the point-by-point kernel that
+  // also serves the manufactured problems; it is the parity partner of the other two in tests/test_gpu_extra.py)
+  const int variant = (kind == PECS_KIND_PRODUCTION && a.d.nodal_int) ? carrier_rhs_variant() : 0;
+  if (variant == 1) {
+    carrier_rhs_direct_kernel<<<blocks_a + blocks_b, kThreads, 0, s>>>(pp, blocks_a, X);
+    return;
+  }
+  if (variant >= 2) {
+    static int wave_of[64] = {}; // blocks of one resident wave, per device
+    int dev = 0;
+    PECS_CUDA(cudaGetDevice(&dev));
+    int& wave = wave_of[dev & 63];
+    if (wave == 0) {
+      PECS_CUDA(cudaFuncSetAttribute(carrier_rhs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
+      int sms = 0, per_sm = 0;
+      PECS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      PECS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, carrier_rhs_stream_kernel, kThreads, kStreamSmemBytes));
+      wave = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int tiles = blocks_a + blocks_b;
+    int grid = tiles < wave ? tiles : wave;
+    if (const char* e = std::getenv("PECS_B200_RHS_GRID")) // tests: force several tiles per block on small meshes
+      if (std::atoi(e) > 0 && std::atoi(e) < grid) grid = std::atoi(e);
+    carrier_rhs_stream_kernel<<<grid, kThreads, kStreamSmemBytes, s>>>(pp, blocks_a, tiles, X);
+    return;
+  }
 #define CALL(K) carrier_rhs_kernel<K><<<blocks_a + blocks_b, kThreads, 0, s>>>(pp, blocks_a, X)
   PECS_DISPATCH_KIND(kind, CALL)
 #undef CALL

@@ -20,6 +20,9 @@ struct DomainView {
   const int* bnb_cell;   // [n_bcells] matched cell of the other subdomain across the interface (or -1)
   const int* bnb_face;   // [n_bcells] its face number
   const int* brecord;    // [n_cells] index of the cell's boundary record, -1 for interior cells
+  // static cell integrals (production; launch_static_cell_integrals), NULL when absent
+  const double* nodal_int; // [n_cells][4] int N_a
+  const double* gen_int;   // [n_cells][4] int N_a G   (semiconductor under illumination only)
 };
 
 // scalars of one subdomain pass (see include/pecs_b200.h PECS_P_*)
@@ -47,6 +50,13 @@ struct CarrierPass {
   const double *o1, *o2;   // the other subdomain's carriers: traces across the interface
   double *rhs1, *rhs2;
 };
+
+// one-time: the static per-cell integrals the production kernels read (gen_int may be NULL: dark, or electrolyte)
+void launch_static_cell_integrals(const DomainView& d, const RhsParams& p, double* nodal_int, double* gen_int,
+                                  cudaStream_t s);
+// which production carrier kernel launch_carrier_rhs uses: 0 point-by-point (v7), 1 sum-factorised one thread per cell,
+// 2 (default) sum-factorised streaming kernel; PECS_B200_RHS_KERNEL overrides
+int carrier_rhs_variant();
 
 // rhs_c = M u_c + cell terms + boundary / interface / Schottky face terms for both carriers of both passes, one launch
 // (SURVEY K1-K3); X = Poisson solution (electric field)

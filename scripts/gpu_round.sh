@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU-box call: GPU tests, bench line, ncu launch list of one step, ncu --set full of the carrier RHS kernel.
+# Usage (from the repo root, under gpurun): bash scripts/gpu_round.sh <tag> [skip-tests]
+tag=${1:-vX}
+mkdir -p gpurun_out
+if [ "$2" != "skip-tests" ]; then
+  timeout 1200 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/pytest_$tag.log 2>&1
+  echo "pytest exit $?" >> gpurun_out/pytest_$tag.log
+  tail -15 gpurun_out/pytest_$tag.log
+fi
+timeout 600 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+tail -c 3000 gpurun_out/bench_$tag.json
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv \
+  --log-file gpurun_out/launches_$tag.csv python scripts/profile_step.py --steps 2 > gpurun_out/ncu_launches_$tag.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:carrier_rhs -c 2 -o gpurun_out/rhs_$tag -f \
+  python scripts/profile_step.py --steps 2 > gpurun_out/ncu_rhs_$tag.log 2>&1
+ncu -i gpurun_out/rhs_$tag.ncu-rep --page raw --csv > gpurun_out/rhs_${tag}_raw.csv 2>/dev/null
+ls -la gpurun_out | tail -12

@@ -131,3 +131,46 @@ def test_other_configurations_match_oracle(case):
     xg, xo = prob.get_solution(pecs.POISSON), o.solution(4)
     assert rel_err(xg[n_rt:], xo[n_rt:]) <= 1e-9 and rel_err(xg[:n_rt], xo[:n_rt]) <= 1e-9
     prob.close()
+
+
+@pytest.mark.parametrize("g,l,overrides", [(4, 1, {}), (3, 2, {"mesh__radius_one": 0.2})])
+def test_production_rhs_kernels_agree(g, l, overrides, monkeypatch):
+    """The three production carrier kernels (0: point-by-point, 1: sum-factorised, 2: sum-factorised streaming kernel,
+    also with several tiles per block) and the static-table Poisson rows, from one perturbed state: each within 1e-12 of
+    the oracle, the sum-factorised pair bit-identical to each other."""
+    from helpers import SPECIES, block_rel_err, make_oracle, perturbed
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **overrides))
+    prob.setup_full_system()
+    o = make_oracle(prob, True)
+    o.project_initial_conditions()
+    o.assemble_Poisson_rhs()
+    o.solve_Poisson()
+    for s in SPECIES:
+        u = perturbed(o.solution(s), 4321 + s)
+        prob.set_solution(s, u)
+        o.set_vector(s, 0, u)
+    X = perturbed(o.solution(4), 77)
+    prob.set_solution(pecs.POISSON, X)
+    o.set_vector(4, 0, X)
+    o.assemble_semiconductor_rhs()
+    o.assemble_electrolyte_rhs()
+    o.assemble_Poisson_rhs()
+    got = {}
+    for name, env in {"points": {"PECS_B200_RHS_KERNEL": "0"}, "direct": {"PECS_B200_RHS_KERNEL": "1"},
+                      "stream": {"PECS_B200_RHS_KERNEL": "2"},
+                      "stream3": {"PECS_B200_RHS_KERNEL": "2", "PECS_B200_RHS_GRID": "3"}}.items():
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for s in SPECIES:
+            prob.set_rhs(s, np.full(prob.n_dofs(s), np.nan))
+        prob.assemble_semiconductor_rhs()
+        prob.assemble_electrolyte_rhs()
+        got[name] = [prob.get_rhs(s) for s in SPECIES]
+        for s in SPECIES:
+            assert block_rel_err(got[name][s], o.rhs(s)) <= 1e-12, f"{name}: species {s}"
+        monkeypatch.delenv("PECS_B200_RHS_GRID", raising=False)
+    for s in SPECIES:
+        assert np.array_equal(got["direct"][s], got["stream"][s]) and np.array_equal(got["stream"][s], got["stream3"][s])
+    prob.assemble_Poisson_rhs()
+    assert rel_err(prob.get_rhs(pecs.POISSON), o.rhs(4)) <= 1e-12
+    prob.close()
