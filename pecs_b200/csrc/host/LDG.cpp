@@ -1,6 +1,9 @@
 // LDG.cpp -- see LDG.hpp.
 #include "LDG.hpp"
 
+#include <omp.h>
+
+#include <algorithm>
 #include <cmath>
 
 #include "../fe.hpp"
@@ -109,18 +112,22 @@ void LDG::assemble_system_matrices(const MeshTables& mesh, int dirichlet_id, dou
                                    double transient_or_steady, double penalty, CsrMatrix& matrix_1,
                                    CsrMatrix& matrix_2) const {
   CarrierDofs dofs{mesh.n_cells};
-  TripletList t1(dofs.n_dofs()), t2(dofs.n_dofs());
-  t1.reserve(240 * (size_t)mesh.n_cells);
-  t2.reserve(240 * (size_t)mesh.n_cells);
-  auto both = [&](int i, int j, double v) {
-    t1.add(i, j, v);
-    t2.add(i, j, v);
-  };
+  // one chunk of triplets per thread over a contiguous range of cells; compressed in chunk order, so the result does
+  // not depend on the number of threads (reference LDG.cpp:283-426 assembles the flux terms sequentially)
+  const int n_chunks = std::max(1, std::min(omp_get_max_threads(), mesh.n_cells / 64));
+  pecs::PairedTripletChunks chunks(dofs.n_dofs(), n_chunks);
   const double beta[2] = {1.0 / std::sqrt(2.0), 1.0 / std::sqrt(2.0)};
   const double mass_scale = transient_or_steady / delta_t;
 
+#pragma omp parallel for schedule(static, 1) num_threads(n_chunks)
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+  pecs::PairedTripletChunks::Chunk& out = chunks.chunk(chunk);
+  const int c_begin = (int)((long long)mesh.n_cells * chunk / n_chunks);
+  const int c_end = (int)((long long)mesh.n_cells * (chunk + 1) / n_chunks);
+  out.reserve(250 * (size_t)(c_end - c_begin));
+  auto both = [&](int i, int j, double v) { out.add(i, j, v, v); };
   double M[4][4], Dx[4][4], Dy[4][4];
-  for (int c = 0; c < mesh.n_cells; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     const CellVerts v = load_verts(mesh, c);
     const double h = pecs::fe::cell_diameter(v);
     cell_tables(v, M, Dx, Dy);
@@ -128,10 +135,8 @@ void LDG::assemble_system_matrices(const MeshTables& mesh, int dirichlet_id, dou
       for (int b = 0; b < 4; ++b) {
         const int ja = dofs.global(c, a), ka = dofs.global(c, 4 + a), ua = dofs.global(c, 8 + a);
         const int jb = dofs.global(c, b), kb = dofs.global(c, 4 + b), ub = dofs.global(c, 8 + b);
-        t1.add(ja, jb, M[a][b] / mu1);
-        t1.add(ka, kb, M[a][b] / mu1);
-        t2.add(ja, jb, M[a][b] / mu2);
-        t2.add(ka, kb, M[a][b] / mu2);
+        out.add(ja, jb, M[a][b] / mu1, M[a][b] / mu2);
+        out.add(ka, kb, M[a][b] / mu1, M[a][b] / mu2);
         both(ja, ub, -Dx[a][b]); // -(div p) u
         both(ka, ub, -Dy[a][b]);
         both(ua, jb, -Dx[a][b]); // -grad v . q
@@ -205,8 +210,8 @@ void LDG::assemble_system_matrices(const MeshTables& mesh, int dirichlet_id, dou
       }
     }
   }
-  matrix_1 = t1.compress(true);
-  matrix_2 = t2.compress(true);
+  } // chunk
+  chunks.compress(true, matrix_1, matrix_2);
 }
 
 } // namespace LDG_System
