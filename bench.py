@@ -227,7 +227,7 @@ def run_gpu_arm(args):
             "config": {"workload": workload_name(g, l), "parallelism": "1 context per GPU, one applied bias per rank"
                        if world > 1 else "single context",
                        "l2": "inputs larger than L2: every step streams the factor tables "
-                             f"({factor_bytes / 1e9:.1f} GB) once; the isolated RHS timing flushes L2 (256 MB memset)",
+                             f"({factor_bytes / 1e9:.1f} GB) once; the isolated RHS timing flushes L2 (256 MB memset + 256 MB read sweep, so evictions are clean)",
                        "setup_seconds": t_setup},
             "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes,

@@ -203,6 +203,22 @@ pecs_status pecs_step_host(pecs_ctx* ctx, int32_t n_steps, double* const states[
 void* pecs_host_alloc(uint64_t bytes);
 void pecs_host_free(void* p);
 
+/* ---- output path: what the reference's print_results does per time stamp (source/SolarCell.cpp:1826-1858):
+ * LDG::output_rescaled_results (source/LDG.cpp:1195-1232) and MixedFEM::output_rescaled_results
+ * (source/MixedFEM.cpp:297-320) run DataOut::build_patches over every cell and PostProcessor
+ * (source/PostProcessor.cpp:80-123) rescales the values to physical units.  Here the rescaled patch values (one patch of
+ * 4 vertices per cell, deal.II vertex order) are produced on the device in the layout of the VTU data arrays and copied
+ * to the caller's buffers on a separate stream, so the time loop does not stall on output.
+ *   host[0] semiconductor pair, host[1] electrolyte pair: n = cells, doubles
+ *       current_1 [4n][3] | density_1 [4n] | current_2 [4n][3] | density_2 [4n]        (pecs_output_doubles = 32 n)
+ *   host[2] Poisson: field [4n][3] | potential [4n]                                     (16 n)
+ * scales = {potential, field, density (unused, as in the reference), current}.  NULL entries of host are skipped.
+ * pecs_output_snapshot returns after enqueueing: the values are those of the state after the steps enqueued so far;
+ * the buffers (page-locked: pecs_host_alloc, for the copy to be asynchronous) are complete after pecs_output_wait. */
+int64_t pecs_output_doubles(const pecs_ctx* ctx, int32_t which);
+pecs_status pecs_output_snapshot(pecs_ctx* ctx, const double scales[4], double* const host[3]);
+pecs_status pecs_output_wait(pecs_ctx* ctx);
+
 /* measurement support for bench.py: run n_steps and report device times measured with CUDA events on the
  * context's own streams.  ms[0] = whole region.  sectioned == 0: n_steps replays of the step graph; sectioned == 1:
  * ms[1..5] = the reference's five TimerOutput sections summed over the steps, launched one by one

@@ -34,6 +34,20 @@ pecs_status pecs_solarcell_setup_test_host(pecs_solarcell* p, int32_t kind, int3
 pecs_status pecs_solarcell_setup_test(pecs_solarcell* p, int32_t kind, int32_t n_refine);
 /* the reference's public entry points */
 pecs_status pecs_solarcell_run_full_system(pecs_solarcell* p);
+/* output path: where print_results / run_full_system put the .vtu files (default "."), whether run_full_system writes
+ * them at every time stamp (default yes, as the reference does: source/SolarCell.cpp:2037-2087) */
+pecs_status pecs_solarcell_set_output(pecs_solarcell* p, const char* directory, int32_t write_output);
+/* print_results(time_step_number) of the reference (source/SolarCell.cpp:1826-1858): Poisson-NNN.vtu,
+ * Semiconductor-NNN.vtu, Electrolyte-NNN.vtu, rescaled to physical units.  Returns once the snapshot is enqueued; the
+ * files are complete after pecs_solarcell_finish_output. */
+pecs_status pecs_solarcell_print_results(pecs_solarcell* p, int32_t time_step_number);
+pecs_status pecs_solarcell_finish_output(pecs_solarcell* p);
+/* host half of the output path alone (no device): write the file of mesh `which` (0 Semiconductor-, 1 Electrolyte-,
+ * 2 Poisson-) for caller-provided patch values in the pecs_output_snapshot layout */
+pecs_status pecs_solarcell_write_patches(pecs_solarcell* p, int32_t which, const double* patches, int32_t time_step_number,
+                                         const char* directory);
+/* the four PostProcessor scales {potential, field, density, current} (reference source/PostProcessor.cpp:14-18) */
+pecs_status pecs_solarcell_output_scales(const pecs_solarcell* p, double scales[4]);
 /* test_steady_state / test_transient / test_DD_Poisson at one refinement level; errors[4] = {u, J, Phi, D} */
 pecs_status pecs_solarcell_run_test(pecs_solarcell* p, int32_t kind, int32_t n_refine, double errors[4]);
 

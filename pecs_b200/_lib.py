@@ -54,6 +54,9 @@ SIGNATURES = {
     "pecs_step_host": (C.c_int, [VOIDP, C.c_int32, C.POINTER(c_double_p)]),
     "pecs_host_alloc": (VOIDP, [C.c_uint64]),
     "pecs_host_free": (None, [VOIDP]),
+    "pecs_output_doubles": (C.c_int64, [VOIDP, C.c_int32]),
+    "pecs_output_snapshot": (C.c_int, [VOIDP, c_double_p, C.POINTER(c_double_p)]),
+    "pecs_output_wait": (C.c_int, [VOIDP]),
     "pecs_step_timed": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p]),
     "pecs_time_kernel": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p, c_int32_p]),
     "pecs_get_info": (C.c_int64, [VOIDP, C.c_int32]),
@@ -66,6 +69,11 @@ SIGNATURES = {
     "pecs_solarcell_setup_test_host": (C.c_int, [VOIDP, C.c_int32, C.c_int32]),
     "pecs_solarcell_setup_test": (C.c_int, [VOIDP, C.c_int32, C.c_int32]),
     "pecs_solarcell_run_full_system": (C.c_int, [VOIDP]),
+    "pecs_solarcell_set_output": (C.c_int, [VOIDP, C.c_char_p, C.c_int32]),
+    "pecs_solarcell_print_results": (C.c_int, [VOIDP, C.c_int32]),
+    "pecs_solarcell_finish_output": (C.c_int, [VOIDP]),
+    "pecs_solarcell_write_patches": (C.c_int, [VOIDP, C.c_int32, c_double_p, C.c_int32, C.c_char_p]),
+    "pecs_solarcell_output_scales": (C.c_int, [VOIDP, c_double_p]),
     "pecs_solarcell_run_test": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p]),
     "pecs_solarcell_ctx": (VOIDP, [VOIDP]),
     "pecs_solarcell_get_params": (C.c_int, [VOIDP, c_double_p]),

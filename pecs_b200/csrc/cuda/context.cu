@@ -26,6 +26,7 @@
 #include "device_util.cuh"
 #include "factor_device.cuh"
 #include "../host/SchurReduction.hpp"
+#include "output_kernels.cuh"
 #include "rhs_kernels.cuh"
 #include "schur_kernels.cuh"
 #include "solve_kernels.cuh"
@@ -285,6 +286,13 @@ struct pecs_ctx {
   // Poisson
   int n_rt = 0, n_pcells = 0, n_constraints = 0;
   DeviceBuffer<double> p_solution, p_rhs, p_static;
+  DeviceBuffer<double> p_vx, p_vy; // [4][n_pcells]
+  DeviceBuffer<int> p_face_dof;    // [n_pcells][4]
+  // output path (pecs_output_snapshot): rescaled patch values of the three output files, device side
+  DeviceBuffer<double> patches[3];
+  cudaStream_t out_stream = nullptr;
+  cudaEvent_t patches_ready = nullptr, patches_copied = nullptr;
+  bool snapshot_pending = false;
   DeviceBuffer<int> c_dof, c_master;
   DeviceBuffer<double> c_weight;
   DeviceSystem p_system;
@@ -315,6 +323,9 @@ struct pecs_ctx {
 
   ~pecs_ctx() {
     cudaSetDevice(device);
+    if (out_stream) cudaStreamDestroy(out_stream);
+    if (patches_ready) cudaEventDestroy(patches_ready);
+    if (patches_copied) cudaEventDestroy(patches_copied);
     if (step_graph) cudaGraphExecDestroy(step_graph);
     if (solve_graph) cudaGraphExecDestroy(solve_graph);
     if (rhs_graph) cudaGraphExecDestroy(rhs_graph);
@@ -547,6 +558,15 @@ void enqueue_poisson_solve(pecs_ctx* ctx, cudaStream_t s) {
   launch_distribute(ctx->n_constraints, ctx->c_dof.get(), ctx->c_master.get(), ctx->c_weight.get(),
                     ctx->p_solution.get(), s);
 }
+// measurement only (pecs_time_kernel): stream a buffer larger than L2 through it, leaving clean lines behind
+__global__ void l2_read_sweep_kernel(const double2* __restrict__ p, size_t n, double* sink) {
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double2 v = p[i];
+    acc += v.x + v.y;
+  }
+  if (acc == 123.456) *sink = acc; // never true for the zero-filled buffer: keeps the loads alive
+}
 // ---- cross-GPU flags of the sharded step (single-thread kernels, all on the context's streams) ----
 constexpr int kFlagPublished = 8, kFlagStep = 16, kFlagWords = 32;
 // after the assembly kernel: open step n and tell every rank that this rank no longer reads the old densities
@@ -778,8 +798,11 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
         }
       std::vector<int> is_semi(P.n_cells, 0);
       for (int c = 0; c < desc->semiconductor.n_cells; ++c) is_semi[desc->semiconductor.poisson_cell[c]] = 1;
-      DeviceBuffer<double> dvx, dvy, dw;
-      DeviceBuffer<int> dcell, dface, did, dsemi, dfd, dmaster;
+      // vertices and face dofs of the Poisson cells stay resident: the output path evaluates the field with them
+      DeviceBuffer<double>&dvx = ctx->p_vx, &dvy = ctx->p_vy;
+      DeviceBuffer<int>& dfd = ctx->p_face_dof;
+      DeviceBuffer<double> dw;
+      DeviceBuffer<int> dcell, dface, did, dsemi, dmaster;
       dvx.upload(vx);
       dvy.upload(vy);
       dsemi.upload(is_semi);
@@ -1096,20 +1119,78 @@ pecs_status pecs_step_timed(pecs_ctx* ctx, int32_t n_steps, int32_t sectioned, d
   });
 }
 
+int64_t pecs_output_doubles(const pecs_ctx* ctx, int32_t which) {
+  if (!ctx) return -1;
+  if (which == 0) return (int64_t)kCarrierPatchDoubles * ctx->dom[0].n_cells;
+  if (which == 1) return ctx->full ? (int64_t)kCarrierPatchDoubles * ctx->dom[1].n_cells : 0;
+  if (which == 2) return (int64_t)kPoissonPatchDoubles * ctx->n_pcells;
+  return -1;
+}
+
+pecs_status pecs_output_snapshot(pecs_ctx* ctx, const double scales[4], double* const host[3]) {
+  return guarded([&] {
+    require(ctx != nullptr && scales != nullptr && host != nullptr, "pecs_output_snapshot: NULL argument");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->out_stream) {
+      PECS_CUDA(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+      PECS_CUDA(cudaEventCreateWithFlags(&ctx->patches_ready, cudaEventDisableTiming));
+      PECS_CUDA(cudaEventCreateWithFlags(&ctx->patches_copied, cudaEventDisableTiming));
+    }
+    for (int w = 0; w < 3; ++w)
+      if (host[w] && ctx->patches[w].size() != (size_t)pecs_output_doubles(ctx, w))
+        ctx->patches[w].resize((size_t)pecs_output_doubles(ctx, w));
+    // the patch kernels run in stream order after whatever step was enqueued last; they may not overwrite the patch
+    // buffers before the previous snapshot's copies have left them
+    if (ctx->snapshot_pending) PECS_CUDA(cudaStreamWaitEvent(ctx->main, ctx->patches_copied, 0));
+    const double s_potential = scales[0], s_field = scales[1], s_current = scales[3]; // scales[2] (density): not applied,
+                                                                                      // reference PostProcessor.cpp:100-101
+    for (int w = 0; w < ctx->n_domains(); ++w)
+      if (host[w])
+        launch_carrier_patches(ctx->dom[w].n_cells, ctx->dom[w].solution[0].get(), ctx->dom[w].solution[1].get(), s_current,
+                               ctx->patches[w].get(), ctx->main);
+    if (host[2])
+      launch_poisson_patches(ctx->n_pcells, ctx->p_vx.get(), ctx->p_vy.get(), ctx->p_face_dof.get(), ctx->n_rt,
+                             ctx->p_solution.get(), s_field, s_potential, ctx->patches[2].get(), ctx->main);
+    PECS_CUDA(cudaGetLastError());
+    PECS_CUDA(cudaEventRecord(ctx->patches_ready, ctx->main));
+    // the copies leave on the output stream: the next steps on the main stream do not wait for them
+    PECS_CUDA(cudaStreamWaitEvent(ctx->out_stream, ctx->patches_ready, 0));
+    for (int w = 0; w < 3; ++w)
+      if (host[w] && ctx->patches[w].size() > 0)
+        PECS_CUDA(cudaMemcpyAsync(host[w], ctx->patches[w].get(), ctx->patches[w].bytes(), cudaMemcpyDeviceToHost,
+                                  ctx->out_stream));
+    PECS_CUDA(cudaEventRecord(ctx->patches_copied, ctx->out_stream));
+    ctx->snapshot_pending = true;
+  });
+}
+
+pecs_status pecs_output_wait(pecs_ctx* ctx) {
+  return guarded([&] {
+    require(ctx != nullptr, "pecs_output_wait: NULL context");
+    if (ctx->snapshot_pending) PECS_CUDA(cudaEventSynchronize(ctx->patches_copied));
+  });
+}
+
 pecs_status pecs_time_kernel(pecs_ctx* ctx, int32_t which, int32_t repeats, double* avg_ms, int32_t* launches) {
   return guarded([&] {
     require(ctx != nullptr && repeats > 0 && avg_ms && launches, "pecs_time_kernel: bad argument");
     PECS_CUDA(cudaSetDevice(ctx->device));
     sync_all(ctx);
-    // flush L2 (126 MB) before every timed launch group so that the figure is an HBM figure
-    if (ctx->l2_flush.size() == 0) ctx->l2_flush.resize((size_t)256 << 20);
+    // flush L2 (126 MB) before every timed launch group so that the figure is an HBM figure: overwrite 256 MB, then
+    // read another 256 MB so that what the timed kernels evict are CLEAN lines (after the memset alone L2 is full of
+    // dirty lines whose write-back would be charged to the kernel under test)
+    if (ctx->l2_flush.size() == 0) ctx->l2_flush.resize((size_t)512 << 20);
+    const size_t half = ctx->l2_flush.size() / 2;
+    PECS_CUDA(cudaMemset(ctx->l2_flush.get(), 0, ctx->l2_flush.bytes()));
     cudaEvent_t a, b;
     PECS_CUDA(cudaEventCreate(&a));
     PECS_CUDA(cudaEventCreate(&b));
     double total = 0.0;
     int n_launch = 0;
     for (int r = 0; r < repeats; ++r) {
-      PECS_CUDA(cudaMemsetAsync(ctx->l2_flush.get(), r & 0xff, ctx->l2_flush.bytes(), ctx->main));
+      PECS_CUDA(cudaMemsetAsync(ctx->l2_flush.get(), r & 0xff, half, ctx->main));
+      l2_read_sweep_kernel<<<1184, 256, 0, ctx->main>>>(reinterpret_cast<const double2*>(ctx->l2_flush.get() + half),
+                                                        half / sizeof(double2), reinterpret_cast<double*>(ctx->l2_flush.get()));
       PECS_CUDA(cudaEventRecord(a, ctx->main));
       switch (which) {
         case 0:

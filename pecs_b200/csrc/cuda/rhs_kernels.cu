@@ -182,23 +182,15 @@ __device__ __forceinline__ double trace(const double N[4], const double r[4]) {
 
 // Face terms of boundary cell record r, added to what the cell terms of the same thread have just stored.  Kept out
 // of line: 1.5 % of the cells take this path and its registers must not burden the other 98.5 %.
+// accumulate form: the cell's vertices and densities come in registers, the face terms are ADDED to jx1 .. rh2
 template <int KIND>
-__device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int other_n_cells, const RhsParams& p, int r,
-                                                    const double* __restrict__ u1, const double* __restrict__ u2,
-                                                    const double* __restrict__ o1, const double* __restrict__ o2, double* rhs1,
-                                                    double* rhs2) {
+__device__ __forceinline__ void boundary_terms_accumulate(const DomainView& d, int other_n_cells, const RhsParams& p, int r,
+                                                          const fe::CellVerts& v, const double r1[4], const double r2[4],
+                                                          const double* __restrict__ o1, const double* __restrict__ o2,
+                                                          double jx1[4], double jy1[4], double rh1[4], double jx2[4],
+                                                          double jy2[4], double rh2[4]) {
   constexpr bool kProduction = KIND == PECS_KIND_PRODUCTION;
-  const int c = d.bcell[r];
-  const size_t n = (size_t)d.n_cells;
-  const fe::CellVerts v = load_verts(d, c);
   const double h = fe::cell_diameter(v);
-  double r1[4], r2[4] = {0, 0, 0, 0};
-  load4(u1 + 8 * n + 4 * (size_t)c, r1);
-  if (kProduction) load4(u2 + 8 * n + 4 * (size_t)c, r2);
-
-  double jx1[4] = {0, 0, 0, 0}, jy1[4] = {0, 0, 0, 0}, rh1[4] = {0, 0, 0, 0};
-  double jx2[4] = {0, 0, 0, 0}, jy2[4] = {0, 0, 0, 0}, rh2[4] = {0, 0, 0, 0};
-
   for (int f = 0; f < 4; ++f) {
     const int id = d.bface_id[4 * r + f];
     if (id < 0 || id == PECS_NEUMANN) continue; // interior face, or insulating: nothing to do
@@ -286,6 +278,23 @@ __device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int oth
       }
     }
   }
+}
+
+template <int KIND>
+__device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int other_n_cells, const RhsParams& p, int r,
+                                                    const double* __restrict__ u1, const double* __restrict__ u2,
+                                                    const double* __restrict__ o1, const double* __restrict__ o2, double* rhs1,
+                                                    double* rhs2) {
+  constexpr bool kProduction = KIND == PECS_KIND_PRODUCTION;
+  const int c = d.bcell[r];
+  const size_t n = (size_t)d.n_cells;
+  const fe::CellVerts v = load_verts(d, c);
+  double r1[4], r2[4] = {0, 0, 0, 0};
+  load4(u1 + 8 * n + 4 * (size_t)c, r1);
+  if (kProduction) load4(u2 + 8 * n + 4 * (size_t)c, r2);
+  double jx1[4] = {0, 0, 0, 0}, jy1[4] = {0, 0, 0, 0}, rh1[4] = {0, 0, 0, 0};
+  double jx2[4] = {0, 0, 0, 0}, jy2[4] = {0, 0, 0, 0}, rh2[4] = {0, 0, 0, 0};
+  boundary_terms_accumulate<KIND>(d, other_n_cells, p, r, v, r1, r2, o1, o2, jx1, jy1, rh1, jx2, jy2, rh2);
   add4(rhs1 + 4 * (size_t)c, jx1);
   add4(rhs1 + 4 * n + 4 * (size_t)c, jy1);
   add4(rhs1 + 8 * n + 4 * (size_t)c, rh1);
@@ -449,15 +458,23 @@ __device__ __forceinline__ void production_cell_terms(const double vx[4], const 
   }
 }
 
-// Streaming production kernel.  A block owns tiles of kThreads consecutive cells (both subdomains form one tile
-// sequence) and walks them with stride gridDim.x; the grid is one resident wave.  Every thread keeps the inputs of
-// its NEXT cell in flight while it computes the current one: vertices, the two density 4-vectors, the generation
-// integrals and the four gathered Poisson fluxes go global -> shared with cp.async (LDGSTS) into the thread's own slot
-// of a two-stage ring, so no barrier is needed and the prefetch costs no registers.  The flux indices of the cell
-// after next are fetched one iteration earlier with ordinary loads, which removes the dependent gather from the
-// critical path.  Output: six 256-bit stores per cell.
-constexpr int kStageDoubles = 24; // per thread and stage: 8 vertices + 8 densities + 4 generation + 4 fluxes
-constexpr int kStreamSmemBytes = 2 * kStageDoubles * kThreads * (int)sizeof(double);
+// Streaming production kernel.  One resident wave of blocks; a block owns tiles of kThreads consecutive cells (both
+// subdomains form one tile sequence) and walks them with stride gridDim.x.  Every thread keeps the inputs of its NEXT
+// cell in flight while it computes the current one: vertices, the two density 4-vectors, the generation integrals and
+// the four gathered Poisson fluxes go global -> shared with cp.async (LDGSTS) into the thread's own slot of a two-stage
+// ring -- no barrier, no registers.  The flux indices and the boundary record of the tile after next travel the same
+// way one group earlier, so the dependent gather never sits on the critical path and nothing loaded is carried in
+// registers across the arithmetic.  Cells with boundary faces (1.5 %) are skipped by the cell tiles and done -- cell
+// terms + face terms, one store -- by dense BOUNDARY tiles (thread = boundary record) that the first blocks work off
+// while their first cell tile is in flight: no warp waits on a divergent lane.  Output: six 256-bit stores per cell.
+constexpr int kStageDoubles = 24;                        // per thread and stage: 8 vertices + 8 densities + 4 generation + 4 fluxes
+constexpr int kRingDoubles = 2 * kStageDoubles * kThreads;
+constexpr int kIndexInts = 5;                            // per thread and stage: 4 flux dofs + boundary record
+constexpr int kStreamSmemBytes = kRingDoubles * (int)sizeof(double) + 2 * kIndexInts * kThreads * (int)sizeof(int);
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 
 struct TileCell {
   int sel; // pass
@@ -470,20 +487,25 @@ __device__ __forceinline__ TileCell locate(const CarrierPassPair& pp, int tile, 
   t.c = (tile < tiles_total && c < pp.pass[t.sel].d.n_cells) ? c : -1;
   return t;
 }
-__device__ __forceinline__ void load_flux_index(const CarrierPassPair& pp, TileCell t, int idx[4]) {
+// flux dofs and boundary record of a cell -> index stage (ints, [5][T])
+__device__ __forceinline__ void issue_index(const CarrierPassPair& pp, TileCell t, int* istage) {
   if (t.c < 0) return;
   const DomainView& d = pp.pass[t.sel].d;
+  const int tid = threadIdx.x;
 #pragma unroll
-  for (int f = 0; f < 4; ++f) idx[f] = __ldg(d.rt_dof + (size_t)f * d.n_cells + t.c);
+  for (int f = 0; f < 4; ++f) cp_async4(istage + f * kThreads + tid, d.rt_dof + (size_t)f * d.n_cells + t.c);
+  cp_async4(istage + 4 * kThreads + tid, d.brecord + t.c);
 }
 // stage layout (doubles, T = kThreads): [0,8T) vertices SoA | [8T,16T) densities as 16-byte pieces [4][T] |
-// [16T,20T) generation [2][T] 16-byte pieces | [20T,24T) fluxes SoA
-__device__ __forceinline__ void issue_cell(const CarrierPassPair& pp, TileCell t, const int idx[4], const double* X,
+// [16T,20T) generation [2][T] 16-byte pieces | [20T,24T) fluxes SoA; the flux dofs are read from the (landed) index stage
+__device__ __forceinline__ void issue_cell(const CarrierPassPair& pp, TileCell t, const int* istage, const double* X,
                                            double* stage) {
   if (t.c < 0) return;
   const CarrierPass& w = pp.pass[t.sel];
   const size_t n = (size_t)w.d.n_cells;
   const int tid = threadIdx.x;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) cp_async8(stage + (20 + f) * kThreads + tid, X + istage[f * kThreads + tid]);
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     cp_async8(stage + a * kThreads + tid, w.d.vx + (size_t)a * n + t.c);
@@ -501,36 +523,87 @@ __device__ __forceinline__ void issue_cell(const CarrierPassPair& pp, TileCell t
     cp_async16(gs + 2 * (0 * kThreads + tid), w.d.gen_int + 4 * (size_t)t.c);
     cp_async16(gs + 2 * (1 * kThreads + tid), w.d.gen_int + 4 * (size_t)t.c + 2);
   }
+}
+
+__device__ __forceinline__ void store_cell(const CarrierPass& w, int c, const double jx1[4], const double jy1[4],
+                                           const double rh1[4], const double jx2[4], const double jy2[4],
+                                           const double rh2[4]) {
+  const size_t n = (size_t)w.d.n_cells, o = 4 * (size_t)c;
+  store4_256(w.rhs1 + o, jx1);
+  store4_256(w.rhs1 + 4 * n + o, jy1);
+  store4_256(w.rhs1 + 8 * n + o, rh1);
+  store4_256(w.rhs2 + o, jx2);
+  store4_256(w.rhs2 + 4 * n + o, jy2);
+  store4_256(w.rhs2 + 8 * n + o, rh2);
+}
+
+// one boundary record: cell terms + face terms of its cell, single writer of the cell's 24 rows
+__device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const double* __restrict__ X) {
+  const DomainView& d = w.d;
+  const size_t n = (size_t)d.n_cells;
+  const int c = __ldg(d.bcell + r);
+  fe::CellVerts v;
+  double r1[4], r2[4], Xf[4], gen[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int f = 0; f < 4; ++f) cp_async8(stage + (20 + f) * kThreads + tid, X + idx[f]);
+  for (int a = 0; a < 4; ++a) {
+    v.x[a] = __ldg(d.vx + (size_t)a * n + c);
+    v.y[a] = __ldg(d.vy + (size_t)a * n + c);
+    Xf[a] = __ldg(X + __ldg(d.rt_dof + (size_t)a * n + c));
+  }
+  load4_256(w.u1 + 8 * n + 4 * (size_t)c, r1);
+  load4_256(w.u2 + 8 * n + 4 * (size_t)c, r2);
+  if (d.gen_int) load4_256(d.gen_int + 4 * (size_t)c, gen);
+  double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
+  production_cell_terms(v.x, v.y, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
+                        jy1, rh1, jx2, jy2, rh2);
+  double bx1[4] = {0, 0, 0, 0}, by1[4] = {0, 0, 0, 0}, bh1[4] = {0, 0, 0, 0};
+  double bx2[4] = {0, 0, 0, 0}, by2[4] = {0, 0, 0, 0}, bh2[4] = {0, 0, 0, 0};
+  boundary_terms_accumulate<PECS_KIND_PRODUCTION>(d, w.other_n_cells, w.p, r, v, r1, r2, w.o1, w.o2, bx1, by1, bh1, bx2, by2,
+                                                  bh2);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) { // same order of additions as "store the cell terms, then add the face terms"
+    jx1[a] += bx1[a];
+    jy1[a] += by1[a];
+    rh1[a] += bh1[a];
+    jx2[a] += bx2[a];
+    jy2[a] += by2[a];
+    rh2[a] += bh2[a];
+  }
+  store_cell(w, c, jx1, jy1, rh1, jx2, jy2, rh2);
 }
 
 __global__ void __launch_bounds__(kThreads, 4)
-    carrier_rhs_stream_kernel(const __grid_constant__ CarrierPassPair pp, int tiles_a, int tiles_total,
-                              const double* __restrict__ X) {
+    carrier_rhs_stream_kernel(const __grid_constant__ CarrierPassPair pp, int tiles_a, int tiles_total, int btiles_a,
+                              int btiles_total, const double* __restrict__ X) {
   extern __shared__ __align__(16) double ring[];
-  const int tid = threadIdx.x;
-  int tile = blockIdx.x;
-  TileCell cur = locate(pp, tile, tiles_a, tiles_total);
-  TileCell nxt = locate(pp, tile + (int)gridDim.x, tiles_a, tiles_total);
-  int idx[4] = {0, 0, 0, 0}, nidx[4] = {0, 0, 0, 0};
-  load_flux_index(pp, cur, idx);
-  load_flux_index(pp, nxt, nidx);
-  issue_cell(pp, cur, idx, X, ring);
+  int* iring = reinterpret_cast<int*>(ring + kRingDoubles);
+  const int tid = threadIdx.x, grid = gridDim.x;
+  // cell tiles are dealt from the LAST block backwards, so that the blocks left with one tile more are not the first
+  // ones, which also work off the boundary tiles
+  const int first = grid - 1 - (int)blockIdx.x;
+  issue_index(pp, locate(pp, first, tiles_a, tiles_total), iring);
+  issue_index(pp, locate(pp, first + grid, tiles_a, tiles_total), iring + kIndexInts * kThreads);
+  cp_async_commit();
+  for (int bt = blockIdx.x; bt < btiles_total; bt += grid) {
+    const int sel = bt < btiles_a ? 0 : 1;
+    const int r = (bt - (sel ? btiles_a : 0)) * kThreads + tid;
+    if (r < pp.pass[sel].d.n_bcells) boundary_record(pp.pass[sel], r, X);
+  }
+  cp_async_wait<0>();
+  issue_cell(pp, locate(pp, first, tiles_a, tiles_total), iring, X, ring);
   cp_async_commit();
   int s = 0;
-  for (; tile < tiles_total; tile += (int)gridDim.x) {
-    double* stage = ring + s * kStageDoubles * kThreads;
-    issue_cell(pp, nxt, nidx, X, ring + (s ^ 1) * kStageDoubles * kThreads);
+  for (int tile = first; tile < tiles_total; tile += grid, s ^= 1) {
+    cp_async_wait<0>(); // the current cell's values, the next cell's flux dofs and record have landed
+    const TileCell cur = locate(pp, tile, tiles_a, tiles_total);
+    const int record = cur.c >= 0 ? iring[(s * kIndexInts + 4) * kThreads + tid] : 0;
+    issue_cell(pp, locate(pp, tile + grid, tiles_a, tiles_total), iring + (s ^ 1) * kIndexInts * kThreads, X,
+               ring + (s ^ 1) * kStageDoubles * kThreads);
+    issue_index(pp, locate(pp, tile + 2 * grid, tiles_a, tiles_total), iring + s * kIndexInts * kThreads);
     cp_async_commit();
-    const TileCell after = locate(pp, tile + 2 * (int)gridDim.x, tiles_a, tiles_total);
-    load_flux_index(pp, after, nidx); // consumed by the next iteration's issue_cell
-    int record = -1;
-    if (cur.c >= 0 && pp.pass[cur.sel].d.brecord) record = __ldg(pp.pass[cur.sel].d.brecord + cur.c);
-    cp_async_wait<1>(); // everything but the group just committed has landed: the current cell is in shared memory
-    if (cur.c >= 0) {
+    if (cur.c >= 0 && record < 0) {
+      const double* stage = ring + s * kStageDoubles * kThreads;
       const CarrierPass& w = pp.pass[cur.sel];
-      const size_t n = (size_t)w.d.n_cells;
       double vx[4], vy[4], r1[4], r2[4], Xf[4], gen[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
@@ -551,20 +624,8 @@ __global__ void __launch_bounds__(kThreads, 4)
       double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
       production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps,
                             jx1, jy1, rh1, jx2, jy2, rh2);
-      const size_t o = 4 * (size_t)cur.c;
-      store4_256(w.rhs1 + o, jx1);
-      store4_256(w.rhs1 + 4 * n + o, jy1);
-      store4_256(w.rhs1 + 8 * n + o, rh1);
-      store4_256(w.rhs2 + o, jx2);
-      store4_256(w.rhs2 + 4 * n + o, jy2);
-      store4_256(w.rhs2 + 8 * n + o, rh2);
-      if (record >= 0)
-        carrier_boundary_terms<PECS_KIND_PRODUCTION>(w.d, w.other_n_cells, w.p, record, w.u1, w.u2, w.o1, w.o2, w.rhs1,
-                                                     w.rhs2);
+      store_cell(w, cur.c, jx1, jy1, rh1, jx2, jy2, rh2);
     }
-    cur = nxt;
-    nxt = after;
-    s ^= 1;
   }
   cp_async_wait<0>();
 }
@@ -760,10 +821,11 @@ void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, co
       wave = sms * (per_sm > 0 ? per_sm : 1);
     }
     const int tiles = blocks_a + blocks_b;
+    const int btiles_a = blocks_for(a.d.n_bcells), btiles_b = blocks_for(b.d.n_bcells);
     int grid = tiles < wave ? tiles : wave;
     if (const char* e = std::getenv("PECS_B200_RHS_GRID")) // tests: force several tiles per block on small meshes
       if (std::atoi(e) > 0 && std::atoi(e) < grid) grid = std::atoi(e);
-    carrier_rhs_stream_kernel<<<grid, kThreads, kStreamSmemBytes, s>>>(pp, blocks_a, tiles, X);
+    carrier_rhs_stream_kernel<<<grid, kThreads, kStreamSmemBytes, s>>>(pp, blocks_a, tiles, btiles_a, btiles_a + btiles_b, X);
     return;
   }
 #define CALL(K) carrier_rhs_kernel<K><<<blocks_a + blocks_b, kThreads, 0, s>>>(pp, blocks_a, X)

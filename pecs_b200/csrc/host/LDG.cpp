@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <string>
 
 #include "../fe.hpp"
 
@@ -212,6 +213,27 @@ void LDG::assemble_system_matrices(const MeshTables& mesh, int dirichlet_id, dou
   }
   } // chunk
   chunks.compress(true, matrix_1, matrix_2);
+}
+
+std::string int_to_string_3(unsigned int n) {
+  std::string t = std::to_string(n);
+  while (t.size() < 3) t = "0" + t;
+  return t;
+}
+
+void LDG::output_rescaled_results(const pecs::VtuMesh& patches_mesh, const ChargeCarrierSpace::CarrierPair& carrier_pair,
+                                  const ParameterSpace::Parameters& sim_params, const double* patches,
+                                  const unsigned int time_step_number, const std::string& directory) const {
+  const PostProcessor postprocessor_1(sim_params, true, carrier_pair.carrier_1.name);
+  const PostProcessor postprocessor_2(sim_params, true, carrier_pair.carrier_2.name);
+  const size_t n = (size_t)patches_mesh.n_cells();
+  const std::vector<pecs::VtuField> fields = {
+      {postprocessor_1.current_name, 3, patches},
+      {postprocessor_1.density_name, 1, patches + 12 * n},
+      {postprocessor_2.current_name, 3, patches + 16 * n},
+      {postprocessor_2.density_name, 1, patches + 28 * n},
+  };
+  patches_mesh.write(directory + "/" + carrier_pair.material_name + int_to_string_3(time_step_number) + ".vtu", fields);
 }
 
 } // namespace LDG_System

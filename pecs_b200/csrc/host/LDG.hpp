@@ -14,8 +14,10 @@
 // Hanging faces are integrated sub-face by sub-face from the coarse side with the coarse cell's basis evaluated
 // on the sub-face (the intended integral; the reference reads a stale evaluator there).
 #pragma once
+#include "Carrier.hpp"
 #include "Csr.hpp"
 #include "DoFTables.hpp"
+#include "PostProcessor.hpp"
 #include "Triangulation.hpp"
 
 namespace LDG_System {
@@ -29,6 +31,16 @@ public:
   void assemble_system_matrices(const pecs::MeshTables& mesh, int dirichlet_id, double scaled_mobility_1,
                                 double scaled_mobility_2, double delta_t, double transient_or_steady, double penalty,
                                 pecs::CsrMatrix& matrix_1, pecs::CsrMatrix& matrix_2) const;
+
+  // reference LDG.cpp:1195-1232: file "<material_name><NNN>.vtu" holding "<carrier> Current" (vector) and
+  // "<carrier> Density" of both carriers of the pair on one patch per cell.  `patches` are the rescaled patch values
+  // the device produced (pecs_output_snapshot layout: current_1 | density_1 | current_2 | density_2).
+  void output_rescaled_results(const pecs::VtuMesh& patches_mesh, const ChargeCarrierSpace::CarrierPair& carrier_pair,
+                               const ParameterSpace::Parameters& sim_params, const double* patches,
+                               const unsigned int time_step_number, const std::string& directory = ".") const;
 };
+
+// Utilities::int_to_string(n, 3)
+std::string int_to_string_3(unsigned int n);
 
 } // namespace LDG_System

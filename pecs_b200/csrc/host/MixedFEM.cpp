@@ -71,6 +71,18 @@ CsrMatrix MixedFEM::assemble_Poisson_matrix(const MeshTables& mesh, const Poisso
   return tl.compress();
 }
 
+void MixedFEM::output_rescaled_results(const pecs::VtuMesh& patches_mesh, const double* patches,
+                                       const ParameterSpace::Parameters& sim_params, const unsigned int time_step_number,
+                                       const std::string& directory) const {
+  const PostProcessor postprocessor(sim_params, false, "noname");
+  const std::vector<std::string> names = postprocessor.get_names();
+  const size_t n = (size_t)patches_mesh.n_cells();
+  std::string number = std::to_string(time_step_number);
+  while (number.size() < 3) number = "0" + number;
+  patches_mesh.write(directory + "/Poisson-" + number + ".vtu",
+                     {{names[0], 3, patches}, {names[2], 1, patches + 12 * n}});
+}
+
 void distribute_local_to_global(const PoissonDofs& dofs, const double* local, const int* local_dofs, int n,
                                 double* global) {
   for (int i = 0; i < n; ++i) {

@@ -7,6 +7,7 @@
 #pragma once
 #include "Csr.hpp"
 #include "DoFTables.hpp"
+#include "PostProcessor.hpp"
 #include "Triangulation.hpp"
 
 namespace MixedPoisson {
@@ -17,6 +18,12 @@ public:
   pecs::CsrMatrix assemble_Poisson_matrix(const pecs::MeshTables& mesh, const pecs::PoissonDofs& dofs,
                                           double semi_permittivity, double elec_permittivity,
                                           double scaled_debye_length) const;
+
+  // reference MixedFEM.cpp:297-320: file "Poisson-<NNN>.vtu" with "Field" (vector) and "Potential";
+  // `patches` = pecs_output_snapshot layout field | potential
+  void output_rescaled_results(const pecs::VtuMesh& patches_mesh, const double* patches,
+                               const ParameterSpace::Parameters& sim_params, const unsigned int time_step_number,
+                               const std::string& directory = ".") const;
 };
 
 // scatter a local vector through the constraints (ConstraintMatrix::distribute_local_to_global, vector form)

@@ -79,6 +79,20 @@ void ConvergenceTable::write_text(std::ostream& out, const std::vector<std::stri
 }
 
 // ------------------------------------------------------------------------------------------- construction
+struct SolarCellProblem::OutputState {
+  std::unique_ptr<pecs::VtuMesh> mesh[3];
+  double* slot[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  unsigned long ticket[2] = {0, 0}; // writer job that still reads the slot
+  int next = 0;
+  pecs::OutputQueue queue; // declared last: destroyed (drained) first
+  ~OutputState() {
+    queue.wait_idle();
+    for (auto& s : slot)
+      for (double* p : s)
+        if (p) pecs_host_free(p);
+  }
+};
+
 SolarCellProblem::SolarCellProblem(const unsigned int degree_, ParameterSpace::ParameterHandler& param)
     : degree(degree_), prm(param) {
   if (degree != 1) throw std::runtime_error("SolarCellProblem: only degree 1 is built (reference main.cpp:11 uses 1)");
@@ -105,6 +119,7 @@ SolarCellProblem::SolarCellProblem(const unsigned int degree_, ParameterSpace::P
 SolarCellProblem::~SolarCellProblem() { release_ctx(); }
 
 void SolarCellProblem::release_ctx() {
+  output_.reset(); // drains the writer thread, which still uses the context
   if (ctx) pecs_ctx_destroy(ctx);
   ctx = nullptr;
   for (ChargeCarrierSpace::Carrier* c : {&electron_hole_pair.carrier_1, &electron_hole_pair.carrier_2,
@@ -418,6 +433,52 @@ void SolarCellProblem::setup_full_system() {
   solve_Poisson();
 }
 
+// ------------------------------------------------------------------------------------------------- output path
+void SolarCellProblem::print_results(unsigned int time_step_number) {
+  require_ctx(ctx, "SolarCellProblem::print_results");
+  if (!output_) {
+    output_.reset(new OutputState());
+    output_->mesh[0].reset(new pecs::VtuMesh(semiconductor_triangulation.tables()));
+    if (full_system) output_->mesh[1].reset(new pecs::VtuMesh(electrolyte_triangulation.tables()));
+    output_->mesh[2].reset(new pecs::VtuMesh(Poisson_triangulation.tables()));
+    for (auto& s : output_->slot)
+      for (int w = 0; w < 3; ++w) {
+        const int64_t n = pecs_output_doubles(ctx, w);
+        if (n > 0 && output_->mesh[w]) {
+          s[w] = static_cast<double*>(pecs_host_alloc((uint64_t)n * sizeof(double)));
+          if (!s[w]) throw std::runtime_error("print_results: cannot allocate page-locked output buffers");
+        }
+      }
+  }
+  OutputState& out = *output_;
+  const int k = out.next;
+  out.next ^= 1;
+  out.queue.wait_for(out.ticket[k]); // the job that wrote the files of two stamps ago has released this slot
+  const PostProcessor scales(sim_params, true, "");
+  double sc[4];
+  scales.get_scales(sc);
+  check(pecs_output_snapshot(ctx, sc, out.slot[k]), "print_results");
+  // the reference runs these three as tasks of a TaskGroup (SolarCell.cpp:1829-1857); here they are one job of the
+  // writer thread, which first waits for the snapshot's copies to land
+  pecs_ctx* c = ctx;
+  double* const* slot = out.slot[k];
+  const std::string dir = output_directory;
+  out.ticket[k] = out.queue.submit([this, c, slot, dir, time_step_number] {
+    check(pecs_output_wait(c), "print_results (writer)");
+    Mixed_Assembler.output_rescaled_results(*output_->mesh[2], slot[2], sim_params, time_step_number, dir);
+    LDG_Assembler.output_rescaled_results(*output_->mesh[0], electron_hole_pair, sim_params, slot[0], time_step_number, dir);
+    if (full_system)
+      LDG_Assembler.output_rescaled_results(*output_->mesh[1], redox_pair, sim_params, slot[1], time_step_number, dir);
+  });
+}
+
+void SolarCellProblem::finish_output() {
+  if (!output_) return;
+  output_->queue.wait_idle();
+  const std::string e = output_->queue.error();
+  if (!e.empty()) throw std::runtime_error("output path: " + e);
+}
+
 void SolarCellProblem::run_full_system() {
   setup_full_system();
   const unsigned int number_outputs = sim_params.time_stamps;
@@ -431,6 +492,9 @@ void SolarCellProblem::run_full_system() {
     for (unsigned int i = 0; i < number_outputs; i++) timeStamps[i] = (i + 1) * sim_params.t_end / number_outputs;
     time = 0.0;
   }
+  unsigned int time_step_number = 0;
+  if (write_output) print_results(time_step_number); // the initial values, reference SolarCell.cpp:2037-2039
+  time_step_number++;
   for (unsigned int k = 0; k < number_outputs; k++) {
     // same floating-point loop condition as the reference (SolarCell.cpp:2055-2080); the steps between two time
     // stamps are counted first and then replayed as one graph launch sequence
@@ -440,9 +504,12 @@ void SolarCellProblem::run_full_system() {
       ++n;
     }
     step(n);
-    // print_results(k) of the reference (VTU output) is out of scope; states stay on the device
+    // reference SolarCell.cpp:2082-2087; returns at once, the next steps run while the files are written
+    if (write_output) print_results(time_step_number);
+    time_step_number++;
   }
   synchronize();
+  finish_output();
   electron_hole_pair.print_dofs();
   redox_pair.print_dofs();
 }

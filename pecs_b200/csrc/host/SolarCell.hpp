@@ -10,6 +10,7 @@
 // that the Python binding, the parity tests and bench.py can drive them one by one.
 #pragma once
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -67,6 +68,11 @@ public:
   void assemble_Poisson_rhs();
   void solve_Poisson();
   void step(int n_steps); // n iterations of the loop body through the captured CUDA graph
+  // reference SolarCell.cpp:1826-1858: the three rescaled .vtu files of one time stamp.  The patch values are computed
+  // and rescaled on the device and leave on the context's output stream; the files are written by a background thread.
+  // Returns at once: the time loop goes on while the output drains (finish_output() waits for it).
+  void print_results(unsigned int time_step_number);
+  void finish_output();
   void set_time(double time);
   void synchronize();
 
@@ -87,6 +93,8 @@ public:
   int owned_species = 0; // bit k: carrier k is solved by this process' context; 0 = all (pecs_problem_desc::owned_species)
   double delta_t = 0.0;
   bool verbose = false;
+  bool write_output = true;           // run_full_system writes the reference's .vtu files
+  std::string output_directory = "."; // where print_results / print_dofs put them
 
   pecs::Triangulation Poisson_triangulation, semiconductor_triangulation, electrolyte_triangulation;
   Poisson::PoissonData Poisson_object;
@@ -101,6 +109,9 @@ public:
   pecs_ctx* ctx = nullptr;
 
 private:
+  // output path state: geometry of the three patch meshes, a ring of two page-locked host slots, the writer thread
+  struct OutputState;
+  std::unique_ptr<OutputState> output_;
   struct BoundaryFaces {
     std::vector<int> cell, face, id;
   };

@@ -91,6 +91,37 @@ PECS_FORWARD(pecs_solarcell_setup_full_system_host, p->problem->setup_full_syste
 PECS_FORWARD(pecs_solarcell_setup_full_system, p->problem->setup_full_system())
 PECS_FORWARD(pecs_solarcell_run_full_system, p->problem->run_full_system())
 
+PECS_FORWARD(pecs_solarcell_finish_output, p->problem->finish_output())
+pecs_status pecs_solarcell_set_output(pecs_solarcell* p, const char* directory, int32_t write_output) {
+  return guarded([&] {
+    if (directory && *directory) p->problem->output_directory = directory;
+    p->problem->write_output = write_output != 0;
+  });
+}
+pecs_status pecs_solarcell_print_results(pecs_solarcell* p, int32_t time_step_number) {
+  return guarded([&] {
+    if (time_step_number < 0) throw pecs::StatusError(PECS_ERR_INVALID, "time_step_number must be >= 0");
+    p->problem->print_results((unsigned)time_step_number);
+  });
+}
+pecs_status pecs_solarcell_write_patches(pecs_solarcell* p, int32_t which, const double* patches, int32_t time_step_number,
+                                         const char* directory) {
+  return guarded([&] {
+    if (!patches || time_step_number < 0) throw pecs::StatusError(PECS_ERR_INVALID, "write_patches: bad argument");
+    SolarCellProblem& s = *p->problem;
+    const pecs::VtuMesh mesh(tria(p, which).tables());
+    const std::string dir = directory && *directory ? directory : ".";
+    if (which == 2)
+      s.Mixed_Assembler.output_rescaled_results(mesh, patches, s.sim_params, (unsigned)time_step_number, dir);
+    else
+      s.LDG_Assembler.output_rescaled_results(mesh, which == 0 ? s.electron_hole_pair : s.redox_pair, s.sim_params, patches,
+                                              (unsigned)time_step_number, dir);
+  });
+}
+pecs_status pecs_solarcell_output_scales(const pecs_solarcell* p, double scales[4]) {
+  return guarded([&] { PostProcessor(p->problem->sim_params, true, "").get_scales(scales); });
+}
+
 pecs_status pecs_solarcell_setup_test_host(pecs_solarcell* p, int32_t kind, int32_t n_refine) {
   return guarded([&] { p->problem->setup_test_host(kind, (unsigned)n_refine); });
 }

@@ -114,6 +114,51 @@ class SolarCellProblem:
     def run_full_system(self):
         check(self._lib.pecs_solarcell_run_full_system(self._h))
 
+    # ---- output path (reference SolarCell.cpp:1826-1858) ----
+    def set_output(self, directory=None, write_output=True):
+        check(self._lib.pecs_solarcell_set_output(self._h, (directory or "").encode(), int(bool(write_output))))
+
+    def print_results(self, time_step_number):
+        """Poisson-NNN.vtu, Semiconductor-NNN.vtu, Electrolyte-NNN.vtu of the current state; asynchronous."""
+        check(self._lib.pecs_solarcell_print_results(self._h, int(time_step_number)))
+
+    def finish_output(self):
+        check(self._lib.pecs_solarcell_finish_output(self._h))
+
+    def write_patches(self, which, patches, time_step_number, directory="."):
+        """host half of the output path alone: the .vtu file of mesh `which` from given patch values"""
+        patches = np.ascontiguousarray(patches, dtype=np.float64)
+        check(self._lib.pecs_solarcell_write_patches(self._h, which, _dp(patches), int(time_step_number),
+                                                     directory.encode()))
+
+    @property
+    def output_scales(self):
+        """PostProcessor scales {potential, field, density, current}"""
+        s = np.zeros(4)
+        check(self._lib.pecs_solarcell_output_scales(self._h, _dp(s)))
+        return s
+
+    def output_snapshot(self):
+        """The rescaled patch values straight from pecs_output_snapshot: list of three dicts of arrays
+        (pairs: current_1 [4n,3], density_1 [4n], current_2, density_2; Poisson: field [4n,3], potential [4n])."""
+        n = [int(self._lib.pecs_output_doubles(self.ctx, w)) for w in range(3)]
+        bufs = [np.zeros(max(k, 0)) for k in n]
+        ptrs = (_lib.c_double_p * 3)(*[_dp(b) if b.size else None for b in bufs])
+        check(self._lib.pecs_output_snapshot(self.ctx, _dp(self.output_scales), ptrs))
+        check(self._lib.pecs_output_wait(self.ctx))
+        out = []
+        for w, b in enumerate(bufs):
+            if b.size == 0:
+                out.append(None)
+            elif w < 2:
+                c = b.size // 32
+                out.append({"current_1": b[:12 * c].reshape(-1, 3), "density_1": b[12 * c:16 * c],
+                            "current_2": b[16 * c:28 * c].reshape(-1, 3), "density_2": b[28 * c:]})
+            else:
+                c = b.size // 16
+                out.append({"field": b[:12 * c].reshape(-1, 3), "potential": b[12 * c:]})
+        return out
+
     def run_test(self, kind, n_refine):
         """test_steady_state / test_transient / test_DD_Poisson at one level -> dict of L2 errors."""
         e = np.zeros(4)

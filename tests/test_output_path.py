@@ -1,0 +1,121 @@
+"""Output path: the reference's print_results (source/SolarCell.cpp:1826-1858) = DataOut patches
++ PostProcessor rescaling + write_vtu.  CPU tests cover the host half (names, scales, file layout); the GPU tests
+compare the device-made patch values with the numpy restatement in oracle/output.py and read the files back."""
+import os
+
+import numpy as np
+import pytest
+
+import pecs_b200 as pecs
+from oracle import output as oracle_output
+from pecs_b200.vtu import read_vtu
+
+
+def _problem(g=2, l=1):
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l))
+    prob.setup_full_system_host()
+    return prob
+
+
+def test_scales_match_postprocessor_formulas():
+    prob = _problem()
+    # default input: characteristic length 1e-4, density 1e16, time 1e-12 (reference input_file.prm)
+    expect = oracle_output.scales(1.0e-4, 1.0e16, 1.0e-12)
+    assert np.allclose(prob.output_scales, expect, rtol=1e-15, atol=0)
+    assert expect[3] == 1.6e-19 * 1.0e16 * 1.0e-4 / 1.0e-12
+    prob.close()
+
+
+@pytest.mark.parametrize("which,name,fields", [
+    (0, "Semiconductor-007.vtu", [("Electrons Current", 3), ("Electrons Density", 1), ("Holes Current", 3), ("Holes Density", 1)]),
+    (1, "Electrolyte-007.vtu", [("Reductants Current", 3), ("Reductants Density", 1), ("Oxidants Current", 3), ("Oxidants Density", 1)]),
+    (2, "Poisson-007.vtu", [("Field", 3), ("Potential", 1)])])
+def test_vtu_files_round_trip(tmp_path, which, name, fields):
+    """file names and field names of the reference (LDG.cpp:1195-1232, MixedFEM.cpp:297-320, PostProcessor.cpp:20-55),
+    one 4-vertex patch per cell, values bit-exact through the base64 stream"""
+    prob = _problem()
+    n = prob.n_cells(which)
+    rng = np.random.default_rng(5 + which)
+    patches = rng.standard_normal((32 if which < 2 else 16) * n)
+    prob.write_patches(which, patches, 7, str(tmp_path))
+    f = read_vtu(os.path.join(tmp_path, name))
+    assert f["n_cells"] == n and f["n_points"] == 4 * n
+    verts = prob.mesh(which)["vertices"]
+    assert np.array_equal(f["points"][:, :2], verts.reshape(-1, 2)) and not f["points"][:, 2].any()
+    base = 4 * np.arange(n)[:, None]
+    assert np.array_equal(f["connectivity"].reshape(n, 4), base + np.array([0, 1, 3, 2]))  # VTK_QUAD from lexicographic
+    assert np.array_equal(f["offsets"], 4 * (np.arange(n) + 1)) and set(f["types"]) == {9}
+    assert list(f["point_data"]) == [k for k, _ in fields]
+    off = 0
+    for key, comps in fields:
+        a = f["point_data"][key]
+        assert np.array_equal(a.ravel(), patches[off:off + 4 * n * comps])
+        off += 4 * n * comps
+    # every quad is counter-clockwise in the VTK order
+    p = f["points"][f["connectivity"].reshape(n, 4)]
+    area2 = sum(p[:, i, 0] * p[:, (i + 1) % 4, 1] - p[:, (i + 1) % 4, 0] * p[:, i, 1] for i in range(4))
+    assert (area2 > 0).all()
+    prob.close()
+
+
+def test_print_results_needs_the_device():
+    """no CPU fallback: without a context print_results fails loudly"""
+    prob = _problem()
+    with pytest.raises(pecs.PecsError):
+        prob.print_results(0)
+    prob.close()
+
+
+def _expected_patches(prob):
+    sc = prob.output_scales
+    out = []
+    for w, (a, b) in enumerate([(pecs.ELECTRONS, pecs.HOLES), (pecs.REDUCTANTS, pecs.OXIDANTS)]):
+        c1, d1 = oracle_output.carrier_patches(prob.get_solution(a), sc[3])
+        c2, d2 = oracle_output.carrier_patches(prob.get_solution(b), sc[3])
+        out.append({"current_1": c1, "density_1": d1, "current_2": c2, "density_2": d2})
+    field, potential = oracle_output.poisson_patches(prob.mesh(2)["vertices"], prob.poisson_face_dofs(), prob.n_rt,
+                                                     prob.get_solution(pecs.POISSON), sc[1], sc[0])
+    out.append({"field": field, "potential": potential})
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("g,l,overrides", [(3, 1, {}), (3, 2, {"mesh__radius_one": 0.2})])
+def test_snapshot_matches_output_oracle(g, l, overrides):
+    """device patch values after a few steps against the numpy restatement of DataOut + PostProcessor"""
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **overrides))
+    prob.setup_full_system()
+    prob.step(3)
+    got, want = prob.output_snapshot(), _expected_patches(prob)
+    for g_, w_ in zip(got, want):
+        for key in w_:
+            scale = np.abs(w_[key]).max() or 1.0
+            assert np.abs(g_[key] - w_[key]).max() <= 1e-14 * scale, key
+    prob.close()
+
+
+@pytest.mark.gpu
+def test_print_results_files_and_time_loop_overlap(tmp_path):
+    """print_results returns before the files exist, steps go on meanwhile, and every stamp's files hold the state of
+    ITS stamp (two host slots in flight)"""
+    prob = pecs.SolarCellProblem(pecs.default_input_file(3, 1))
+    prob.setup_full_system()
+    prob.set_output(str(tmp_path))
+    expected = []
+    for k in range(4):
+        prob.synchronize()
+        expected.append(_expected_patches(prob))
+        prob.print_results(k)
+        prob.step(2)
+    prob.finish_output()
+    for k in range(4):
+        f = read_vtu(os.path.join(tmp_path, f"Semiconductor-{k:03d}.vtu"))
+        assert np.allclose(f["point_data"]["Electrons Density"], expected[k][0]["density_1"], rtol=1e-14, atol=0)
+        assert np.allclose(f["point_data"]["Holes Current"], expected[k][0]["current_2"], rtol=1e-14, atol=1e-300)
+        f = read_vtu(os.path.join(tmp_path, f"Electrolyte-{k:03d}.vtu"))
+        assert np.allclose(f["point_data"]["Oxidants Density"], expected[k][1]["density_2"], rtol=1e-14, atol=0)
+        f = read_vtu(os.path.join(tmp_path, f"Poisson-{k:03d}.vtu"))
+        scale = np.abs(expected[k][2]["field"]).max()
+        assert np.abs(f["point_data"]["Field"] - expected[k][2]["field"]).max() <= 1e-14 * scale
+        assert np.allclose(f["point_data"]["Potential"], expected[k][2]["potential"], rtol=1e-14, atol=0)
+    prob.close()
