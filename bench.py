@@ -210,7 +210,7 @@ def run_gpu_arm(args):
     rhs_ms, rhs_launches = prob.time_kernel(0, 20)
     # the production carrier kernels side by side (0 point-by-point, 1 sum-factorised, 2 streaming = default)
     rhs_variants = {}
-    for v in ("0", "1", "2"):
+    for v in ("0", "1", "11", "12", "13", "2"):
         os.environ["PECS_B200_RHS_KERNEL"] = v
         rhs_variants[v] = prob.time_kernel(0, 20)[0]
     del os.environ["PECS_B200_RHS_KERNEL"]

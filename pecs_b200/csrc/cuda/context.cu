@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <map>
 #include <memory>
 #include <vector>
@@ -375,8 +376,34 @@ CsrMatrix copy_csr(const pecs_csr& a, int expected_n, const char* name) {
   return A;
 }
 
+// Host half of building one linear system -- copy of the matrix, Schur reduction of the currents, nested dissection and
+// the symbolic front layout -- needs no device and dominates pecs_ctx_create; the (up to) five systems are prepared
+// concurrently on host threads, then factorised on the device one after the other.
+struct PreparedSystem {
+  bool present = false, reduced = false;
+  CsrMatrix A;       // the matrix that is factorised (S when reduced)
+  SchurReduction R;
+  SolvePlan plan;
+};
+
+PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k) {
+  PreparedSystem ps;
+  ps.present = true;
+  const int n = d.n_cells;
+  CsrMatrix A = copy_csr(d.system_matrix[k], 12 * n, "domain: system matrix size");
+  if (schur_reduction_enabled() && build_schur_reduction(A, n, ps.R)) {
+    ps.reduced = true;
+    ps.A = ps.R.S;
+    ps.plan = plan_from_layout(ps.A, carrier_density_nodes(d), default_leaf_nodes(false));
+  } else {
+    ps.A = std::move(A);
+    ps.plan = plan_from_layout(ps.A, carrier_nodes(d), default_leaf_nodes(false));
+  }
+  return ps;
+}
+
 void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pecs_poisson_desc& P,
-                  const pecs_interface_desc& I, bool factor_on_device) {
+                  const pecs_interface_desc& I, bool factor_on_device, std::future<PreparedSystem> (&prepared)[2]) {
   DeviceDomain& D = ctx.dom[which];
   const int n = d.n_cells;
   require(n > 0 && d.vertices && d.poisson_cell, "domain: empty mesh tables");
@@ -454,22 +481,19 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
     D.view.gen_int = D.gen_int.get();
   }
   // factorise the two fixed carrier matrices
-  const NodeLayout layout = carrier_nodes(d);
   for (int k = 0; k < 2; ++k) {
-    if (ctx.kind != PECS_KIND_PRODUCTION && k == 1) break; // the manufactured tests only solve carrier_1
-    if (!(ctx.owned >> (2 * which + k) & 1)) continue;       // another shard owns this carrier
-    const CsrMatrix A = copy_csr(d.system_matrix[k], 12 * n, "domain: system matrix size");
-    SchurReduction R;
-    if (schur_reduction_enabled() && build_schur_reduction(A, n, R)) {
+    if (!prepared[k].valid()) continue; // not solved here: manufactured tests only solve carrier_1; other shards' carriers
+    PreparedSystem ps = prepared[k].get();
+    if (ps.reduced) {
       DeviceDomain::Reduced& red = D.reduced[k];
       red.active = true;
-      D.system[k].build(R.S, carrier_density_nodes(d), default_leaf_nodes(false), factor_on_device);
-      red.T1.upload(R.T1, &D.system[k].plan.iperm); // r~ is produced directly in elimination order
-      red.Ainv.upload(R.Ainv);
-      red.T2.upload(R.T2);
+      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device);
+      red.T1.upload(ps.R.T1, &D.system[k].plan.iperm); // r~ is produced directly in elimination order
+      red.Ainv.upload(ps.R.Ainv);
+      red.T2.upload(ps.R.T2);
       red.rtilde.resize(4 * (size_t)n);
     } else {
-      D.system[k].build(A, layout, default_leaf_nodes(false), factor_on_device);
+      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device);
     }
   }
 }
@@ -765,8 +789,28 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     const bool factor_on_device = device_factorization_enabled();
 
     fill_rhs_params(*ctx);
-    setup_domain(*ctx, 0, desc->semiconductor, P, desc->interface_pairs, factor_on_device);
-    if (ctx->full) setup_domain(*ctx, 1, desc->electrolyte, P, desc->interface_pairs, factor_on_device);
+    // host preparation of all systems at once (threads), device work in order
+    std::future<PreparedSystem> prepared[2][2];
+    for (int w = 0; w < ctx->n_domains(); ++w) {
+      const pecs_domain_desc* d = w == 0 ? &desc->semiconductor : &desc->electrolyte;
+      require(d->n_cells > 0, "domain: empty mesh tables");
+      for (int k = 0; k < 2; ++k) {
+        if (ctx->kind != PECS_KIND_PRODUCTION && k == 1) break; // the manufactured tests only solve carrier_1
+        if (!(ctx->owned >> (2 * w + k) & 1)) continue;          // another shard owns this carrier
+        prepared[w][k] = std::async(std::launch::async, [d, k] { return prepare_carrier(*d, k); });
+      }
+    }
+    const int n_pdofs = ctx->n_pdofs();
+    std::future<PreparedSystem> prepared_poisson = std::async(std::launch::async, [&P, n_pdofs] {
+      PreparedSystem ps;
+      ps.present = true;
+      ps.A = copy_csr(P.system_matrix, n_pdofs, "poisson: system matrix size");
+      ps.plan = poisson_plan(ps.A, P, default_leaf_nodes(true));
+      return ps;
+    });
+    // on any failure below the futures' destructors wait for the host threads before desc goes away
+    setup_domain(*ctx, 0, desc->semiconductor, P, desc->interface_pairs, factor_on_device, prepared[0]);
+    if (ctx->full) setup_domain(*ctx, 1, desc->electrolyte, P, desc->interface_pairs, factor_on_device, prepared[1]);
 
     // Poisson vectors, constraints, static boundary data
     const int np = ctx->n_pdofs();
@@ -822,8 +866,8 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
       PECS_CUDA(cudaStreamSynchronize(ctx->main));
     }
     {
-      const CsrMatrix A = copy_csr(P.system_matrix, np, "poisson: system matrix size");
-      ctx->p_system.build(A, poisson_plan(A, P, default_leaf_nodes(true)), factor_on_device);
+      PreparedSystem ps = prepared_poisson.get();
+      ctx->p_system.build(ps.A, std::move(ps.plan), factor_on_device);
     }
     size_t smem = ctx->p_system.max_smem_bytes();
     for (int w = 0; w < ctx->n_domains(); ++w)

@@ -21,6 +21,7 @@
 // Algorithmic traffic 368 B per cell (both carriers); the kernel is HBM-bound.
 #include "rhs_kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "device_util.cuh"
@@ -182,27 +183,36 @@ __device__ __forceinline__ double trace(const double N[4], const double r[4]) {
 
 // Face terms of boundary cell record r, added to what the cell terms of the same thread have just stored.  Kept out
 // of line: 1.5 % of the cells take this path and its registers must not burden the other 98.5 %.
-// accumulate form: the cell's vertices and densities come in registers, the face terms are ADDED to jx1 .. rh2
+// one boundary record as the face routine wants it: all loads are independent of each other
+struct BoundaryRecord {
+  int id[4];   // boundary id of face f, -1: interior face
+  int nb_cell; // matched cell of the other subdomain across the interface face, -1: none
+  int nb_face;
+};
+__device__ __forceinline__ BoundaryRecord load_record(const DomainView& d, int r) {
+  BoundaryRecord b;
+  const int4 ids = __ldg(reinterpret_cast<const int4*>(d.bface_id) + r);
+  b.id[0] = ids.x, b.id[1] = ids.y, b.id[2] = ids.z, b.id[3] = ids.w;
+  b.nb_cell = __ldg(d.bnb_cell + r);
+  b.nb_face = __ldg(d.bnb_face + r);
+  return b;
+}
+
+// accumulate form: the record, the cell's vertices and densities and the interface neighbour's densities (q1, q2; the
+// same quadrature index on both sides) come in registers, the face terms are ADDED to jx1 .. rh2
 template <int KIND>
-__device__ __forceinline__ void boundary_terms_accumulate(const DomainView& d, int other_n_cells, const RhsParams& p, int r,
+__device__ __forceinline__ void boundary_terms_accumulate(const RhsParams& p, const BoundaryRecord& rec,
                                                           const fe::CellVerts& v, const double r1[4], const double r2[4],
-                                                          const double* __restrict__ o1, const double* __restrict__ o2,
-                                                          double jx1[4], double jy1[4], double rh1[4], double jx2[4],
-                                                          double jy2[4], double rh2[4]) {
+                                                          const double q1[4], const double q2[4], double jx1[4],
+                                                          double jy1[4], double rh1[4], double jx2[4], double jy2[4],
+                                                          double rh2[4]) {
   constexpr bool kProduction = KIND == PECS_KIND_PRODUCTION;
   const double h = fe::cell_diameter(v);
+  const int nb_face = rec.nb_face;
+#pragma unroll 1
   for (int f = 0; f < 4; ++f) {
-    const int id = d.bface_id[4 * r + f];
+    const int id = f == 0 ? rec.id[0] : (f == 1 ? rec.id[1] : (f == 2 ? rec.id[2] : rec.id[3]));
     if (id < 0 || id == PECS_NEUMANN) continue; // interior face, or insulating: nothing to do
-    // the other subdomain's traces on an interface face (same q index on both sides)
-    double q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
-    int nb_face = 0;
-    if (kProduction && id == PECS_INTERFACE) {
-      const int nc = d.bnb_cell[r];
-      nb_face = d.bnb_face[r];
-      load4(o1 + 8 * (size_t)other_n_cells + 4 * (size_t)nc, q1);
-      load4(o2 + 8 * (size_t)other_n_cells + 4 * (size_t)nc, q2);
-    }
     for (int q = 0; q < 3; ++q) {
       const double t = fe::gauss_x(q);
       double xi, eta, nx, ny, ds, N[4];
@@ -294,7 +304,13 @@ __device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int oth
   if (kProduction) load4(u2 + 8 * n + 4 * (size_t)c, r2);
   double jx1[4] = {0, 0, 0, 0}, jy1[4] = {0, 0, 0, 0}, rh1[4] = {0, 0, 0, 0};
   double jx2[4] = {0, 0, 0, 0}, jy2[4] = {0, 0, 0, 0}, rh2[4] = {0, 0, 0, 0};
-  boundary_terms_accumulate<KIND>(d, other_n_cells, p, r, v, r1, r2, o1, o2, jx1, jy1, rh1, jx2, jy2, rh2);
+  const BoundaryRecord rec = load_record(d, r);
+  double q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
+  if (kProduction && rec.nb_cell >= 0) {
+    load4(o1 + 8 * (size_t)other_n_cells + 4 * (size_t)rec.nb_cell, q1);
+    load4(o2 + 8 * (size_t)other_n_cells + 4 * (size_t)rec.nb_cell, q2);
+  }
+  boundary_terms_accumulate<KIND>(p, rec, v, r1, r2, q1, q2, jx1, jy1, rh1, jx2, jy2, rh2);
   add4(rhs1 + 4 * (size_t)c, jx1);
   add4(rhs1 + 4 * n + 4 * (size_t)c, jy1);
   add4(rhs1 + 8 * n + 4 * (size_t)c, rh1);
@@ -537,29 +553,37 @@ __device__ __forceinline__ void store_cell(const CarrierPass& w, int c, const do
   store4_256(w.rhs2 + 8 * n + o, rh2);
 }
 
-// one boundary record: cell terms + face terms of its cell, single writer of the cell's 24 rows
+// one boundary record: cell terms + face terms of its cell, single writer of the cell's 24 rows.  Three dependent
+// round trips to memory at most: {record, cell index} -> {vertices, densities, flux dofs, neighbour densities} -> fluxes
 __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const double* __restrict__ X) {
   const DomainView& d = w.d;
   const size_t n = (size_t)d.n_cells;
   const int c = __ldg(d.bcell + r);
+  const BoundaryRecord rec = load_record(d, r);
   fe::CellVerts v;
-  double r1[4], r2[4], Xf[4], gen[4] = {0, 0, 0, 0};
+  double r1[4], r2[4], Xf[4], gen[4] = {0, 0, 0, 0}, q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
+  int dof[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
+    dof[a] = __ldg(d.rt_dof + (size_t)a * n + c);
     v.x[a] = __ldg(d.vx + (size_t)a * n + c);
     v.y[a] = __ldg(d.vy + (size_t)a * n + c);
-    Xf[a] = __ldg(X + __ldg(d.rt_dof + (size_t)a * n + c));
   }
   load4_256(w.u1 + 8 * n + 4 * (size_t)c, r1);
   load4_256(w.u2 + 8 * n + 4 * (size_t)c, r2);
   if (d.gen_int) load4_256(d.gen_int + 4 * (size_t)c, gen);
+  if (rec.nb_cell >= 0) {
+    load4_256(w.o1 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q1);
+    load4_256(w.o2 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q2);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) Xf[a] = __ldg(X + dof[a]);
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
   production_cell_terms(v.x, v.y, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
                         jy1, rh1, jx2, jy2, rh2);
   double bx1[4] = {0, 0, 0, 0}, by1[4] = {0, 0, 0, 0}, bh1[4] = {0, 0, 0, 0};
   double bx2[4] = {0, 0, 0, 0}, by2[4] = {0, 0, 0, 0}, bh2[4] = {0, 0, 0, 0};
-  boundary_terms_accumulate<PECS_KIND_PRODUCTION>(d, w.other_n_cells, w.p, r, v, r1, r2, w.o1, w.o2, bx1, by1, bh1, bx2, by2,
-                                                  bh2);
+  boundary_terms_accumulate<PECS_KIND_PRODUCTION>(w.p, rec, v, r1, r2, q1, q2, bx1, by1, bh1, bx2, by2, bh2);
 #pragma unroll
   for (int a = 0; a < 4; ++a) { // same order of additions as "store the cell terms, then add the face terms"
     jx1[a] += bx1[a];
@@ -576,19 +600,21 @@ __global__ void __launch_bounds__(kThreads, 4)
     carrier_rhs_stream_kernel(const __grid_constant__ CarrierPassPair pp, int tiles_a, int tiles_total, int btiles_a,
                               int btiles_total, const double* __restrict__ X) {
   extern __shared__ __align__(16) double ring[];
+  const int tid = threadIdx.x;
+  // the FIRST blocks of the grid do nothing but one boundary tile each: the face terms are a chain of dependent loads
+  // and branchy arithmetic several microseconds long, which must start at once and share its SM with streaming blocks
+  // instead of being the tail of one
+  if ((int)blockIdx.x < btiles_total) {
+    const int sel = (int)blockIdx.x < btiles_a ? 0 : 1;
+    const int r = ((int)blockIdx.x - (sel ? btiles_a : 0)) * kThreads + tid;
+    if (r < pp.pass[sel].d.n_bcells) boundary_record(pp.pass[sel], r, X);
+    return;
+  }
   int* iring = reinterpret_cast<int*>(ring + kRingDoubles);
-  const int tid = threadIdx.x, grid = gridDim.x;
-  // cell tiles are dealt from the LAST block backwards, so that the blocks left with one tile more are not the first
-  // ones, which also work off the boundary tiles
-  const int first = grid - 1 - (int)blockIdx.x;
+  const int grid = (int)gridDim.x - btiles_total, first = (int)blockIdx.x - btiles_total;
   issue_index(pp, locate(pp, first, tiles_a, tiles_total), iring);
   issue_index(pp, locate(pp, first + grid, tiles_a, tiles_total), iring + kIndexInts * kThreads);
   cp_async_commit();
-  for (int bt = blockIdx.x; bt < btiles_total; bt += grid) {
-    const int sel = bt < btiles_a ? 0 : 1;
-    const int r = (bt - (sel ? btiles_a : 0)) * kThreads + tid;
-    if (r < pp.pass[sel].d.n_bcells) boundary_record(pp.pass[sel], r, X);
-  }
   cp_async_wait<0>();
   issue_cell(pp, locate(pp, first, tiles_a, tiles_total), iring, X, ring);
   cp_async_commit();
@@ -632,13 +658,23 @@ __global__ void __launch_bounds__(kThreads, 4)
 
 // One-thread-per-cell production kernel on the sum-factorised cell terms (no staging): the variant for meshes too
 // small to fill a resident wave, and the A/B partner of the streaming kernel (PECS_B200_RHS_KERNEL=1).
-__global__ void __launch_bounds__(kThreads, 4)
-    carrier_rhs_direct_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a, const double* __restrict__ X) {
-  const bool first = (int)blockIdx.x < blocks_a;
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, MIN_BLOCKS)
+    carrier_rhs_direct_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a, int btiles_a, int btiles_total,
+                              const double* __restrict__ X) {
+  if ((int)blockIdx.x < btiles_total) { // leading blocks: one boundary tile each (see the streaming kernel)
+    const int sel = (int)blockIdx.x < btiles_a ? 0 : 1;
+    const int r = ((int)blockIdx.x - (sel ? btiles_a : 0)) * kThreads + threadIdx.x;
+    if (r < pp.pass[sel].d.n_bcells) boundary_record(pp.pass[sel], r, X);
+    return;
+  }
+  const int block = (int)blockIdx.x - btiles_total;
+  const bool first = block < blocks_a;
   const CarrierPass& w = pp.pass[first ? 0 : 1];
-  const int c = ((int)blockIdx.x - (first ? 0 : blocks_a)) * blockDim.x + threadIdx.x;
+  const int c = (block - (first ? 0 : blocks_a)) * blockDim.x + threadIdx.x;
   if (c >= w.d.n_cells) return;
   const size_t n = (size_t)w.d.n_cells;
+  const int record = __ldg(w.d.brecord + c);
   double vx[4], vy[4], r1[4], r2[4], Xf[4], gen[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
@@ -649,19 +685,11 @@ __global__ void __launch_bounds__(kThreads, 4)
   load4_256(w.u1 + 8 * n + 4 * (size_t)c, r1);
   load4_256(w.u2 + 8 * n + 4 * (size_t)c, r2);
   if (w.d.gen_int) load4_256(w.d.gen_int + 4 * (size_t)c, gen);
+  if (record >= 0) return; // done by a boundary tile
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
   production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
                         jy1, rh1, jx2, jy2, rh2);
-  const size_t o = 4 * (size_t)c;
-  store4_256(w.rhs1 + o, jx1);
-  store4_256(w.rhs1 + 4 * n + o, jy1);
-  store4_256(w.rhs1 + 8 * n + o, rh1);
-  store4_256(w.rhs2 + o, jx2);
-  store4_256(w.rhs2 + 4 * n + o, jy2);
-  store4_256(w.rhs2 + 8 * n + o, rh2);
-  const int r = w.d.brecord ? w.d.brecord[c] : -1;
-  if (r >= 0)
-    carrier_boundary_terms<PECS_KIND_PRODUCTION>(w.d, w.other_n_cells, w.p, r, w.u1, w.u2, w.o1, w.o2, w.rhs1, w.rhs2);
+  store_cell(w, c, jx1, jy1, rh1, jx2, jy2, rh2);
 }
 
 // ------------------------------------------------------------------------------------------ Poisson cells
@@ -804,8 +832,13 @@ void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, co
   // production: the sum-factorised kernels on the static cell tables (variant 0 keeps the point-by-point kernel that
   // also serves the manufactured problems; it is the parity partner of the other two in tests/test_gpu_extra.py)
   const int variant = (kind == PECS_KIND_PRODUCTION && a.d.nodal_int) ? carrier_rhs_variant() : 0;
-  if (variant == 1) {
-    carrier_rhs_direct_kernel<<<blocks_a + blocks_b, kThreads, 0, s>>>(pp, blocks_a, X);
+  const int btiles_a = blocks_for(a.d.n_bcells), btiles_b = blocks_for(b.d.n_bcells), btiles = btiles_a + btiles_b;
+  if (variant == 1 || (variant >= 11 && variant <= 13)) { // 11..13: the same kernel compiled for 5 / 6 / 8 blocks per SM
+    const int grid = btiles + blocks_a + blocks_b;
+    if (variant == 1) carrier_rhs_direct_kernel<4><<<grid, kThreads, 0, s>>>(pp, blocks_a, btiles_a, btiles, X);
+    if (variant == 11) carrier_rhs_direct_kernel<5><<<grid, kThreads, 0, s>>>(pp, blocks_a, btiles_a, btiles, X);
+    if (variant == 12) carrier_rhs_direct_kernel<6><<<grid, kThreads, 0, s>>>(pp, blocks_a, btiles_a, btiles, X);
+    if (variant == 13) carrier_rhs_direct_kernel<8><<<grid, kThreads, 0, s>>>(pp, blocks_a, btiles_a, btiles, X);
     return;
   }
   if (variant >= 2) {
@@ -821,11 +854,10 @@ void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, co
       wave = sms * (per_sm > 0 ? per_sm : 1);
     }
     const int tiles = blocks_a + blocks_b;
-    const int btiles_a = blocks_for(a.d.n_bcells), btiles_b = blocks_for(b.d.n_bcells);
-    int grid = tiles < wave ? tiles : wave;
+    int cell_blocks = std::max(1, std::min(tiles, wave - btiles));
     if (const char* e = std::getenv("PECS_B200_RHS_GRID")) // tests: force several tiles per block on small meshes
-      if (std::atoi(e) > 0 && std::atoi(e) < grid) grid = std::atoi(e);
-    carrier_rhs_stream_kernel<<<grid, kThreads, kStreamSmemBytes, s>>>(pp, blocks_a, tiles, btiles_a, btiles_a + btiles_b, X);
+      if (std::atoi(e) > 0 && std::atoi(e) < cell_blocks) cell_blocks = std::atoi(e);
+    carrier_rhs_stream_kernel<<<btiles + cell_blocks, kThreads, kStreamSmemBytes, s>>>(pp, blocks_a, tiles, btiles_a, btiles, X);
     return;
   }
 #define CALL(K) carrier_rhs_kernel<K><<<blocks_a + blocks_b, kThreads, 0, s>>>(pp, blocks_a, X)

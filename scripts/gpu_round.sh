@@ -15,4 +15,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:carrier_rhs -c 2 -o gpurun_out/rhs_$tag -f \
   python scripts/profile_step.py --steps 2 > gpurun_out/ncu_rhs_$tag.log 2>&1
 ncu -i gpurun_out/rhs_$tag.ncu-rep --page raw --csv > gpurun_out/rhs_${tag}_raw.csv 2>/dev/null
+if [ -n "$RHS_ALT" ]; then  # the same capture with another production kernel variant
+  PECS_B200_RHS_KERNEL=$RHS_ALT timeout 600 ncu --set full --clock-control none --import-source on -k regex:carrier_rhs -c 2 \
+    -o gpurun_out/rhs_${tag}_alt$RHS_ALT -f python scripts/profile_step.py --steps 2 > gpurun_out/ncu_rhs_${tag}_alt.log 2>&1
+  ncu -i gpurun_out/rhs_${tag}_alt$RHS_ALT.ncu-rep --page raw --csv > gpurun_out/rhs_${tag}_alt${RHS_ALT}_raw.csv 2>/dev/null
+fi
 ls -la gpurun_out | tail -12
