@@ -541,16 +541,29 @@ __device__ __forceinline__ void issue_cell(const CarrierPassPair& pp, TileCell t
   }
 }
 
+// WIDE: six 256-bit stores.  The out-of-line boundary routine uses the 128-bit form: inside a non-inlined function
+// ptxas 12.9 lowers the inline-PTX st.global.v4.f64 to a 64-bit store of the first element only (seen in the SASS and
+// as unwritten rows in tests/test_gpu_extra.py::test_production_rhs_kernels_agree).
+template <bool WIDE>
 __device__ __forceinline__ void store_cell(const CarrierPass& w, int c, const double jx1[4], const double jy1[4],
                                            const double rh1[4], const double jx2[4], const double jy2[4],
                                            const double rh2[4]) {
   const size_t n = (size_t)w.d.n_cells, o = 4 * (size_t)c;
-  store4_256(w.rhs1 + o, jx1);
-  store4_256(w.rhs1 + 4 * n + o, jy1);
-  store4_256(w.rhs1 + 8 * n + o, rh1);
-  store4_256(w.rhs2 + o, jx2);
-  store4_256(w.rhs2 + 4 * n + o, jy2);
-  store4_256(w.rhs2 + 8 * n + o, rh2);
+  if (WIDE) {
+    store4_256(w.rhs1 + o, jx1);
+    store4_256(w.rhs1 + 4 * n + o, jy1);
+    store4_256(w.rhs1 + 8 * n + o, rh1);
+    store4_256(w.rhs2 + o, jx2);
+    store4_256(w.rhs2 + 4 * n + o, jy2);
+    store4_256(w.rhs2 + 8 * n + o, rh2);
+  } else {
+    store4(w.rhs1 + o, jx1);
+    store4(w.rhs1 + 4 * n + o, jy1);
+    store4(w.rhs1 + 8 * n + o, rh1);
+    store4(w.rhs2 + o, jx2);
+    store4(w.rhs2 + 4 * n + o, jy2);
+    store4(w.rhs2 + 8 * n + o, rh2);
+  }
 }
 
 // one boundary record: cell terms + face terms of its cell, single writer of the cell's 24 rows.  Three dependent
@@ -593,7 +606,7 @@ __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const 
     jy2[a] += by2[a];
     rh2[a] += bh2[a];
   }
-  store_cell(w, c, jx1, jy1, rh1, jx2, jy2, rh2);
+  store_cell<false>(w, c, jx1, jy1, rh1, jx2, jy2, rh2);
 }
 
 __global__ void __launch_bounds__(kThreads, 4)
@@ -650,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 4)
       double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
       production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps,
                             jx1, jy1, rh1, jx2, jy2, rh2);
-      store_cell(w, cur.c, jx1, jy1, rh1, jx2, jy2, rh2);
+      store_cell<true>(w, cur.c, jx1, jy1, rh1, jx2, jy2, rh2);
     }
   }
   cp_async_wait<0>();
@@ -689,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS)
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
   production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
                         jy1, rh1, jx2, jy2, rh2);
-  store_cell(w, c, jx1, jy1, rh1, jx2, jy2, rh2);
+  store_cell<true>(w, c, jx1, jy1, rh1, jx2, jy2, rh2);
 }
 
 // ------------------------------------------------------------------------------------------ Poisson cells

@@ -10,7 +10,8 @@ if [ "$2" != "skip-tests" ]; then
 fi
 timeout 600 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 tail -c 3000 gpurun_out/bench_$tag.json
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+  -k 'regex:carrier_rhs|poisson_cell_rhs|poisson_face_rhs|level_kernel|ell_|distribute_kernel|gather_kernel' -c 700 --csv \
   --log-file gpurun_out/launches_$tag.csv python scripts/profile_step.py --steps 2 > gpurun_out/ncu_launches_$tag.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:carrier_rhs -c 2 -o gpurun_out/rhs_$tag -f \
   python scripts/profile_step.py --steps 2 > gpurun_out/ncu_rhs_$tag.log 2>&1
