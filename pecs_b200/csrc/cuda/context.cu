@@ -260,6 +260,7 @@ struct DeviceDomain {
   DeviceBuffer<double> vx, vy;
   DeviceBuffer<int> rt_dof, phi_dof, bcell, bface_id, bnb_cell, bnb_face, brecord;
   DeviceBuffer<double> nodal_int, gen_int; // static cell integrals of the production kernels
+  DeviceBuffer<double> bgeom;              // static face geometry of the boundary cells
   DeviceBuffer<double> solution[2], rhs[2];
   DeviceSystem system[2];
   // Schur-reduced carriers (host/SchurReduction.hpp): system[k] then factorises S (4 unknowns per cell)
@@ -470,7 +471,13 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
   }
   D.view = DomainView{n,          D.vx.get(),       D.vy.get(),       D.rt_dof.get(),  D.phi_dof.get(),
                       D.n_bcells, D.bcell.get(), D.bface_id.get(), D.bnb_cell.get(), D.bnb_face.get(), D.brecord.get(),
-                      nullptr,    nullptr};
+                      nullptr,    nullptr,       nullptr};
+  if (D.n_bcells > 0) {
+    D.bgeom.resize(16 * (size_t)D.n_bcells);
+    launch_boundary_geometry(D.view, D.prm.tau, D.bgeom.get(), ctx.main);
+    PECS_CUDA(cudaStreamSynchronize(ctx.main));
+    D.view.bgeom = D.bgeom.get();
+  }
   if (ctx.kind == PECS_KIND_PRODUCTION) {
     // time-independent cell integrals: int N_a (Poisson charge rows) and int N_a G (illumination, semiconductor only)
     D.nodal_int.resize(4 * (size_t)n);

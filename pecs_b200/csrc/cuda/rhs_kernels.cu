@@ -198,27 +198,54 @@ __device__ __forceinline__ BoundaryRecord load_record(const DomainView& d, int r
   return b;
 }
 
+__device__ __forceinline__ void load_geometry(const DomainView& d, int r, double geom[4][4]) {
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(d.bgeom + 16 * (size_t)r + 4 * f));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(d.bgeom + 16 * (size_t)r + 4 * f + 2));
+    geom[f][0] = a.x, geom[f][1] = a.y, geom[f][2] = b.x, geom[f][3] = b.y;
+  }
+}
+
+// one-time: {n_x, n_y, ds, tau/h} of the four faces of every boundary cell (launch_boundary_geometry)
+__global__ void boundary_geometry_kernel(DomainView d, double tau, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.n_bcells) return;
+  const fe::CellVerts v = load_verts(d, d.bcell[r]);
+  const double pen = tau / fe::cell_diameter(v);
+  for (int f = 0; f < 4; ++f) {
+    double xi, eta, nx, ny, ds;
+    fe::face_point(f, 0.5, xi, eta);
+    fe::face_normal_ds(fe::jacobian(v, xi, eta), f, nx, ny, ds);
+    double* o = out + 16 * (size_t)r + 4 * f;
+    o[0] = nx, o[1] = ny, o[2] = ds, o[3] = pen;
+  }
+}
+
 // accumulate form: the record, the cell's vertices and densities and the interface neighbour's densities (q1, q2; the
 // same quadrature index on both sides) come in registers, the face terms are ADDED to jx1 .. rh2
+// geom[f] = {n_x, n_y, |dx/dt|, tau/h} of face f: the edges of a bilinear cell are straight, so normal and surface
+// element are constant along a face and time independent -- evaluated once (boundary_geometry_kernel) instead of a
+// square root and two divisions per quadrature point and step.  The face and point loops are unrolled: the traces
+// N_a(x_q) become immediates (two of the four vanish on a face).
 template <int KIND>
 __device__ __forceinline__ void boundary_terms_accumulate(const RhsParams& p, const BoundaryRecord& rec,
-                                                          const fe::CellVerts& v, const double r1[4], const double r2[4],
-                                                          const double q1[4], const double q2[4], double jx1[4],
-                                                          double jy1[4], double rh1[4], double jx2[4], double jy2[4],
-                                                          double rh2[4]) {
+                                                          const double geom[4][4], const fe::CellVerts& v,
+                                                          const double r1[4], const double r2[4], const double q1[4],
+                                                          const double q2[4], double jx1[4], double jy1[4], double rh1[4],
+                                                          double jx2[4], double jy2[4], double rh2[4]) {
   constexpr bool kProduction = KIND == PECS_KIND_PRODUCTION;
-  const double h = fe::cell_diameter(v);
   const int nb_face = rec.nb_face;
-#pragma unroll 1
+#pragma unroll
   for (int f = 0; f < 4; ++f) {
-    const int id = f == 0 ? rec.id[0] : (f == 1 ? rec.id[1] : (f == 2 ? rec.id[2] : rec.id[3]));
+    const int id = rec.id[f];
     if (id < 0 || id == PECS_NEUMANN) continue; // interior face, or insulating: nothing to do
+    const double nx = geom[f][0], ny = geom[f][1], ds = geom[f][2], pen = geom[f][3];
+#pragma unroll
     for (int q = 0; q < 3; ++q) {
       const double t = fe::gauss_x(q);
-      double xi, eta, nx, ny, ds, N[4];
+      double xi, eta, N[4];
       fe::face_point(f, t, xi, eta);
-      const fe::Jac j = fe::jacobian(v, xi, eta);
-      fe::face_normal_ds(j, f, nx, ny, ds);
       fe::shape(xi, eta, N);
       const double W = ds * fe::gauss_w(q);
       if (id == PECS_DIRICHLET) {
@@ -232,7 +259,6 @@ __device__ __forceinline__ void boundary_terms_accumulate(const RhsParams& p, co
           fe::map_point(v, xi, eta, x, y);
           bc1 = (KIND == PECS_KIND_TEST_STEADY) ? testfn::poisson_bc(x, y) : testfn::density(x, y, p.time);
         }
-        const double pen = p.tau / h;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           jx1[a] += -N[a] * nx * bc1 * W;
@@ -310,7 +336,9 @@ __device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int oth
     load4(o1 + 8 * (size_t)other_n_cells + 4 * (size_t)rec.nb_cell, q1);
     load4(o2 + 8 * (size_t)other_n_cells + 4 * (size_t)rec.nb_cell, q2);
   }
-  boundary_terms_accumulate<KIND>(p, rec, v, r1, r2, q1, q2, jx1, jy1, rh1, jx2, jy2, rh2);
+  double geom[4][4];
+  load_geometry(d, r, geom);
+  boundary_terms_accumulate<KIND>(p, rec, geom, v, r1, r2, q1, q2, jx1, jy1, rh1, jx2, jy2, rh2);
   add4(rhs1 + 4 * (size_t)c, jx1);
   add4(rhs1 + 4 * n + 4 * (size_t)c, jy1);
   add4(rhs1 + 8 * n + 4 * (size_t)c, rh1);
@@ -573,6 +601,8 @@ __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const 
   const size_t n = (size_t)d.n_cells;
   const int c = __ldg(d.bcell + r);
   const BoundaryRecord rec = load_record(d, r);
+  double geom[4][4];
+  load_geometry(d, r, geom);
   fe::CellVerts v;
   double r1[4], r2[4], Xf[4], gen[4] = {0, 0, 0, 0}, q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
   int dof[4];
@@ -596,7 +626,7 @@ __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const 
                         jy1, rh1, jx2, jy2, rh2);
   double bx1[4] = {0, 0, 0, 0}, by1[4] = {0, 0, 0, 0}, bh1[4] = {0, 0, 0, 0};
   double bx2[4] = {0, 0, 0, 0}, by2[4] = {0, 0, 0, 0}, bh2[4] = {0, 0, 0, 0};
-  boundary_terms_accumulate<PECS_KIND_PRODUCTION>(w.p, rec, v, r1, r2, q1, q2, bx1, by1, bh1, bx2, by2, bh2);
+  boundary_terms_accumulate<PECS_KIND_PRODUCTION>(w.p, rec, geom, v, r1, r2, q1, q2, bx1, by1, bh1, bx2, by2, bh2);
 #pragma unroll
   for (int a = 0; a < 4; ++a) { // same order of additions as "store the cell terms, then add the face terms"
     jx1[a] += bx1[a];
@@ -830,6 +860,11 @@ void launch_static_cell_integrals(const DomainView& d, const RhsParams& p, doubl
                                   cudaStream_t s) {
   if (d.n_cells == 0) return;
   static_cell_integrals_kernel<<<blocks_for(d.n_cells), kThreads, 0, s>>>(d, p, nodal_int, gen_int);
+}
+
+void launch_boundary_geometry(const DomainView& d, double tau, double* out, cudaStream_t s) {
+  if (d.n_bcells == 0) return;
+  boundary_geometry_kernel<<<blocks_for(d.n_bcells), kThreads, 0, s>>>(d, tau, out);
 }
 
 int carrier_rhs_variant() {

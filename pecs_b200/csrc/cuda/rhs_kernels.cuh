@@ -20,6 +20,7 @@ struct DomainView {
   const int* bnb_cell;   // [n_bcells] matched cell of the other subdomain across the interface (or -1)
   const int* bnb_face;   // [n_bcells] its face number
   const int* brecord;    // [n_cells] index of the cell's boundary record, -1 for interior cells
+  const double* bgeom;   // [n_bcells][4][4] {n_x, n_y, ds, tau/h} per face of a boundary cell (launch_boundary_geometry)
   // static cell integrals (production; launch_static_cell_integrals), NULL when absent
   const double* nodal_int; // [n_cells][4] int N_a
   const double* gen_int;   // [n_cells][4] int N_a G   (semiconductor under illumination only)
@@ -54,6 +55,8 @@ struct CarrierPass {
 // one-time: the static per-cell integrals the production kernels read (gen_int may be NULL: dark, or electrolyte)
 void launch_static_cell_integrals(const DomainView& d, const RhsParams& p, double* nodal_int, double* gen_int,
                                   cudaStream_t s);
+// one-time: normals, surface elements and penalty weights of the faces of the boundary cells
+void launch_boundary_geometry(const DomainView& d, double tau, double* out, cudaStream_t s);
 // which production carrier kernel launch_carrier_rhs uses: 0 point-by-point (v7), 1 sum-factorised one thread per cell,
 // 2 (default) sum-factorised streaming kernel; PECS_B200_RHS_KERNEL overrides
 int carrier_rhs_variant();
