@@ -208,9 +208,9 @@ def run_gpu_arm(args):
     solve_bytes = prob.info(sc.INFO_SOLVE_BYTES_PER_STEP)
     n_solve_launches = prob.info(sc.INFO_LAUNCHES_PER_STEP) - 6
     rhs_ms, rhs_launches = prob.time_kernel(0, 20)
-    # the production carrier kernels side by side (0 point-by-point, 1 sum-factorised, 2 streaming = default)
+    # the production carrier kernels side by side (0 point-by-point, 1 sum-factorised = default, 2 streaming, 1x shapes)
     rhs_variants = {}
-    for v in ("0", "1", "11", "12", "13", "2"):
+    for v in ("0", "1", "11", "14", "15", "2"):
         os.environ["PECS_B200_RHS_KERNEL"] = v
         rhs_variants[v] = prob.time_kernel(0, 20)[0]
     del os.environ["PECS_B200_RHS_KERNEL"]
@@ -245,7 +245,7 @@ def run_gpu_arm(args):
                                  "ELL entry, each read once) / device time of the solves inside the step graph (step graph "
                                  "minus assembly-only graph, CUDA events); traffic = DRAM bytes read+written by the same "
                                  "kernels in the committed ncu pass (profiles/)"},
-            "rhs_roofline": {"bound": "hbm", "kernel": "carrier_rhs_stream_kernel: cell + boundary terms of all four "
+            "rhs_roofline": {"bound": "hbm", "kernel": "carrier_rhs_direct_kernel: cell + boundary terms of all four "
                                                        "carriers, both subdomains, one launch, L2 flushed before it",
                              "achieved": rhs_gbs, "peak": peak, "unit": "GB/s", "frac": rhs_gbs / peak,
                              "algorithmic_bytes_per_launch_group": rhs_bytes, "ms": rhs_ms, "launches": rhs_launches,

@@ -701,13 +701,13 @@ __global__ void __launch_bounds__(kThreads, 4)
 
 // One-thread-per-cell production kernel on the sum-factorised cell terms (no staging): the variant for meshes too
 // small to fill a resident wave, and the A/B partner of the streaming kernel (PECS_B200_RHS_KERNEL=1).
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(kThreads, MIN_BLOCKS)
+template <int MIN_BLOCKS, int THREADS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     carrier_rhs_direct_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a, int btiles_a, int btiles_total,
                               const double* __restrict__ X) {
   if ((int)blockIdx.x < btiles_total) { // leading blocks: one boundary tile each (see the streaming kernel)
     const int sel = (int)blockIdx.x < btiles_a ? 0 : 1;
-    const int r = ((int)blockIdx.x - (sel ? btiles_a : 0)) * kThreads + threadIdx.x;
+    const int r = ((int)blockIdx.x - (sel ? btiles_a : 0)) * THREADS + threadIdx.x;
     if (r < pp.pass[sel].d.n_bcells) boundary_record(pp.pass[sel], r, X);
     return;
   }
@@ -870,7 +870,7 @@ void launch_boundary_geometry(const DomainView& d, double tau, double* out, cuda
 int carrier_rhs_variant() {
   // read at every launch (a graph freezes the choice at capture): tests flip it between calls of one process
   const char* e = std::getenv("PECS_B200_RHS_KERNEL");
-  return e && *e ? std::atoi(e) : 2;
+  return e && *e ? std::atoi(e) : 1;
 }
 
 void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, const double* X, cudaStream_t s) {
@@ -881,12 +881,18 @@ void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, co
   // also serves the manufactured problems; it is the parity partner of the other two in tests/test_gpu_extra.py)
   const int variant = (kind == PECS_KIND_PRODUCTION && a.d.nodal_int) ? carrier_rhs_variant() : 0;
   const int btiles_a = blocks_for(a.d.n_bcells), btiles_b = blocks_for(b.d.n_bcells), btiles = btiles_a + btiles_b;
-  if (variant == 1 || (variant >= 11 && variant <= 13)) { // 11..13: the same kernel compiled for 5 / 6 / 8 blocks per SM
-    const int grid = btiles + blocks_a + blocks_b;
-    if (variant == 1) carrier_rhs_direct_kernel<4><<<grid, kThreads, 0, s>>>(pp, blocks_a, btiles_a, btiles, X);
-    if (variant == 11) carrier_rhs_direct_kernel<5><<<grid, kThreads, 0, s>>>(pp, blocks_a, btiles_a, btiles, X);
-    if (variant == 12) carrier_rhs_direct_kernel<6><<<grid, kThreads, 0, s>>>(pp, blocks_a, btiles_a, btiles, X);
-    if (variant == 13) carrier_rhs_direct_kernel<8><<<grid, kThreads, 0, s>>>(pp, blocks_a, btiles_a, btiles, X);
+  if (variant == 1 || (variant >= 11 && variant <= 15)) {
+    // 1: 128 threads, 4 blocks per SM (no spills).  11: compiled for 5 blocks per SM; 14 / 15: 64- / 32-thread blocks
+    // (finer tail).  Measured at cfg3 (bench.py variants_ms): 1 is the fastest.
+    auto launch = [&](auto kernel, int threads) {
+      auto nb = [threads](int n) { return (n + threads - 1) / threads; };
+      const int ba = nb(a.d.n_cells), bb = nb(b.d.n_cells), ta = nb(a.d.n_bcells), tb = nb(b.d.n_bcells);
+      kernel<<<ta + tb + ba + bb, threads, 0, s>>>(pp, ba, ta, ta + tb, X);
+    };
+    if (variant == 1) launch(carrier_rhs_direct_kernel<4, 128>, 128);
+    if (variant == 11) launch(carrier_rhs_direct_kernel<5, 128>, 128);
+    if (variant == 14) launch(carrier_rhs_direct_kernel<8, 64>, 64);
+    if (variant == 15) launch(carrier_rhs_direct_kernel<16, 32>, 32);
     return;
   }
   if (variant >= 2) {

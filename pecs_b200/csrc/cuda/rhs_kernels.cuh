@@ -57,8 +57,9 @@ void launch_static_cell_integrals(const DomainView& d, const RhsParams& p, doubl
                                   cudaStream_t s);
 // one-time: normals, surface elements and penalty weights of the faces of the boundary cells
 void launch_boundary_geometry(const DomainView& d, double tau, double* out, cudaStream_t s);
-// which production carrier kernel launch_carrier_rhs uses: 0 point-by-point (v7), 1 sum-factorised one thread per cell,
-// 2 (default) sum-factorised streaming kernel; PECS_B200_RHS_KERNEL overrides
+// which production carrier kernel launch_carrier_rhs uses: 0 point-by-point (v7), 1 (default) sum-factorised, one thread
+// per cell, 2 sum-factorised streaming kernel (cp.async ring; measured slower at 2.2 cells per thread), 11/14/15 launch
+// shapes of 1; PECS_B200_RHS_KERNEL overrides
 int carrier_rhs_variant();
 
 // rhs_c = M u_c + cell terms + boundary / interface / Schottky face terms for both carriers of both passes, one launch

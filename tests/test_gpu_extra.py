@@ -135,9 +135,9 @@ def test_other_configurations_match_oracle(case):
 
 @pytest.mark.parametrize("g,l,overrides", [(4, 1, {}), (3, 2, {"mesh__radius_one": 0.2})])
 def test_production_rhs_kernels_agree(g, l, overrides, monkeypatch):
-    """The three production carrier kernels (0: point-by-point, 1: sum-factorised, 2: sum-factorised streaming kernel,
-    also with several tiles per block) and the static-table Poisson rows, from one perturbed state: each within 1e-12 of
-    the oracle, the sum-factorised pair bit-identical to each other."""
+    """The production carrier kernels (0: point-by-point, 1: sum-factorised = default, its 64- and 32-thread launch
+    shapes, 2: sum-factorised streaming kernel, also with several tiles per block) and the static-table Poisson rows,
+    from one perturbed state: each within 1e-12 of the oracle, the sum-factorised ones bit-identical to each other."""
     from helpers import SPECIES, block_rel_err, make_oracle, perturbed
     prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **overrides))
     prob.setup_full_system()
@@ -157,6 +157,7 @@ def test_production_rhs_kernels_agree(g, l, overrides, monkeypatch):
     o.assemble_Poisson_rhs()
     got = {}
     for name, env in {"points": {"PECS_B200_RHS_KERNEL": "0"}, "direct": {"PECS_B200_RHS_KERNEL": "1"},
+                      "direct64": {"PECS_B200_RHS_KERNEL": "14"}, "direct32": {"PECS_B200_RHS_KERNEL": "15"},
                       "stream": {"PECS_B200_RHS_KERNEL": "2"},
                       "stream3": {"PECS_B200_RHS_KERNEL": "2", "PECS_B200_RHS_GRID": "3"}}.items():
         for k, v in env.items():
@@ -170,7 +171,8 @@ def test_production_rhs_kernels_agree(g, l, overrides, monkeypatch):
             assert block_rel_err(got[name][s], o.rhs(s)) <= 1e-12, f"{name}: species {s}"
         monkeypatch.delenv("PECS_B200_RHS_GRID", raising=False)
     for s in SPECIES:
-        assert np.array_equal(got["direct"][s], got["stream"][s]) and np.array_equal(got["stream"][s], got["stream3"][s])
+        for other in ("direct64", "direct32", "stream", "stream3"):
+            assert np.array_equal(got["direct"][s], got[other][s]), other
     prob.assemble_Poisson_rhs()
     assert rel_err(prob.get_rhs(pecs.POISSON), o.rhs(4)) <= 1e-12
     prob.close()
