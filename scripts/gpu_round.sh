@@ -22,3 +22,4 @@ if [ -n "$RHS_ALT" ]; then  # the same capture with another production kernel va
   ncu -i gpurun_out/rhs_${tag}_alt$RHS_ALT.ncu-rep --page raw --csv > gpurun_out/rhs_${tag}_alt${RHS_ALT}_raw.csv 2>/dev/null
 fi
 ls -la gpurun_out | tail -12
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.log 2>&1; tail -2 gpurun_out/smoke_$tag.log
