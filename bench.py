@@ -35,6 +35,15 @@ def measured_traffic():
     return None
 
 
+def measured_rhs_traffic():
+    """DRAM bytes of one launch of the carrier RHS kernel from the committed ncu capture, or None"""
+    path = os.path.join(ROOT, "profiles", "r01_rhs_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -249,6 +258,7 @@ def run_gpu_arm(args):
                                                        "carriers, both subdomains, one launch, L2 flushed before it",
                              "achieved": rhs_gbs, "peak": peak, "unit": "GB/s", "frac": rhs_gbs / peak,
                              "algorithmic_bytes_per_launch_group": rhs_bytes, "ms": rhs_ms, "launches": rhs_launches,
+                             "traffic": measured_rhs_traffic(),
                              "variants_ms": rhs_variants,
                              "poisson_rhs_ms": prhs_ms,
                              "poisson_rhs_gbs": 140 * (prob.n_cells(0) + prob.n_cells(1)) / (prhs_ms * 1e-3) / 1e9},
