@@ -99,9 +99,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+CONIC = False  # --workload cfg4: BASELINE.json configs[3]
+
+
 def workload_name(g, l):
+    if CONIC:
+        return (f"conic nanowire (radius one 0.2, radius two 0.6), illumination on, global refinements {g}, local "
+                f"refinements {l} (2:1-smoothed interface refinement), fp64, degree 1 (cfg4)")
     return (f"default input_file.prm geometry, global refinements {g}, local refinements {l}, fp64, degree 1" +
             (" (cfg3: 983040 DoF per carrier, Poisson 492800 DoF)" if (g, l) == (7, 1) else ""))
+
+
+def workload_overrides():
+    return {"mesh__radius_one": 0.2, "mesh__radius_two": 0.6} if CONIC else {}
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
@@ -171,9 +181,9 @@ def run_gpu_arm(args):
     if pecs.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device; pecs_b200 has no CPU fallback")
     g, l = args.global_refinements, args.local_refinements
-    overrides = {}
+    overrides = workload_overrides()
     if world > 1:  # one applied bias per rank; the bias only acts through Dirichlet faces at x == 0 (insulated=false)
-        overrides = {"physical__insulated": False, "physical__applied_bias": sweep.bias_for_rank(rank, world)}
+        overrides.update({"physical__insulated": False, "physical__applied_bias": sweep.bias_for_rank(rank, world)})
     t_setup = time.perf_counter()
     prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **overrides), device=device)
     prob.setup_full_system()
@@ -301,7 +311,7 @@ def run_sharded_arm(args):
     torch.cuda.set_device(device)
     g, l = args.global_refinements, args.local_refinements
     t_setup = time.perf_counter()
-    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l), device=device)
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **workload_overrides()), device=device)
     prob.set_owned_species(shard.owned_mask(rank, world))
     prob.setup_full_system()
     prob.synchronize()
@@ -378,7 +388,18 @@ def main():
     ap.add_argument("--parallelism", choices=["sweep", "subdomain", "species"], default="sweep",
                     help="N > 1: 'sweep' = one applied bias per rank (weak scaling, default); 'subdomain' (2 ranks) / "
                          "'species' (4 ranks) = one step sharded over the ranks with an NCCL density exchange (strong)")
+    ap.add_argument("--workload", choices=["cfg3", "cfg4"], default="cfg3",
+                    help="cfg3 = the headline configuration (default); cfg4 = conic wire, two levels of interface "
+                         "refinement, global refinements 6 unless given (BASELINE.json configs[3]; a parity-test "
+                         "configuration, benchable for the sharded layouts)")
     args = ap.parse_args()
+    if args.workload == "cfg4":
+        global CONIC
+        CONIC = True
+        if "--global-refinements" not in sys.argv:
+            args.global_refinements = 6
+        if "--local-refinements" not in sys.argv:
+            args.local_refinements = 2
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.parallelism != "sweep":
