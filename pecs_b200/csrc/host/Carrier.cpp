@@ -71,15 +71,15 @@ void CarrierPair::print_info() const {
   std::cout << "Number of DOFS " << material_name << ": " << 2 * dofs.n_dofs() << " = 2 x (" << 8 * dofs.n_cells << " + "
             << 4 * dofs.n_cells << ")" << std::endl;
 }
-void CarrierPair::print_dofs() {
+void CarrierPair::print_dofs(const std::string& directory) {
   carrier_1.pull_solution();
   carrier_2.pull_solution();
-  block_write(carrier_1.name + ".dofs", carrier_1.solution);
-  block_write(carrier_2.name + ".dofs", carrier_2.solution);
+  block_write(directory + "/" + carrier_1.name + ".dofs", carrier_1.solution);
+  block_write(directory + "/" + carrier_2.name + ".dofs", carrier_2.solution);
 }
-void CarrierPair::read_dofs() {
-  block_read(carrier_1.name + ".dofs", carrier_1.solution);
-  block_read(carrier_2.name + ".dofs", carrier_2.solution);
+void CarrierPair::read_dofs(const std::string& directory) {
+  block_read(directory + "/" + carrier_1.name + ".dofs", carrier_1.solution);
+  block_read(directory + "/" + carrier_2.name + ".dofs", carrier_2.solution);
 }
 void CarrierPair::set_semiconductor_for_testing(double mobility_1, double mobility_2) {
   penalty = 1.0;

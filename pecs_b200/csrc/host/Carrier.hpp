@@ -52,8 +52,8 @@ struct CarrierPair {
   void setup_dofs(const pecs::MeshTables& mesh);
   void print_info() const;
   // restart files, reference CarrierPair.cpp:89-121 (Vector::block_write / block_read layout)
-  void print_dofs();
-  void read_dofs();
+  void print_dofs(const std::string& directory = ".");
+  void read_dofs(const std::string& directory = ".");
   // reference CarrierPair.cpp:124-142
   void set_semiconductor_for_testing(double mobility_1, double mobility_2);
 };

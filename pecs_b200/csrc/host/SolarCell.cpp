@@ -419,8 +419,8 @@ void SolarCellProblem::setup_full_system() {
   setup_full_system_host();
   set_solvers();
   if (sim_params.restart_status) {
-    electron_hole_pair.read_dofs();
-    redox_pair.read_dofs();
+    electron_hole_pair.read_dofs(output_directory);
+    redox_pair.read_dofs(output_directory);
   } else {
     project_initial_conditions();
   }
@@ -510,8 +510,8 @@ void SolarCellProblem::run_full_system() {
   }
   synchronize();
   finish_output();
-  electron_hole_pair.print_dofs();
-  redox_pair.print_dofs();
+  electron_hole_pair.print_dofs(output_directory);
+  redox_pair.print_dofs(output_directory);
 }
 
 // ------------------------------------------------------------------------------------------- manufactured tests

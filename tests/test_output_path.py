@@ -119,3 +119,44 @@ def test_print_results_files_and_time_loop_overlap(tmp_path):
         assert np.abs(f["point_data"]["Field"] - expected[k][2]["field"]).max() <= 1e-14 * scale
         assert np.allclose(f["point_data"]["Potential"], expected[k][2]["potential"], rtol=1e-14, atol=0)
     prob.close()
+
+
+@pytest.mark.gpu
+def test_run_full_system_writes_the_reference_files(tmp_path):
+    """run_full_system with the reference's cadence (source/SolarCell.cpp:2036-2092): stamp 0 = initial values, one
+    set of files per time stamp, restart files at the end; the last stamp holds the state after all steps"""
+    prm = pecs.default_input_file(2, 1, computational__end_time=0.2, computational__time_stamps=2)
+    prob = pecs.SolarCellProblem(prm)
+    prob.set_output(str(tmp_path))
+    prob.run_full_system()
+    names = sorted(os.listdir(tmp_path))
+    for k in range(3):
+        for stem in ("Poisson-", "Semiconductor-", "Electrolyte-"):
+            assert f"{stem}{k:03d}.vtu" in names
+    assert not any(n.endswith("003.vtu") for n in names)
+    for carrier in ("Electrons", "Holes", "Reductants", "Oxidants"):
+        assert f"{carrier}.dofs" in names
+    # 0.2 / 0.05 = 4 steps (the reference's floating-point loop: time < timeStamps[k]); compare with a stepped problem
+    other = pecs.SolarCellProblem(prm)
+    other.setup_full_system()
+    first = read_vtu(os.path.join(tmp_path, "Semiconductor-000.vtu"))
+    assert np.allclose(first["point_data"]["Electrons Density"],
+                       oracle_output.carrier_patches(other.get_solution(pecs.ELECTRONS), 1.0)[1], rtol=1e-14, atol=0)
+    n_steps = 0
+    t = 0.0
+    for stamp in (0.1, 0.2):
+        while t < stamp:
+            t += 0.05
+            n_steps += 1
+    other.step(n_steps)
+    last = read_vtu(os.path.join(tmp_path, "Electrolyte-002.vtu"))
+    assert np.allclose(last["point_data"]["Reductants Density"],
+                       oracle_output.carrier_patches(other.get_solution(pecs.REDUCTANTS), 1.0)[1], rtol=1e-13, atol=0)
+    # restart file = dealii::Vector::block_write layout: "<n>\\n[" + raw doubles + "]"
+    raw = open(os.path.join(tmp_path, "Oxidants.dofs"), "rb").read()
+    n = other.n_dofs(pecs.OXIDANTS)
+    head = f"{n}\n[".encode()
+    assert raw.startswith(head) and raw.endswith(b"]")
+    assert np.array_equal(np.frombuffer(raw[len(head):-1], np.float64), other.get_solution(pecs.OXIDANTS))
+    prob.close()
+    other.close()
