@@ -302,6 +302,7 @@ struct pecs_ctx {
   cudaStream_t main = nullptr, side[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr}; // host-buffer step: a species' download has finished
+  cudaEvent_t dens[4] = {nullptr, nullptr, nullptr, nullptr};   // step: a species' new densities are final (currents pending)
   cudaGraphExec_t step_graph = nullptr;
   cudaGraphExec_t solve_graph = nullptr;     // the five solves only (measurement, pecs_step_timed mode 2)
   cudaGraphExec_t rhs_graph = nullptr;       // the three assembly passes only (measurement, pecs_step_timed mode 3)
@@ -338,6 +339,8 @@ struct pecs_ctx {
     for (cudaEvent_t e : join)
       if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : copied)
+      if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : dens)
       if (e) cudaEventDestroy(e);
     if (fork) cudaEventDestroy(fork);
     for (cudaStream_t s : side)
@@ -630,12 +633,16 @@ __global__ void p2p_wait_published_kernel(const unsigned long long* mine) {
   __threadfence_system();
 }
 
-void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s) {
+// densities_final: recorded on s as soon as the new densities are complete, i.e. before the LDG currents are recovered
+// (q = Ainv r_q - T2 u): nothing inside a step reads the currents, so the step lets that last kernel overlap the
+// latency-bound Poisson part instead of keeping it on the critical path (enqueue_step)
+void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s, cudaEvent_t densities_final = nullptr) {
   DeviceDomain& D = ctx->dom[which / 2];
   const int k = which % 2;
   require(D.system[k].n > 0, "this species has no factorised system in this context");
   if (!D.reduced[k].active) {
     D.system[k].solve(D.rhs[k].get(), D.solution[k].get(), s);
+    if (densities_final) PECS_CUDA(cudaEventRecord(densities_final, s));
     return;
   }
   DeviceDomain::Reduced& red = D.reduced[k];
@@ -648,22 +655,25 @@ void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s) {
   D.system[k].forward_sweep(red.rtilde.get(), s);
   if (ctx->p2p.active) p2p_wait_assembled_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.world);
   D.system[k].backward_sweep(red.rtilde.get(), x + nq, s);
+  if (densities_final) PECS_CUDA(cudaEventRecord(densities_final, s));
   launch_ell_combine(nq, nullptr, nullptr, EllTerm{&red.Ainv, r, 1.0}, EllTerm{&red.T2, x + nq, -1.0}, EllTerm{}, x, s);
   if (ctx->p2p.active)
     p2p_publish_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.all_flags.get(), ctx->p2p.world, which);
 }
 // host != nullptr: every species' solution is downloaded into host[k] on its own stream as soon as its solve is done
 // (the copy engine works while the other solves and the Poisson part still run); *n_copies counts them
-void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_copies = nullptr) {
+// defer_currents: the main stream goes on as soon as every species' densities are final; the caller must wait for
+// join[k] (currents recovered) itself before it ends the step (enqueue_step does)
+void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_copies = nullptr, bool defer_currents = false) {
   // four concurrent solves, reference SolarCell.cpp:1763-1781 (Threads::new_task x4 + join_all)
   const int n_species = ctx->full ? 4 : (ctx->kind == PECS_KIND_PRODUCTION ? 2 : 1);
   PECS_CUDA(cudaEventRecord(ctx->fork, ctx->main));
   for (int k = 0; k < n_species; ++k) {
     if (!(ctx->owned >> k & 1)) continue;
     PECS_CUDA(cudaStreamWaitEvent(ctx->side[k], ctx->fork, 0));
-    enqueue_species_solve(ctx, k, ctx->side[k]);
+    enqueue_species_solve(ctx, k, ctx->side[k], defer_currents ? ctx->dens[k] : nullptr);
     PECS_CUDA(cudaEventRecord(ctx->join[k], ctx->side[k]));
-    PECS_CUDA(cudaStreamWaitEvent(ctx->main, ctx->join[k], 0));
+    PECS_CUDA(cudaStreamWaitEvent(ctx->main, defer_currents ? ctx->dens[k] : ctx->join[k], 0));
     if (host && host[k]) {
       PECS_CUDA(cudaMemcpyAsync(host[k], vector_of(ctx, k, false), (size_t)n_dofs_of(ctx, k) * sizeof(double),
                                 cudaMemcpyDeviceToHost, ctx->side[k]));
@@ -672,12 +682,24 @@ void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_cop
     }
   }
 }
+bool deferred_currents_enabled() {
+  const char* e = std::getenv("PECS_B200_DEFER_CURRENTS");
+  return !(e && *e == '0');
+}
 void enqueue_step(pecs_ctx* ctx, double* const* host = nullptr) {
   enqueue_carrier_rhs(ctx, 2, ctx->main);
   int n_copies = 0;
-  enqueue_full_solve(ctx, host, &n_copies);
+  // the recovery of the LDG currents (outputs only) overlaps the Poisson part; not in the sharded step, whose
+  // cross-GPU flags are published after it
+  const bool defer = !ctx->p2p.active && deferred_currents_enabled();
+  enqueue_full_solve(ctx, host, &n_copies, defer);
   enqueue_poisson_rhs(ctx, ctx->main);
   enqueue_poisson_solve(ctx, ctx->main);
+  if (defer) {
+    const int n_species = ctx->full ? 4 : (ctx->kind == PECS_KIND_PRODUCTION ? 2 : 1);
+    for (int k = 0; k < n_species; ++k)
+      if (ctx->owned >> k & 1) PECS_CUDA(cudaStreamWaitEvent(ctx->main, ctx->join[k], 0));
+  }
   if (host) {
     if (host[PECS_POISSON])
       PECS_CUDA(cudaMemcpyAsync(host[PECS_POISSON], ctx->p_solution.get(), ctx->p_solution.bytes(), cudaMemcpyDeviceToHost,
@@ -786,6 +808,7 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
       PECS_CUDA(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
       PECS_CUDA(cudaEventCreateWithFlags(&ctx->join[k], cudaEventDisableTiming));
       PECS_CUDA(cudaEventCreateWithFlags(&ctx->copied[k], cudaEventDisableTiming));
+      PECS_CUDA(cudaEventCreateWithFlags(&ctx->dens[k], cudaEventDisableTiming));
     }
     PECS_CUDA(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
 
