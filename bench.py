@@ -60,8 +60,35 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device, self.lines, self.proc = device, [], None
+        self.nvml, self.samples, self.stop_flag, self.thread = None, [], False, None
+
+    # NVML in-process (a query takes well under a millisecond, so a 0.1 s timed region still gets tens of samples);
+    # nvidia-smi -lms as the fallback
+    def _nvml_loop(self, handle):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(handle)))
+            except Exception:
+                break
+            time.sleep(0.004)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            index = self.device
+            if visible and all(t.strip().isdigit() for t in visible.split(",")):
+                index = int(visible.split(",")[self.device])
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.handle = pynvml, handle
+            self.thread = threading.Thread(target=self._nvml_loop, args=(handle,), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -75,6 +102,25 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            nv = self.nvml
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(c for c, _ in self.samples)
+            bits = 0
+            for _, r in self.samples:
+                bits |= r
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            try:
+                smax = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            except Exception:
+                smax = None
+            load = sm[len(sm) // 2:] if sm else []
+            return {"sm_mhz": float(load[len(load) // 2]) if load else None, "sm_max_mhz": smax,
+                    "reasons": sorted(k for k, v in names.items() if bits & v), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -96,7 +142,7 @@ class ClockSampler:
         # samples under load: the upper half of the clock readings
         load = sm[len(sm) // 2:] if sm else []
         return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 CONIC = False  # --workload cfg4: BASELINE.json configs[3]
