@@ -300,9 +300,6 @@ struct pecs_ctx {
   DeviceSystem p_system;
   // streams / graph
   cudaStream_t main = nullptr, side[4] = {nullptr, nullptr, nullptr, nullptr};
-  // host-buffer step: the four solves run on streams of descending priority, so that they finish one after the other
-  // and every species' download overlaps the solves still running (same total work; pecs_step_host only)
-  cudaStream_t staggered[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr}; // host-buffer step: a species' download has finished
   cudaEvent_t dens[4] = {nullptr, nullptr, nullptr, nullptr};   // step: a species' new densities are final (currents pending)
@@ -347,8 +344,6 @@ struct pecs_ctx {
       if (e) cudaEventDestroy(e);
     if (fork) cudaEventDestroy(fork);
     for (cudaStream_t s : side)
-      if (s) cudaStreamDestroy(s);
-    for (cudaStream_t s : staggered)
       if (s) cudaStreamDestroy(s);
     if (main) cudaStreamDestroy(main);
   }
@@ -544,8 +539,6 @@ void sync_all(pecs_ctx* ctx) {
   PECS_CUDA(cudaSetDevice(ctx->device));
   PECS_CUDA(cudaStreamSynchronize(ctx->main));
   for (cudaStream_t s : ctx->side) PECS_CUDA(cudaStreamSynchronize(s));
-  for (cudaStream_t s : ctx->staggered)
-    if (s) PECS_CUDA(cudaStreamSynchronize(s));
 }
 
 double* vector_of(pecs_ctx* ctx, int which, bool rhs) {
@@ -677,7 +670,7 @@ void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_cop
   PECS_CUDA(cudaEventRecord(ctx->fork, ctx->main));
   for (int k = 0; k < n_species; ++k) {
     if (!(ctx->owned >> k & 1)) continue;
-    cudaStream_t side = (host && ctx->staggered[k]) ? ctx->staggered[k] : ctx->side[k];
+    cudaStream_t side = ctx->side[k];
     PECS_CUDA(cudaStreamWaitEvent(side, ctx->fork, 0));
     enqueue_species_solve(ctx, k, side, defer_currents ? ctx->dens[k] : nullptr);
     PECS_CUDA(cudaEventRecord(ctx->join[k], side));
@@ -689,10 +682,6 @@ void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_cop
       if (n_copies) ++*n_copies;
     }
   }
-}
-bool staggered_solves_enabled() {
-  const char* e = std::getenv("PECS_B200_STAGGER");
-  return !(e && *e == '0');
 }
 bool deferred_currents_enabled() {
   const char* e = std::getenv("PECS_B200_DEFER_CURRENTS");
@@ -818,12 +807,6 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     PECS_CUDA(cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking));
     for (int k = 0; k < 4; ++k) {
       PECS_CUDA(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
-      if (staggered_solves_enabled()) {
-        int least = 0, greatest = 0; // numerically: greatest priority <= least priority
-        PECS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        const int prio = std::min(least, greatest + k);
-        PECS_CUDA(cudaStreamCreateWithPriority(&ctx->staggered[k], cudaStreamNonBlocking, prio));
-      }
       PECS_CUDA(cudaEventCreateWithFlags(&ctx->join[k], cudaEventDisableTiming));
       PECS_CUDA(cudaEventCreateWithFlags(&ctx->copied[k], cudaEventDisableTiming));
       PECS_CUDA(cudaEventCreateWithFlags(&ctx->dens[k], cudaEventDisableTiming));
