@@ -683,9 +683,13 @@ void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_cop
     }
   }
 }
+// OFF by default.  Measured +1 % (2.49 -> 2.46 ms per step at cfg3), but one of three complete GPU suite runs with it
+// failed tests/test_gpu_parity.py::test_states_after_n_steps with a 5.6e-6 density difference after 25 steps that a
+// determinism check (scripts/race_check.py, 59 x 25 steps, bit-identical) did not reproduce; until that is explained
+// the step keeps the v15 topology (PECS_B200_DEFER_CURRENTS=1 enables the overlap).
 bool deferred_currents_enabled() {
   const char* e = std::getenv("PECS_B200_DEFER_CURRENTS");
-  return !(e && *e == '0');
+  return e && *e == '1';
 }
 void enqueue_step(pecs_ctx* ctx, double* const* host = nullptr) {
   enqueue_carrier_rhs(ctx, 2, ctx->main);
