@@ -633,6 +633,8 @@ __global__ void p2p_wait_published_kernel(const unsigned long long* mine) {
   __threadfence_system();
 }
 
+int deferred_currents_mode();
+__global__ void completion_fence_kernel() {}
 // densities_final: recorded on s as soon as the new densities are complete, i.e. before the LDG currents are recovered
 // (q = Ainv r_q - T2 u): nothing inside a step reads the currents, so the step lets that last kernel overlap the
 // latency-bound Poisson part instead of keeping it on the critical path (enqueue_step)
@@ -655,7 +657,13 @@ void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s, cudaEvent_t
   D.system[k].forward_sweep(red.rtilde.get(), s);
   if (ctx->p2p.active) p2p_wait_assembled_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.world);
   D.system[k].backward_sweep(red.rtilde.get(), x + nq, s);
-  if (densities_final) PECS_CUDA(cudaEventRecord(densities_final, s));
+  if (densities_final) {
+    // mode 2: a plainly launched (non-programmatic) empty kernel first, so that the event stands behind a node whose
+    // dependency on the last backward kernel is its full completion whatever the runtime does with events recorded
+    // after a kernel that has already released its programmatic dependents (hypothesis for the v16 failure)
+    if (deferred_currents_mode() == 2) completion_fence_kernel<<<1, 1, 0, s>>>();
+    PECS_CUDA(cudaEventRecord(densities_final, s));
+  }
   launch_ell_combine(nq, nullptr, nullptr, EllTerm{&red.Ainv, r, 1.0}, EllTerm{&red.T2, x + nq, -1.0}, EllTerm{}, x, s);
   if (ctx->p2p.active)
     p2p_publish_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.all_flags.get(), ctx->p2p.world, which);
@@ -687,10 +695,11 @@ void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_cop
 // failed tests/test_gpu_parity.py::test_states_after_n_steps with a 5.6e-6 density difference after 25 steps that a
 // determinism check (scripts/race_check.py, 59 x 25 steps, bit-identical) did not reproduce; until that is explained
 // the step keeps the v15 topology (PECS_B200_DEFER_CURRENTS=1 enables the overlap).
-bool deferred_currents_enabled() {
+int deferred_currents_mode() {
   const char* e = std::getenv("PECS_B200_DEFER_CURRENTS");
-  return e && *e == '1';
+  return e && (*e == '1' || *e == '2') ? *e - '0' : 0;
 }
+bool deferred_currents_enabled() { return deferred_currents_mode() != 0; }
 void enqueue_step(pecs_ctx* ctx, double* const* host = nullptr) {
   enqueue_carrier_rhs(ctx, 2, ctx->main);
   int n_copies = 0;

@@ -123,3 +123,28 @@ def test_oracle_matches_golden():
         for s in range(5):
             ref = gold[f"state_after_steps_{s}"]
             assert abs(o.solution(s) - ref).max() <= 1e-10 * abs(ref).max()
+
+
+def test_ldg_matrices_do_not_depend_on_the_thread_count(tmp_path):
+    """host/LDG.cpp assembles the system matrices in per-thread chunks and compresses them in chunk order, so the
+    sums of duplicates are taken in the order of a sequential assembly whatever the number of threads: bit-identical"""
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import pecs_b200 as pecs\n"
+        "p = pecs.SolarCellProblem(pecs.default_input_file(3, 2, mesh__radius_one=0.2))\n"
+        "p.setup_full_system_host()\n"
+        "h = hashlib.sha256()\n"
+        "for w in range(4):\n"
+        "    m = p.matrix(w)\n"
+        "    for a in (m.indptr, m.indices, m.data):\n"
+        "        h.update(np.ascontiguousarray(a).tobytes())\n"
+        "print(h.hexdigest())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    digests = []
+    for threads in ("1", "3", "8"):
+        env = dict(os.environ, OMP_NUM_THREADS=threads)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
+        digests.append(out.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1] == digests[2]
