@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "../fe.hpp"
@@ -115,6 +117,7 @@ void LDG::assemble_system_matrices(const MeshTables& mesh, int dirichlet_id, dou
   CarrierDofs dofs{mesh.n_cells};
   // one chunk of triplets per thread over a contiguous range of cells; compressed in chunk order, so the result does
   // not depend on the number of threads (reference LDG.cpp:283-426 assembles the flux terms sequentially)
+  const double t_begin = omp_get_wtime();
   const int n_chunks = std::max(1, std::min(omp_get_max_threads(), mesh.n_cells / 64));
   pecs::PairedTripletChunks chunks(dofs.n_dofs(), n_chunks);
   const double beta[2] = {1.0 / std::sqrt(2.0), 1.0 / std::sqrt(2.0)};
@@ -212,7 +215,11 @@ void LDG::assemble_system_matrices(const MeshTables& mesh, int dirichlet_id, dou
     }
   }
   } // chunk
+  const double t_fill = omp_get_wtime();
   chunks.compress(true, matrix_1, matrix_2);
+  if (std::getenv("PECS_B200_SETUP_TIMING"))
+    std::fprintf(stderr, "LDG::assemble_system_matrices: %d cells, %d chunks: fill %.2f s, compress %.2f s\n", mesh.n_cells,
+                 n_chunks, t_fill - t_begin, omp_get_wtime() - t_fill);
 }
 
 std::string int_to_string_3(unsigned int n) {
