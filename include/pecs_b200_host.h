@@ -46,6 +46,14 @@ pecs_status pecs_solarcell_finish_output(pecs_solarcell* p);
  * 2 Poisson-) for caller-provided patch values in the pecs_output_snapshot layout */
 pecs_status pecs_solarcell_write_patches(pecs_solarcell* p, int32_t which, const double* patches, int32_t time_step_number,
                                          const char* directory);
+/* CPU check of the arithmetic the production RHS kernels run (pecs_b200/csrc/rhs_math.hpp is compiled into both the
+ * kernels and this function): the carrier right-hand sides of subdomain `which` (0 / 1) from host states -- u1, u2 the
+ * two carrier vectors of the subdomain, o1, o2 those of the other subdomain (interface traces; NULL: cell terms only, no
+ * face terms), X the Poisson vector; rhs1 / rhs2 in the [Jx|Jy|rho] layout.  Test infrastructure: the product's per-step
+ * path never calls it. */
+pecs_status pecs_solarcell_selftest_carrier_rhs(pecs_solarcell* p, int32_t which, const double* u1, const double* u2,
+                                                const double* o1, const double* o2, const double* X, double* rhs1,
+                                                double* rhs2);
 /* the four PostProcessor scales {potential, field, density, current} (reference source/PostProcessor.cpp:14-18) */
 pecs_status pecs_solarcell_output_scales(const pecs_solarcell* p, double scales[4]);
 /* test_steady_state / test_transient / test_DD_Poisson at one refinement level; errors[4] = {u, J, Phi, D} */

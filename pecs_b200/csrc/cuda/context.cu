@@ -509,30 +509,7 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
 }
 
 void fill_rhs_params(pecs_ctx& ctx) {
-  const double* p = ctx.params;
-  for (int w = 0; w < 2; ++w) {
-    RhsParams& r = ctx.dom[w].prm;
-    r.kind = ctx.kind;
-    r.is_semiconductor = w == 0;
-    r.inv_dt = 1.0 / p[PECS_P_DELTA_T];
-    r.tau = p[PECS_P_PENALTY];
-    r.charge1 = -1.0; // reference SolarCell.cpp:54,59,71,76
-    r.charge2 = 1.0;
-    r.inv_eps = 1.0 / (w == 0 ? p[PECS_P_EPS_S] : p[PECS_P_EPS_E]);
-    r.gen_scale = w == 0 ? p[PECS_P_GEN_ALPHA] * p[PECS_P_GEN_FLUX] : 0.0;
-    r.gen_alpha = p[PECS_P_GEN_ALPHA];
-    r.gen_location = p[PECS_P_GEN_LOCATION];
-    r.rho1_e = w == 0 ? p[PECS_P_RHO_N_E] : p[PECS_P_RHO_R_E];
-    r.rho2_e = w == 0 ? p[PECS_P_RHO_P_E] : p[PECS_P_RHO_O_E];
-    r.other1_e = p[PECS_P_RHO_N_E];
-    r.other2_e = p[PECS_P_RHO_P_E];
-    r.k_et = p[PECS_P_K_ET];
-    r.k_ht = p[PECS_P_K_HT];
-    r.v_n = p[PECS_P_V_N];
-    r.v_p = p[PECS_P_V_P];
-    r.doping = w == 0 ? p[PECS_P_RHO_N_E] - p[PECS_P_RHO_P_E] : 0.0; // N_D = electrons_e, N_A = holes_e (SolarCell.cpp:542-548)
-    r.time = 0.0;
-  }
+  for (int w = 0; w < 2; ++w) ctx.dom[w].prm = make_rhs_params(ctx.params, ctx.kind, w);
 }
 
 void sync_all(pecs_ctx* ctx) {

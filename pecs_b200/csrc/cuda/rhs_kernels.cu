@@ -28,6 +28,7 @@
 
 #include "../../../include/pecs_b200.h"
 #include "../fe.hpp"
+#include "../rhs_math.hpp"
 #include "../test_functions.hpp"
 
 namespace pecs {
@@ -176,21 +177,10 @@ __device__ __forceinline__ void carrier_cell_terms(const DomainView& d, const Rh
 }
 
 // ------------------------------------------------------------------------------------------ boundary faces
-// trace of the density of a cell at a face point
-__device__ __forceinline__ double trace(const double N[4], const double r[4]) {
-  return N[0] * r[0] + N[1] * r[1] + N[2] * r[2] + N[3] * r[3];
-}
-
 // Face terms of boundary cell record r, added to what the cell terms of the same thread have just stored.  Kept out
 // of line: 1.5 % of the cells take this path and its registers must not burden the other 98.5 %.
-// one boundary record as the face routine wants it: all loads are independent of each other
-struct BoundaryRecord {
-  int id[4];   // boundary id of face f, -1: interior face
-  int nb_cell; // matched cell of the other subdomain across the interface face, -1: none
-  int nb_face;
-};
-__device__ __forceinline__ BoundaryRecord load_record(const DomainView& d, int r) {
-  BoundaryRecord b;
+__device__ __forceinline__ rhsmath::BoundaryRecord load_record(const DomainView& d, int r) {
+  rhsmath::BoundaryRecord b;
   const int4 ids = __ldg(reinterpret_cast<const int4*>(d.bface_id) + r);
   b.id[0] = ids.x, b.id[1] = ids.y, b.id[2] = ids.z, b.id[3] = ids.w;
   b.nb_cell = __ldg(d.bnb_cell + r);
@@ -212,110 +202,10 @@ __global__ void boundary_geometry_kernel(DomainView d, double tau, double* __res
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= d.n_bcells) return;
   const fe::CellVerts v = load_verts(d, d.bcell[r]);
-  const double pen = tau / fe::cell_diameter(v);
-  for (int f = 0; f < 4; ++f) {
-    double xi, eta, nx, ny, ds;
-    fe::face_point(f, 0.5, xi, eta);
-    fe::face_normal_ds(fe::jacobian(v, xi, eta), f, nx, ny, ds);
-    double* o = out + 16 * (size_t)r + 4 * f;
-    o[0] = nx, o[1] = ny, o[2] = ds, o[3] = pen;
-  }
+  rhsmath::boundary_geometry(v, tau, out + 16 * (size_t)r);
 }
 
-// accumulate form: the record, the cell's vertices and densities and the interface neighbour's densities (q1, q2; the
-// same quadrature index on both sides) come in registers, the face terms are ADDED to jx1 .. rh2
-// geom[f] = {n_x, n_y, |dx/dt|, tau/h} of face f: the edges of a bilinear cell are straight, so normal and surface
-// element are constant along a face and time independent -- evaluated once (boundary_geometry_kernel) instead of a
-// square root and two divisions per quadrature point and step.  The face and point loops are unrolled: the traces
-// N_a(x_q) become immediates (two of the four vanish on a face).
-template <int KIND>
-__device__ __forceinline__ void boundary_terms_accumulate(const RhsParams& p, const BoundaryRecord& rec,
-                                                          const double geom[4][4], const fe::CellVerts& v,
-                                                          const double r1[4], const double r2[4], const double q1[4],
-                                                          const double q2[4], double jx1[4], double jy1[4], double rh1[4],
-                                                          double jx2[4], double jy2[4], double rh2[4]) {
-  constexpr bool kProduction = KIND == PECS_KIND_PRODUCTION;
-  const int nb_face = rec.nb_face;
-#pragma unroll
-  for (int f = 0; f < 4; ++f) {
-    const int id = rec.id[f];
-    if (id < 0 || id == PECS_NEUMANN) continue; // interior face, or insulating: nothing to do
-    const double nx = geom[f][0], ny = geom[f][1], ds = geom[f][2], pen = geom[f][3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const double t = fe::gauss_x(q);
-      double xi, eta, N[4];
-      fe::face_point(f, t, xi, eta);
-      fe::shape(xi, eta, N);
-      const double W = ds * fe::gauss_w(q);
-      if (id == PECS_DIRICHLET) {
-        // int ( -p.n + (tau/h) v ) u_D
-        double bc1, bc2 = 0.0;
-        if (kProduction) {
-          bc1 = p.rho1_e;
-          bc2 = p.rho2_e;
-        } else {
-          double x, y;
-          fe::map_point(v, xi, eta, x, y);
-          bc1 = (KIND == PECS_KIND_TEST_STEADY) ? testfn::poisson_bc(x, y) : testfn::density(x, y, p.time);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          jx1[a] += -N[a] * nx * bc1 * W;
-          jy1[a] += -N[a] * ny * bc1 * W;
-          rh1[a] += pen * N[a] * bc1 * W;
-          if (kProduction) {
-            jx2[a] += -N[a] * nx * bc2 * W;
-            jy2[a] += -N[a] * ny * bc2 * W;
-            rh2[a] += pen * N[a] * bc2 * W;
-          }
-        }
-      } else if (id == PECS_INTERFACE) {
-        if (kProduction) {
-          double xin, etan, Nn[4];
-          fe::face_point(nb_face, t, xin, etan);
-          fe::shape(xin, etan, Nn);
-          if (p.is_semiconductor) {
-            // -v k_et (rho_n - rho_n^e) rho_o -> electrons ; +v k_ht (rho_p - rho_p^e) rho_r -> holes
-            const double e = -p.k_et * (trace(N, r1) - p.rho1_e) * trace(Nn, q2) * W;
-            const double hl = p.k_ht * (trace(N, r2) - p.rho2_e) * trace(Nn, q1) * W;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              rh1[a] += N[a] * e;
-              rh2[a] += N[a] * hl;
-            }
-          } else {
-            // current = -k_et (rho_n - rho_n^e) rho_o + k_ht (rho_p - rho_p^e) rho_r ; reductants += , oxidants -=
-            const double cur = (-p.k_et * (trace(Nn, q1) - p.other1_e) * trace(N, r2) +
-                                p.k_ht * (trace(Nn, q2) - p.other2_e) * trace(N, r1)) * W;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              rh1[a] += N[a] * cur;
-              rh2[a] -= N[a] * cur;
-            }
-          }
-        } else if (KIND == PECS_KIND_TEST_TRANSIENT) {
-          double x, y;
-          fe::map_point(v, xi, eta, x, y);
-          const double g = -testfn::ldg_interface(x, y, p.time) * W;
-#pragma unroll
-          for (int a = 0; a < 4; ++a) rh1[a] += N[a] * g;
-        }
-      } else if (id == PECS_SCHOTTKY) {
-        if (kProduction && p.is_semiconductor) {
-          const double e = -p.v_n * (trace(N, r1) - p.rho1_e) * W;
-          const double hl = p.v_p * (trace(N, r2) - p.rho2_e) * W;
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            rh1[a] += N[a] * e;
-            rh2[a] += N[a] * hl;
-          }
-        }
-      }
-    }
-  }
-}
-
+// face terms of boundary record r added to the rows the cell terms have just been stored to (point-by-point kernel)
 template <int KIND>
 __device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int other_n_cells, const RhsParams& p, int r,
                                                     const double* __restrict__ u1, const double* __restrict__ u2,
@@ -330,7 +220,7 @@ __device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int oth
   if (kProduction) load4(u2 + 8 * n + 4 * (size_t)c, r2);
   double jx1[4] = {0, 0, 0, 0}, jy1[4] = {0, 0, 0, 0}, rh1[4] = {0, 0, 0, 0};
   double jx2[4] = {0, 0, 0, 0}, jy2[4] = {0, 0, 0, 0}, rh2[4] = {0, 0, 0, 0};
-  const BoundaryRecord rec = load_record(d, r);
+  const rhsmath::BoundaryRecord rec = load_record(d, r);
   double q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
   if (kProduction && rec.nb_cell >= 0) {
     load4(o1 + 8 * (size_t)other_n_cells + 4 * (size_t)rec.nb_cell, q1);
@@ -338,7 +228,7 @@ __device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int oth
   }
   double geom[4][4];
   load_geometry(d, r, geom);
-  boundary_terms_accumulate<KIND>(p, rec, geom, v, r1, r2, q1, q2, jx1, jy1, rh1, jx2, jy2, rh2);
+  rhsmath::boundary_terms_accumulate<KIND>(p, rec, geom, v, r1, r2, q1, q2, jx1, jy1, rh1, jx2, jy2, rh2);
   add4(rhs1 + 4 * (size_t)c, jx1);
   add4(rhs1 + 4 * n + 4 * (size_t)c, jy1);
   add4(rhs1 + 8 * n + 4 * (size_t)c, rh1);
@@ -375,27 +265,8 @@ __global__ void static_cell_integrals_kernel(DomainView d, RhsParams p, double* 
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d.n_cells) return;
   const fe::CellVerts v = load_verts(d, c);
-  double m[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int qy = 0; qy < 3; ++qy)
-#pragma unroll
-    for (int qx = 0; qx < 3; ++qx) {
-      const double xi = fe::gauss_x(qx), eta = fe::gauss_x(qy), w = fe::gauss_w(qx) * fe::gauss_w(qy);
-      const fe::Jac j = fe::jacobian(v, xi, eta);
-      double N[4];
-      fe::shape(xi, eta, N);
-      const double JxW = j.det * w;
-      double gen = 0.0;
-      if (gen_int) {
-        const double y = v.y[0] * N[0] + v.y[1] * N[1] + v.y[2] * N[2] + v.y[3] * N[3];
-        gen = p.gen_scale * exp(p.gen_alpha * (y - p.gen_location));
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        m[a] += N[a] * JxW;
-        g[a] += N[a] * (gen * JxW);
-      }
-    }
+  double m[4], g[4];
+  rhsmath::static_cell_integrals(v, gen_int != nullptr, p.gen_scale, p.gen_alpha, p.gen_location, m, g);
   store4(nodal_int + 4 * (size_t)c, m);
   if (gen_int) store4(gen_int + 4 * (size_t)c, g);
 }
@@ -417,90 +288,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Cell terms of both carriers of one production cell from values in registers, sum-factorised over the 3 x 3 tensor
-// Gauss rule: with N_a = L_ax(xi) L_ay(eta), XA_j = w_j x_xi(eta_j), XB_i = w_i x_eta(xi_i), HX_i = w_i Dhat_x(xi_i),
-// HY_j = w_j Dhat_y(eta_j) (and Y likewise)
-//     JxW_ij = XA_j YB_i - XB_i YA_j,   JxW_ij eps E_x = XA_j HX_i + XB_i HY_j,   JxW_ij eps E_y = YA_j HX_i + YB_i HY_j
-// are shared by both carriers; per carrier the three integrands rho {JxW, Ex, Ey} are contracted first along xi, then
-// along eta: ~420 fp64 operations per cell instead of ~800 for the point-by-point form, no division, no exp.
-__device__ __forceinline__ void production_cell_terms(const double vx[4], const double vy[4], const double r1[4],
-                                                      const double r2[4], const double Xf[4], const double gen[4],
-                                                      double inv_dt, double s1, double s2, double jx1[4], double jy1[4],
-                                                      double rh1[4], double jx2[4], double jy2[4], double rh2[4]) {
-  const double ax = vx[1] - vx[0], bx = vx[3] - vx[2], cx = vx[2] - vx[0], dx = vx[3] - vx[1];
-  const double ay = vy[1] - vy[0], by = vy[3] - vy[2], cy = vy[2] - vy[0], dy = vy[3] - vy[1];
-  double XA[3], YA[3], XB[3], YB[3], HX[3], HY[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const double l0w = (1.0 - fe::gauss_x(k)) * fe::gauss_w(k), l1w = fe::gauss_x(k) * fe::gauss_w(k);
-    XA[k] = ax * l0w + bx * l1w;
-    YA[k] = ay * l0w + by * l1w;
-    XB[k] = cx * l0w + dx * l1w;
-    YB[k] = cy * l0w + dy * l1w;
-    HX[k] = Xf[0] * l0w + Xf[1] * l1w;
-    HY[k] = Xf[2] * l0w + Xf[3] * l1w;
-  }
-  double JxW[3][3], Ex[3][3], Ey[3][3]; // [j][i]
-#pragma unroll
-  for (int j = 0; j < 3; ++j)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      JxW[j][i] = XA[j] * YB[i] - XB[i] * YA[j];
-      Ex[j][i] = XA[j] * HX[i] + XB[i] * HY[j];
-      Ey[j][i] = YA[j] * HX[i] + YB[i] * HY[j];
-    }
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const double* r = k == 0 ? r1 : r2;
-    double* jx = k == 0 ? jx1 : jx2;
-    double* jy = k == 0 ? jy1 : jy2;
-    double* rh = k == 0 ? rh1 : rh2;
-    const double s = k == 0 ? s1 : s2;
-    double bot[3], top[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double l0 = 1.0 - fe::gauss_x(i), l1 = fe::gauss_x(i);
-      bot[i] = r[0] * l0 + r[1] * l1;
-      top[i] = r[2] * l0 + r[3] * l1;
-    }
-    double ax_[4] = {0, 0, 0, 0}, ay_[4] = {0, 0, 0, 0}, am[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const double m0 = 1.0 - fe::gauss_x(j), m1 = fe::gauss_x(j);
-      double sm0 = 0, sm1 = 0, sx0 = 0, sx1 = 0, sy0 = 0, sy1 = 0;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double rho = bot[i] * m0 + top[i] * m1;
-        const double rho0 = rho * (1.0 - fe::gauss_x(i)), rho1 = rho * fe::gauss_x(i);
-        sm0 += rho0 * JxW[j][i];
-        sm1 += rho1 * JxW[j][i];
-        sx0 += rho0 * Ex[j][i];
-        sx1 += rho1 * Ex[j][i];
-        sy0 += rho0 * Ey[j][i];
-        sy1 += rho1 * Ey[j][i];
-      }
-      am[0] += m0 * sm0;
-      am[1] += m0 * sm1;
-      am[2] += m1 * sm0;
-      am[3] += m1 * sm1;
-      ax_[0] += m0 * sx0;
-      ax_[1] += m0 * sx1;
-      ax_[2] += m1 * sx0;
-      ax_[3] += m1 * sx1;
-      ay_[0] += m0 * sy0;
-      ay_[1] += m0 * sy1;
-      ay_[2] += m1 * sy0;
-      ay_[3] += m1 * sy1;
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      rh[a] = am[a] * inv_dt + gen[a];
-      jx[a] = s * ax_[a];
-      jy[a] = s * ay_[a];
-    }
-  }
-}
 
 // Streaming production kernel.  One resident wave of blocks; a block owns tiles of kThreads consecutive cells (both
 // subdomains form one tile sequence) and walks them with stride gridDim.x.  Every thread keeps the inputs of its NEXT
@@ -600,7 +387,7 @@ __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const 
   const DomainView& d = w.d;
   const size_t n = (size_t)d.n_cells;
   const int c = __ldg(d.bcell + r);
-  const BoundaryRecord rec = load_record(d, r);
+  const rhsmath::BoundaryRecord rec = load_record(d, r);
   double geom[4][4];
   load_geometry(d, r, geom);
   fe::CellVerts v;
@@ -622,11 +409,11 @@ __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const 
 #pragma unroll
   for (int a = 0; a < 4; ++a) Xf[a] = __ldg(X + dof[a]);
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
-  production_cell_terms(v.x, v.y, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
+  rhsmath::production_cell_terms(v.x, v.y, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
                         jy1, rh1, jx2, jy2, rh2);
   double bx1[4] = {0, 0, 0, 0}, by1[4] = {0, 0, 0, 0}, bh1[4] = {0, 0, 0, 0};
   double bx2[4] = {0, 0, 0, 0}, by2[4] = {0, 0, 0, 0}, bh2[4] = {0, 0, 0, 0};
-  boundary_terms_accumulate<PECS_KIND_PRODUCTION>(w.p, rec, geom, v, r1, r2, q1, q2, bx1, by1, bh1, bx2, by2, bh2);
+  rhsmath::boundary_terms_accumulate<PECS_KIND_PRODUCTION>(w.p, rec, geom, v, r1, r2, q1, q2, bx1, by1, bh1, bx2, by2, bh2);
 #pragma unroll
   for (int a = 0; a < 4; ++a) { // same order of additions as "store the cell terms, then add the face terms"
     jx1[a] += bx1[a];
@@ -691,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 4)
         gen[0] = g0.x, gen[1] = g0.y, gen[2] = g1.x, gen[3] = g1.y;
       }
       double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
-      production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps,
+      rhsmath::production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps,
                             jx1, jy1, rh1, jx2, jy2, rh2);
       store_cell<true>(w, cur.c, jx1, jy1, rh1, jx2, jy2, rh2);
     }
@@ -730,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
   if (w.d.gen_int) load4_256(w.d.gen_int + 4 * (size_t)c, gen);
   if (record >= 0) return; // done by a boundary tile
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
-  production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
+  rhsmath::production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
                         jy1, rh1, jx2, jy2, rh2);
   store_cell<true>(w, c, jx1, jy1, rh1, jx2, jy2, rh2);
 }
@@ -777,12 +564,12 @@ __global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(const __grid
       fe::shape(xi, eta, N);
       double f;
       if (KIND == PECS_KIND_PRODUCTION) {
-        f = p.doping + (p.charge1 * trace(N, r1) + p.charge2 * trace(N, r2));
+        f = p.doping + (p.charge1 * rhsmath::trace(N, r1) + p.charge2 * rhsmath::trace(N, r2));
       } else {
         double x, y;
         fe::map_point(v, xi, eta, x, y);
         f = (KIND == PECS_KIND_TEST_STEADY) ? testfn::poisson_rhs(x, y)
-                                            : (testfn::dd_poisson_rhs(x, y, p.time) - trace(N, r1));
+                                            : (testfn::dd_poisson_rhs(x, y, p.time) - rhsmath::trace(N, r1));
       }
       acc += -f * (j.det * w);
     }

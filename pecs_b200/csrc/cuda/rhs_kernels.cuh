@@ -4,6 +4,8 @@
 
 #include <cstdint>
 
+#include "../rhs_math.hpp"
+
 namespace pecs {
 
 // one carrier subdomain as the kernels see it (structure of arrays, all device pointers)
@@ -24,22 +26,6 @@ struct DomainView {
   // static cell integrals (production; launch_static_cell_integrals), NULL when absent
   const double* nodal_int; // [n_cells][4] int N_a
   const double* gen_int;   // [n_cells][4] int N_a G   (semiconductor under illumination only)
-};
-
-// scalars of one subdomain pass (see include/pecs_b200.h PECS_P_*)
-struct RhsParams {
-  int kind;            // PECS_KIND_*
-  int is_semiconductor;
-  double inv_dt;       // 1 / delta_t (carried by the mass matrix in the reference, LDG.cpp:77-79)
-  double tau;          // penalty
-  double charge1, charge2;
-  double inv_eps;
-  double gen_scale, gen_alpha, gen_location; // alpha*G0, alpha, H (0 scale = dark)
-  double rho1_e, rho2_e;                     // equilibrium / Dirichlet densities of this subdomain's carriers
-  double other1_e, other2_e;                 // electrons_e, holes_e as seen from the electrolyte side
-  double k_et, k_ht, v_n, v_p;
-  double doping;       // N_D - N_A (semiconductor) or 0 (electrolyte)
-  double time;         // manufactured right-hand sides
 };
 
 // everything one subdomain contributes to a fused launch; n_cells == 0: pass absent

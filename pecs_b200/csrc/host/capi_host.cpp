@@ -7,6 +7,7 @@
 
 #include "../../../include/pecs_b200_host.h"
 #include "../error.hpp"
+#include "../rhs_math.hpp"
 #include "SolarCell.hpp"
 #include "SolverSetup.hpp"
 
@@ -116,6 +117,77 @@ pecs_status pecs_solarcell_write_patches(pecs_solarcell* p, int32_t which, const
     else
       s.LDG_Assembler.output_rescaled_results(mesh, which == 0 ? s.electron_hole_pair : s.redox_pair, s.sim_params, patches,
                                               (unsigned)time_step_number, dir);
+  });
+}
+pecs_status pecs_solarcell_selftest_carrier_rhs(pecs_solarcell* p, int32_t which, const double* u1, const double* u2,
+                                                const double* o1, const double* o2, const double* X, double* rhs1,
+                                                double* rhs2) {
+  return guarded([&] {
+    if (which < 0 || which > 1 || !u1 || !u2 || !X || !rhs1 || !rhs2)
+      throw pecs::StatusError(PECS_ERR_INVALID, "selftest_carrier_rhs: bad argument");
+    SolarCellProblem& s = *p->problem;
+    const pecs::MeshTables& mesh = tria(p, which).tables();
+    const std::vector<int>& to_poisson = which == 0 ? s.s_2_p_map : s.e_2_p_map;
+    const std::vector<int>& face_dof = s.Poisson_object.dofs.face_dof;
+    double prm[32];
+    s.fill_params(prm);
+    const pecs::RhsParams rp = pecs::make_rhs_params(prm, PECS_KIND_PRODUCTION, which);
+    const size_t n = (size_t)mesh.n_cells;
+    const size_t n_other = (size_t)tria(p, 1 - which).tables().n_cells;
+    // interface neighbour of a cell of this subdomain (one interface face per cell at most)
+    std::vector<int> nb_cell(n, -1), nb_face(n, 0);
+    const std::vector<int>& mine_c = which == 0 ? s.semi_interface_cells : s.elec_interface_cells;
+    const std::vector<int>& other_c = which == 0 ? s.elec_interface_cells : s.semi_interface_cells;
+    const std::vector<int>& other_f = which == 0 ? s.elec_interface_faces : s.semi_interface_faces;
+    for (size_t k = 0; k < mine_c.size(); ++k) {
+      nb_cell[mine_c[k]] = other_c[k];
+      nb_face[mine_c[k]] = other_f[k];
+    }
+    for (size_t c = 0; c < n; ++c) {
+      pecs::fe::CellVerts v;
+      const double* vt = mesh.vtx((int)c);
+      for (int a = 0; a < 4; ++a) {
+        v.x[a] = vt[2 * a];
+        v.y[a] = vt[2 * a + 1];
+      }
+      double m[4], gen[4], Xf[4];
+      pecs::rhsmath::static_cell_integrals(v, rp.gen_scale != 0.0, rp.gen_scale, rp.gen_alpha, rp.gen_location, m, gen);
+      for (int f = 0; f < 4; ++f) Xf[f] = X[face_dof[4 * (size_t)to_poisson[c] + f]];
+      const double* r1 = u1 + 8 * n + 4 * c;
+      const double* r2 = u2 + 8 * n + 4 * c;
+      double o[6][4];
+      pecs::rhsmath::production_cell_terms(v.x, v.y, r1, r2, Xf, gen, rp.inv_dt, rp.charge1 * rp.inv_eps,
+                                           rp.charge2 * rp.inv_eps, o[0], o[1], o[2], o[3], o[4], o[5]);
+      // face terms exactly as cuda/rhs_kernels.cu boundary_record adds them (skipped when o1 / o2 are not given)
+      pecs::rhsmath::BoundaryRecord rec{{-1, -1, -1, -1}, nb_cell[c], nb_face[c]};
+      bool boundary = false;
+      for (int f = 0; f < 4; ++f)
+        if (mesh.face_kind[4 * c + f] == pecs::FACE_BOUNDARY) {
+          rec.id[f] = mesh.boundary_id[4 * c + f];
+          boundary = true;
+        }
+      if (boundary && o1 && o2) {
+        double geom[4][4], q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0}, b[6][4] = {};
+        pecs::rhsmath::boundary_geometry(v, rp.tau, &geom[0][0]);
+        if (rec.nb_cell >= 0)
+          for (int a = 0; a < 4; ++a) {
+            q1[a] = o1[8 * n_other + 4 * (size_t)rec.nb_cell + a];
+            q2[a] = o2[8 * n_other + 4 * (size_t)rec.nb_cell + a];
+          }
+        pecs::rhsmath::boundary_terms_accumulate<PECS_KIND_PRODUCTION>(rp, rec, geom, v, r1, r2, q1, q2, b[0], b[1], b[2], b[3],
+                                                                       b[4], b[5]);
+        for (int k = 0; k < 6; ++k)
+          for (int a = 0; a < 4; ++a) o[k][a] += b[k][a];
+      }
+      for (int a = 0; a < 4; ++a) {
+        rhs1[4 * c + a] = o[0][a];
+        rhs1[4 * n + 4 * c + a] = o[1][a];
+        rhs1[8 * n + 4 * c + a] = o[2][a];
+        rhs2[4 * c + a] = o[3][a];
+        rhs2[4 * n + 4 * c + a] = o[4][a];
+        rhs2[8 * n + 4 * c + a] = o[5][a];
+      }
+    }
   });
 }
 pecs_status pecs_solarcell_output_scales(const pecs_solarcell* p, double scales[4]) {

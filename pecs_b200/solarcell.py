@@ -159,6 +159,18 @@ class SolarCellProblem:
                 out.append({"field": b[:12 * c].reshape(-1, 3), "potential": b[12 * c:]})
         return out
 
+    def selftest_carrier_rhs(self, which, u1, u2, X, o1=None, o2=None):
+        """CPU evaluation of the production kernels' arithmetic (csrc/rhs_math.hpp): carrier right-hand sides of
+        subdomain `which`; without o1/o2 (the other subdomain's carriers) only the cell terms -> (rhs1, rhs2)"""
+        u1, u2, X = (np.ascontiguousarray(a, dtype=np.float64) for a in (u1, u2, X))
+        if o1 is not None:
+            o1, o2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (o1, o2))
+        r1, r2 = np.zeros_like(u1), np.zeros_like(u2)
+        check(self._lib.pecs_solarcell_selftest_carrier_rhs(
+            self._h, which, _dp(u1), _dp(u2), _dp(o1) if o1 is not None else None, _dp(o2) if o2 is not None else None,
+            _dp(X), _dp(r1), _dp(r2)))
+        return r1, r2
+
     def run_test(self, kind, n_refine):
         """test_steady_state / test_transient / test_DD_Poisson at one level -> dict of L2 errors."""
         e = np.zeros(4)

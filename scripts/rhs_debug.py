@@ -29,7 +29,7 @@ for v in ("1", "2"):
             scale = np.abs(y).max()
             bad |= ~(np.abs(x - y).max(axis=1) <= 1e-12 * scale)
         mesh = prob.mesh(s // 2)
-        bdry = (mesh["face_kind"] == 0).any(axis=1) if "face_kind" in mesh else None
+        bdry = (mesh["face_kind"] == 1).any(axis=1) if "face_kind" in mesh else None
         print(f"variant {v} species {s}: {bad.sum()} of {n} cells differ; nan cells {np.isnan(a.reshape(3, n, 4)).any(axis=(0, 2)).sum()}",
               "first bad:", np.flatnonzero(bad)[:10])
         if bad.any():

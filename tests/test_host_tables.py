@@ -148,3 +148,41 @@ def test_ldg_matrices_do_not_depend_on_the_thread_count(tmp_path):
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
         digests.append(out.stdout.strip().splitlines()[-1])
     assert digests[0] == digests[1] == digests[2]
+
+
+@pytest.mark.parametrize("g,l,overrides", [
+    (3, 1, {}), (3, 2, {"mesh__radius_one": 0.2}),
+    (2, 1, {"physical__illumination_status": False, "physical__schottky_status": False, "physical__insulated": False,
+            "physical__applied_bias": 0.2})])
+def test_production_rhs_arithmetic_matches_oracle_on_cpu(g, l, overrides):
+    """The arithmetic of the production RHS kernels -- csrc/rhs_math.hpp: static generation integrals, sum-factorised
+    cell terms, static face geometry and the Dirichlet / interface / Schottky face terms, the very inline functions
+    the CUDA kernels call -- evaluated on the CPU against the oracle's assembly from a perturbed state: all four
+    carrier right-hand sides, 1e-12 relative per block (the tolerance of the GPU parity tests).  What only the GPU
+    tests can cover is the kernels' data movement: loads, stores, launch shapes, boundary blocks."""
+    from helpers import block_rel_err, perturbed
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **overrides))
+    prob.setup_full_system_host()
+    o = make_oracle(prob, True)
+    o.project_initial_conditions()
+    o.assemble_Poisson_rhs()
+    o.solve_Poisson()
+    for s in range(4):
+        o.set_vector(s, 0, perturbed(o.solution(s), 4321 + s))
+    o.set_vector(4, 0, perturbed(o.solution(4), 77))
+    o.assemble_semiconductor_rhs()
+    o.assemble_electrolyte_rhs()
+    u, X = [o.solution(s) for s in range(4)], o.solution(4)
+    for w in range(2):
+        got = prob.selftest_carrier_rhs(w, u[2 * w], u[2 * w + 1], X, u[2 - 2 * w], u[3 - 2 * w])
+        for k in range(2):
+            assert block_rel_err(got[k], o.rhs(2 * w + k)) <= 1e-12, (w, k)
+        # without the other subdomain's vectors: cell terms only, equal on the cells without boundary faces
+        cells_only = prob.selftest_carrier_rhs(w, u[2 * w], u[2 * w + 1], X)
+        interior = ~(prob.mesh(w)["face_kind"] == 1).any(axis=1)  # FACE_BOUNDARY == 1
+        n = interior.size
+        assert 0 < interior.sum() < n
+        for k in range(2):
+            a, b = cells_only[k].reshape(3, n, 4), got[k].reshape(3, n, 4)
+            assert np.array_equal(a[:, interior], b[:, interior]) and not np.array_equal(a, b)
+    prob.close()
