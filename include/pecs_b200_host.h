@@ -54,6 +54,10 @@ pecs_status pecs_solarcell_write_patches(pecs_solarcell* p, int32_t which, const
 pecs_status pecs_solarcell_selftest_carrier_rhs(pecs_solarcell* p, int32_t which, const double* u1, const double* u2,
                                                 const double* o1, const double* o2, const double* X, double* rhs1,
                                                 double* rhs2);
+/* the same for the potential rows of the Poisson right-hand side (static int N_a table + charge row; rows of the Poisson
+ * cells, phi_rows[n_poisson_cells]) and for the RT0 field at the patch vertices of the output path (field[4n][2]) */
+pecs_status pecs_solarcell_selftest_poisson_rows(pecs_solarcell* p, const double* const densities[4], double* phi_rows);
+pecs_status pecs_solarcell_selftest_field_patches(pecs_solarcell* p, const double* X, double scale, double* field);
 /* the four PostProcessor scales {potential, field, density, current} (reference source/PostProcessor.cpp:14-18) */
 pecs_status pecs_solarcell_output_scales(const pecs_solarcell* p, double scales[4]);
 /* test_steady_state / test_transient / test_DD_Poisson at one refinement level; errors[4] = {u, J, Phi, D} */

@@ -75,6 +75,8 @@ SIGNATURES = {
     "pecs_solarcell_write_patches": (C.c_int, [VOIDP, C.c_int32, c_double_p, C.c_int32, C.c_char_p]),
     "pecs_solarcell_selftest_carrier_rhs": (C.c_int, [VOIDP, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p,
                                                      c_double_p, c_double_p, c_double_p]),
+    "pecs_solarcell_selftest_poisson_rows": (C.c_int, [VOIDP, C.POINTER(c_double_p), c_double_p]),
+    "pecs_solarcell_selftest_field_patches": (C.c_int, [VOIDP, c_double_p, C.c_double, c_double_p]),
     "pecs_solarcell_output_scales": (C.c_int, [VOIDP, c_double_p]),
     "pecs_solarcell_run_test": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p]),
     "pecs_solarcell_ctx": (VOIDP, [VOIDP]),

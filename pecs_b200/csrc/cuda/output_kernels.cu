@@ -9,6 +9,7 @@
 #include "output_kernels.cuh"
 
 #include "../fe.hpp"
+#include "../rhs_math.hpp"
 
 namespace pecs {
 
@@ -57,13 +58,11 @@ __global__ void poisson_patch_kernel(int n, const double* __restrict__ vx, const
   double* pot = out + 12 * N;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const double xi = (double)(a & 1), eta = (double)(a >> 1);
-    const fe::Jac j = fe::jacobian(v, xi, eta);
-    const double dhx = Xf[0] * (1.0 - xi) + Xf[1] * xi, dhy = Xf[2] * (1.0 - eta) + Xf[3] * eta;
-    const double s = scale_field / j.det;
     const size_t p = 4 * (size_t)c + a;
-    field[3 * p + 0] = s * (j.xxi * dhx + j.xeta * dhy);
-    field[3 * p + 1] = s * (j.yxi * dhx + j.yeta * dhy);
+    double fx, fy;
+    rhsmath::rt0_field_at_vertex(v, Xf, a, scale_field, fx, fy);
+    field[3 * p + 0] = fx;
+    field[3 * p + 1] = fy;
     field[3 * p + 2] = 0.0;
     pot[p] = potential;
   }

@@ -542,10 +542,7 @@ __global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(const __grid
     load4_256(u1 + 8 * n + 4 * (size_t)c, r1);
     load4_256(u2 + 8 * n + 4 * (size_t)c, r2);
     load4_256(d.nodal_int + 4 * (size_t)c, m);
-    double acc = 0.0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) acc -= m[a] * (p.doping + (p.charge1 * r1[a] + p.charge2 * r2[a]));
-    poisson_rhs[d.phi_dof[c]] = acc;
+    poisson_rhs[d.phi_dof[c]] = rhsmath::poisson_charge_row(p, m, r1, r2);
     return;
   }
   const fe::CellVerts v = load_verts(d, c);

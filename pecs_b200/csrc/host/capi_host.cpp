@@ -190,6 +190,53 @@ pecs_status pecs_solarcell_selftest_carrier_rhs(pecs_solarcell* p, int32_t which
     }
   });
 }
+pecs_status pecs_solarcell_selftest_poisson_rows(pecs_solarcell* p, const double* const densities[4], double* phi_rows) {
+  return guarded([&] {
+    if (!densities || !phi_rows) throw pecs::StatusError(PECS_ERR_INVALID, "selftest_poisson_rows: bad argument");
+    SolarCellProblem& s = *p->problem;
+    double prm[32];
+    s.fill_params(prm);
+    for (int w = 0; w < (s.full_system ? 2 : 1); ++w) {
+      const pecs::MeshTables& mesh = tria(p, w).tables();
+      const std::vector<int>& to_poisson = w == 0 ? s.s_2_p_map : s.e_2_p_map;
+      const pecs::RhsParams rp = pecs::make_rhs_params(prm, PECS_KIND_PRODUCTION, w);
+      const size_t n = (size_t)mesh.n_cells;
+      const double *u1 = densities[2 * w], *u2 = densities[2 * w + 1];
+      if (!u1 || !u2) throw pecs::StatusError(PECS_ERR_INVALID, "selftest_poisson_rows: missing carrier vector");
+      for (size_t c = 0; c < n; ++c) {
+        pecs::fe::CellVerts v;
+        const double* vt = mesh.vtx((int)c);
+        for (int a = 0; a < 4; ++a) {
+          v.x[a] = vt[2 * a];
+          v.y[a] = vt[2 * a + 1];
+        }
+        double m[4], g[4];
+        pecs::rhsmath::static_cell_integrals(v, false, 0.0, 0.0, 0.0, m, g);
+        phi_rows[to_poisson[c]] = pecs::rhsmath::poisson_charge_row(rp, m, u1 + 8 * n + 4 * c, u2 + 8 * n + 4 * c);
+      }
+    }
+  });
+}
+pecs_status pecs_solarcell_selftest_field_patches(pecs_solarcell* p, const double* X, double scale, double* field) {
+  return guarded([&] {
+    if (!X || !field) throw pecs::StatusError(PECS_ERR_INVALID, "selftest_field_patches: bad argument");
+    SolarCellProblem& s = *p->problem;
+    const pecs::MeshTables& mesh = s.Poisson_triangulation.tables();
+    const std::vector<int>& face_dof = s.Poisson_object.dofs.face_dof;
+    for (size_t c = 0; c < (size_t)mesh.n_cells; ++c) {
+      pecs::fe::CellVerts v;
+      const double* vt = mesh.vtx((int)c);
+      double Xf[4];
+      for (int a = 0; a < 4; ++a) {
+        v.x[a] = vt[2 * a];
+        v.y[a] = vt[2 * a + 1];
+        Xf[a] = X[face_dof[4 * c + a]];
+      }
+      for (int a = 0; a < 4; ++a)
+        pecs::rhsmath::rt0_field_at_vertex(v, Xf, a, scale, field[2 * (4 * c + a)], field[2 * (4 * c + a) + 1]);
+    }
+  });
+}
 pecs_status pecs_solarcell_output_scales(const pecs_solarcell* p, double scales[4]) {
   return guarded([&] { PostProcessor(p->problem->sim_params, true, "").get_scales(scales); });
 }

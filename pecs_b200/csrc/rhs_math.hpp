@@ -288,5 +288,28 @@ PECS_HD void boundary_terms_accumulate(const RhsParams& p, const BoundaryRecord&
   }
 }
 
+// Potential row of the Poisson right-hand side of one carrier cell on the static table m_a = int N_a:
+//   -int (doping + z1 rho1 + z2 rho2) = -sum_a m_a (doping + z1 r1_a + z2 r2_a)
+// (reference source/SolarCell.cpp:551-578, 741-762: only the DG0 potential test function is non-zero)
+PECS_HD double poisson_charge_row(const RhsParams& p, const double m[4], const double r1[4], const double r2[4]) {
+  double acc = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 4; ++a) acc -= m[a] * (p.doping + (p.charge1 * r1[a] + p.charge2 * r2[a]));
+  return acc;
+}
+
+// Output path: RT0 field J psihat / det J at patch vertex a (deal.II lexicographic) of a Poisson cell with face fluxes
+// Xf, times scale (reference DataOut::build_patches + PostProcessor.cpp:105-118)
+PECS_HD void rt0_field_at_vertex(const fe::CellVerts& v, const double Xf[4], int a, double scale, double& fx, double& fy) {
+  const double xi = (double)(a & 1), eta = (double)(a >> 1);
+  const fe::Jac j = fe::jacobian(v, xi, eta);
+  const double dhx = Xf[0] * (1.0 - xi) + Xf[1] * xi, dhy = Xf[2] * (1.0 - eta) + Xf[3] * eta;
+  const double s = scale / j.det;
+  fx = s * (j.xxi * dhx + j.xeta * dhy);
+  fy = s * (j.yxi * dhx + j.yeta * dhy);
+}
+
 } // namespace rhsmath
 } // namespace pecs

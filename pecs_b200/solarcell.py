@@ -171,6 +171,21 @@ class SolarCellProblem:
             _dp(X), _dp(r1), _dp(r2)))
         return r1, r2
 
+    def selftest_poisson_rows(self, densities):
+        """CPU evaluation of the Poisson charge rows the device computes (csrc/rhs_math.hpp) -> [n_poisson_cells]"""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in densities]
+        ptrs = (_lib.c_double_p * 4)(*[_dp(a) for a in arrs])
+        out = np.zeros(self.n_cells(POISSON_MESH))
+        check(self._lib.pecs_solarcell_selftest_poisson_rows(self._h, ptrs, _dp(out)))
+        return out
+
+    def selftest_field_patches(self, X, scale):
+        """CPU evaluation of the RT0 field at the patch vertices as the output kernel computes it -> [4n, 2]"""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        out = np.zeros((4 * self.n_cells(POISSON_MESH), 2))
+        check(self._lib.pecs_solarcell_selftest_field_patches(self._h, _dp(X), float(scale), _dp(out)))
+        return out
+
     def run_test(self, kind, n_refine):
         """test_steady_state / test_transient / test_DD_Poisson at one level -> dict of L2 errors."""
         e = np.zeros(4)

@@ -186,3 +186,27 @@ def test_production_rhs_arithmetic_matches_oracle_on_cpu(g, l, overrides):
             a, b = cells_only[k].reshape(3, n, 4), got[k].reshape(3, n, 4)
             assert np.array_equal(a[:, interior], b[:, interior]) and not np.array_equal(a, b)
     prob.close()
+
+
+def test_poisson_rows_and_output_field_arithmetic_on_cpu():
+    """same idea for the other two device formulas of the path: the Poisson charge rows on the static int N_a table
+    against the oracle's Poisson assembly (1e-12), and the RT0 field at the patch vertices of the output path against
+    the numpy restatement in oracle/output.py (1e-14)"""
+    from helpers import perturbed, rel_err
+    from oracle import output as oracle_output
+    prob = pecs.SolarCellProblem(pecs.default_input_file(3, 2, mesh__radius_one=0.2))
+    prob.setup_full_system_host()
+    o = make_oracle(prob, True)
+    o.project_initial_conditions()
+    for s_ in range(4):
+        o.set_vector(s_, 0, perturbed(o.solution(s_), 99 + s_))
+    o.assemble_Poisson_rhs()
+    o.solve_Poisson()
+    n_rt = prob.n_rt
+    rows = prob.selftest_poisson_rows([o.solution(s_) for s_ in range(4)])
+    assert rel_err(rows, o.rhs(4)[n_rt:]) <= 1e-12
+    X = o.solution(4)
+    got = prob.selftest_field_patches(X, 2.5)
+    want, _ = oracle_output.poisson_patches(prob.mesh(2)["vertices"], prob.poisson_face_dofs(), n_rt, X, 2.5, 1.0)
+    assert np.abs(got - want[:, :2]).max() <= 1e-14 * np.abs(want).max()
+    prob.close()
