@@ -46,6 +46,10 @@ pecs_status pecs_solarcell_finish_output(pecs_solarcell* p);
  * 2 Poisson-) for caller-provided patch values in the pecs_output_snapshot layout */
 pecs_status pecs_solarcell_write_patches(pecs_solarcell* p, int32_t which, const double* patches, int32_t time_step_number,
                                          const char* directory);
+/* I-V post-processing: the two charge-transfer currents through the interface in scaled units,
+ * out = { int k_et (rho_n - rho_n^e) rho_o ds, int k_ht (rho_p - rho_p^e) rho_r ds }, from host state vectors
+ * states[PECS_ELECTRONS..PECS_OXIDANTS] or, with states == NULL, from the current device state */
+pecs_status pecs_solarcell_interface_currents(pecs_solarcell* p, const double* const states[4], double out[2]);
 /* CPU check of the arithmetic the production RHS kernels run (pecs_b200/csrc/rhs_math.hpp is compiled into both the
  * kernels and this function): the carrier right-hand sides of subdomain `which` (0 / 1) from host states -- u1, u2 the
  * two carrier vectors of the subdomain, o1, o2 those of the other subdomain (interface traces; NULL: cell terms only, no

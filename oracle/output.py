@@ -51,3 +51,33 @@ def poisson_patches(vertices, face_dof, n_rt, solution, scale_field, scale_poten
         field[:, a, 1] = scale_field * (yxi * dhx + yeta * dhy) / det
     potential = np.repeat(scale_potential * X[n_rt:n_rt + n], 4)
     return field.reshape(-1, 3), potential
+
+
+_GAUSS_X = np.array([0.5 - np.sqrt(0.15), 0.5, 0.5 + np.sqrt(0.15)])
+_GAUSS_W = np.array([5.0, 8.0, 5.0]) / 18.0
+
+
+def _face_point(f, t):
+    return (float(f), t) if f < 2 else (t, float(f - 2))
+
+
+def _shape(xi, eta):
+    return np.array([(1 - xi) * (1 - eta), xi * (1 - eta), (1 - xi) * eta, xi * eta])
+
+
+def interface_currents(semi_vertices, pairs, states, k_et, k_ht, rho_n_e, rho_p_e):
+    """I-V post-processing (no counterpart in the reference; integrals of its two interface terms,
+    source/SolarCell.cpp:1265-1347): (int k_et (rho_n - rho_n^e) rho_o ds, int k_ht (rho_p - rho_p^e) rho_r ds) over the
+    interface faces, QGauss(3) per face, the same quadrature index on both sides.
+    pairs = (semi_cell, semi_face, elec_cell, elec_face) arrays; states = four [Jx|Jy|rho] vectors."""
+    v = np.asarray(semi_vertices)
+    rho = [np.asarray(s)[2 * (s.size // 3):].reshape(-1, 4) for s in states]
+    i_et = i_ht = 0.0
+    for cs, fs, ce, fe in zip(*pairs):
+        a, b = {0: (0, 2), 1: (1, 3), 2: (0, 1), 3: (2, 3)}[int(fs)]  # the two vertices of face fs
+        ds = np.hypot(*(v[cs, b] - v[cs, a]))
+        for t, w in zip(_GAUSS_X, _GAUSS_W):
+            n_s, n_e = _shape(*_face_point(int(fs), t)), _shape(*_face_point(int(fe), t))
+            i_et += k_et * (n_s @ rho[0][cs] - rho_n_e) * (n_e @ rho[3][ce]) * ds * w
+            i_ht += k_ht * (n_s @ rho[1][cs] - rho_p_e) * (n_e @ rho[2][ce]) * ds * w
+    return np.array([i_et, i_ht])

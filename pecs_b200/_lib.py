@@ -73,6 +73,7 @@ SIGNATURES = {
     "pecs_solarcell_print_results": (C.c_int, [VOIDP, C.c_int32]),
     "pecs_solarcell_finish_output": (C.c_int, [VOIDP]),
     "pecs_solarcell_write_patches": (C.c_int, [VOIDP, C.c_int32, c_double_p, C.c_int32, C.c_char_p]),
+    "pecs_solarcell_interface_currents": (C.c_int, [VOIDP, C.POINTER(c_double_p), c_double_p]),
     "pecs_solarcell_selftest_carrier_rhs": (C.c_int, [VOIDP, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p,
                                                      c_double_p, c_double_p, c_double_p]),
     "pecs_solarcell_selftest_poisson_rows": (C.c_int, [VOIDP, C.POINTER(c_double_p), c_double_p]),

@@ -12,6 +12,7 @@
 #include <unordered_map>
 
 #include "../fe.hpp"
+#include "../rhs_math.hpp"
 #include "../test_functions.hpp"
 
 namespace SOLARCELL {
@@ -512,6 +513,55 @@ void SolarCellProblem::run_full_system() {
   finish_output();
   electron_hole_pair.print_dofs(output_directory);
   redox_pair.print_dofs(output_directory);
+}
+
+// ------------------------------------------------------------------------------------------- I-V post-processing
+void SolarCellProblem::interface_currents(const double* const states[4], double out[2]) {
+  if (!full_system) throw std::runtime_error("interface_currents: needs the full (two-subdomain) system");
+  const double* u[4];
+  if (states) {
+    for (int k = 0; k < 4; ++k) {
+      if (!states[k]) throw std::runtime_error("interface_currents: missing state vector");
+      u[k] = states[k];
+    }
+  } else {
+    require_ctx(ctx, "SolarCellProblem::interface_currents");
+    ChargeCarrierSpace::Carrier* carriers[4] = {&electron_hole_pair.carrier_1, &electron_hole_pair.carrier_2,
+                                                 &redox_pair.carrier_1, &redox_pair.carrier_2};
+    for (int k = 0; k < 4; ++k) {
+      carriers[k]->pull_solution();
+      u[k] = carriers[k]->solution.data();
+    }
+  }
+  double prm[32];
+  fill_params(prm);
+  const pecs::MeshTables& S = semiconductor_triangulation.tables();
+  const size_t ns = (size_t)S.n_cells, ne = (size_t)electrolyte_triangulation.tables().n_cells;
+  double i_et = 0.0, i_ht = 0.0;
+  for (size_t k = 0; k < semi_interface_cells.size(); ++k) {
+    const int cs = semi_interface_cells[k], fs = semi_interface_faces[k];
+    const int ce = elec_interface_cells[k], fe = elec_interface_faces[k];
+    const pecs::fe::CellVerts v = verts_of(S, cs);
+    double geom[4][4];
+    pecs::rhsmath::boundary_geometry(v, 1.0, &geom[0][0]);
+    const double* rn = u[0] + 8 * ns + 4 * (size_t)cs;
+    const double* rp = u[1] + 8 * ns + 4 * (size_t)cs;
+    const double* rr = u[2] + 8 * ne + 4 * (size_t)ce;
+    const double* ro = u[3] + 8 * ne + 4 * (size_t)ce;
+    for (int q = 0; q < 3; ++q) {
+      const double t = pecs::fe::gauss_x(q), W = geom[fs][2] * pecs::fe::gauss_w(q);
+      double xi, eta, N[4], Nn[4];
+      pecs::fe::face_point(fs, t, xi, eta);
+      pecs::fe::shape(xi, eta, N);
+      pecs::fe::face_point(fe, t, xi, eta); // same quadrature index on both sides
+      pecs::fe::shape(xi, eta, Nn);
+      using pecs::rhsmath::trace;
+      i_et += prm[PECS_P_K_ET] * (trace(N, rn) - prm[PECS_P_RHO_N_E]) * trace(Nn, ro) * W;
+      i_ht += prm[PECS_P_K_HT] * (trace(N, rp) - prm[PECS_P_RHO_P_E]) * trace(Nn, rr) * W;
+    }
+  }
+  out[0] = i_et;
+  out[1] = i_ht;
 }
 
 // ------------------------------------------------------------------------------------------- manufactured tests

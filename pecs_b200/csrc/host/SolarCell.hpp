@@ -76,6 +76,14 @@ public:
   void set_time(double time);
   void synchronize();
 
+  // ---- I-V post-processing (the reference has no counterpart: `applied bias` is one scalar) ----
+  // Charge-transfer currents through the semiconductor-electrolyte interface, the integrals of the two interface terms
+  // the step assembles (reference SolarCell.cpp:1265-1347, 1692-1712), in scaled units:
+  //   out[0] = int_Sigma k_et (rho_n - rho_n^e) rho_o ds  (electron transfer),
+  //   out[1] = int_Sigma k_ht (rho_p - rho_p^e) rho_r ds  (hole transfer)
+  // from host state vectors (electrons, holes, reductants, oxidants); NULL: the current device state is downloaded.
+  void interface_currents(const double* const states[4], double out[2]);
+
   // ---- post-processing of the manufactured tests (host, after download) ----
   void ldg_errors(int which, double time, double& density_error, double& current_error);
   void mixed_errors(double& potential_error, double& field_error);

@@ -119,6 +119,12 @@ pecs_status pecs_solarcell_write_patches(pecs_solarcell* p, int32_t which, const
                                               (unsigned)time_step_number, dir);
   });
 }
+pecs_status pecs_solarcell_interface_currents(pecs_solarcell* p, const double* const states[4], double out[2]) {
+  return guarded([&] {
+    if (!out) throw pecs::StatusError(PECS_ERR_INVALID, "interface_currents: out is NULL");
+    p->problem->interface_currents(states, out);
+  });
+}
 pecs_status pecs_solarcell_selftest_carrier_rhs(pecs_solarcell* p, int32_t which, const double* u1, const double* u2,
                                                 const double* o1, const double* o2, const double* X, double* rhs1,
                                                 double* rhs2) {

@@ -159,6 +159,18 @@ class SolarCellProblem:
                 out.append({"field": b[:12 * c].reshape(-1, 3), "potential": b[12 * c:]})
         return out
 
+    def interface_currents(self, states=None):
+        """(electron-transfer, hole-transfer) current through the semiconductor-electrolyte interface, scaled units;
+        states = four carrier vectors, or None for the current device state (one point of an I-V curve)"""
+        out = np.zeros(2)
+        if states is None:
+            check(self._lib.pecs_solarcell_interface_currents(self._h, None, _dp(out)))
+        else:
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in states]
+            ptrs = (_lib.c_double_p * 4)(*[_dp(a) for a in arrs])
+            check(self._lib.pecs_solarcell_interface_currents(self._h, ptrs, _dp(out)))
+        return out
+
     def selftest_carrier_rhs(self, which, u1, u2, X, o1=None, o2=None):
         """CPU evaluation of the production kernels' arithmetic (csrc/rhs_math.hpp): carrier right-hand sides of
         subdomain `which`; without o1/o2 (the other subdomain's carriers) only the cell terms -> (rhs1, rhs2)"""

@@ -53,3 +53,15 @@ def sum_over_ranks(value, dist, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=f"cuda:{device}" if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def gather_iv(dist, bias, currents):
+    """One point of the I-V curve per rank -> the whole curve on every rank, sorted by bias:
+    list of (applied bias [V], electron-transfer current, hole-transfer current) in scaled units
+    (SolarCellProblem.interface_currents).  The only communication of a sweep, and not on the data path."""
+    point = (float(bias), float(currents[0]), float(currents[1]))
+    if dist is None:
+        return [point]
+    points = [None] * dist.get_world_size()
+    dist.all_gather_object(points, point)
+    return sorted(points)

@@ -24,6 +24,16 @@ WORKER = textwrap.dedent("""
     t = sweep.max_over_ranks(1.0 + rank, dist)
     total = sweep.sum_over_ranks(prob.n_cells(0), dist)
     assert t == 2.0 and total == 2 * prob.n_cells(0)
+    # one I-V point per rank from a host state (constant densities: closed form), gathered into the curve
+    import numpy as np
+    states = [np.full(12 * prob.n_cells(w // 2), c + rank) for w, c in enumerate((5.0, 3.0, 7.0, 11.0))]
+    curve = sweep.gather_iv(dist, bias, prob.interface_currents(states))
+    p = prob.params
+    length = np.hypot(0.3, 1.0)
+    assert [round(b, 12) for b, _, _ in curve] == [0.0, 0.05]
+    for r, (b, i_et, i_ht) in enumerate(curve):
+        assert abs(i_et - p[9] * (5.0 + r - p[16]) * (11.0 + r) * length) <= 1e-12 * abs(i_et)
+        assert abs(i_ht - p[10] * (3.0 + r - p[17]) * (7.0 + r) * length) <= 1e-12 * abs(i_ht)
     sys.stdout.write("rank " + str(rank) + " bias " + str(bias) + " ok" + chr(10))  # ONE write: the ranks share the pipe
     sys.stdout.flush()
 """) % ROOT

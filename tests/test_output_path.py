@@ -160,3 +160,23 @@ def test_run_full_system_writes_the_reference_files(tmp_path):
     assert np.array_equal(np.frombuffer(raw[len(head):-1], np.float64), other.get_solution(pecs.OXIDANTS))
     prob.close()
     other.close()
+
+
+def test_interface_currents_on_cpu():
+    """I-V post-processing: the interface integrals against the numpy restatement from random states, and
+    exactly for constant densities: k (rho - rho^e) rho' x the length of the interface (the straight line from
+    (radius one, height) to (radius two, 0) of the default wire)"""
+    prob = _problem(3, 1)
+    rng = np.random.default_rng(11)
+    p = prob.params
+    k_et, k_ht, rho_n_e, rho_p_e = p[9], p[10], p[16], p[17]  # PECS_P_K_ET, K_HT, RHO_N_E, RHO_P_E
+    states = [rng.uniform(0.5, 3.0, 12 * prob.n_cells(w // 2)) for w in range(4)]
+    pairs = prob.interface_pairs()
+    want = oracle_output.interface_currents(prob.mesh(0)["vertices"], pairs, states, k_et, k_ht, rho_n_e, rho_p_e)
+    got = prob.interface_currents(states)
+    assert np.allclose(got, want, rtol=1e-13, atol=0)
+    const = [np.full(12 * prob.n_cells(w // 2), c) for w, c in enumerate((5.0, 3.0, 7.0, 11.0))]
+    length = np.hypot(0.6 - 0.3, 1.0)
+    exact = np.array([k_et * (5.0 - rho_n_e) * 11.0, k_ht * (3.0 - rho_p_e) * 7.0]) * length
+    assert np.allclose(prob.interface_currents(const), exact, rtol=1e-12, atol=0)
+    prob.close()
