@@ -180,3 +180,15 @@ def test_interface_currents_on_cpu():
     exact = np.array([k_et * (5.0 - rho_n_e) * 11.0, k_ht * (3.0 - rho_p_e) * 7.0]) * length
     assert np.allclose(prob.interface_currents(const), exact, rtol=1e-12, atol=0)
     prob.close()
+
+
+@pytest.mark.gpu
+def test_interface_currents_from_the_device_state():
+    """one I-V point straight from the device state equals the integral over the downloaded vectors"""
+    prob = pecs.SolarCellProblem(pecs.default_input_file(3, 1, physical__insulated=False, physical__applied_bias=0.1))
+    prob.setup_full_system()
+    prob.step(5)
+    got = prob.interface_currents()
+    want = prob.interface_currents([prob.get_solution(s) for s in range(4)])
+    assert np.array_equal(got, want) and np.isfinite(got).all()
+    prob.close()
