@@ -48,8 +48,29 @@ def production_case(g, l, n_steps, **overrides):
     return out
 
 
+def output_case(g, l, n_steps, **overrides):
+    """output path and I-V post-processing of the oracle state after n_steps (oracle/output.py)"""
+    from oracle import output as oracle_output
+    state = production_case(g, l, n_steps, **overrides)
+    prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **overrides))
+    prob.setup_full_system_host()
+    sc = prob.output_scales
+    u = [state[f"state_after_steps_{s}"] for s in range(5)]
+    field, potential = oracle_output.poisson_patches(prob.mesh(2)["vertices"], prob.poisson_face_dofs(), prob.n_rt, u[4],
+                                                     sc[1], sc[0])
+    p = prob.params
+    out = {"field": field, "potential": potential, "n_steps": np.array(n_steps),
+           "interface_currents": oracle_output.interface_currents(prob.mesh(0)["vertices"], prob.interface_pairs(), u[:4],
+                                                                  p[9], p[10], p[16], p[17])}
+    for s in range(4):
+        out[f"current_{s}"], out[f"density_{s}"] = oracle_output.carrier_patches(u[s], sc[3])
+    return out
+
+
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "production_g2_l1.npz"), **production_case(2, 1, 10))
     np.savez_compressed(os.path.join(HERE, "production_g3_l1_biased.npz"),
                         **production_case(3, 1, 5, physical__insulated=False, physical__applied_bias=0.1))
+    np.savez_compressed(os.path.join(HERE, "output_g3_l1_biased.npz"),
+                        **output_case(3, 1, 5, physical__insulated=False, physical__applied_bias=0.1))
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))

@@ -192,3 +192,37 @@ def test_interface_currents_from_the_device_state():
     want = prob.interface_currents([prob.get_solution(s) for s in range(4)])
     assert np.array_equal(got, want) and np.isfinite(got).all()
     prob.close()
+
+
+GOLDEN_OUTPUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "output_g3_l1_biased.npz")
+GOLDEN_OVERRIDES = {"physical__insulated": False, "physical__applied_bias": 0.1}
+
+
+def test_output_golden_is_what_the_oracle_produces():
+    """tests/golden/output_g3_l1_biased.npz (make_golden.py: oracle state after 5 steps -> oracle/output.py) guards
+    the restatement of the output path and the I-V integrals against drift"""
+    import sys
+    sys.path.insert(0, os.path.dirname(GOLDEN_OUTPUT))
+    import make_golden
+    gold = np.load(GOLDEN_OUTPUT)
+    fresh = make_golden.output_case(3, 1, int(gold["n_steps"]), **GOLDEN_OVERRIDES)
+    for key in gold.files:
+        assert np.allclose(fresh[key], gold[key], rtol=1e-12, atol=1e-300), key
+
+
+@pytest.mark.gpu
+def test_device_output_matches_golden_fixture():
+    """the GPU box compares against numbers produced in the build container: patches of all five vectors after 5 steps
+    (1e-9: the state tolerance) and the I-V point (1e-5: a small difference of nearly equal densities)"""
+    gold = np.load(GOLDEN_OUTPUT)
+    prob = pecs.SolarCellProblem(pecs.default_input_file(3, 1, **GOLDEN_OVERRIDES))
+    prob.setup_full_system()
+    prob.step(int(gold["n_steps"]))
+    semi, elec, poisson = prob.output_snapshot()
+    for s, (snap, k) in enumerate([(semi, 1), (semi, 2), (elec, 1), (elec, 2)]):
+        assert np.abs(snap[f"density_{k}"] - gold[f"density_{s}"]).max() <= 1e-9 * np.abs(gold[f"density_{s}"]).max()
+        assert np.abs(snap[f"current_{k}"] - gold[f"current_{s}"]).max() <= 1e-7 * np.abs(gold[f"current_{s}"]).max()
+    assert np.abs(poisson["potential"] - gold["potential"]).max() <= 1e-9 * np.abs(gold["potential"]).max()
+    assert np.abs(poisson["field"] - gold["field"]).max() <= 1e-9 * np.abs(gold["field"]).max()
+    assert np.allclose(prob.interface_currents(), gold["interface_currents"], rtol=1e-5, atol=0)
+    prob.close()
