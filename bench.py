@@ -261,6 +261,25 @@ def run_gpu_arm(args):
     e2e_s = sweep.max_over_ranks(e2e_s, dist, device)
     h2d_bytes, d2h_bytes = prob.info(sc.INFO_HOST_STEP_H2D_BYTES), prob.info(sc.INFO_HOST_STEP_D2H_BYTES)
 
+    # ---- the benchmarked configuration is a VALIDATED configuration (outside every timed region): the states after the
+    # timed steps are finite, and one pass of the hot path from a perturbed state (seed 1234) is checked on THIS mesh:
+    # five right-hand sides against the CPU oracle's assembly (1e-12), five solves through |b - A x| / |b| with the
+    # host CSR matrices (tests/helpers.py: validate_workload).  The oracle is the checker here, nothing it computes is
+    # timed or returned.
+    finite_after_timed = bool(all(np.isfinite(prob.get_solution(w)).all() for w in range(5)))
+    parity = None
+    if rank == 0 and not args.no_validate:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import validate_workload
+        parity = validate_workload(prob)
+        parity["tolerance"] = {"rhs_rel": 1e-12, "residual_rel": 1e-12}
+        parity["finite_after_timed_steps"] = finite_after_timed
+        parity["ok"] = bool(parity["rhs_rel"] <= 1e-12 and parity["finite"] and finite_after_timed)
+        parity["what"] = ("this workload, perturbed state seed 1234: rhs_rel = worst block of the five assembled right-hand "
+                          "sides vs the CPU oracle; residual_rel = max |b - A x|_inf / |b|_inf over the five solves "
+                          "(host CSR mat-vec); backward_err = the same residual / (|A| |x| + |b|)")
+    sweep.barrier(dist, device)
+
     line = None
     # ---- roofline of the dominant kernels: device time of the solves INSIDE a step = step graph - assembly-only graph
     # (the assembly passes run strictly before / between the solves; both timed with CUDA events on the launching
@@ -321,6 +340,9 @@ def run_gpu_arm(args):
             "section_ms_per_step": dict(zip(["Assemble semiconductor rhs", "Assemble electrolyte rhs",
                                              "Solve LDG Systems", "Assemble Poisson rhs", "Solve Poisson system"],
                                             [float(x) for x in sect[1:]])),
+            "section_note": "sections are timed one call at a time (no overlap between sections, launch gaps included); "
+                            "their sum exceeds ms_per_step, which is the captured graph",
+            "parity": parity,
         }
     prob.close()
     if rank == 0:
@@ -428,6 +450,7 @@ def main():
                     help="mesh of the bounded CPU sample (the oracle's sparse LU at refinement 7 does not fit the budget)")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-validate", action="store_true", help="skip the parity check of the benchmarked workload")
     ap.add_argument("--exchange", choices=["nccl", "p2p"], default="p2p",
                     help="sharded step: 'p2p' = density exchange fused into the solves over peer memory (default), "
                          "'nccl' = broadcasts between the two halves of the step")

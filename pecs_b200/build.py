@@ -38,27 +38,40 @@ def headers():
     return [h for p in pats for h in glob.glob(os.path.join(CSRC, p))]
 
 
-def compile_one(src, force, newest_header):
-    obj = os.path.join(OBJ, os.path.relpath(src, CSRC).replace(os.sep, "_") + ".o")
+# Experiment builds (never loaded by the product): "nc" = the round-1 non-coherent loads of step-varying vectors, the
+# A side of scripts/race_repro.py.  They get their own object directory and library name.
+VARIANTS = {"nc": ["-DPECS_B200_NC_STEP_VECTORS=1"]}
+
+
+def variant_paths(variant):
+    if not variant:
+        return OBJ, LIB
+    return OBJ + "_" + variant, os.path.join(HERE, "lib", f"libpecs_b200_{variant}.so")
+
+
+def compile_one(src, force, newest_header, obj_dir=OBJ, extra=()):
+    obj = os.path.join(obj_dir, os.path.relpath(src, CSRC).replace(os.sep, "_") + ".o")
     if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), newest_header):
         return obj, ""
     if src.endswith(".cu"):
-        cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + NVCC_FLAGS + list(extra) + ["-c", src, "-o", obj]
     else:
-        cmd = [HOST_CXX] + CXX_FLAGS + ["-c", src, "-o", obj]
+        cmd = [HOST_CXX] + CXX_FLAGS + list(extra) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"compile failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
     return obj, r.stderr
 
 
-def build(force=False, jobs=None, verbose=False):
+def build(force=False, jobs=None, verbose=False, variant=None):
+    OBJ, LIB = variant_paths(variant)
+    extra = VARIANTS[variant] if variant else []
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     cpp, cu = sources()
     newest_header = max(os.path.getmtime(h) for h in headers())
     with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count()) as ex:
-        results = list(ex.map(lambda s: compile_one(s, force, newest_header), cpp + cu))
+        results = list(ex.map(lambda s: compile_one(s, force, newest_header, OBJ, extra), cpp + cu))
     objs = [o for o, _ in results]
     log = "\n".join(e for _, e in results if e)
     if verbose and log:
@@ -79,5 +92,6 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--jobs", type=int, default=None)
     ap.add_argument("-v", "--verbose", action="store_true")
+    ap.add_argument("--variant", choices=sorted(VARIANTS), default=None)
     a = ap.parse_args()
-    print(build(a.force, a.jobs, a.verbose))
+    print(build(a.force, a.jobs, a.verbose, a.variant))

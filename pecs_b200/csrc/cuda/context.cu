@@ -63,6 +63,9 @@ struct DeviceSystem {
   DeviceEll matrix_rows;
   double* mirror[3] = {nullptr, nullptr, nullptr}; // peer copies of the solution vector (sharded step, pecs_p2p_connect)
   int n_mirror = 0;
+  // right-hand sides one pass over the tables can carry: 2 when two carriers share this factorisation (identical
+  // matrices: reductants and oxidants at equal mobility), else 1.  Work vectors hold n_rhs slots.
+  int n_rhs = 1;
 
   int64_t factor_bytes() const { return (int64_t)(fwd.bytes() + bwd.bytes() + matrix_rows.bytes()); }
   int64_t logical_bytes() const { return plan.logical_entries() * (int64_t)sizeof(double) + (int64_t)matrix_rows.bytes(); }
@@ -70,8 +73,8 @@ struct DeviceSystem {
     size_t m = 0;
     for (const Level& l : levels)
       for (const Sweep* sw : {&l.fwd, &l.bwd})
-        m = std::max(m, std::max(solve_smem_bytes(sw->vec_block, false, sw->warps, sw->stages, sw->chunk),
-                                 solve_smem_bytes(sw->vec_warp, true, solve_warps(), sw->stages_warp)));
+        m = std::max(m, std::max(solve_smem_bytes(sw->vec_block, false, sw->warps, sw->stages, n_rhs),
+                                 solve_smem_bytes(sw->vec_warp, true, solve_warps(), sw->stages_warp, n_rhs)));
     return m;
   }
 
@@ -88,8 +91,8 @@ struct DeviceSystem {
   // that with 4 warps and 2-deep rings at 10+ blocks per SM -- measured best (scripts/tune_solve.py: 6 stages 2 889
   // GB/s, 4: 3 757, 2: 4 505; 4 warps beat 8); levels whose vector eats the shared memory (top of the tree, 30-45 KB)
   // get 8 warps per block, which share one vector, and deeper rings.
-  static void pick_shape(int vec_doubles, int& warps, int& stages, int& chunk) {
-    chunk = env_int("PECS_B200_CHUNK", kChunkDoubles) == 512 ? 512 : 256;
+  static void pick_shape(int vec_doubles, int n_rhs, int& warps, int& stages, int& chunk) {
+    chunk = kChunkDoubles;
     const int forced_stages = env_int("PECS_B200_SOLVE_STAGES", 0), forced_warps = env_int("PECS_B200_SOLVE_WARPS", 0);
     const size_t sm_bytes = 227 * 1024, target = (size_t)env_int("PECS_B200_INFLIGHT_KB", 160) * 1024;
     size_t best_inflight = 0;
@@ -100,7 +103,7 @@ struct DeviceSystem {
       if (forced_warps && w != warps) continue;
       for (int st : {2, 3, 4}) {
         if (forced_stages && st != stages) continue;
-        const size_t smem = solve_smem_bytes(vec_doubles, false, w, st, chunk) + 1024;
+        const size_t smem = solve_smem_bytes(vec_doubles, false, w, st, n_rhs) + 1024;
         const int blocks = (int)std::min<size_t>(std::min<size_t>(sm_bytes / smem, 64 / w), 32);
         if (blocks < 2 && best_blocks >= 2) continue;
         const size_t inflight = std::min(target, (size_t)blocks * w * st * chunk * sizeof(double));
@@ -125,18 +128,19 @@ struct DeviceSystem {
   void build(const CsrMatrix& A, const NodeLayout& layout, int leaf_nodes, bool factor_on_device) {
     build(A, plan_from_layout(A, layout, leaf_nodes), factor_on_device);
   }
-  void build(const CsrMatrix& A, SolvePlan&& ready_plan, bool factor_on_device) {
+  void build(const CsrMatrix& A, SolvePlan&& ready_plan, bool factor_on_device, int right_hand_sides = 1) {
     n = A.n;
+    n_rhs = right_hand_sides;
     plan = std::move(ready_plan);
     bd_index.upload(plan.bd_index.data(), std::max<size_t>(plan.bd_index.size(), 1));
     out_map.upload(plan.out_map.data(), std::max<size_t>(plan.out_map.size(), 1));
     iperm.upload(plan.iperm);
     matrix_rows.upload(A, &plan.iperm);
-    cbuf.resize((size_t)std::max<int64_t>(plan.upd_entries, 2));
+    cbuf.resize((size_t)n_rhs * cbuf_stride());
     cbuf.zero(); // slots no child ever writes must read as zero forever
-    w_in.resize(n);
-    w_fin.resize(n);
-    x_perm.resize(n);
+    w_in.resize((size_t)n_rhs * n);
+    w_fin.resize((size_t)n_rhs * n);
+    x_perm.resize((size_t)n_rhs * n);
     fwd.resize((size_t)std::max<int64_t>(plan.fwd_entries, 2));
     bwd.resize((size_t)std::max<int64_t>(plan.bwd_entries, 2));
     if (factor_on_device) {
@@ -166,7 +170,7 @@ struct DeviceSystem {
             vec_block = std::max(vec_block, T.cols_pad);
           }
         }
-        pick_shape(vec_block, sw.warps, sw.stages, sw.chunk);
+        pick_shape(vec_block, n_rhs, sw.warps, sw.stages, sw.chunk);
         const int ppt = panels_per_tile(panels, sw.warps);
         for (int f : plan.levels[d]) {
           const Front& F = plan.fronts[f];
@@ -213,44 +217,52 @@ struct DeviceSystem {
   // solution += A^-1 w, all on stream s; w = residual of the current content of `solution`, in elimination order
   // (residual() below, or the caller's own fused kernel).  The two sweeps can be enqueued separately: the sharded step
   // puts a cross-GPU wait between them.
-  SolveTables tables() const {
-    SolveTables t{bd_index.get(), out_map.get(), iperm.get(), fwd.get(), bwd.get(), {mirror[0], mirror[1], mirror[2]}, n_mirror};
-    return t;
+  SolveTables tables() const { return SolveTables{bd_index.get(), out_map.get(), iperm.get(), fwd.get(), bwd.get()}; }
+  size_t cbuf_stride() const { return (size_t)std::max<int64_t>(plan.upd_entries, 2); }
+  // vectors of a solve of `count` right-hand sides in the work-vector slots [slot0, slot0 + count); w: their residuals,
+  // n apart; solution[r]: where right-hand side r adds its result
+  SolveVectors vectors(const double* w, int slot0, int count, double* const* solution) const {
+    SolveVectors io{};
+    io.n_rhs = count;
+    io.n_stride = n;
+    io.cbuf_stride = (long long)cbuf_stride();
+    io.w_in = w;
+    io.w_fin = w_fin.get() + (size_t)slot0 * n;
+    io.cbuf = cbuf.get() + (size_t)slot0 * cbuf_stride();
+    io.x_perm = x_perm.get() + (size_t)slot0 * n;
+    for (int r = 0; r < count; ++r) io.solution[r] = solution[r];
+    return io;
   }
-  void forward_sweep(const double* w, cudaStream_t s) {
+  void forward_sweep(const SolveVectors& io, cudaStream_t s) {
     const SolveTables t = tables();
     const int warps = solve_warps();
     for (int d = (int)levels.size() - 1; d >= 0; --d) {
       Sweep& sw = levels[d].fwd;
-      launch_forward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, kChunkDoubles,
-                           w, w_fin.get(), cbuf.get(), s);
-      launch_forward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages, sw.chunk,
-                           w, w_fin.get(), cbuf.get(), s);
+      launch_forward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, io, s);
+      launch_forward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages, io, s);
     }
   }
-  void backward_sweep(const double* w, double* solution, cudaStream_t s) {
+  void backward_sweep(const SolveVectors& io, cudaStream_t s) {
     const SolveTables t = tables();
     const int warps = solve_warps();
     for (size_t d = 0; d < levels.size(); ++d) {
       Sweep& sw = levels[d].bwd;
-      launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages,
-                            sw.chunk, w, cbuf.get(), w_fin.get(), x_perm.get(), solution, s);
-      launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp,
-                            kChunkDoubles, w, cbuf.get(), w_fin.get(), x_perm.get(), solution, s);
+      launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages, io, s);
+      launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, io, s);
     }
-  }
-  void solve_increment(const double* w, double* solution, cudaStream_t s) {
-    forward_sweep(w, s);
-    backward_sweep(w, solution, s);
   }
   // w_in = rhs - A solution (rows in elimination order)
   void residual(const double* rhs, const double* solution, cudaStream_t s) {
     launch_ell_combine(n, rhs, iperm.get(), EllTerm{&matrix_rows, solution, -1.0}, EllTerm{}, EllTerm{}, w_in.get(), s);
   }
-  // solution = A^-1 rhs in increment form
+  // solution = A^-1 rhs in increment form (one right-hand side; mirrors of this system apply)
   void solve(const double* rhs, double* solution, cudaStream_t s) {
     residual(rhs, solution, s);
-    solve_increment(w_in.get(), solution, s);
+    SolveVectors io = vectors(w_in.get(), 0, 1, &solution);
+    io.n_mirror[0] = n_mirror;
+    for (int m = 0; m < n_mirror; ++m) io.mirror[0][m] = mirror[m];
+    forward_sweep(io, s);
+    backward_sweep(io, s);
   }
 };
 
@@ -270,9 +282,18 @@ struct DeviceDomain {
     DeviceBuffer<double> rtilde;
     int64_t bytes() const { return active ? (int64_t)(T1.bytes() + Ainv.bytes() + T2.bytes()) : 0; }
   } reduced[2];
+  // both carriers of the pair have the SAME constant matrix (bitwise: reductants / oxidants at equal mobility, reference
+  // source/LDG.cpp:624-678 + input_file.prm:77,128): one factorisation in system[0] / reduced[0] serves both, and a
+  // solve of the pair streams every table ONCE for two right-hand sides
+  bool shared_pair = false;
   DomainView view{};
   RhsParams prm{};
   int n_dofs() const { return 12 * n_cells; }
+  // the factorised system / reduction tables that solve carrier k
+  DeviceSystem& system_of(int k) { return shared_pair ? system[0] : system[k]; }
+  const DeviceSystem& system_of(int k) const { return shared_pair ? system[0] : system[k]; }
+  Reduced& reduced_of(int k) { return shared_pair ? reduced[0] : reduced[k]; }
+  const Reduced& reduced_of(int k) const { return shared_pair ? reduced[0] : reduced[k]; }
 };
 
 } // namespace pecs
@@ -406,6 +427,19 @@ PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k) {
   return ps;
 }
 
+// bitwise equality of two constant matrices handed over the ABI
+bool same_matrix(const pecs_csr& a, const pecs_csr& b) {
+  if (a.n != b.n || !a.row_ptr || !b.row_ptr || !a.col || !b.col || !a.val || !b.val) return false;
+  const size_t nnz = (size_t)a.row_ptr[a.n];
+  return std::memcmp(a.row_ptr, b.row_ptr, ((size_t)a.n + 1) * sizeof(int)) == 0 &&
+         std::memcmp(a.col, b.col, nnz * sizeof(int)) == 0 && std::memcmp(a.val, b.val, nnz * sizeof(double)) == 0;
+}
+// PECS_B200_NO_SHARED_FACTORS=1 factorises and streams identical matrices twice (round-1 behaviour; A/B and parity tests)
+bool shared_factors_enabled() {
+  const char* e = std::getenv("PECS_B200_NO_SHARED_FACTORS");
+  return !(e && *e == '1');
+}
+
 void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pecs_poisson_desc& P,
                   const pecs_interface_desc& I, bool factor_on_device, std::future<PreparedSystem> (&prepared)[2]) {
   DeviceDomain& D = ctx.dom[which];
@@ -497,12 +531,14 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
     if (ps.reduced) {
       DeviceDomain::Reduced& red = D.reduced[k];
       red.active = true;
-      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device);
+      const int n_rhs = (k == 0 && D.shared_pair) ? 2 : 1;
+      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, n_rhs);
       red.T1.upload(ps.R.T1, &D.system[k].plan.iperm); // r~ is produced directly in elimination order
       red.Ainv.upload(ps.R.Ainv);
       red.T2.upload(ps.R.T2);
-      red.rtilde.resize(4 * (size_t)n);
+      red.rtilde.resize((size_t)n_rhs * 4 * (size_t)n);
     } else {
+      if (D.shared_pair) throw StatusError(PECS_ERR_INTERNAL, "shared factorisation needs the Schur-reduced system");
       D.system[k].build(ps.A, std::move(ps.plan), factor_on_device);
     }
   }
@@ -612,60 +648,84 @@ __global__ void p2p_wait_published_kernel(const unsigned long long* mine) {
 
 int deferred_currents_mode();
 __global__ void completion_fence_kernel() {}
-// densities_final: recorded on s as soon as the new densities are complete, i.e. before the LDG currents are recovered
-// (q = Ainv r_q - T2 u): nothing inside a step reads the currents, so the step lets that last kernel overlap the
-// latency-bound Poisson part instead of keeping it on the critical path (enqueue_step)
-void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s, cudaEvent_t densities_final = nullptr) {
-  DeviceDomain& D = ctx->dom[which / 2];
-  const int k = which % 2;
-  require(D.system[k].n > 0, "this species has no factorised system in this context");
-  if (!D.reduced[k].active) {
-    D.system[k].solve(D.rhs[k].get(), D.solution[k].get(), s);
-    if (densities_final) PECS_CUDA(cudaEventRecord(densities_final, s));
+// Solve `count` (1 or 2) carriers of one subdomain, k0 first, on stream s.  count == 2 only for a shared pair: both
+// right-hand sides ride on ONE pass over the tables (reduction, two sweeps, recovery).
+// densities_final[r]: recorded on s as soon as the new densities are complete, i.e. before the LDG currents are
+// recovered (q = Ainv r_q - T2 u): nothing inside a step reads the currents, so the step lets that last kernel overlap
+// the latency-bound Poisson part instead of keeping it on the critical path (enqueue_step)
+void enqueue_carrier_solve(pecs_ctx* ctx, int w, int k0, int count, cudaStream_t s, cudaEvent_t* densities_final = nullptr) {
+  DeviceDomain& D = ctx->dom[w];
+  DeviceSystem& S = D.system_of(k0);
+  require(S.n > 0, "this species has no factorised system in this context");
+  require(count == 1 || (D.shared_pair && k0 == 0 && count == 2), "two right-hand sides need a shared factorisation");
+  if (!D.reduced_of(k0).active) {
+    S.solve(D.rhs[k0].get(), D.solution[k0].get(), s);
+    if (densities_final) PECS_CUDA(cudaEventRecord(densities_final[0], s));
     return;
   }
-  DeviceDomain::Reduced& red = D.reduced[k];
+  DeviceDomain::Reduced& red = D.reduced_of(k0);
   const int nq = 8 * D.n_cells, nu = 4 * D.n_cells;
-  const double* r = D.rhs[k].get();
-  double* x = D.solution[k].get();
+  const int slot0 = D.shared_pair ? k0 : 0; // work-vector slot of the first right-hand side
+  const double* r[2] = {D.rhs[k0].get(), count == 2 ? D.rhs[k0 + 1].get() : nullptr};
+  double* x[2] = {D.solution[k0].get(), count == 2 ? D.solution[k0 + 1].get() : nullptr};
+  double* rt = red.rtilde.get() + (size_t)slot0 * nu;
   // S du = r_u - T1 r_q - S u_old ;  u = u_old + du ;  q = Ainv r_q - T2 u
-  launch_ell_combine(nu, r + nq, D.system[k].iperm.get(), EllTerm{&red.T1, r, -1.0},
-                     EllTerm{&D.system[k].matrix_rows, x + nq, -1.0}, EllTerm{}, red.rtilde.get(), s);
-  D.system[k].forward_sweep(red.rtilde.get(), s);
-  if (ctx->p2p.active) p2p_wait_assembled_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.world);
-  D.system[k].backward_sweep(red.rtilde.get(), x + nq, s);
-  if (densities_final) {
-    // mode 2: a plainly launched (non-programmatic) empty kernel first, so that the event stands behind a node whose
-    // dependency on the last backward kernel is its full completion whatever the runtime does with events recorded
-    // after a kernel that has already released its programmatic dependents (hypothesis for the v16 failure)
-    if (deferred_currents_mode() == 2) completion_fence_kernel<<<1, 1, 0, s>>>();
-    PECS_CUDA(cudaEventRecord(densities_final, s));
+  if (count == 2)
+    launch_ell_combine2(nu, r[0] + nq, r[1] + nq, S.iperm.get(), EllTerm{&red.T1, r[0], -1.0, r[1]},
+                        EllTerm{&S.matrix_rows, x[0] + nq, -1.0, x[1] + nq}, EllTerm{}, rt, rt + nu, s);
+  else
+    launch_ell_combine(nu, r[0] + nq, S.iperm.get(), EllTerm{&red.T1, r[0], -1.0}, EllTerm{&S.matrix_rows, x[0] + nq, -1.0},
+                       EllTerm{}, rt, s);
+  double* dens[2] = {x[0] + nq, count == 2 ? x[1] + nq : nullptr};
+  SolveVectors io = S.vectors(rt, slot0, count, dens);
+  for (int i = 0; i < count; ++i) { // peer copies of the density blocks (sharded step)
+    const DeviceSystem& M = D.system[k0 + i];
+    io.n_mirror[i] = M.n_mirror;
+    for (int m = 0; m < M.n_mirror; ++m) io.mirror[i][m] = M.mirror[m];
   }
-  launch_ell_combine(nq, nullptr, nullptr, EllTerm{&red.Ainv, r, 1.0}, EllTerm{&red.T2, x + nq, -1.0}, EllTerm{}, x, s);
+  S.forward_sweep(io, s);
+  if (ctx->p2p.active) p2p_wait_assembled_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.world);
+  S.backward_sweep(io, s);
+  if (densities_final) {
+    if (deferred_currents_mode() == 2) completion_fence_kernel<<<1, 1, 0, s>>>(); // experiment, scripts/race_repro.py
+    for (int i = 0; i < count; ++i) PECS_CUDA(cudaEventRecord(densities_final[i], s));
+  }
+  if (count == 2)
+    launch_ell_combine2(nq, nullptr, nullptr, nullptr, EllTerm{&red.Ainv, r[0], 1.0, r[1]},
+                        EllTerm{&red.T2, x[0] + nq, -1.0, x[1] + nq}, EllTerm{}, x[0], x[1], s);
+  else
+    launch_ell_combine(nq, nullptr, nullptr, EllTerm{&red.Ainv, r[0], 1.0}, EllTerm{&red.T2, x[0] + nq, -1.0}, EllTerm{}, x[0], s);
   if (ctx->p2p.active)
-    p2p_publish_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.all_flags.get(), ctx->p2p.world, which);
+    for (int i = 0; i < count; ++i)
+      p2p_publish_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.all_flags.get(), ctx->p2p.world, 2 * w + k0 + i);
 }
+void enqueue_species_solve(pecs_ctx* ctx, int which, cudaStream_t s) { enqueue_carrier_solve(ctx, which / 2, which % 2, 1, s); }
 // host != nullptr: every species' solution is downloaded into host[k] on its own stream as soon as its solve is done
 // (the copy engine works while the other solves and the Poisson part still run); *n_copies counts them
 // defer_currents: the main stream goes on as soon as every species' densities are final; the caller must wait for
 // join[k] (currents recovered) itself before it ends the step (enqueue_step does)
 void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_copies = nullptr, bool defer_currents = false) {
-  // four concurrent solves, reference SolarCell.cpp:1763-1781 (Threads::new_task x4 + join_all)
+  // four concurrent solves, reference SolarCell.cpp:1763-1781 (Threads::new_task x4 + join_all); a shared pair is ONE
+  // solve with two right-hand sides on the stream of its first carrier
   const int n_species = ctx->full ? 4 : (ctx->kind == PECS_KIND_PRODUCTION ? 2 : 1);
   PECS_CUDA(cudaEventRecord(ctx->fork, ctx->main));
   for (int k = 0; k < n_species; ++k) {
     if (!(ctx->owned >> k & 1)) continue;
+    const int count = (ctx->dom[k / 2].shared_pair && k % 2 == 0) ? 2 : 1;
     cudaStream_t side = ctx->side[k];
     PECS_CUDA(cudaStreamWaitEvent(side, ctx->fork, 0));
-    enqueue_species_solve(ctx, k, side, defer_currents ? ctx->dens[k] : nullptr);
-    PECS_CUDA(cudaEventRecord(ctx->join[k], side));
-    PECS_CUDA(cudaStreamWaitEvent(ctx->main, defer_currents ? ctx->dens[k] : ctx->join[k], 0));
-    if (host && host[k]) {
-      PECS_CUDA(cudaMemcpyAsync(host[k], vector_of(ctx, k, false), (size_t)n_dofs_of(ctx, k) * sizeof(double),
-                                cudaMemcpyDeviceToHost, side));
-      PECS_CUDA(cudaEventRecord(ctx->copied[k], side));
-      if (n_copies) ++*n_copies;
+    enqueue_carrier_solve(ctx, k / 2, k % 2, count, side, defer_currents ? &ctx->dens[k] : nullptr);
+    for (int i = 0; i < count; ++i) {
+      PECS_CUDA(cudaEventRecord(ctx->join[k + i], side));
+      PECS_CUDA(cudaStreamWaitEvent(ctx->main, defer_currents ? ctx->dens[k + i] : ctx->join[k + i], 0));
+      if (host && host[k + i]) {
+        PECS_CUDA(cudaMemcpyAsync(host[k + i], vector_of(ctx, k + i, false), (size_t)n_dofs_of(ctx, k + i) * sizeof(double),
+                                  cudaMemcpyDeviceToHost, side));
+        PECS_CUDA(cudaEventRecord(ctx->copied[k + i], side));
+        if (n_copies) ++*n_copies;
+      }
     }
+    k += count - 1;
   }
 }
 // OFF by default.  Measured +1 % (2.49 -> 2.46 ms per step at cfg3), but one of three complete GPU suite runs with it
@@ -815,9 +875,14 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     for (int w = 0; w < ctx->n_domains(); ++w) {
       const pecs_domain_desc* d = w == 0 ? &desc->semiconductor : &desc->electrolyte;
       require(d->n_cells > 0, "domain: empty mesh tables");
+      // identical matrices (reductants / oxidants at equal mobility) are factorised once and solved together
+      ctx->dom[w].shared_pair = ctx->kind == PECS_KIND_PRODUCTION && (ctx->owned >> (2 * w) & 3) == 3 &&
+                                shared_factors_enabled() && schur_reduction_enabled() &&
+                                same_matrix(d->system_matrix[0], d->system_matrix[1]);
       for (int k = 0; k < 2; ++k) {
         if (ctx->kind != PECS_KIND_PRODUCTION && k == 1) break; // the manufactured tests only solve carrier_1
         if (!(ctx->owned >> (2 * w + k) & 1)) continue;          // another shard owns this carrier
+        if (k == 1 && ctx->dom[w].shared_pair) continue;         // served by carrier_1's factorisation
         prepared[w][k] = std::async(std::launch::async, [d, k] { return prepare_carrier(*d, k); });
       }
     }
@@ -1046,7 +1111,7 @@ pecs_status pecs_p2p_connect(pecs_ctx* ctx, int32_t rank, int32_t world, const v
         ctx->p2p.opened.push_back(q);
         DeviceDomain& D = ctx->dom[s / 2];
         DeviceSystem& S = D.system[s % 2];
-        require(D.reduced[s % 2].active, "pecs_p2p_connect: needs the Schur-reduced (density) systems");
+        require(D.reduced_of(s % 2).active, "pecs_p2p_connect: needs the Schur-reduced (density) systems");
         S.mirror[S.n_mirror++] = static_cast<double*>(q) + 8 * (size_t)D.n_cells; // the peer's density block
       }
     }

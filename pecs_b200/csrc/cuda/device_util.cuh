@@ -65,6 +65,35 @@ private:
 };
 
 #ifdef __CUDACC__
+// Loads of STEP-VARYING vectors (states, right-hand sides, work vectors of the solves, child-update buffers).
+// Most kernels of a step are launched programmatically (launch_pdl): a consumer grid is resident -- prologue running,
+// L1 of its SMs alive -- while its producer still writes these vectors.  PTX allows ld.global.nc (__ldg, or what nvcc
+// emits for `const T* __restrict__`) only for data that is read-only for the WHOLE lifetime of the grid, and the
+// non-coherent path may be served from an L1 sector another block on the same SM filled before the producer's store
+// (round 1: sporadic 5.6e-6 density error).  These vectors are therefore read with ld.global.cg:
+// L2 is the point of coherence, griddepcontrol.wait orders the producer's stores before it, and nothing here is reused
+// from L1 anyway.  .nc stays for the static tables only.  -DPECS_B200_NC_STEP_VECTORS=1 restores the round-1 loads
+// (the A side of the A/B experiment in scripts/race_repro.py; never shipped).
+#ifndef PECS_B200_NC_STEP_VECTORS
+#define PECS_B200_NC_STEP_VECTORS 0
+#endif
+template <class T>
+__device__ __forceinline__ T ld_step(const T* p) {
+#if PECS_B200_NC_STEP_VECTORS
+  return __ldg(p);
+#else
+  return __ldcg(p);
+#endif
+}
+// 256-bit form (sm_100a): one instruction per 4-vector of nodal values
+__device__ __forceinline__ void ld_step4(const double* p, double v[4]) {
+#if PECS_B200_NC_STEP_VECTORS
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+#else
+  asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+#endif
+}
+
 // Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream is still
 // running and synchronises itself with griddepcontrol.wait (wait_for_predecessor).  PECS_B200_PDL=0 launches plainly.
 template <class... KArgs, class... Args>

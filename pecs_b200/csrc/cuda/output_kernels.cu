@@ -18,7 +18,7 @@ namespace {
 constexpr int kThreads = 128;
 
 // DGQ1 support points are the cell vertices in lexicographic order: the patch value at vertex a IS nodal value a.
-__global__ void carrier_patch_kernel(int n, const double* __restrict__ u1, const double* __restrict__ u2, double scale_current,
+__global__ void carrier_patch_kernel(int n, const double* u1, const double* u2, double scale_current,
                                      double* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
@@ -40,7 +40,7 @@ __global__ void carrier_patch_kernel(int n, const double* __restrict__ u1, const
 }
 
 __global__ void poisson_patch_kernel(int n, const double* __restrict__ vx, const double* __restrict__ vy,
-                                     const int* __restrict__ face_dof, int n_rt, const double* __restrict__ X,
+                                     const int* __restrict__ face_dof, int n_rt, const double* X,
                                      double scale_field, double scale_potential, double* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;

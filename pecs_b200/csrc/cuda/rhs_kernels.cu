@@ -59,6 +59,15 @@ __device__ __forceinline__ void load4(const double* p, double out[4]) {
   out[2] = b.x;
   out[3] = b.y;
 }
+// 4-vector of a step-varying vector (state): coherent loads, see device_util.cuh: ld_step
+__device__ __forceinline__ void load4_step(const double* p, double out[4]) {
+  const double2 a = ld_step(reinterpret_cast<const double2*>(p));
+  const double2 b = ld_step(reinterpret_cast<const double2*>(p + 2));
+  out[0] = a.x;
+  out[1] = a.y;
+  out[2] = b.x;
+  out[3] = b.y;
+}
 __device__ __forceinline__ void store4(double* p, const double v[4]) {
   *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
   *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
@@ -74,9 +83,8 @@ __device__ __forceinline__ void add4(double* p, const double v[4]) {
 // ------------------------------------------------------------------------------------------ carrier cell terms
 template <int KIND>
 __device__ __forceinline__ void carrier_cell_terms(const DomainView& d, const RhsParams& p, int c,
-                                                   const double* __restrict__ u1, const double* __restrict__ u2,
-                                                   const double* __restrict__ X, double* __restrict__ rhs1,
-                                                   double* __restrict__ rhs2) {
+                                                   const double* u1, const double* u2, const double* X, double* rhs1,
+                                                   double* rhs2) {
   const size_t n = (size_t)d.n_cells;
   constexpr bool kProduction = KIND == PECS_KIND_PRODUCTION;
   constexpr bool kDrift = KIND != PECS_KIND_TEST_STEADY;
@@ -84,11 +92,11 @@ __device__ __forceinline__ void carrier_cell_terms(const DomainView& d, const Rh
 
   const fe::CellVerts v = load_verts(d, c);
   double r1[4] = {0, 0, 0, 0}, r2[4] = {0, 0, 0, 0}, Xf[4] = {0, 0, 0, 0};
-  if (KIND != PECS_KIND_TEST_STEADY) load4(u1 + 8 * n + 4 * (size_t)c, r1);
-  if (kProduction) load4(u2 + 8 * n + 4 * (size_t)c, r2);
+  if (KIND != PECS_KIND_TEST_STEADY) load4_step(u1 + 8 * n + 4 * (size_t)c, r1);
+  if (kProduction) load4_step(u2 + 8 * n + 4 * (size_t)c, r2);
   if (kPoissonField) {
 #pragma unroll
-    for (int f = 0; f < 4; ++f) Xf[f] = __ldg(X + __ldg(d.rt_dof + (size_t)f * n + c));
+    for (int f = 0; f < 4; ++f) Xf[f] = ld_step(X + __ldg(d.rt_dof + (size_t)f * n + c));
   }
 
   double jx1[4] = {0, 0, 0, 0}, jy1[4] = {0, 0, 0, 0}, rh1[4] = {0, 0, 0, 0};
@@ -208,23 +216,22 @@ __global__ void boundary_geometry_kernel(DomainView d, double tau, double* __res
 // face terms of boundary record r added to the rows the cell terms have just been stored to (point-by-point kernel)
 template <int KIND>
 __device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int other_n_cells, const RhsParams& p, int r,
-                                                    const double* __restrict__ u1, const double* __restrict__ u2,
-                                                    const double* __restrict__ o1, const double* __restrict__ o2, double* rhs1,
-                                                    double* rhs2) {
+                                                    const double* u1, const double* u2, const double* o1, const double* o2,
+                                                    double* rhs1, double* rhs2) {
   constexpr bool kProduction = KIND == PECS_KIND_PRODUCTION;
   const int c = d.bcell[r];
   const size_t n = (size_t)d.n_cells;
   const fe::CellVerts v = load_verts(d, c);
   double r1[4], r2[4] = {0, 0, 0, 0};
-  load4(u1 + 8 * n + 4 * (size_t)c, r1);
-  if (kProduction) load4(u2 + 8 * n + 4 * (size_t)c, r2);
+  load4_step(u1 + 8 * n + 4 * (size_t)c, r1);
+  if (kProduction) load4_step(u2 + 8 * n + 4 * (size_t)c, r2);
   double jx1[4] = {0, 0, 0, 0}, jy1[4] = {0, 0, 0, 0}, rh1[4] = {0, 0, 0, 0};
   double jx2[4] = {0, 0, 0, 0}, jy2[4] = {0, 0, 0, 0}, rh2[4] = {0, 0, 0, 0};
   const rhsmath::BoundaryRecord rec = load_record(d, r);
   double q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
   if (kProduction && rec.nb_cell >= 0) {
-    load4(o1 + 8 * (size_t)other_n_cells + 4 * (size_t)rec.nb_cell, q1);
-    load4(o2 + 8 * (size_t)other_n_cells + 4 * (size_t)rec.nb_cell, q2);
+    load4_step(o1 + 8 * (size_t)other_n_cells + 4 * (size_t)rec.nb_cell, q1);
+    load4_step(o2 + 8 * (size_t)other_n_cells + 4 * (size_t)rec.nb_cell, q2);
   }
   double geom[4][4];
   load_geometry(d, r, geom);
@@ -244,7 +251,7 @@ __device__ __noinline__ void carrier_boundary_terms(const DomainView& d, int oth
 // boundary faces, their terms right after.
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 4) carrier_rhs_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a,
-                                                               const double* __restrict__ X) {
+                                                               const double* X) {
   const bool first = (int)blockIdx.x < blocks_a;
   const CarrierPass& w = pp.pass[first ? 0 : 1]; // stays in the constant bank: no local copy
   const int c = ((int)blockIdx.x - (first ? 0 : blocks_a)) * blockDim.x + threadIdx.x;
@@ -276,6 +283,7 @@ __global__ void static_cell_integrals_kernel(DomainView d, RhsParams p, double* 
 __device__ __forceinline__ void store4_256(double* p, const double v[4]) {
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
+// static tables only (read-only for the lifetime of every grid); states go through ld_step4
 __device__ __forceinline__ void load4_256(const double* p, double v[4]) {
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
@@ -383,7 +391,7 @@ __device__ __forceinline__ void store_cell(const CarrierPass& w, int c, const do
 
 // one boundary record: cell terms + face terms of its cell, single writer of the cell's 24 rows.  Three dependent
 // round trips to memory at most: {record, cell index} -> {vertices, densities, flux dofs, neighbour densities} -> fluxes
-__device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const double* __restrict__ X) {
+__device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const double* X) {
   const DomainView& d = w.d;
   const size_t n = (size_t)d.n_cells;
   const int c = __ldg(d.bcell + r);
@@ -399,15 +407,15 @@ __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const 
     v.x[a] = __ldg(d.vx + (size_t)a * n + c);
     v.y[a] = __ldg(d.vy + (size_t)a * n + c);
   }
-  load4_256(w.u1 + 8 * n + 4 * (size_t)c, r1);
-  load4_256(w.u2 + 8 * n + 4 * (size_t)c, r2);
+  ld_step4(w.u1 + 8 * n + 4 * (size_t)c, r1);
+  ld_step4(w.u2 + 8 * n + 4 * (size_t)c, r2);
   if (d.gen_int) load4_256(d.gen_int + 4 * (size_t)c, gen);
   if (rec.nb_cell >= 0) {
-    load4_256(w.o1 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q1);
-    load4_256(w.o2 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q2);
+    ld_step4(w.o1 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q1);
+    ld_step4(w.o2 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q2);
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a) Xf[a] = __ldg(X + dof[a]);
+  for (int a = 0; a < 4; ++a) Xf[a] = ld_step(X + dof[a]);
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
   rhsmath::production_cell_terms(v.x, v.y, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
                         jy1, rh1, jx2, jy2, rh2);
@@ -428,7 +436,7 @@ __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const 
 
 __global__ void __launch_bounds__(kThreads, 4)
     carrier_rhs_stream_kernel(const __grid_constant__ CarrierPassPair pp, int tiles_a, int tiles_total, int btiles_a,
-                              int btiles_total, const double* __restrict__ X) {
+                              int btiles_total, const double* X) {
   extern __shared__ __align__(16) double ring[];
   const int tid = threadIdx.x;
   // the FIRST blocks of the grid do nothing but one boundary tile each: the face terms are a chain of dependent loads
@@ -491,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 template <int MIN_BLOCKS, int THREADS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     carrier_rhs_direct_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a, int btiles_a, int btiles_total,
-                              const double* __restrict__ X) {
+                              const double* X) {
   if ((int)blockIdx.x < btiles_total) { // leading blocks: one boundary tile each (see the streaming kernel)
     const int sel = (int)blockIdx.x < btiles_a ? 0 : 1;
     const int r = ((int)blockIdx.x - (sel ? btiles_a : 0)) * THREADS + threadIdx.x;
@@ -510,10 +518,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
   for (int a = 0; a < 4; ++a) {
     vx[a] = __ldg(w.d.vx + (size_t)a * n + c);
     vy[a] = __ldg(w.d.vy + (size_t)a * n + c);
-    Xf[a] = __ldg(X + __ldg(w.d.rt_dof + (size_t)a * n + c));
+    Xf[a] = ld_step(X + __ldg(w.d.rt_dof + (size_t)a * n + c));
   }
-  load4_256(w.u1 + 8 * n + 4 * (size_t)c, r1);
-  load4_256(w.u2 + 8 * n + 4 * (size_t)c, r2);
+  ld_step4(w.u1 + 8 * n + 4 * (size_t)c, r1);
+  ld_step4(w.u2 + 8 * n + 4 * (size_t)c, r2);
   if (w.d.gen_int) load4_256(w.d.gen_int + 4 * (size_t)c, gen);
   if (record >= 0) return; // done by a boundary tile
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
@@ -530,8 +538,8 @@ __global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(const __grid
   const CarrierPass& w = pp.pass[first ? 0 : 1];
   const DomainView& d = w.d;
   const RhsParams& p = w.p;
-  const double* __restrict__ u1 = w.u1;
-  const double* __restrict__ u2 = w.u2;
+  const double* u1 = w.u1;
+  const double* u2 = w.u2;
   const int c = ((int)blockIdx.x - (first ? 0 : blocks_a)) * blockDim.x + threadIdx.x;
   if (c >= d.n_cells) return;
   const size_t n = (size_t)d.n_cells;
@@ -539,16 +547,16 @@ __global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(const __grid
     // -int (doping + z1 rho1 + z2 rho2) = -sum_a m_a (doping + z1 r1_a + z2 r2_a) with the static m_a = int N_a:
     // the same quadrature sum, reordered; 108 B per cell
     double r1[4], r2[4], m[4];
-    load4_256(u1 + 8 * n + 4 * (size_t)c, r1);
-    load4_256(u2 + 8 * n + 4 * (size_t)c, r2);
+    ld_step4(u1 + 8 * n + 4 * (size_t)c, r1);
+    ld_step4(u2 + 8 * n + 4 * (size_t)c, r2);
     load4_256(d.nodal_int + 4 * (size_t)c, m);
     poisson_rhs[d.phi_dof[c]] = rhsmath::poisson_charge_row(p, m, r1, r2);
     return;
   }
   const fe::CellVerts v = load_verts(d, c);
   double r1[4] = {0, 0, 0, 0}, r2[4] = {0, 0, 0, 0};
-  if (KIND != PECS_KIND_TEST_STEADY) load4(u1 + 8 * n + 4 * (size_t)c, r1);
-  if (KIND == PECS_KIND_PRODUCTION) load4(u2 + 8 * n + 4 * (size_t)c, r2);
+  if (KIND != PECS_KIND_TEST_STEADY) load4_step(u1 + 8 * n + 4 * (size_t)c, r1);
+  if (KIND == PECS_KIND_PRODUCTION) load4_step(u2 + 8 * n + 4 * (size_t)c, r2);
   double acc = 0.0;
 #pragma unroll
   for (int qy = 0; qy < 3; ++qy)

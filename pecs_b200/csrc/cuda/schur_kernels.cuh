@@ -29,10 +29,22 @@ struct EllTerm {
   const DeviceEll* A = nullptr;
   const double* x = nullptr;
   double sign = 1.0;
+  const double* x2 = nullptr; // second vector of launch_ell_combine2
+};
+struct EllBase {
+  const double* p[2];
+};
+struct EllOut {
+  double* p[2];
 };
 
 // y[i] = (base ? base[base_index ? base_index[i] : i] : 0) + sum over the terms of sign * (A x)[i]
 void launch_ell_combine(int n_rows, const double* base, const int* base_index, EllTerm t0, EllTerm t1, EllTerm t2, double* y,
                         cudaStream_t s);
+
+// the same for two vectors at once: y = base + sum sign * A x and y2 = base2 + sum sign * A x2 with ONE pass over every
+// table (two carriers with identical matrices); per vector the arithmetic and its order are those of launch_ell_combine
+void launch_ell_combine2(int n_rows, const double* base, const double* base2, const int* base_index, EllTerm t0, EllTerm t1,
+                         EllTerm t2, double* y, double* y2, cudaStream_t s);
 
 } // namespace pecs

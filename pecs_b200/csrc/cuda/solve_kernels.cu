@@ -104,8 +104,11 @@ struct PanelStream {
     if (lane == 0)
       for (int q = 0; q < stages && q < total; ++q) issue();
   }
-  template <class Emit>
-  __device__ __forceinline__ void run(const double* sv, int rows, Emit emit) {
+  // NRHS right-hand sides share ONE pass over the table (the two redox carriers of the default input have identical
+  // matrices, reference source/LDG.cpp:624-678 + equal mobilities): sv holds NRHS vectors `vec_stride` apart; every
+  // right-hand side keeps the accumulation order of the single-vector kernel, so results are bit-identical to two solves
+  template <int NRHS, class Emit>
+  __device__ __forceinline__ void run(const double* sv, int vec_stride, int rows, Emit emit) {
     const int P = 1 << log2P;
     const int cg = 32 >> log2P; // columns covered by 32 consecutive doubles
     const int row_in_panel = lane & (P - 1);
@@ -114,7 +117,9 @@ struct PanelStream {
     uint32_t phase = 0;
     for (int k = 0; k < n_my; ++k) {
       const int panel = panel0 + rank + k * n_ranks;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      double a[NRHS][4];
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.0;
       for (int c = 0; c < cpp; ++c) {
         mbar_wait(bars + slot, phase);
         const double* ch = ring + slot * CHUNK + lane;
@@ -124,13 +129,22 @@ struct PanelStream {
         if (elems == CHUNK) {
 #pragma unroll
           for (int s = 0; s < CHUNK / 32; s += 4) {
-            a0 += ch[32 * s] * v[s * cg];
-            a1 += ch[32 * s + 32] * v[(s + 1) * cg];
-            a2 += ch[32 * s + 64] * v[(s + 2) * cg];
-            a3 += ch[32 * s + 96] * v[(s + 3) * cg];
+            const double t0 = ch[32 * s], t1 = ch[32 * s + 32], t2 = ch[32 * s + 64], t3 = ch[32 * s + 96];
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+              const double* vr = v + r * vec_stride;
+              a[r][0] += t0 * vr[s * cg];
+              a[r][1] += t1 * vr[(s + 1) * cg];
+              a[r][2] += t2 * vr[(s + 2) * cg];
+              a[r][3] += t3 * vr[(s + 3) * cg];
+            }
           }
         } else {
-          for (int s = 0; s < elems; s += 32) a0 += ch[s] * v[(s >> 5) * cg];
+          for (int s = 0; s < elems; s += 32) {
+            const double t0 = ch[s];
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) a[r][0] += t0 * v[r * vec_stride + (s >> 5) * cg];
+          }
         }
         __syncwarp();
         if (lane == 0 && issued < total) issue();
@@ -139,8 +153,12 @@ struct PanelStream {
           phase ^= 1u;
         }
       }
-      double sum = (a0 + a1) + (a2 + a3);
-      for (int o = P; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      double sum[NRHS];
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) {
+        sum[r] = (a[r][0] + a[r][1]) + (a[r][2] + a[r][3]);
+        for (int o = P; o < 32; o <<= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+      }
       const int row = (panel << log2P) + row_in_panel;
       if (lane < P && row < rows) emit(row, sum);
     }
@@ -161,6 +179,7 @@ struct BlockSmem {
   double* my_ring;
   unsigned long long* my_bars;
 };
+// vec_doubles: all NRHS vectors of one front (NRHS * padded length)
 template <bool PER_WARP, int CHUNK>
 __device__ __forceinline__ BlockSmem carve(unsigned char* raw, int vec_doubles, int stages) {
   const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -171,13 +190,12 @@ __device__ __forceinline__ BlockSmem carve(unsigned char* raw, int vec_doubles, 
                    bars + warp * stages};
 }
 
-template <bool PER_WARP, int CHUNK>
+template <bool PER_WARP, int CHUNK, int NRHS>
 __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
                                                                         int n_tiles, int vec_doubles, int stages,
-                                                                        const double* __restrict__ w_in,
-                                                                        double* __restrict__ w_fin, double* cbuf) {
+                                                                        SolveVectors io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles, stages);
+  const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles * NRHS, stages);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
   if (PER_WARP && tile_index >= n_tiles) return;
@@ -188,56 +206,60 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
   stream.start();
   wait_for_predecessor();
   const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
-  const double* c0 = tile.cbuf_off[0] >= 0 ? cbuf + tile.cbuf_off[0] : nullptr;
-  const double* c1 = tile.cbuf_off[1] >= 0 ? cbuf + tile.cbuf_off[1] : nullptr;
-  // finalised pivot right-hand side: w_P = b_P - what the children eliminated into it
-  {
+  const int* omap = t.out_map + tile.bd_off;
+#pragma unroll
+  for (int r = 0; r < NRHS; ++r) {
+    const double* cb = io.cbuf + (size_t)r * io.cbuf_stride;
+    const double* c0 = tile.cbuf_off[0] >= 0 ? cb + tile.cbuf_off[0] : nullptr;
+    const double* c1 = tile.cbuf_off[1] >= 0 ? cb + tile.cbuf_off[1] : nullptr;
+    const double* w_in = io.w_in + (size_t)r * io.n_stride;
+    double* w_fin = io.w_fin + (size_t)r * io.n_stride;
+    double* sv = sm.sv + r * vec_doubles;
+    // finalised pivot right-hand side: w_P = b_P - what the children eliminated into it
     const int count = max(tile.np, tile.cols_pad);
     for (int l = first_thread; l < count; l += n_threads) {
       double v = 0.0;
       if (l < tile.np) {
-        v = w_in[tile.p0 + l];
-        if (c0) v -= c0[l];
-        if (c1) v -= c1[l];
+        v = ld_step(w_in + tile.p0 + l);
+        if (c0) v -= ld_step(c0 + l);
+        if (c1) v -= ld_step(c1 + l);
         if (tile.first) w_fin[tile.p0 + l] = v;
       }
-      if (l < tile.cols_pad) sm.sv[l] = v;
+      if (l < tile.cols_pad) sv[l] = v;
     }
-  }
-  const double* carry0 = c0 ? c0 + tile.np : nullptr;
-  const double* carry1 = c1 ? c1 + tile.np : nullptr;
-  const int* omap = t.out_map + tile.bd_off;
-  double* out = cbuf + tile.out_off;
-  if (tile.np == 0) {
-    // a front without pivots (its region fell apart into unconnected pieces) only hands its children's updates on
-    for (int row = first_thread; row < tile.nb; row += n_threads) {
-      double carry = 0.0;
-      if (carry0) carry += carry0[row];
-      if (carry1) carry += carry1[row];
-      out[omap[row]] = carry;
+    if (tile.np == 0) {
+      // a front without pivots (its region fell apart into unconnected pieces) only hands its children's updates on
+      double* out = io.cbuf + (size_t)r * io.cbuf_stride + tile.out_off;
+      for (int row = first_thread; row < tile.nb; row += n_threads) {
+        double carry = 0.0;
+        if (c0) carry += ld_step(c0 + tile.np + row);
+        if (c1) carry += ld_step(c1 + tile.np + row);
+        out[omap[row]] = carry;
+      }
     }
   }
   if (PER_WARP)
     __syncwarp();
   else
     __syncthreads();
-  stream.run(sm.sv, tile.nb, [&](int row, double dot) {
-    double carry = 0.0;
-    if (carry0) carry += carry0[row];
-    if (carry1) carry += carry1[row];
-    out[omap[row]] = carry + dot;
+  stream.template run<NRHS>(sm.sv, vec_doubles, tile.nb, [&](int row, const double (&dot)[NRHS]) {
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+      double* cb = io.cbuf + (size_t)r * io.cbuf_stride;
+      double carry = 0.0;
+      if (tile.cbuf_off[0] >= 0) carry += ld_step(cb + tile.cbuf_off[0] + tile.np + row);
+      if (tile.cbuf_off[1] >= 0) carry += ld_step(cb + tile.cbuf_off[1] + tile.np + row);
+      cb[tile.out_off + omap[row]] = carry + dot[r];
+    }
   });
 }
 
-template <bool PER_WARP, int CHUNK>
+template <bool PER_WARP, int CHUNK, int NRHS>
 __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
                                                                          int n_tiles, int vec_doubles, int stages,
-                                                                         const double* __restrict__ w_in,
-                                                                         const double* __restrict__ cbuf,
-                                                                         const double* __restrict__ w_fin, double* x_perm,
-                                                                         double* solution) {
+                                                                         SolveVectors io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles, stages);
+  const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles * NRHS, stages);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
   if (PER_WARP && tile_index >= n_tiles) return;
@@ -251,35 +273,46 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
     const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
     const int np = tile.np, m = tile.np + tile.nb;
     const int* bd = t.bd_index + tile.bd_off;
-    if (tile.first) {
-      // no boundary, hence no forward tile: w_P = b_P - what the children eliminated into it, finalised here
-      const double* c0 = tile.cbuf_off[0] >= 0 ? cbuf + tile.cbuf_off[0] : nullptr;
-      const double* c1 = tile.cbuf_off[1] >= 0 ? cbuf + tile.cbuf_off[1] : nullptr;
-      for (int l = first_thread; l < tile.cols_pad; l += n_threads) {
-        double v = 0.0;
-        if (l < np) {
-          v = w_in[tile.p0 + l];
-          if (c0) v -= c0[l];
-          if (c1) v -= c1[l];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+      double* sv = sm.sv + r * vec_doubles;
+      if (tile.first) {
+        // no boundary, hence no forward tile: w_P = b_P - what the children eliminated into it, finalised here
+        const double* cb = io.cbuf + (size_t)r * io.cbuf_stride;
+        const double* c0 = tile.cbuf_off[0] >= 0 ? cb + tile.cbuf_off[0] : nullptr;
+        const double* c1 = tile.cbuf_off[1] >= 0 ? cb + tile.cbuf_off[1] : nullptr;
+        const double* w_in = io.w_in + (size_t)r * io.n_stride;
+        for (int l = first_thread; l < tile.cols_pad; l += n_threads) {
+          double v = 0.0;
+          if (l < np) {
+            v = ld_step(w_in + tile.p0 + l);
+            if (c0) v -= ld_step(c0 + l);
+            if (c1) v -= ld_step(c1 + l);
+          }
+          sv[l] = v;
         }
-        sm.sv[l] = v;
+      } else {
+        const double* wp = io.w_fin + (size_t)r * io.n_stride + tile.p0;
+        const double* xp = io.x_perm + (size_t)r * io.n_stride;
+        for (int l = first_thread; l < tile.cols_pad; l += n_threads)
+          sv[l] = l < np ? ld_step(wp + l) : (l < m ? ld_step(xp + bd[l - np]) : 0.0);
       }
-    } else {
-      const double* wp = w_fin + tile.p0;
-      for (int l = first_thread; l < tile.cols_pad; l += n_threads)
-        sm.sv[l] = l < np ? wp[l] : (l < m ? x_perm[bd[l - np]] : 0.0);
     }
   }
   if (PER_WARP)
     __syncwarp();
   else
     __syncthreads();
-  stream.run(sm.sv, tile.np, [&](int row, double x) {
-    x_perm[tile.p0 + row] = x;
+  stream.template run<NRHS>(sm.sv, vec_doubles, tile.np, [&](int row, const double (&x)[NRHS]) {
     const int i = t.iperm[tile.p0 + row];
-    const double v = solution[i] + x; // increment form: the right-hand side was the residual of `solution`
-    solution[i] = v;
-    for (int m = 0; m < t.n_mirror; ++m) t.mirror[m][i] = v; // peer copies (sharded step)
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+      io.x_perm[(size_t)r * io.n_stride + tile.p0 + row] = x[r];
+      double* solution = io.solution[r];
+      const double v = ld_step(solution + i) + x[r]; // increment form: the right-hand side was the residual of `solution`
+      solution[i] = v;
+      for (int m = 0; m < io.n_mirror[r]; ++m) io.mirror[r][m][i] = v; // peer copies (sharded step)
+    }
   });
 }
 
@@ -290,48 +323,48 @@ __global__ void gather_kernel(int n, const int* __restrict__ index, const double
 
 } // namespace
 
-template <bool PER_WARP, int CHUNK>
+template <bool PER_WARP, int NRHS>
 void configure_one(int max_smem_bytes) {
-  cudaFuncSetAttribute(forward_level_kernel<PER_WARP, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
-  cudaFuncSetAttribute(backward_level_kernel<PER_WARP, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_bytes);
+  cudaFuncSetAttribute(forward_level_kernel<PER_WARP, kChunkDoubles, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       max_smem_bytes);
+  cudaFuncSetAttribute(backward_level_kernel<PER_WARP, kChunkDoubles, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       max_smem_bytes);
 }
 void configure_solve_kernels(int max_smem_bytes) {
-  configure_one<false, 256>(max_smem_bytes);
-  configure_one<true, 256>(max_smem_bytes);
-  configure_one<false, 512>(max_smem_bytes);
-  configure_one<true, 512>(max_smem_bytes);
+  configure_one<false, 1>(max_smem_bytes);
+  configure_one<true, 1>(max_smem_bytes);
+  configure_one<false, 2>(max_smem_bytes);
+  configure_one<true, 2>(max_smem_bytes);
 }
 
 void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                          int stages, int chunk, const double* w_in, double* w_fin, double* cbuf, cudaStream_t s) {
+                          int stages, const SolveVectors& io, cudaStream_t s) {
   if (n_tiles == 0) return;
   const int vec = (vec_doubles + 15) / 16 * 16;
-  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, chunk);
+  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, io.n_rhs);
   const int grid = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
-#define PECS_LAUNCH(PW, CH) \
-  launch_pdl(forward_level_kernel<PW, CH>, grid, warps * 32, smem, s, t, tiles, n_tiles, vec, stages, w_in, w_fin, cbuf)
-  if (chunk == 512) {
-    if (per_warp) PECS_LAUNCH(true, 512); else PECS_LAUNCH(false, 512);
+#define PECS_LAUNCH(PW, NR) \
+  launch_pdl(forward_level_kernel<PW, kChunkDoubles, NR>, grid, warps * 32, smem, s, t, tiles, n_tiles, vec, stages, io)
+  if (io.n_rhs == 2) {
+    if (per_warp) PECS_LAUNCH(true, 2); else PECS_LAUNCH(false, 2);
   } else {
-    if (per_warp) PECS_LAUNCH(true, 256); else PECS_LAUNCH(false, 256);
+    if (per_warp) PECS_LAUNCH(true, 1); else PECS_LAUNCH(false, 1);
   }
 #undef PECS_LAUNCH
 }
 
 void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                           int stages, int chunk, const double* w_in, const double* cbuf, const double* w_fin, double* x_perm,
-                           double* solution, cudaStream_t s) {
+                           int stages, const SolveVectors& io, cudaStream_t s) {
   if (n_tiles == 0) return;
   const int vec = (vec_doubles + 15) / 16 * 16;
-  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, chunk);
+  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, io.n_rhs);
   const int grid = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
-#define PECS_LAUNCH(PW, CH)                                                                                           \
-  launch_pdl(backward_level_kernel<PW, CH>, grid, warps * 32, smem, s, t, tiles, n_tiles, vec, stages, w_in, cbuf, w_fin, \
-             x_perm, solution)
-  if (chunk == 512) {
-    if (per_warp) PECS_LAUNCH(true, 512); else PECS_LAUNCH(false, 512);
+#define PECS_LAUNCH(PW, NR) \
+  launch_pdl(backward_level_kernel<PW, kChunkDoubles, NR>, grid, warps * 32, smem, s, t, tiles, n_tiles, vec, stages, io)
+  if (io.n_rhs == 2) {
+    if (per_warp) PECS_LAUNCH(true, 2); else PECS_LAUNCH(false, 2);
   } else {
-    if (per_warp) PECS_LAUNCH(true, 256); else PECS_LAUNCH(false, 256);
+    if (per_warp) PECS_LAUNCH(true, 1); else PECS_LAUNCH(false, 1);
   }
 #undef PECS_LAUNCH
 }

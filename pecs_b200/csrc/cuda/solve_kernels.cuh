@@ -28,31 +28,43 @@ struct SolveTables {
   const int* iperm;    // iperm[position in the elimination order] = unknown
   const double* fwd;
   const double* bwd;
-  // sharded step over several GPUs: the backward sweep also stores every finished solution entry into the other
-  // ranks' copies of the vector (peer memory over NVLink), so the exchange rides on the solve itself
-  double* mirror[3];
-  int n_mirror;
 };
 
-constexpr int kChunkDoubles = 256; // one bulk asynchronous copy: 2 KB of a panel (512 = 4 KB is the other compiled variant)
+constexpr int kMaxRhs = 2;
+// The step-varying vectors of a solve.  Up to kMaxRhs right-hand sides share ONE pass over the factor tables (two
+// carriers whose constant matrices are identical -- reductants and oxidants at equal mobility); right-hand side r uses
+// w_in + r * n_stride etc. and adds its solution into solution[r].
+struct SolveVectors {
+  int n_rhs;
+  long long n_stride;     // between the right-hand sides in w_in, w_fin, x_perm
+  long long cbuf_stride;  // ... in the child-update buffers
+  const double* w_in;     // residual in elimination order
+  double* w_fin;          // finalised pivot right-hand sides (written by the `first` tile of every front)
+  double* cbuf;           // child-update buffers
+  double* x_perm;         // solution increment in elimination order (read by the deeper levels)
+  double* solution[kMaxRhs];
+  // sharded step over several GPUs: the backward sweep also stores every finished solution entry into the other
+  // ranks' copies of the vector (peer memory over NVLink), so the exchange rides on the solve itself
+  double* mirror[kMaxRhs][3];
+  int n_mirror[kMaxRhs];
+};
+
+constexpr int kChunkDoubles = 256; // one bulk asynchronous copy: 2 KB of a panel (4 KB chunks lost in tuning and are gone)
 constexpr int kSolveWarps = 8;
 
-// shared memory of one thread block: the vector (one per block, or one per warp), one ring of `stages` chunks per
-// warp, one mbarrier per slot
-inline size_t solve_smem_bytes(int vec_doubles, bool per_warp, int warps, int stages, int chunk = kChunkDoubles) {
-  const size_t vec = ((size_t)vec_doubles + 15) / 16 * 16 * (per_warp ? warps : 1);
-  return (vec + (size_t)warps * stages * chunk) * sizeof(double) + (size_t)warps * stages * sizeof(unsigned long long);
+// shared memory of one thread block: n_rhs vectors (per block, or per warp), one ring of `stages` chunks per warp, one
+// mbarrier per slot
+inline size_t solve_smem_bytes(int vec_doubles, bool per_warp, int warps, int stages, int n_rhs = 1) {
+  const size_t vec = ((size_t)vec_doubles + 15) / 16 * 16 * (per_warp ? warps : 1) * n_rhs;
+  return (vec + (size_t)warps * stages * kChunkDoubles) * sizeof(double) + (size_t)warps * stages * sizeof(unsigned long long);
 }
 
-// forward sweep of one level.  w_in: right-hand side in elimination order; w_fin: finalised pivot right-hand sides
-// (written by the `first` tile of every front); cbuf: child-update buffers.  per_warp: one small front per warp.
+// forward sweep of one level.  per_warp: one small front per warp.
 void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                          int stages, int chunk, const double* w_in, double* w_fin, double* cbuf, cudaStream_t s);
-// backward sweep of one level; writes x_perm (elimination order, read by the deeper levels) and ADDS the result to the
-// caller's solution vector (increment form)
+                          int stages, const SolveVectors& io, cudaStream_t s);
+// backward sweep of one level; writes x_perm and ADDS the result to the caller's solution vectors (increment form)
 void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                           int stages, int chunk, const double* w_in, const double* cbuf, const double* w_fin, double* x_perm,
-                           double* solution, cudaStream_t s);
+                           int stages, const SolveVectors& io, cudaStream_t s);
 // out[i] = in[index[i]]
 void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s);
 // opt in to large dynamic shared memory once per process

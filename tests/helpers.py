@@ -37,3 +37,66 @@ def perturbed(values, seed):
     rng = np.random.default_rng(seed)
     v = np.asarray(values)
     return v * (1.0 + 1e-3 * rng.uniform(-1, 1, v.size)) + 1e-3 * rng.uniform(-1, 1, v.size)
+
+
+def validate_workload(prob, oracle=None, seed=1234):
+    """Parity of ONE pass of the hot path on whatever mesh `prob` holds (used by bench.py at the benchmarked
+    configuration and by tests/test_gpu_large.py), outside any timed region.  From a perturbed state (seed 1234):
+
+      rhs_rel      all five assembled right-hand sides against the oracle's assembly of the same state, worst block,
+                   max-norm relative (north_star: 1e-12).  The oracle is built WITHOUT its LU (factor=False).
+      residual_rel max over the five systems of |b - A x|_inf / |b|_inf with the host CSR matrices (scipy mat-vec),
+                   x = the vector pecs_solve_* returned for right-hand side b: reference Carrier.cpp:34-40 semantics
+                   x = A^-1 b, checked without any second solver.  Constrained Poisson rows (hanging / Neumann
+                   fluxes) are excluded: the solver eliminates them and `distribute` overwrites them.
+      backward_err the same residuals normwise: |r|_inf / (|A|_inf |x|_inf + |b|_inf)
+      finite       every state entry is finite
+    The caller's state is restored."""
+    import time
+    t0 = time.perf_counter()
+    saved = [prob.get_solution(s) for s in range(5)]
+    o = oracle if oracle is not None else make_oracle(prob, True, factor=False)
+    out = {}
+    try:
+        state = [perturbed(saved[s], seed + s) for s in range(4)] + [perturbed(saved[4], 99)]
+        for s in range(5):
+            prob.set_solution(s, state[s])
+            o.set_vector(s, 0, state[s])
+        prob.assemble_semiconductor_rhs()
+        prob.assemble_electrolyte_rhs()
+        prob.assemble_Poisson_rhs()
+        o.assemble_semiconductor_rhs()
+        o.assemble_electrolyte_rhs()
+        o.assemble_Poisson_rhs()
+        b = [prob.get_rhs(s) for s in range(5)]
+        per = {f"species_{s}": block_rel_err(b[s], o.rhs(s)) for s in range(4)}
+        per["poisson"] = rel_err(b[4], o.rhs(4))
+        out["rhs_rel"] = max(per.values())
+        out["rhs_rel_per_vector"] = per
+        prob.solve_full_system()
+        prob.solve_Poisson()
+        x = [prob.get_solution(s) for s in range(5)]
+        out["finite"] = bool(all(np.isfinite(v).all() for v in x))
+        free = np.ones(b[4].size, bool)
+        cdof = prob.constraints()[0]
+        free[cdof] = False
+        res, bwd = {}, {}
+        for s in range(5):
+            A = prob.matrix(s)
+            r = b[s] - A @ x[s]
+            if s == 4:
+                r = r[free]
+            name = f"species_{s}" if s < 4 else "poisson"
+            res[name] = float(np.abs(r).max() / np.abs(b[s]).max())
+            bwd[name] = float(np.abs(r).max() / (abs(A).sum(axis=1).max() * np.abs(x[s]).max() + np.abs(b[s]).max()))
+        out["residual_rel"] = max(res.values())
+        out["residual_rel_per_system"] = res
+        out["backward_err"] = max(bwd.values())
+        out["n_dofs_per_carrier"] = int(b[0].size)
+    finally:
+        for s in range(5):
+            prob.set_solution(s, saved[s])
+        if oracle is None:
+            o.close()
+    out["seconds"] = time.perf_counter() - t0
+    return out
