@@ -176,3 +176,93 @@ def test_production_rhs_kernels_agree(g, l, overrides, monkeypatch):
     prob.assemble_Poisson_rhs()
     assert rel_err(prob.get_rhs(pecs.POISSON), o.rhs(4)) <= 1e-12
     prob.close()
+
+
+def test_shared_factors_bit_identical(monkeypatch):
+    """Reductants and oxidants have the same constant matrix at equal mobilities (reference source/LDG.cpp:624-678,
+    input_file.prm:77,128): the default context factorises it once and solves the pair with two right-hand sides per
+    pass over the tables.  Per right-hand side the arithmetic and its order are those of the one-vector kernels, so
+    the states must equal those of two separate factorisations BIT FOR BIT -- through the graph, the five calls and
+    pecs_solve_species."""
+    def run(shared):
+        if shared:
+            monkeypatch.delenv("PECS_B200_NO_SHARED_FACTORS", raising=False)
+        else:
+            monkeypatch.setenv("PECS_B200_NO_SHARED_FACTORS", "1")
+        prob = pecs.SolarCellProblem(pecs.default_input_file(4, 1))
+        prob.setup_full_system()
+        bytes_per_step = prob.info(2)
+        prob.step(6)
+        after_graph = [prob.get_solution(s) for s in range(5)]
+        prob.assemble_semiconductor_rhs()
+        prob.assemble_electrolyte_rhs()
+        for s in (3, 2, 1, 0):  # one species at a time: the single-vector path on the shared tables
+            prob.solve_species(s)
+        prob.assemble_Poisson_rhs()
+        prob.solve_Poisson()
+        after_calls = [prob.get_solution(s) for s in range(5)]
+        prob.close()
+        return bytes_per_step, after_graph, after_calls
+    b1, g1, c1 = run(True)
+    b0, g0, c0 = run(False)
+    assert b1 < 0.85 * b0, "the shared factorisation must stream fewer bytes per step"
+    for s in range(5):
+        assert np.array_equal(g1[s], g0[s]), f"graph, vector {s}"
+        assert np.array_equal(c1[s], c0[s]), f"calls, vector {s}"
+    # different mobilities: no sharing, and still the oracle's answer (covered by the other tests through electrons / holes)
+
+
+SCHEDULING = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+import pecs_b200 as pecs
+prob = pecs.SolarCellProblem(pecs.default_input_file(4, 1))
+prob.setup_full_system()
+out = []
+start = [prob.get_solution(s) for s in range(5)]
+for rep in range(8):
+    for s in range(5):
+        prob.set_solution(s, start[s])
+    prob.step(25)
+    out.append(np.concatenate([prob.get_solution(s) for s in range(5)]))
+assert all(np.array_equal(o, out[0]) for o in out), "repetitions differ"
+np.save(sys.argv[1], out[0])
+"""
+
+
+def test_step_scheduling_variants_match_oracle(tmp_path):
+    """Regression test for the round-1 overlap failure: the step graph with programmatic
+    dependent launches on / off and with the deferred recovery of the currents on / off is the same arithmetic in a
+    different schedule -- bit-identical states after 25 steps, 8 repetitions each, and all of them within the parity
+    tolerance of the oracle.  (scripts/race_repro.py is the long version of this with hundreds of repetitions.)"""
+    from helpers import SPECIES, make_oracle
+    script = tmp_path / "sched.py"
+    script.write_text(SCHEDULING % ROOT)
+    results = {}
+    for name, env in {"default": {}, "pdl_off": {"PECS_B200_PDL": "0"}, "defer_on": {"PECS_B200_DEFER_CURRENTS": "1"},
+                      "defer_off": {"PECS_B200_DEFER_CURRENTS": "0"},
+                      "defer_on_pdl_off": {"PECS_B200_DEFER_CURRENTS": "1", "PECS_B200_PDL": "0"}}.items():
+        out = tmp_path / f"{name}.npy"
+        r = subprocess.run([sys.executable, str(script), str(out)], env=dict(os.environ, **env), capture_output=True,
+                           text=True, timeout=900)
+        assert r.returncode == 0, f"{name}: {r.stderr[-2000:]}"
+        results[name] = np.load(out)
+    for name, v in results.items():
+        assert np.array_equal(v, results["default"]), name
+    prob = pecs.SolarCellProblem(pecs.default_input_file(4, 1))
+    prob.setup_full_system_host()
+    o = make_oracle(prob, True)
+    o.project_initial_conditions()
+    o.assemble_Poisson_rhs()
+    o.solve_Poisson()
+    o.step(25)
+    off = 0
+    for s in range(5):
+        n = o.n_dofs(s)
+        got, want = results["default"][off:off + n], o.solution(s)
+        off += n
+        if s < 4:
+            assert rel_err(got[8 * (n // 12):], want[8 * (n // 12):]) <= 1e-9, f"density of species {s}"
+        else:
+            assert rel_err(got[prob.n_rt:], want[prob.n_rt:]) <= 1e-9
+    prob.close()
