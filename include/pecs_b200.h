@@ -240,7 +240,9 @@ enum {
   PECS_INFO_TREE_LEVELS_MAX = 3,
   PECS_INFO_RHS_BYTES_PER_STEP = 4, /* algorithmic bytes of the carrier + Poisson RHS kernels of one step */
   PECS_INFO_HOST_STEP_H2D_BYTES = 5, /* bytes pecs_step_host uploads per call */
-  PECS_INFO_HOST_STEP_D2H_BYTES = 6  /* bytes pecs_step_host downloads per call */
+  PECS_INFO_HOST_STEP_D2H_BYTES = 6, /* bytes pecs_step_host downloads per call */
+  PECS_INFO_SOLVE_WAIT_ERRORS = 7,   /* systems whose level kernels ever gave up waiting for a front (must be 0; synchronises) */
+  PECS_INFO_SHARED_FACTOR_PAIRS = 8  /* carrier pairs whose two identical matrices share one factorisation */
 };
 int64_t pecs_get_info(const pecs_ctx* ctx, int32_t what);
 

@@ -40,6 +40,7 @@ struct DeviceSystem {
   SolvePlan plan;
   DeviceBuffer<double> fwd, bwd, cbuf, w_in, w_fin, x_perm;
   DeviceBuffer<int> bd_index, out_map, iperm;
+  DeviceBuffer<int> done; // completion counters of the fronts: [0, F) forward tiles, [F, 2F) backward tiles, [2F] error word
   // one sweep of one level: large fronts cut into block tiles, small fronts one warp each
   struct Sweep {
     DeviceBuffer<SolveTile> block_tiles, warp_tiles;
@@ -99,13 +100,17 @@ struct DeviceSystem {
     int best_blocks = 0;
     warps = forced_warps ? std::min(forced_warps, kSolveWarps) : kWarpsPerFront;
     stages = forced_stages ? forced_stages : 2;
-    for (int w : {4, 8}) {
+    // 16 warps: only where the vectors leave room for a single block per SM (two right-hand sides at the top of the
+    // tree, 60-90 KB): one fat block then keeps 128 KB in flight where 4 warps x 2 stages x 2 blocks kept 32 KB
+    // (measured r02a: 121 us instead of 48 us for such a level)
+    for (int w : {4, 8, 16}) {
       if (forced_warps && w != warps) continue;
       for (int st : {2, 3, 4}) {
         if (forced_stages && st != stages) continue;
         const size_t smem = solve_smem_bytes(vec_doubles, false, w, st, n_rhs) + 1024;
         const int blocks = (int)std::min<size_t>(std::min<size_t>(sm_bytes / smem, 64 / w), 32);
-        if (blocks < 2 && best_blocks >= 2) continue;
+        if (blocks < 1) continue;
+        if (w == 16 && best_blocks >= 2) continue;
         const size_t inflight = std::min(target, (size_t)blocks * w * st * chunk * sizeof(double));
         // more bytes in flight up to the target; then more resident blocks; then shallower rings
         if (inflight > best_inflight || (inflight == best_inflight && blocks > best_blocks)) {
@@ -153,14 +158,22 @@ struct DeviceSystem {
       fwd.upload(hf);
       bwd.upload(hb);
     }
-    // tile lists per level
+    // tile lists per level; a tile waits for the fronts it reads through their completion counters (solve_kernels.cu),
+    // so it carries how many tiles those fronts have
+    const int n_fronts = (int)plan.fronts.size();
     levels.resize(plan.levels.size());
     launches_per_solve = 0;
+    std::vector<int> n_fwd_tiles(n_fronts, 0), n_bwd_tiles(n_fronts, 0);
+    struct Lists {
+      std::vector<SolveTile> bt, wt;
+      std::vector<int> bt_front, wt_front;
+    };
+    std::vector<Lists> lists(2 * plan.levels.size());
     for (size_t d = 0; d < plan.levels.size(); ++d) {
       Level& L = levels[d];
       for (int which = 0; which < 2; ++which) {
         Sweep& sw = which == 0 ? L.fwd : L.bwd;
-        std::vector<SolveTile> bt, wt;
+        Lists& out = lists[2 * d + which];
         int64_t panels = 0;
         int vec_block = 0;
         for (int f : plan.levels[d]) {
@@ -186,32 +199,60 @@ struct DeviceSystem {
           tile.cbuf_off[0] = F.cbuf_off[0];
           tile.cbuf_off[1] = F.cbuf_off[1];
           tile.out_off = F.parent >= 0 ? plan.fronts[F.parent].cbuf_off[F.which_child] : -1;
+          tile.front = f;
           // a front without boundary (the root) has no forward work at all: the backward sweep finalises its
           // right-hand side itself; a front without pivots still hands its children's updates on in the forward sweep
           if (which == 0 ? F.nb == 0 : F.np == 0) continue;
           tile.first = which == 0 ? 1 : (F.nb == 0 ? 1 : 0);
           const bool per_warp = T.small || T.n_panels() == 0;
+          int& count = (which == 0 ? n_fwd_tiles : n_bwd_tiles)[f];
           if (per_warp) {
             tile.panel0 = 0;
             tile.npanels = T.n_panels();
-            wt.push_back(tile);
+            out.wt.push_back(tile);
+            ++count;
             sw.vec_warp = std::max(sw.vec_warp, T.cols_pad);
           } else {
             for (int p0 = 0; p0 < T.n_panels(); p0 += ppt) {
               tile.panel0 = p0;
               tile.npanels = std::min(ppt, T.n_panels() - p0);
-              bt.push_back(tile);
+              out.bt.push_back(tile);
+              ++count;
               if (which == 0) tile.first = 0; // one publisher per front; the backward flag holds for every tile
             }
             sw.vec_block = std::max(sw.vec_block, T.cols_pad);
           }
         }
         sw.stages_warp = env_int("PECS_B200_SOLVE_STAGES_WARP", 4);
-        sw.block_tiles.upload(bt);
-        sw.warp_tiles.upload(wt);
-        launches_per_solve += (bt.empty() ? 0 : 1) + (wt.empty() ? 0 : 1);
       }
     }
+    // dependencies: forward = the two children; backward = the nearest ancestor that has backward tiles, the front's
+    // own forward tiles and (front without boundary: it finalises its right-hand side itself) the children
+    auto fill = [&](SolveTile& t) {
+      const Front& F = plan.fronts[t.front];
+      for (int k = 0; k < 2; ++k) {
+        const int c = F.child[k];
+        t.dep[k] = (c >= 0 && n_fwd_tiles[c] > 0) ? c : -1;
+        t.need[k] = c >= 0 ? n_fwd_tiles[c] : 0;
+      }
+      int a = F.parent;
+      while (a >= 0 && n_bwd_tiles[a] == 0) a = plan.fronts[a].parent;
+      t.up = a;
+      t.need_up = a >= 0 ? n_bwd_tiles[a] : 0;
+      t.need_self = n_fwd_tiles[t.front];
+    };
+    for (size_t d = 0; d < plan.levels.size(); ++d)
+      for (int which = 0; which < 2; ++which) {
+        Sweep& sw = which == 0 ? levels[d].fwd : levels[d].bwd;
+        Lists& out = lists[2 * d + which];
+        for (SolveTile& t : out.bt) fill(t);
+        for (SolveTile& t : out.wt) fill(t);
+        sw.block_tiles.upload(out.bt);
+        sw.warp_tiles.upload(out.wt);
+        launches_per_solve += (out.bt.empty() ? 0 : 1) + (out.wt.empty() ? 0 : 1);
+      }
+    done.resize(2 * (size_t)n_fronts + 1);
+    done.zero();
   }
 
   // solution += A^-1 w, all on stream s; w = residual of the current content of `solution`, in elimination order
@@ -231,15 +272,49 @@ struct DeviceSystem {
     io.cbuf = cbuf.get() + (size_t)slot0 * cbuf_stride();
     io.x_perm = x_perm.get() + (size_t)slot0 * n;
     for (int r = 0; r < count; ++r) io.solution[r] = solution[r];
+    const size_t n_fronts = plan.fronts.size();
+    io.done_fwd = done.get();
+    io.done_bwd = done.get() + n_fronts;
+    io.error = done.get() + 2 * n_fronts;
+    io.grid_wait = dataflow_enabled() ? 0 : 1;
     return io;
   }
-  void forward_sweep(const SolveVectors& io, cudaStream_t s) {
+  // PECS_B200_DATAFLOW=0: every level kernel waits for its whole predecessor grid (round-1 behaviour; A/B)
+  static bool dataflow_enabled() {
+    const char* e = std::getenv("PECS_B200_DATAFLOW");
+    return !(e && *e == '0');
+  }
+  // zero the completion counters of the fronts (the error word stays): first thing of every solve, BEFORE the kernel
+  // that produces the residual, so that the chain residual -> forward levels -> backward levels is one unbroken chain
+  // of programmatic launches
+  void reset_counters(cudaStream_t s) {
+    PECS_CUDA(cudaMemsetAsync(done.get(), 0, 2 * plan.fronts.size() * sizeof(int), s));
+  }
+  int error_flag() const {
+    int e = 0;
+    if (done.size() > 0)
+      PECS_CUDA(cudaMemcpy(&e, done.get() + 2 * plan.fronts.size(), sizeof(int), cudaMemcpyDeviceToHost));
+    return e;
+  }
+  // The kernel that produced the residual signals no counters: the FIRST forward kernel waits for that whole grid
+  // before it reads anything and only then releases its successor, so no later kernel of the chain can start earlier.
+  void forward_sweep(SolveVectors io, cudaStream_t s) {
     const SolveTables t = tables();
     const int warps = solve_warps();
+    bool first = true;
     for (int d = (int)levels.size() - 1; d >= 0; --d) {
       Sweep& sw = levels[d].fwd;
-      launch_forward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, io, s);
-      launch_forward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages, io, s);
+      for (int per_warp = 1; per_warp >= 0; --per_warp) {
+        const DeviceBuffer<SolveTile>& tiles = per_warp ? sw.warp_tiles : sw.block_tiles;
+        if (tiles.size() == 0) continue;
+        SolveVectors v = io;
+        if (first) v.grid_wait = 1;
+        first = false;
+        if (per_warp)
+          launch_forward_level(t, tiles.get(), (int)tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, v, s);
+        else
+          launch_forward_level(t, tiles.get(), (int)tiles.size(), false, sw.vec_block, sw.warps, sw.stages, v, s);
+      }
     }
   }
   void backward_sweep(const SolveVectors& io, cudaStream_t s) {
@@ -257,6 +332,7 @@ struct DeviceSystem {
   }
   // solution = A^-1 rhs in increment form (one right-hand side; mirrors of this system apply)
   void solve(const double* rhs, double* solution, cudaStream_t s) {
+    reset_counters(s);
     residual(rhs, solution, s);
     SolveVectors io = vectors(w_in.get(), 0, 1, &solution);
     io.n_mirror[0] = n_mirror;
@@ -670,6 +746,7 @@ void enqueue_carrier_solve(pecs_ctx* ctx, int w, int k0, int count, cudaStream_t
   double* x[2] = {D.solution[k0].get(), count == 2 ? D.solution[k0 + 1].get() : nullptr};
   double* rt = red.rtilde.get() + (size_t)slot0 * nu;
   // S du = r_u - T1 r_q - S u_old ;  u = u_old + du ;  q = Ainv r_q - T2 u
+  S.reset_counters(s);
   if (count == 2)
     launch_ell_combine2(nu, r[0] + nq, r[1] + nq, S.iperm.get(), EllTerm{&red.T1, r[0], -1.0, r[1]},
                         EllTerm{&S.matrix_rows, x[0] + nq, -1.0, x[1] + nq}, EllTerm{}, rt, rt + nu, s);
@@ -972,12 +1049,32 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
 
 void pecs_ctx_destroy(pecs_ctx* ctx) { delete ctx; }
 
+// Host -> device upload that is COMPLETE when it returns and ordered with the context's own streams.  Round 1 used a
+// plain cudaMemcpy: for pageable host memory that call returns once the data sit in the driver's staging buffer -- the
+// DMA into the vector may still be in flight ("API synchronization behavior" of the CUDA runtime) -- and it runs on
+// the legacy default stream, which the context's NON-BLOCKING streams do not synchronise with.  A pecs_step enqueued
+// right after pecs_set_state could therefore read a vector that was still being overwritten (the
+// round-1 failure came right after five such uploads).  PECS_B200_LEGACY_SET_STATE=1 keeps the old call for the
+// reproducer (scripts/race_repro.py, tag *_legacyset).
+static void upload_vector(pecs_ctx* ctx, double* device, const double* host, size_t count) {
+  sync_all(ctx);
+  static const bool legacy = [] {
+    const char* e = std::getenv("PECS_B200_LEGACY_SET_STATE");
+    return e && *e == '1';
+  }();
+  if (legacy) {
+    PECS_CUDA(cudaMemcpy(device, host, count * sizeof(double), cudaMemcpyHostToDevice));
+    return;
+  }
+  PECS_CUDA(cudaMemcpyAsync(device, host, count * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
+  PECS_CUDA(cudaStreamSynchronize(ctx->main));
+}
+
 pecs_status pecs_set_state(pecs_ctx* ctx, int32_t which, const double* solution) {
   return guarded([&] {
     require(ctx && solution, "pecs_set_state: NULL argument");
-    sync_all(ctx);
-    PECS_CUDA(cudaMemcpy(vector_of(ctx, which, false), solution, (size_t)n_dofs_of(ctx, which) * sizeof(double),
-                         cudaMemcpyHostToDevice));
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    upload_vector(ctx, vector_of(ctx, which, false), solution, (size_t)n_dofs_of(ctx, which));
   });
 }
 pecs_status pecs_get_state(pecs_ctx* ctx, int32_t which, double* solution) {
@@ -999,9 +1096,8 @@ pecs_status pecs_get_rhs(pecs_ctx* ctx, int32_t which, double* system_rhs) {
 pecs_status pecs_set_rhs(pecs_ctx* ctx, int32_t which, const double* system_rhs) {
   return guarded([&] {
     require(ctx && system_rhs, "pecs_set_rhs: NULL argument");
-    sync_all(ctx);
-    PECS_CUDA(cudaMemcpy(vector_of(ctx, which, true), system_rhs, (size_t)n_dofs_of(ctx, which) * sizeof(double),
-                         cudaMemcpyHostToDevice));
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    upload_vector(ctx, vector_of(ctx, which, true), system_rhs, (size_t)n_dofs_of(ctx, which));
   });
 }
 int32_t pecs_n_dofs(const pecs_ctx* ctx, int32_t which) { return ctx ? n_dofs_of(ctx, which) : 0; }
@@ -1382,6 +1478,19 @@ int64_t pecs_get_info(const pecs_ctx* ctx, int32_t what) {
     // two carriers per subdomain; up: their density blocks (4 of 12 unknowns per cell) + Poisson, down: everything
     case PECS_INFO_HOST_STEP_H2D_BYTES: return (int64_t)(2 * 4 * sizeof(double)) * cells + (int64_t)ctx->p_solution.bytes();
     case PECS_INFO_HOST_STEP_D2H_BYTES: return (int64_t)(2 * 12 * sizeof(double)) * cells + (int64_t)ctx->p_solution.bytes();
+    case PECS_INFO_SOLVE_WAIT_ERRORS: {
+      if (cudaSetDevice(ctx->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -1;
+      int64_t bad = 0;
+      try {
+        bad += ctx->p_system.error_flag();
+        for (int w = 0; w < ctx->n_domains(); ++w)
+          for (int k = 0; k < 2; ++k) bad += ctx->dom[w].system[k].error_flag();
+      } catch (...) {
+        return -1;
+      }
+      return bad;
+    }
+    case PECS_INFO_SHARED_FACTOR_PAIRS: return (ctx->dom[0].shared_pair ? 1 : 0) + (ctx->full && ctx->dom[1].shared_pair ? 1 : 0);
   }
   return -1;
 }

@@ -61,8 +61,8 @@ __device__ __forceinline__ void load4(const double* p, double out[4]) {
 }
 // 4-vector of a step-varying vector (state): coherent loads, see device_util.cuh: ld_step
 __device__ __forceinline__ void load4_step(const double* p, double out[4]) {
-  const double2 a = ld_step(reinterpret_cast<const double2*>(p));
-  const double2 b = ld_step(reinterpret_cast<const double2*>(p + 2));
+  const double2 a = ld_vec(reinterpret_cast<const double2*>(p));
+  const double2 b = ld_vec(reinterpret_cast<const double2*>(p + 2));
   out[0] = a.x;
   out[1] = a.y;
   out[2] = b.x;
@@ -96,7 +96,7 @@ __device__ __forceinline__ void carrier_cell_terms(const DomainView& d, const Rh
   if (kProduction) load4_step(u2 + 8 * n + 4 * (size_t)c, r2);
   if (kPoissonField) {
 #pragma unroll
-    for (int f = 0; f < 4; ++f) Xf[f] = ld_step(X + __ldg(d.rt_dof + (size_t)f * n + c));
+    for (int f = 0; f < 4; ++f) Xf[f] = ld_vec(X + __ldg(d.rt_dof + (size_t)f * n + c));
   }
 
   double jx1[4] = {0, 0, 0, 0}, jy1[4] = {0, 0, 0, 0}, rh1[4] = {0, 0, 0, 0};
@@ -407,15 +407,15 @@ __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const 
     v.x[a] = __ldg(d.vx + (size_t)a * n + c);
     v.y[a] = __ldg(d.vy + (size_t)a * n + c);
   }
-  ld_step4(w.u1 + 8 * n + 4 * (size_t)c, r1);
-  ld_step4(w.u2 + 8 * n + 4 * (size_t)c, r2);
+  ld_vec4(w.u1 + 8 * n + 4 * (size_t)c, r1);
+  ld_vec4(w.u2 + 8 * n + 4 * (size_t)c, r2);
   if (d.gen_int) load4_256(d.gen_int + 4 * (size_t)c, gen);
   if (rec.nb_cell >= 0) {
-    ld_step4(w.o1 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q1);
-    ld_step4(w.o2 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q2);
+    ld_vec4(w.o1 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q1);
+    ld_vec4(w.o2 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, q2);
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a) Xf[a] = ld_step(X + dof[a]);
+  for (int a = 0; a < 4; ++a) Xf[a] = ld_vec(X + dof[a]);
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
   rhsmath::production_cell_terms(v.x, v.y, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
                         jy1, rh1, jx2, jy2, rh2);
@@ -518,10 +518,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
   for (int a = 0; a < 4; ++a) {
     vx[a] = __ldg(w.d.vx + (size_t)a * n + c);
     vy[a] = __ldg(w.d.vy + (size_t)a * n + c);
-    Xf[a] = ld_step(X + __ldg(w.d.rt_dof + (size_t)a * n + c));
+    Xf[a] = ld_vec(X + __ldg(w.d.rt_dof + (size_t)a * n + c));
   }
-  ld_step4(w.u1 + 8 * n + 4 * (size_t)c, r1);
-  ld_step4(w.u2 + 8 * n + 4 * (size_t)c, r2);
+  ld_vec4(w.u1 + 8 * n + 4 * (size_t)c, r1);
+  ld_vec4(w.u2 + 8 * n + 4 * (size_t)c, r2);
   if (w.d.gen_int) load4_256(w.d.gen_int + 4 * (size_t)c, gen);
   if (record >= 0) return; // done by a boundary tile
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
@@ -547,8 +547,8 @@ __global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(const __grid
     // -int (doping + z1 rho1 + z2 rho2) = -sum_a m_a (doping + z1 r1_a + z2 r2_a) with the static m_a = int N_a:
     // the same quadrature sum, reordered; 108 B per cell
     double r1[4], r2[4], m[4];
-    ld_step4(u1 + 8 * n + 4 * (size_t)c, r1);
-    ld_step4(u2 + 8 * n + 4 * (size_t)c, r2);
+    ld_vec4(u1 + 8 * n + 4 * (size_t)c, r1);
+    ld_vec4(u2 + 8 * n + 4 * (size_t)c, r2);
     load4_256(d.nodal_int + 4 * (size_t)c, m);
     poisson_rhs[d.phi_dof[c]] = rhsmath::poisson_charge_row(p, m, r1, r2);
     return;

@@ -75,8 +75,8 @@ __device__ __forceinline__ void ell_row(const EllView& t, int n, int i, double (
       const double a0 = __ldcs(v), a1 = __ldcs(v + n), a2 = __ldcs(v + 2 * (size_t)n), a3 = __ldcs(v + 3 * (size_t)n);
 #pragma unroll
       for (int r = 0; r < NRHS; ++r) {
-        const double2 x01 = ld_step(reinterpret_cast<const double2*>(t.x[r] + j));
-        const double2 x23 = ld_step(reinterpret_cast<const double2*>(t.x[r] + j + 2));
+        const double2 x01 = ld_vec(reinterpret_cast<const double2*>(t.x[r] + j));
+        const double2 x23 = ld_vec(reinterpret_cast<const double2*>(t.x[r] + j + 2));
         acc[r] += (a0 * x01.x + a1 * x01.y) + (a2 * x23.x + a3 * x23.y);
       }
     }
@@ -86,7 +86,7 @@ __device__ __forceinline__ void ell_row(const EllView& t, int n, int i, double (
       const double a = __ldcs(t.val + (size_t)k * n + i);
       const int j = __ldcs(t.col + (size_t)k * n + i);
 #pragma unroll
-      for (int r = 0; r < NRHS; ++r) acc[r] += a * ld_step(t.x[r] + j);
+      for (int r = 0; r < NRHS; ++r) acc[r] += a * ld_vec(t.x[r] + j);
     }
   }
 #pragma unroll
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) ell_combine_kernel(int n, EllBase base, c
   if (i >= n) return;
   double acc[NRHS];
 #pragma unroll
-  for (int r = 0; r < NRHS; ++r) acc[r] = base.p[r] ? ld_step(base.p[r] + (base_index ? base_index[i] : i)) : 0.0;
+  for (int r = 0; r < NRHS; ++r) acc[r] = base.p[r] ? ld_vec(base.p[r] + (base_index ? base_index[i] : i)) : 0.0;
   // every term is added to the sum as a whole, in the order t0, t1, t2 (the summation order of round 1)
   if (t0.val) ell_row<NRHS>(t0, n, i, acc);
   if (t1.val) ell_row<NRHS>(t1, n, i, acc);

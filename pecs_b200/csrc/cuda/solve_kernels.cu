@@ -17,7 +17,20 @@
 //   * a front's update goes to a dense buffer in its parent's local numbering: the parent reads it with unit stride;
 //   * solves are done in increment form (x += A^-1 (b - A x), cuda/context.cu): the residual arrives in elimination
 //     order from the fused ELL kernel and the backward sweep adds the correction to the caller's vector in place;
-//   * every output row has exactly one owner and a fixed summation order: no atomics, bit-reproducible solves.
+//   * every output row has exactly one owner and a fixed summation order: no atomics, bit-reproducible solves;
+//   * DATAFLOW between levels.  A sweep is a chain of programmatically launched level kernels.  Round 1 made every
+//     kernel wait for its whole predecessor grid (griddepcontrol.wait) before touching a vector: 15-30 grid drains per
+//     sweep, the reason a lone solve reached half the HBM peak and the Poisson solve a quarter.  Now a kernel releases
+//     its successor at once (griddepcontrol.launch_dependents first thing), so the blocks of the next levels become
+//     resident and prefetch their tables while this level still computes, and a tile waits only for the FRONTS it
+//     reads: per-front completion counters (forward: the two children; backward: the nearest ancestor with tiles and
+//     the front's own forward tiles), released with __threadfence + atomicAdd by the producing tile, acquired with
+//     ld.acquire.gpu by the consumer, data read from L2 (ld_step).  No deadlock: blocks of kernel k+1 are scheduled only
+//     after ALL blocks of kernel k have started, so whatever a spinning block waits for is already running.  Every
+//     block executes griddepcontrol.wait as its LAST instruction, so a kernel completes only after its predecessor has:
+//     completion stays transitive along the chain, and whatever follows the chain (an event, a plainly launched kernel,
+//     a kernel that waits for its predecessor grid) sees the whole sweep finished.  PECS_B200_DATAFLOW=0 restores the
+//     grid waits (A/B; bit-identical results either way);
 #include "solve_kernels.cuh"
 
 #include "device_util.cuh"
@@ -165,6 +178,34 @@ struct PanelStream {
   }
 };
 
+// ---- per-front completion counters
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// one thread: spin until *counter >= need.  Bounded (about a second): a logic error flags `error` instead of hanging
+__device__ __forceinline__ void wait_count(const int* counter, int need, int* error) {
+  if (need <= 0) return;
+  unsigned spins = 0;
+  while (ld_acquire(counter) < need) {
+    __nanosleep(32);
+    ++spins;
+    if ((spins & 1023u) == 0 && ld_acquire(error) != 0) break; // someone already gave up: do not queue up behind it
+    if (spins > (1u << 20)) {
+      atomicExch(error, 1);
+      break;
+    }
+  }
+}
+// one thread, after the barrier that follows the tile's last store: publish "one more tile of this front is complete"
+__device__ __forceinline__ void signal_count(int* counter) {
+  __threadfence();
+  atomicAdd(counter, 1);
+}
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void release_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void init_pipeline(unsigned long long* my_bars, int stages) {
   if ((threadIdx.x & 31) == 0) {
     for (int q = 0; q < stages; ++q) mbar_init(my_bars + q, 1);
@@ -204,8 +245,18 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
   PanelStream<CHUNK> stream(t.fwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.my_ring, sm.my_bars,
                             stages);
   stream.start();
-  wait_for_predecessor();
+  if (io.grid_wait) grid_dependency_wait();
+  release_dependents();
   const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
+  // the children's updates (their forward tiles) must be complete
+  if (first_thread == 0) {
+    if (tile.dep[0] >= 0) wait_count(io.done_fwd + tile.dep[0], tile.need[0], io.error);
+    if (tile.dep[1] >= 0) wait_count(io.done_fwd + tile.dep[1], tile.need[1], io.error);
+  }
+  if (PER_WARP)
+    __syncwarp();
+  else
+    __syncthreads();
   const int* omap = t.out_map + tile.bd_off;
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) {
@@ -252,6 +303,12 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
       cb[tile.out_off + omap[row]] = carry + dot[r];
     }
   });
+  if (PER_WARP)
+    __syncwarp();
+  else
+    __syncthreads();
+  if (first_thread == 0) signal_count(io.done_fwd + tile.front);
+  if (!io.grid_wait) grid_dependency_wait(); // completion stays transitive along the kernel chain
 }
 
 template <bool PER_WARP, int CHUNK, int NRHS>
@@ -268,9 +325,24 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
   PanelStream<CHUNK> stream(t.bwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.my_ring, sm.my_bars,
                             stages);
   stream.start();
-  wait_for_predecessor();
+  if (io.grid_wait) grid_dependency_wait();
+  release_dependents();
+  const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
+  // x of every ancestor (the nearest one with tiles waited for its own ancestors), this front's finalised right-hand
+  // side (its forward tiles), and -- a front without boundary reads its children's updates itself -- the children
+  if (first_thread == 0) {
+    if (tile.up >= 0) wait_count(io.done_bwd + tile.up, tile.need_up, io.error);
+    wait_count(io.done_fwd + tile.front, tile.need_self, io.error);
+    if (tile.first) {
+      if (tile.dep[0] >= 0) wait_count(io.done_fwd + tile.dep[0], tile.need[0], io.error);
+      if (tile.dep[1] >= 0) wait_count(io.done_fwd + tile.dep[1], tile.need[1], io.error);
+    }
+  }
+  if (PER_WARP)
+    __syncwarp();
+  else
+    __syncthreads();
   {
-    const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
     const int np = tile.np, m = tile.np + tile.nb;
     const int* bd = t.bd_index + tile.bd_off;
 #pragma unroll
@@ -314,6 +386,12 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
       for (int m = 0; m < io.n_mirror[r]; ++m) io.mirror[r][m][i] = v; // peer copies (sharded step)
     }
   });
+  if (PER_WARP)
+    __syncwarp();
+  else
+    __syncthreads();
+  if (first_thread == 0) signal_count(io.done_bwd + tile.front);
+  if (!io.grid_wait) grid_dependency_wait(); // completion stays transitive along the kernel chain
 }
 
 __global__ void gather_kernel(int n, const int* __restrict__ index, const double* __restrict__ in, double* __restrict__ out) {

@@ -20,6 +20,12 @@ struct SolveTile {
   long long bd_off;        // boundary index list (positions in the elimination order); the out map shares the offset
   long long cbuf_off[2];   // dense update buffers written by the two children (np + nb entries each), -1: no child
   long long out_off;       // the parent's buffer this front scatters its own update into, -1: root
+  // dataflow between the level kernels (solve_kernels.cu): per-front completion counters instead of grid-wide barriers
+  int front;               // this front's counter slot
+  int dep[2], need[2];     // children whose forward tiles must all be complete before this tile reads their updates
+  int up, need_up;         // backward: nearest ancestor that has backward tiles (-1: none) and how many it has
+  int need_self;           // backward: forward tiles of this front (they publish its finalised right-hand side)
+  int pad_;
 };
 
 struct SolveTables {
@@ -47,10 +53,16 @@ struct SolveVectors {
   // ranks' copies of the vector (peer memory over NVLink), so the exchange rides on the solve itself
   double* mirror[kMaxRhs][3];
   int n_mirror[kMaxRhs];
+  // completion counters of the fronts (zeroed at the start of every solve): forward tiles done / backward tiles done
+  int* done_fwd;
+  int* done_bwd;
+  int* error;      // set to 1 if a counter wait ever gave up (bounded spin: a logic error must not hang the GPU)
+  int grid_wait;   // 1: wait for the whole predecessor grid BEFORE reading anything (first kernel behind a producer
+                   // that signals no counters, or dataflow switched off); 0: counters only, grid wait at the very end
 };
 
 constexpr int kChunkDoubles = 256; // one bulk asynchronous copy: 2 KB of a panel (4 KB chunks lost in tuning and are gone)
-constexpr int kSolveWarps = 8;
+constexpr int kSolveWarps = 16;
 
 // shared memory of one thread block: n_rhs vectors (per block, or per warp), one ring of `stages` chunks per warp, one
 // mbarrier per slot

@@ -21,7 +21,7 @@ PARAM_NAMES = ["delta_t", "penalty", "mu_n", "mu_p", "mu_r", "mu_o", "eps_s", "e
                "phi_bi", "phi_app", "phi_sch", "sch_location", "transient"]
 
 (INFO_LAUNCHES_PER_STEP, INFO_FACTOR_BYTES, INFO_SOLVE_BYTES_PER_STEP, INFO_TREE_LEVELS_MAX, INFO_RHS_BYTES_PER_STEP,
- INFO_HOST_STEP_H2D_BYTES, INFO_HOST_STEP_D2H_BYTES) = range(7)
+ INFO_HOST_STEP_H2D_BYTES, INFO_HOST_STEP_D2H_BYTES, INFO_SOLVE_WAIT_ERRORS, INFO_SHARED_FACTOR_PAIRS) = range(9)
 
 
 def device_count():
