@@ -161,51 +161,77 @@ def workload_overrides():
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_run(g_sample, l, steps, warmup, threads=None):
-    """Times the oracle (CPU restatement of the reference's WorkStream + UMFPACK path) on a bounded sample mesh.
-    Returns (steps_per_s on the sample mesh, cells per subdomain of the sample, threads, section seconds)."""
-    if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import pecs_b200 as pecs
-    from helpers import make_oracle
-    prob = pecs.SolarCellProblem(pecs.default_input_file(g_sample, l))
-    prob.setup_full_system_host()  # mesh tables only; no device involved
-    o = make_oracle(prob, True)
-    o.project_initial_conditions()
-    o.assemble_Poisson_rhs()
-    o.solve_Poisson()
-    o.step(warmup)
-    t0 = time.perf_counter()
-    sections = o.step(steps)
-    dt = time.perf_counter() - t0
-    cells = prob.n_cells(0)
-    prob.close()
-    return steps / dt, cells, int(os.environ.get("OMP_NUM_THREADS", os.cpu_count())), [float(s) for s in sections]
+def cpu_scaling_samples(g_full, l, steps, threads=None):
+    """The CPU path (oracle/cpu_arm.py: oracle assembly + SuperLU solves, no product library involved) measured on the
+    two refinements below the workload's; returns the samples and the measured exponent of seconds/step in cells."""
+    import math
+    from oracle import cpu_arm
+    samples = [cpu_arm.run(g, l, steps, 1, threads, workload_prm()) for g in (g_full - 2, g_full - 1)]
+    a, b = samples
+    exponent = math.log(b["seconds_per_step"] / a["seconds_per_step"]) / math.log(b["cells_per_subdomain"] / a["cells_per_subdomain"])
+    return samples, exponent
+
+
+def workload_prm():
+    return {"radius one": 0.2, "radius two": 0.6} if CONIC else {}
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU path on the box's host cores ON THE WORKLOAD IT NAMES.  The two smaller
+    refinements are always measured (they give the exponent and the cost estimate); the workload itself is run when the
+    estimated factorisation fits --cpu-budget-seconds and the free memory, and then `same_config` is true.  Rank 0 alone
+    works; under torchrun the value is the one-job figure UNCHANGED (N bias points on one CPU box take N times as long:
+    the whole-job steps/s of the box do not grow with N)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0  # only rank 0 runs and prints the CPU arm
+    from oracle import cpu_arm
+    threads = os.cpu_count()  # never torchrun's OMP_NUM_THREADS=1
     g_full, l = args.global_refinements, args.local_refinements
-    g_s = min(args.cpu_sample_refinements, g_full)
-    sps, cells, threads, sections = cpu_oracle_run(g_s, l, args.steps, max(args.warmup, 1))
-    cells_full = 4 ** g_full + (4 ** (g_full + l) if l > 0 else 0)
-    scale = cells / cells_full  # linear extrapolation in the number of cells: generous to the CPU (LU fill is superlinear)
-    value = sps * scale * args.gpus  # N replicas of the same CPU job would need N boxes; reported per the contract
-    sample = (f"oracle port (OpenMP cell loops + 4 concurrent sparse LU substitutions + 1) on global refinements {g_s} "
-              f"({cells} cells/subdomain, {12 * cells} DoF/carrier), {args.steps} timed steps; steps/s scaled by "
-              f"cells ratio {scale:.5f} to the cfg workload")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 / (sps * scale), "higher_is_better": True, "scaling": "weak",
+    t_start = time.perf_counter()
+    samples, exponent = cpu_scaling_samples(g_full, l, max(3, min(args.steps, 10)), threads)
+    big = samples[-1]
+    ratio = cpu_arm.cells_per_subdomain(g_full, l) / big["cells_per_subdomain"]
+    growth = big["setup_seconds"]["factor"] / max(samples[0]["setup_seconds"]["factor"], 1e-9)
+    est_factor = big["setup_seconds"]["factor"] * growth
+    est_step = big["seconds_per_step"] * ratio ** exponent
+    nnz_growth = sum(big["factor_nnz"]) / sum(samples[0]["factor_nnz"])
+    est_gb = sum(big["factor_nnz"]) * nnz_growth * 12 * 3 / 2 ** 30  # factors + SuperLU work space while factorising
+    free_gb = cpu_arm.available_memory_gb()
+    steps = args.steps
+    fits = (est_factor * 1.5 + est_step * (steps + 1) <= args.cpu_budget_seconds - (time.perf_counter() - t_start)) and \
+           (free_gb is None or est_gb <= 0.8 * free_gb)
+    if not fits:  # fewer timed steps before giving the configuration up
+        steps = max(3, int((args.cpu_budget_seconds - (time.perf_counter() - t_start) - est_factor * 1.5) / max(est_step, 1e-9)) - 1)
+        fits = steps >= 3 and est_factor * 1.5 <= args.cpu_budget_seconds and (free_gb is None or est_gb <= 0.8 * free_gb)
+        steps = min(max(steps, 3), args.steps)
+    estimate = {"factor_seconds": est_factor, "seconds_per_step": est_step, "memory_gb": est_gb, "free_memory_gb": free_gb,
+                "budget_seconds": args.cpu_budget_seconds}
+    if fits and not args.cpu_no_full:
+        full = cpu_arm.run(g_full, l, steps, max(args.warmup, 1), threads, workload_prm())
+        sps, same, used = full["steps_per_s"], True, full
+        sample = (f"the workload itself: oracle assembly (C++/OpenMP, {threads} threads) + SuperLU (scipy splu, COLAMD; 4 "
+                  f"concurrent substitutions + 1) as the UMFPACK stand-in on global refinements {g_full} "
+                  f"({full['dofs_per_carrier']} DoF/carrier), {steps} timed steps; factorisation (untimed, like the "
+                  f"reference's set_solvers) {full['setup_seconds']['factor']:.0f} s")
+    else:
+        sps, same, used = 1.0 / est_step, False, big
+        steps = big["steps"]
+        sample = (f"oracle assembly + SuperLU on global refinements {g_full - 2} and {g_full - 1}, extrapolated to the "
+                  f"workload with the MEASURED exponent {exponent:.3f} of seconds/step in cells (the workload itself was "
+                  f"estimated at {est_factor:.0f} s of factorisation and {est_gb:.0f} GB: outside the budget)")
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(g_full, l), "sample_global_refinements": g_s},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                             "section_seconds": dict(zip(["Assemble semiconductor rhs", "Assemble electrolyte rhs",
-                                                          "Solve LDG Systems", "Assemble Poisson rhs",
-                                                          "Solve Poisson system"], sections))},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": {"workload": workload_name(g_full, l), "same_config": same,
+                       "parallelism": "one CPU box; the figure does not grow with --gpus"},
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "same_config": same, "measured_exponent_seconds_per_step_in_cells": exponent,
+                             "section_seconds_per_step": used["section_seconds_per_step"],
+                             "setup_seconds": used["setup_seconds"], "estimate_for_workload": estimate,
+                             "samples": [{k: v[k] for k in ("g", "dofs_per_carrier", "steps_per_s", "setup_seconds")}
+                                         for v in samples]},
+            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
@@ -352,16 +378,31 @@ def run_gpu_arm(args):
             "parity": parity,
         }
     prob.close()
+    # ---- N = 2 / 4: the COMMUNICATING layouts of the same workload under the same clock (strong scaling of one step:
+    # 2 ranks by subdomain, 4 by species; density exchange fused into the solves over peer memory).  The sweep stays `value`.
+    if world in (2, 4) and not args.no_sharded:
+        sh, _ = measure_sharded(args, rank, device, world, dist, args.exchange)
+        if rank == 0:
+            one_gpu = value / world  # steps/s of one context on one GPU, measured a moment ago in this very run
+            sh["speedup_vs_one_gpu"] = sh["steps_per_s"] / one_gpu
+            sh["strong_scaling_efficiency"] = sh["steps_per_s"] / one_gpu / world
+            sh["one_gpu_steps_per_s"] = one_gpu
+            line["sharded"] = sh
     if rank == 0:
-        # CPU baseline on this box's host cores (rank 0, N = 1 only): bounded sample of the same workload
+        # CPU baseline on this box's host cores (rank 0, N = 1 only): bounded sample of the same workload (the two
+        # refinements below it, MEASURED exponent); `--impl reference` runs the workload itself
         if world == 1 and not args.no_cpu_baseline:
-            g_s = min(args.cpu_sample_refinements, g)
-            sps, cells, threads, _ = cpu_oracle_run(g_s, l, args.cpu_steps, 1)
-            cells_full = prob_cells(g, l)
+            samples, exponent = cpu_scaling_samples(g, l, args.cpu_steps, os.cpu_count())
+            big = samples[-1]
+            ratio = prob_cells(g, l) / big["cells_per_subdomain"]
             line["cpu_baseline"] = {
-                "value": sps * cells / cells_full, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"oracle port on global refinements {g_s} ({cells} cells/subdomain), {args.cpu_steps} steps, "
-                          f"scaled linearly in cells to the workload (generous to the CPU: LU fill grows faster)"}
+                "value": 1.0 / (big["seconds_per_step"] * ratio ** exponent), "unit": UNIT, "cores": big["threads"],
+                "kind": "port",
+                "sample": f"oracle assembly (C++/OpenMP) + SuperLU substitutions (UMFPACK stand-in, 4 concurrent + 1) on "
+                          f"global refinements {g - 2} and {g - 1} ({args.cpu_steps} steps each), extrapolated to the "
+                          f"workload with the measured exponent {exponent:.3f} of seconds/step in cells; "
+                          f"`--impl reference` times the workload itself",
+                "measured": [{k: v[k] for k in ("g", "dofs_per_carrier", "steps_per_s")} for v in samples]}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
@@ -371,19 +412,12 @@ def run_gpu_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------- sharded step
-def run_sharded_arm(args):
-    """ONE step spread over 2 (subdomains) or 4 (species) GPUs with the density exchange over NCCL (pecs_b200/shard.py):
-    strong scaling of the same workload; timed with CUDA events on the context's stream, max over ranks."""
+def measure_sharded(args, rank, device, world, dist, exchange):
+    """ONE step spread over 2 (subdomains) or 4 (species) GPUs (pecs_b200/shard.py): strong scaling of the same workload.
+    Timed with CUDA events on the context's stream, max over ranks.  Returns (dict for rank 0, clocks)."""
     import torch
     import pecs_b200 as pecs
     from pecs_b200 import shard, solarcell as sc, sweep
-
-    rank, local, world, dist = sweep.init_distributed("nccl")
-    want = {"subdomain": 2, "species": 4}[args.parallelism]
-    if world != args.gpus or world != want:
-        raise SystemExit(f"--parallelism {args.parallelism} needs exactly {want} ranks (torchrun --nproc-per-node {want})")
-    device = local
-    torch.cuda.set_device(device)
     g, l = args.global_refinements, args.local_refinements
     t_setup = time.perf_counter()
     prob = pecs.SolarCellProblem(pecs.default_input_file(g, l, **workload_overrides()), device=device)
@@ -392,7 +426,7 @@ def run_sharded_arm(args):
     prob.synchronize()
     t_setup = time.perf_counter() - t_setup
     engine = shard.GpuEngine(prob, device)
-    if args.exchange == "p2p":
+    if exchange == "p2p":
         engine.connect_p2p(dist, rank, world)
     stepper = shard.ShardedStepper(engine, dist, rank, world)
     K, W = args.steps, max(args.warmup, 3)
@@ -413,30 +447,50 @@ def run_sharded_arm(args):
     sweep.barrier(dist, device)
     ms_max = sweep.max_over_ranks(ms, dist, device)
     exchanged = sum(prob.density_block(s)[1] for s in range(4)) * 8
-    factor_bytes = sweep.sum_over_ranks(prob.info(sc.INFO_SOLVE_BYTES_PER_STEP), dist, device)
+    solve_bytes = sweep.sum_over_ranks(prob.info(sc.INFO_SOLVE_BYTES_PER_STEP), dist, device)
     launches = sweep.sum_over_ranks(prob.info(sc.INFO_LAUNCHES_PER_STEP), dist, device)
+    wait_errors = sweep.sum_over_ranks(prob.info(sc.INFO_SOLVE_WAIT_ERRORS), dist, device)
+    finite = all(bool(torch.isfinite(engine.density(s)).all().item()) for s in range(4))
+    finite = sweep.sum_over_ranks(0 if finite else 1, dist, device) == 0
+    prob.close()
+    out = {"layout": shard.mode_name(world), "steps_per_s": K / (ms_max * 1e-3), "ms_per_step": ms_max / K, "steps": K,
+           "exchange": (f"NCCL broadcast of the four density blocks per step ({exchanged} B)" if exchange == "nccl" else
+                        f"fused into the backward sweeps: peer-memory stores over NVLink ({exchanged} B per step and "
+                        "peer), flag kernels, no collective") + "; Poisson solved on every rank",
+           "bytes_exchanged_per_step": int(exchanged) * (world - 1), "solve_bytes_per_step_all_ranks": int(solve_bytes),
+           "gpu_launches_per_step_all_ranks": int(launches), "setup_seconds": t_setup, "finite": bool(finite),
+           "solve_wait_errors": int(wait_errors)}
+    return out, clocks
+
+
+def run_sharded_arm(args):
+    """`--parallelism subdomain|species`: the sharded step as the headline value of the line (strong scaling)"""
+    import torch
+    from pecs_b200 import sweep
+
+    rank, local, world, dist = sweep.init_distributed("nccl")
+    want = {"subdomain": 2, "species": 4}[args.parallelism]
+    if world != args.gpus or world != want:
+        raise SystemExit(f"--parallelism {args.parallelism} needs exactly {want} ranks (torchrun --nproc-per-node {want})")
+    torch.cuda.set_device(local)
+    g, l = args.global_refinements, args.local_refinements
+    sh, clocks = measure_sharded(args, rank, local, world, dist, args.exchange)
     if rank == 0:
         peak, peak_src = measured_peaks()
-        line = {"metric": METRIC, "value": K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": workload_name(g, l), "parallelism": shard.mode_name(world),
-                           "exchange": (f"NCCL broadcast of the four density blocks per step ({exchanged} B)"
-                                        if args.exchange == "nccl" else
-                                        f"fused into the backward sweeps: peer-memory stores over NVLink ({exchanged} B per "
-                                        "step and peer), flag kernels, no collective") +
-                                       "; Poisson solved redundantly on every rank",
+        gbs = sh["solve_bytes_per_step_all_ranks"] / (sh["ms_per_step"] * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": sh["steps_per_s"], "unit": UNIT, "n_gpus": world, "steps": sh["steps"],
+                "warmup": max(args.warmup, 3), "ms_per_step": sh["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(g, l), "parallelism": sh["layout"], "exchange": sh["exchange"],
                            "l2": "inputs larger than L2: every step streams the factor tables once",
-                           "setup_seconds": t_setup},
-                "e2e": None, "gpu_launches": int(launches) * K, "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "level kernels of the solves, all ranks", "achieved":
-                             factor_bytes / (ms_max / K * 1e-3) / 1e9, "peak": peak * world, "peak_source": peak_src,
-                             "unit": "GB/s", "frac": factor_bytes / (ms_max / K * 1e-3) / 1e9 / (peak * world),
+                           "setup_seconds": sh["setup_seconds"]},
+                "e2e": None, "gpu_launches": sh["gpu_launches_per_step_all_ranks"] * sh["steps"], "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "level kernels of the solves, all ranks", "achieved": gbs,
+                             "peak": peak * world, "peak_source": peak_src, "unit": "GB/s", "frac": gbs / (peak * world),
                              "traffic": None, "note": "whole step (incl. exchange and RHS) as denominator; the Poisson "
                                                       "tables are streamed by every rank"},
-                "cpu_baseline": None}
+                "sharded": sh, "cpu_baseline": None}
         print(json.dumps(line))
-    prob.close()
     dist.destroy_process_group()
     return 0
 
@@ -453,10 +507,12 @@ def main():
     ap.add_argument("--impl", choices=["pecs_b200", "reference"], default="pecs_b200")
     ap.add_argument("--global-refinements", type=int, default=7)
     ap.add_argument("--local-refinements", type=int, default=1)
-    ap.add_argument("--cpu-sample-refinements", type=int, default=5,
-                    help="mesh of the bounded CPU sample (the oracle's sparse LU at refinement 7 does not fit the budget)")
-    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--cpu-steps", type=int, default=5, help="timed steps of each bounded CPU sample of the GPU arm")
+    ap.add_argument("--cpu-budget-seconds", type=float, default=1500.0,
+                    help="--impl reference: wall-clock budget; the workload itself is run when its estimated cost fits")
+    ap.add_argument("--cpu-no-full", action="store_true", help="--impl reference: samples + extrapolation only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N = 2 / 4: skip the sharded-step measurement")
     ap.add_argument("--no-validate", action="store_true", help="skip the parity check of the benchmarked workload")
     ap.add_argument("--exchange", choices=["nccl", "p2p"], default="p2p",
                     help="sharded step: 'p2p' = density exchange fused into the solves over peer memory (default), "

@@ -147,6 +147,9 @@ class Oracle:
     def solve_Poisson(self):
         self.call("solve_Poisson")
 
+    def distribute_Poisson(self):
+        self.call("distribute_Poisson")
+
     def set_solvers(self):
         self.call("set_solvers")
 

@@ -151,6 +151,10 @@ ORACLE_CALL(oracle_set_solvers, p->set_solvers())
 ORACLE_CALL(oracle_project_test_initial_condition, p->project_test_initial_condition())
 ORACLE_CALL(oracle_assemble_test_steady_rhs, p->assemble_test_steady_rhs())
 
+// constraints.distribute(solution) alone (reference source/Poisson.cpp:104): for callers that bring their own direct
+// solver for the condensed Poisson matrix (bench.py's CPU arm uses SuperLU as the UMFPACK stand-in)
+ORACLE_CALL(oracle_distribute_Poisson, p->Poisson_object.constraints.distribute(p->Poisson_object.solution))
+
 int oracle_solve_species(void* h, int s) {
   return guarded([&] { species(static_cast<SolarCellProblem*>(h), s).solve(); });
 }

@@ -40,7 +40,7 @@ def headers():
 
 # Experiment builds (never loaded by the product): "nc" = the round-1 non-coherent loads of step-varying vectors, the
 # A side of scripts/race_repro.py.  They get their own object directory and library name.
-VARIANTS = {"nc": ["-DPECS_B200_NC_STEP_VECTORS=1"]}
+VARIANTS = {"nc": ["-DPECS_B200_NC_STEP_VECTORS=1"], "trace": ["-DPECS_B200_TRACE=1"]}
 
 
 def variant_paths(variant):

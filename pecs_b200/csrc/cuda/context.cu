@@ -67,6 +67,7 @@ struct DeviceSystem {
   // right-hand sides one pass over the tables can carry: 2 when two carriers share this factorisation (identical
   // matrices: reductants and oxidants at equal mobility), else 1.  Work vectors hold n_rhs slots.
   int n_rhs = 1;
+  int trace_id = 0; // which system this is in the trace build (0..3 carriers, 4 Poisson)
 
   int64_t factor_bytes() const { return (int64_t)(fwd.bytes() + bwd.bytes() + matrix_rows.bytes()); }
   int64_t logical_bytes() const { return plan.logical_entries() * (int64_t)sizeof(double) + (int64_t)matrix_rows.bytes(); }
@@ -308,6 +309,7 @@ struct DeviceSystem {
         const DeviceBuffer<SolveTile>& tiles = per_warp ? sw.warp_tiles : sw.block_tiles;
         if (tiles.size() == 0) continue;
         SolveVectors v = io;
+        v.tag = trace_id * 10000 + d * 2 + per_warp;
         if (first) v.grid_wait = 1;
         first = false;
         if (per_warp)
@@ -317,12 +319,14 @@ struct DeviceSystem {
       }
     }
   }
-  void backward_sweep(const SolveVectors& io, cudaStream_t s) {
+  void backward_sweep(SolveVectors io, cudaStream_t s) {
     const SolveTables t = tables();
     const int warps = solve_warps();
     for (size_t d = 0; d < levels.size(); ++d) {
       Sweep& sw = levels[d].bwd;
+      io.tag = trace_id * 10000 + 1000 + (int)d * 2;
       launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages, io, s);
+      io.tag += 1;
       launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, io, s);
     }
   }
@@ -608,6 +612,7 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
       DeviceDomain::Reduced& red = D.reduced[k];
       red.active = true;
       const int n_rhs = (k == 0 && D.shared_pair) ? 2 : 1;
+      D.system[k].trace_id = 2 * which + k;
       D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, n_rhs);
       red.T1.upload(ps.R.T1, &D.system[k].plan.iperm); // r~ is produced directly in elimination order
       red.Ainv.upload(ps.R.Ainv);
@@ -1030,6 +1035,7 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     }
     {
       PreparedSystem ps = prepared_poisson.get();
+      ctx->p_system.trace_id = 4;
       ctx->p_system.build(ps.A, std::move(ps.plan), factor_on_device);
     }
     size_t smem = ctx->p_system.max_smem_bytes();
@@ -1233,6 +1239,9 @@ pecs_status pecs_step(pecs_ctx* ctx, int32_t n_steps) {
   return guarded([&] {
     require(ctx != nullptr && n_steps >= 0, "pecs_step: bad argument");
     require(ctx->step_graph != nullptr, "pecs_step: only the production problem has a step graph");
+    // a shard's step graph would skip the carriers other ranks own and exchange nothing: stale densities, no error
+    require(ctx->owned == 0xF && !ctx->p2p.active,
+            "pecs_step: this context is one shard of a step (owned_species / p2p): use pecs_step_local + pecs_step_finish");
     PECS_CUDA(cudaSetDevice(ctx->device));
     for (int s = 0; s < n_steps; ++s) PECS_CUDA(cudaGraphLaunch(ctx->step_graph, ctx->main));
   });
@@ -1242,6 +1251,8 @@ pecs_status pecs_step_host(pecs_ctx* ctx, int32_t n_steps, double* const states[
   return guarded([&] {
     require(ctx != nullptr && n_steps >= 0 && states, "pecs_step_host: bad argument");
     require(ctx->step_graph != nullptr, "pecs_step_host: only the production problem has a step graph");
+    require(ctx->owned == 0xF && !ctx->p2p.active,
+            "pecs_step_host: this context is one shard of a step: use pecs_step_local + pecs_step_finish");
     PECS_CUDA(cudaSetDevice(ctx->device));
     if (n_steps == 0) return;
     bool pinned = true;

@@ -203,6 +203,36 @@ __device__ __forceinline__ void signal_count(int* counter) {
   __threadfence();
   atomicAdd(counter, 1);
 }
+// ---- trace build only (python -m pecs_b200.build --variant trace): per-block timestamps of the level kernels, the ground
+// truth about what overlaps with what (scripts/trace_step.py).  Record = {tag << 32 | block, start, dependencies met, end}
+#ifndef PECS_B200_TRACE
+#define PECS_B200_TRACE 0
+#endif
+#if PECS_B200_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+__device__ unsigned int g_trace_n = 0;
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_record(int tag, unsigned long long t0, unsigned long long t1, unsigned long long t2) {
+  if (!g_trace) return;
+  const unsigned int k = atomicAdd(&g_trace_n, 1u);
+  if (k >= g_trace_cap) return;
+  g_trace[4 * (size_t)k] = ((unsigned long long)(unsigned)tag << 32) | blockIdx.x;
+  g_trace[4 * (size_t)k + 1] = t0;
+  g_trace[4 * (size_t)k + 2] = t1;
+  g_trace[4 * (size_t)k + 3] = t2;
+}
+#define PECS_TRACE_T(name) const unsigned long long name = trace_now()
+#define PECS_TRACE_REC(tag, a, b, c) if (threadIdx.x == 0) trace_record(tag, a, b, c)
+#else
+#define PECS_TRACE_T(name)
+#define PECS_TRACE_REC(tag, a, b, c)
+#endif
+
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void release_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -236,6 +266,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
                                                                         int n_tiles, int vec_doubles, int stages,
                                                                         SolveVectors io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  PECS_TRACE_T(trace_t0);
   const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles * NRHS, stages);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
@@ -257,6 +288,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
     __syncwarp();
   else
     __syncthreads();
+  PECS_TRACE_T(trace_t1);
   const int* omap = t.out_map + tile.bd_off;
 #pragma unroll
   for (int r = 0; r < NRHS; ++r) {
@@ -308,6 +340,8 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
   else
     __syncthreads();
   if (first_thread == 0) signal_count(io.done_fwd + tile.front);
+  PECS_TRACE_T(trace_t2);
+  PECS_TRACE_REC(io.tag, trace_t0, trace_t1, trace_t2);
   if (!io.grid_wait) grid_dependency_wait(); // completion stays transitive along the kernel chain
 }
 
@@ -316,6 +350,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
                                                                          int n_tiles, int vec_doubles, int stages,
                                                                          SolveVectors io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  PECS_TRACE_T(trace_t0);
   const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles * NRHS, stages);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
@@ -342,6 +377,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
     __syncwarp();
   else
     __syncthreads();
+  PECS_TRACE_T(trace_t1);
   {
     const int np = tile.np, m = tile.np + tile.nb;
     const int* bd = t.bd_index + tile.bd_off;
@@ -391,6 +427,8 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
   else
     __syncthreads();
   if (first_thread == 0) signal_count(io.done_bwd + tile.front);
+  PECS_TRACE_T(trace_t2);
+  PECS_TRACE_REC(io.tag, trace_t0, trace_t1, trace_t2);
   if (!io.grid_wait) grid_dependency_wait(); // completion stays transitive along the kernel chain
 }
 
@@ -446,6 +484,34 @@ void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_t
   }
 #undef PECS_LAUNCH
 }
+
+#if PECS_B200_TRACE
+} // namespace pecs
+extern "C" int pecs_trace_start(int capacity) {
+  static unsigned long long* buffer = nullptr;
+  if (buffer) cudaFree(buffer);
+  buffer = nullptr;
+  if (capacity > 0 && cudaMalloc(&buffer, (size_t)capacity * 4 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  const unsigned int cap = capacity > 0 ? (unsigned)capacity : 0, zero = 0;
+  cudaMemcpyToSymbol(pecs::g_trace, &buffer, sizeof(buffer));
+  cudaMemcpyToSymbol(pecs::g_trace_cap, &cap, sizeof(cap));
+  cudaMemcpyToSymbol(pecs::g_trace_n, &zero, sizeof(zero));
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
+}
+extern "C" int pecs_trace_read(unsigned long long* out, int max_records) {
+  cudaDeviceSynchronize();
+  unsigned int n = 0, cap = 0;
+  unsigned long long* buffer = nullptr;
+  cudaMemcpyFromSymbol(&n, pecs::g_trace_n, sizeof(n));
+  cudaMemcpyFromSymbol(&cap, pecs::g_trace_cap, sizeof(cap));
+  cudaMemcpyFromSymbol(&buffer, pecs::g_trace, sizeof(buffer));
+  const unsigned int count = n < cap ? n : cap;
+  const int take = (int)count < max_records ? (int)count : max_records;
+  if (take > 0) cudaMemcpy(out, buffer, (size_t)take * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return take;
+}
+namespace pecs {
+#endif
 
 void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s) {
   if (n == 0) return;

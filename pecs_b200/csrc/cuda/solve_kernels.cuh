@@ -57,6 +57,7 @@ struct SolveVectors {
   int* done_fwd;
   int* done_bwd;
   int* error;      // set to 1 if a counter wait ever gave up (bounded spin: a logic error must not hang the GPU)
+  int tag;         // identifies the launch in the trace build (-DPECS_B200_TRACE=1, scripts/trace_step.py); unused otherwise
   int grid_wait;   // 1: wait for the whole predecessor grid BEFORE reading anything (first kernel behind a producer
                    // that signals no counters, or dataflow switched off); 0: counters only, grid wait at the very end
 };

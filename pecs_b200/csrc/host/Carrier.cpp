@@ -24,6 +24,8 @@ void block_write(const std::string& file, const std::vector<double>& v) {
   out << v.size() << "\n[";
   out.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(v.size() * sizeof(double)));
   out << "]";
+  out.flush();
+  if (!out) throw std::runtime_error("cannot write restart file " + file); // a failed checkpoint must not go unnoticed
 }
 void block_read(const std::string& file, std::vector<double>& v) {
   std::ifstream in(file.c_str(), std::ios::binary);
@@ -35,6 +37,9 @@ void block_read(const std::string& file, std::vector<double>& v) {
   in.get(c); // '['
   if (c != '[' || n != v.size()) throw std::runtime_error("restart file " + file + " does not match this mesh");
   in.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(n * sizeof(double)));
+  // a truncated file must not be accepted silently: all bytes there, and the closing bracket behind them
+  if ((size_t)in.gcount() != n * sizeof(double) || !in.get(c) || c != ']')
+    throw std::runtime_error("restart file " + file + " is truncated or corrupt");
 }
 } // namespace
 

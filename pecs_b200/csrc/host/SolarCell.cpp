@@ -418,13 +418,15 @@ void SolarCellProblem::setup_full_system_host() {
 
 void SolarCellProblem::setup_full_system() {
   setup_full_system_host();
-  set_solvers();
+  // initial values first (reference SolarCell.cpp:1980-2021): a missing or truncated restart file is reported before
+  // the factorisations are paid for
   if (sim_params.restart_status) {
     electron_hole_pair.read_dofs(output_directory);
     redox_pair.read_dofs(output_directory);
   } else {
     project_initial_conditions();
   }
+  set_solvers();
   electron_hole_pair.carrier_1.push_solution();
   electron_hole_pair.carrier_2.push_solution();
   redox_pair.carrier_1.push_solution();
@@ -493,7 +495,9 @@ void SolarCellProblem::run_full_system() {
     for (unsigned int i = 0; i < number_outputs; i++) timeStamps[i] = (i + 1) * sim_params.t_end / number_outputs;
     time = 0.0;
   }
-  unsigned int time_step_number = 0;
+  // a restarted run continues the numbering of the first leg's files (reference SolarCell.cpp:1993: time_step_number =
+  // number_outputs), so it does not overwrite Poisson-000...NNN.vtu, Semiconductor-..., Electrolyte-...
+  unsigned int time_step_number = sim_params.restart_status ? number_outputs : 0;
   if (write_output) print_results(time_step_number); // the initial values, reference SolarCell.cpp:2037-2039
   time_step_number++;
   for (unsigned int k = 0; k < number_outputs; k++) {

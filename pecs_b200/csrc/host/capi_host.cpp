@@ -7,6 +7,7 @@
 
 #include "../../../include/pecs_b200_host.h"
 #include "../error.hpp"
+#include "../Assembly.hpp"
 #include "../rhs_math.hpp"
 #include "SolarCell.hpp"
 #include "SolverSetup.hpp"
@@ -149,50 +150,46 @@ pecs_status pecs_solarcell_selftest_carrier_rhs(pecs_solarcell* p, int32_t which
       nb_cell[mine_c[k]] = other_c[k];
       nb_face[mine_c[k]] = other_f[k];
     }
+    // one AssemblyScratch / CopyData per cell, exactly what a device thread holds in registers (csrc/Assembly.hpp)
     for (size_t c = 0; c < n; ++c) {
-      pecs::fe::CellVerts v;
+      Assembly::AssemblyScratch scratch;
       const double* vt = mesh.vtx((int)c);
       for (int a = 0; a < 4; ++a) {
-        v.x[a] = vt[2 * a];
-        v.y[a] = vt[2 * a + 1];
+        scratch.vertices.x[a] = vt[2 * a];
+        scratch.vertices.y[a] = vt[2 * a + 1];
+        scratch.carrier_1_density[a] = u1[8 * n + 4 * c + a];
+        scratch.carrier_2_density[a] = u2[8 * n + 4 * c + a];
+        scratch.Poisson_flux[a] = X[face_dof[4 * (size_t)to_poisson[c] + a]];
+        scratch.neighbor_carrier_1_density[a] = scratch.neighbor_carrier_2_density[a] = 0.0;
       }
-      double m[4], gen[4], Xf[4];
-      pecs::rhsmath::static_cell_integrals(v, rp.gen_scale != 0.0, rp.gen_scale, rp.gen_alpha, rp.gen_location, m, gen);
-      for (int f = 0; f < 4; ++f) Xf[f] = X[face_dof[4 * (size_t)to_poisson[c] + f]];
-      const double* r1 = u1 + 8 * n + 4 * c;
-      const double* r2 = u2 + 8 * n + 4 * c;
-      double o[6][4];
-      pecs::rhsmath::production_cell_terms(v.x, v.y, r1, r2, Xf, gen, rp.inv_dt, rp.charge1 * rp.inv_eps,
-                                           rp.charge2 * rp.inv_eps, o[0], o[1], o[2], o[3], o[4], o[5]);
+      double m[4];
+      pecs::rhsmath::static_cell_integrals(scratch.vertices, rp.gen_scale != 0.0, rp.gen_scale, rp.gen_alpha, rp.gen_location, m,
+                                           scratch.generation_integrals);
       // face terms exactly as cuda/rhs_kernels.cu boundary_record adds them (skipped when o1 / o2 are not given)
-      pecs::rhsmath::BoundaryRecord rec{{-1, -1, -1, -1}, nb_cell[c], nb_face[c]};
+      scratch.faces = pecs::rhsmath::BoundaryRecord{{-1, -1, -1, -1}, nb_cell[c], nb_face[c]};
       bool boundary = false;
       for (int f = 0; f < 4; ++f)
         if (mesh.face_kind[4 * c + f] == pecs::FACE_BOUNDARY) {
-          rec.id[f] = mesh.boundary_id[4 * c + f];
+          scratch.faces.id[f] = mesh.boundary_id[4 * c + f];
           boundary = true;
         }
-      if (boundary && o1 && o2) {
-        double geom[4][4], q1[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0}, b[6][4] = {};
-        pecs::rhsmath::boundary_geometry(v, rp.tau, &geom[0][0]);
-        if (rec.nb_cell >= 0)
+      scratch.at_boundary = boundary && o1 && o2;
+      if (scratch.at_boundary) {
+        pecs::rhsmath::boundary_geometry(scratch.vertices, rp.tau, &scratch.face_geometry[0][0]);
+        if (scratch.faces.nb_cell >= 0)
           for (int a = 0; a < 4; ++a) {
-            q1[a] = o1[8 * n_other + 4 * (size_t)rec.nb_cell + a];
-            q2[a] = o2[8 * n_other + 4 * (size_t)rec.nb_cell + a];
+            scratch.neighbor_carrier_1_density[a] = o1[8 * n_other + 4 * (size_t)scratch.faces.nb_cell + a];
+            scratch.neighbor_carrier_2_density[a] = o2[8 * n_other + 4 * (size_t)scratch.faces.nb_cell + a];
           }
-        pecs::rhsmath::boundary_terms_accumulate<PECS_KIND_PRODUCTION>(rp, rec, geom, v, r1, r2, q1, q2, b[0], b[1], b[2], b[3],
-                                                                       b[4], b[5]);
-        for (int k = 0; k < 6; ++k)
-          for (int a = 0; a < 4; ++a) o[k][a] += b[k][a];
       }
-      for (int a = 0; a < 4; ++a) {
-        rhs1[4 * c + a] = o[0][a];
-        rhs1[4 * n + 4 * c + a] = o[1][a];
-        rhs1[8 * n + 4 * c + a] = o[2][a];
-        rhs2[4 * c + a] = o[3][a];
-        rhs2[4 * n + 4 * c + a] = o[4][a];
-        rhs2[8 * n + 4 * c + a] = o[5][a];
-      }
+      Assembly::DriftDiffusion::CopyData data;
+      Assembly::assemble_local_carrier_rhs(scratch, rp, data);
+      // the "copier": cell c owns rows 4c..4c+3 of every component block (reference SolarCell.cpp:999-1035)
+      for (int k = 0; k < 3; ++k)
+        for (int a = 0; a < 4; ++a) {
+          rhs1[4 * k * n + 4 * c + a] = data.local_carrier_1_rhs[4 * k + a];
+          rhs2[4 * k * n + 4 * c + a] = data.local_carrier_2_rhs[4 * k + a];
+        }
     }
   });
 }

@@ -226,3 +226,64 @@ def test_device_output_matches_golden_fixture():
     assert np.abs(poisson["field"] - gold["field"]).max() <= 1e-9 * np.abs(gold["field"]).max()
     assert np.allclose(prob.interface_currents(), gold["interface_currents"], rtol=1e-5, atol=0)
     prob.close()
+
+
+@pytest.mark.gpu
+def test_restart_leg_continues_the_first_leg(tmp_path):
+    """restart status = true (reference source/SolarCell.cpp:1980-1995): read_dofs takes the *.dofs files of the first
+    leg as initial values, the time stamps run from `end time` to `end time 2`, and the files continue the numbering
+    (time_step_number = number_outputs).  Two legs of 4 steps must end where one run of 8 steps ends -- bit for bit:
+    the restart files hold the complete state a step reads (densities; the Poisson solve is repeated from them)."""
+    first = pecs.default_input_file(2, 1, computational__end_time=0.2, computational__time_stamps=2)
+    prob = pecs.SolarCellProblem(first)
+    prob.set_output(str(tmp_path))
+    prob.run_full_system()
+    prob.close()
+    before = set(os.listdir(tmp_path))
+    second = pecs.default_input_file(2, 1, computational__end_time=0.2, computational__end_time_2=0.4,
+                                     computational__time_stamps=2, computational__restart_status=True)
+    prob = pecs.SolarCellProblem(second)
+    prob.set_output(str(tmp_path))
+    prob.run_full_system()
+    after = set(os.listdir(tmp_path))
+    # the second leg writes stamps 2 (its initial values), 3 and 4; stamps 0 and 1 of the first leg survive
+    assert {"Poisson-003.vtu", "Poisson-004.vtu", "Semiconductor-004.vtu", "Electrolyte-004.vtu"} <= after - before
+    assert {"Poisson-000.vtu", "Poisson-001.vtu"} <= after
+    restarted = [prob.get_solution(s) for s in range(5)]
+    prob.close()
+    whole = pecs.SolarCellProblem(first)
+    whole.setup_full_system()
+    n_steps, t = 0, 0.0
+    for stamp in (0.1, 0.2):          # the first leg's floating-point loop
+        while t < stamp:
+            t += 0.05
+            n_steps += 1
+    t = 0.2
+    for stamp in (0.3, 0.4):          # the second leg's: time starts at `end time` exactly
+        while t < stamp:
+            t += 0.05
+            n_steps += 1
+    whole.step(n_steps)
+    for s in range(5):
+        got, want = restarted[s], whole.get_solution(s)
+        if s < 4:  # densities are the state; the currents of the restarted leg are recomputed by its last solve
+            nc = got.size // 12
+            assert np.array_equal(got[8 * nc:], want[8 * nc:]), f"density of species {s}"
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-300)
+    whole.close()
+
+
+def test_truncated_restart_file_is_rejected(tmp_path):
+    """block_read checks the byte count and the closing bracket (a truncated checkpoint must not be accepted silently)"""
+    prm = pecs.default_input_file(2, 1, computational__restart_status=True)
+    n = 12 * (4 ** 2 + 4 ** 3)
+    good = f"{n}\n[".encode() + np.arange(n, dtype=np.float64).tobytes() + b"]"
+    for name in ("Electrons", "Holes", "Reductants", "Oxidants"):
+        (tmp_path / f"{name}.dofs").write_bytes(good)
+    (tmp_path / "Holes.dofs").write_bytes(good[:-100])
+    prob = pecs.SolarCellProblem(prm)
+    prob.set_output(str(tmp_path), write_output=False)
+    with pytest.raises(pecs.PecsError) as e:
+        prob.setup_full_system()   # read_dofs comes before the (GPU-only) factorisations
+    assert "truncated" in str(e.value)
+    prob.close()
