@@ -40,11 +40,15 @@ struct DeviceSystem {
   SolvePlan plan;
   DeviceBuffer<double> fwd, bwd, cbuf, w_in, w_fin, x_perm;
   DeviceBuffer<int> bd_index, out_map, iperm;
-  DeviceBuffer<int> done; // completion counters of the fronts: [0, F) forward tiles, [F, 2F) backward tiles, [2F] error word
+  // [0, F) forward tiles done per front, [F, 2F) backward tiles done, [2F, 2F + L) tile counters of the L level launches
+  // of a solve, [2F + L] error word
+  DeviceBuffer<int> done;
+  int n_fwd_launches = 0;
   // one sweep of one level: large fronts cut into block tiles, small fronts one warp each
   struct Sweep {
     DeviceBuffer<SolveTile> block_tiles, warp_tiles;
     int vec_block = 0, vec_warp = 0; // doubles of the staged vector (per block / per warp)
+    int grid_block = 0, grid_warp = 0; // thread blocks of the two launches: one resident wave at most (level_grid)
     int warps = 4;                   // warps per thread block of the block-tile launch
     int stages = 2;                  // depth of the per-warp bulk-copy rings, thread-block tiles
     int stages_warp = 4;             // ... one-warp-per-front tiles: the whole small table is in flight at once
@@ -229,6 +233,14 @@ struct DeviceSystem {
     }
     // dependencies: forward = the two children; backward = the nearest ancestor that has backward tiles, the front's
     // own forward tiles and (front without boundary: it finalises its right-hand side itself) the children
+    // fronts whose backward counter some tile polls: the nearest ancestor-with-tiles of every front that has tiles
+    std::vector<int> waited_for(n_fronts, 0);
+    for (int f = 0; f < n_fronts; ++f) {
+      if (n_bwd_tiles[f] == 0) continue;
+      int a = plan.fronts[f].parent;
+      while (a >= 0 && n_bwd_tiles[a] == 0) a = plan.fronts[a].parent;
+      if (a >= 0) waited_for[a] = 1;
+    }
     auto fill = [&](SolveTile& t) {
       const Front& F = plan.fronts[t.front];
       for (int k = 0; k < 2; ++k) {
@@ -241,6 +253,7 @@ struct DeviceSystem {
       t.up = a;
       t.need_up = a >= 0 ? n_bwd_tiles[a] : 0;
       t.need_self = n_fwd_tiles[t.front];
+      t.signal_bwd = waited_for[t.front];
     };
     for (size_t d = 0; d < plan.levels.size(); ++d)
       for (int which = 0; which < 2; ++which) {
@@ -250,9 +263,16 @@ struct DeviceSystem {
         for (SolveTile& t : out.wt) fill(t);
         sw.block_tiles.upload(out.bt);
         sw.warp_tiles.upload(out.wt);
-        launches_per_solve += (out.bt.empty() ? 0 : 1) + (out.wt.empty() ? 0 : 1);
+        // a level with few tiles cannot fill the device anyway: let every warp keep its whole share of the table in
+        // flight, so that the tiles are done the moment their dependencies are (the top of the tree is a chain)
+        if (out.bt.size() <= 148 * 4 && !env_int("PECS_B200_SOLVE_STAGES", 0)) sw.stages = std::max(sw.stages, 4);
+        sw.grid_block = level_grid(which == 0, false, n_rhs, (int)out.bt.size(), sw.vec_block, sw.warps, sw.stages);
+        sw.grid_warp = level_grid(which == 0, true, n_rhs, (int)out.wt.size(), sw.vec_warp, solve_warps(), sw.stages_warp);
+        const int n = (out.bt.empty() ? 0 : 1) + (out.wt.empty() ? 0 : 1);
+        launches_per_solve += n;
+        if (which == 0) n_fwd_launches += n;
       }
-    done.resize(2 * (size_t)n_fronts + 1);
+    done.resize(2 * (size_t)n_fronts + launches_per_solve + 1);
     done.zero();
   }
 
@@ -276,8 +296,10 @@ struct DeviceSystem {
     const size_t n_fronts = plan.fronts.size();
     io.done_fwd = done.get();
     io.done_bwd = done.get() + n_fronts;
-    io.error = done.get() + 2 * n_fronts;
+    io.work = done.get() + 2 * n_fronts;
+    io.error = done.get() + 2 * n_fronts + launches_per_solve;
     io.grid_wait = dataflow_enabled() ? 0 : 1;
+    io.use_counters = dataflow_enabled() ? 1 : 0;
     return io;
   }
   // PECS_B200_DATAFLOW=0: every level kernel waits for its whole predecessor grid (round-1 behaviour; A/B)
@@ -289,12 +311,12 @@ struct DeviceSystem {
   // that produces the residual, so that the chain residual -> forward levels -> backward levels is one unbroken chain
   // of programmatic launches
   void reset_counters(cudaStream_t s) {
-    PECS_CUDA(cudaMemsetAsync(done.get(), 0, 2 * plan.fronts.size() * sizeof(int), s));
+    PECS_CUDA(cudaMemsetAsync(done.get(), 0, (2 * plan.fronts.size() + launches_per_solve) * sizeof(int), s));
   }
   int error_flag() const {
     int e = 0;
     if (done.size() > 0)
-      PECS_CUDA(cudaMemcpy(&e, done.get() + 2 * plan.fronts.size(), sizeof(int), cudaMemcpyDeviceToHost));
+      PECS_CUDA(cudaMemcpy(&e, done.get() + 2 * plan.fronts.size() + launches_per_solve, sizeof(int), cudaMemcpyDeviceToHost));
     return e;
   }
   // The kernel that produced the residual signals no counters: the FIRST forward kernel waits for that whole grid
@@ -303,6 +325,7 @@ struct DeviceSystem {
     const SolveTables t = tables();
     const int warps = solve_warps();
     bool first = true;
+    int launch = 0;
     for (int d = (int)levels.size() - 1; d >= 0; --d) {
       Sweep& sw = levels[d].fwd;
       for (int per_warp = 1; per_warp >= 0; --per_warp) {
@@ -310,24 +333,35 @@ struct DeviceSystem {
         if (tiles.size() == 0) continue;
         SolveVectors v = io;
         v.tag = trace_id * 10000 + d * 2 + per_warp;
+        v.work = io.work + launch++;
         if (first) v.grid_wait = 1;
         first = false;
         if (per_warp)
-          launch_forward_level(t, tiles.get(), (int)tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, v, s);
+          launch_forward_level(t, tiles.get(), (int)tiles.size(), sw.grid_warp, true, sw.vec_warp, warps, sw.stages_warp, v, s);
         else
-          launch_forward_level(t, tiles.get(), (int)tiles.size(), false, sw.vec_block, sw.warps, sw.stages, v, s);
+          launch_forward_level(t, tiles.get(), (int)tiles.size(), sw.grid_block, false, sw.vec_block, sw.warps, sw.stages, v, s);
       }
     }
   }
   void backward_sweep(SolveVectors io, cudaStream_t s) {
     const SolveTables t = tables();
     const int warps = solve_warps();
+    int* const work = io.work + n_fwd_launches;
+    int launch = 0;
     for (size_t d = 0; d < levels.size(); ++d) {
       Sweep& sw = levels[d].bwd;
       io.tag = trace_id * 10000 + 1000 + (int)d * 2;
-      launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), false, sw.vec_block, sw.warps, sw.stages, io, s);
+      if (sw.block_tiles.size() > 0) {
+        io.work = work + launch++;
+        launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), sw.grid_block, false, sw.vec_block, sw.warps,
+                              sw.stages, io, s);
+      }
       io.tag += 1;
-      launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), true, sw.vec_warp, warps, sw.stages_warp, io, s);
+      if (sw.warp_tiles.size() > 0) {
+        io.work = work + launch++;
+        launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), sw.grid_warp, true, sw.vec_warp, warps,
+                              sw.stages_warp, io, s);
+      }
     }
   }
   // w_in = rhs - A solution (rows in elimination order)
@@ -950,6 +984,11 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     ctx->n_rt = P.n_rt;
     ctx->n_pcells = P.n_cells;
     const bool factor_on_device = device_factorization_enabled();
+    // large dynamic shared memory for the level kernels: before the systems are built, their launch grids are sized by
+    // the occupancy of the kernels at their block shapes (level_grid)
+    int max_optin = 0;
+    PECS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    configure_solve_kernels(max_optin);
 
     fill_rhs_params(*ctx);
     // host preparation of all systems at once (threads), device work in order
@@ -1041,11 +1080,8 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     size_t smem = ctx->p_system.max_smem_bytes();
     for (int w = 0; w < ctx->n_domains(); ++w)
       for (int k = 0; k < 2; ++k) smem = std::max(smem, ctx->dom[w].system[k].max_smem_bytes());
-    int max_optin = 0;
-    PECS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     if (smem > (size_t)max_optin)
       throw StatusError(PECS_ERR_INTERNAL, "a front's vector does not fit into shared memory");
-    configure_solve_kernels(max_optin);
     PECS_CUDA(cudaDeviceSynchronize());
     if (ctx->kind == PECS_KIND_PRODUCTION) build_step_graph(ctx.get());
     PECS_CUDA(cudaGetLastError());

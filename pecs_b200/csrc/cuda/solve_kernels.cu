@@ -33,6 +33,8 @@
 //     grid waits (A/B; bit-identical results either way);
 #include "solve_kernels.cuh"
 
+#include <algorithm>
+
 #include "device_util.cuh"
 
 namespace pecs {
@@ -84,21 +86,33 @@ __device__ __forceinline__ unsigned long long evict_first_policy() {
 // every finished row to emit(row, value).
 template <int CHUNK>
 struct PanelStream {
-  const double* table;
+  // the warp's ring: lives for the whole kernel, across all the tiles the warp works on (mbarrier phases carry over)
   double* ring;
   unsigned long long* bars;
   unsigned long long policy;
-  int lane, log2P, panel_doubles, cpp, n_my, total, stages;
-  int panel0, rank, n_ranks;
-  int ik = 0, ic = 0, issued = 0, islot = 0; // producer state (lane 0 only): next chunk to issue
+  int lane, stages;
+  int slot = 0, islot = 0; // consumer / producer position in the ring
+  uint32_t phase = 0;
+  // the tile being streamed
+  const double* table = nullptr;
+  int log2P = 0, panel_doubles = 0, cpp = 0, n_my = 0, total = 0;
+  int panel0 = 0, rank = 0, n_ranks = 1;
+  int ik = 0, ic = 0, issued = 0; // producer state (lane 0 only): next chunk to issue
 
-  __device__ __forceinline__ PanelStream(const double* table_, const SolveTile& tile, int rank_, int n_ranks_, double* my_ring,
-                                         unsigned long long* my_bars, int stages_)
-      : table(table_), ring(my_ring), bars(my_bars), policy(evict_first_policy()), lane(threadIdx.x & 31), log2P(tile.log2P),
-        panel_doubles(tile.cols_pad << tile.log2P), stages(stages_), panel0(tile.panel0), rank(rank_), n_ranks(n_ranks_) {
+  __device__ __forceinline__ PanelStream(double* my_ring, unsigned long long* my_bars, int stages_)
+      : ring(my_ring), bars(my_bars), policy(evict_first_policy()), lane(threadIdx.x & 31), stages(stages_) {}
+  // next tile; the ring is empty here (every issued chunk of the previous tile has been consumed)
+  __device__ __forceinline__ void begin(const double* table_, const SolveTile& tile, int rank_, int n_ranks_) {
+    table = table_;
+    log2P = tile.log2P;
+    panel_doubles = tile.cols_pad << tile.log2P;
+    panel0 = tile.panel0;
+    rank = rank_;
+    n_ranks = n_ranks_;
     cpp = (panel_doubles + CHUNK - 1) / CHUNK; // chunks per panel
     n_my = rank < tile.npanels ? (tile.npanels - rank + n_ranks - 1) / n_ranks : 0;
     total = n_my * cpp;
+    ik = ic = issued = 0;
   }
   __device__ __forceinline__ void issue() {
     const int panel = panel0 + rank + ik * n_ranks;
@@ -126,8 +140,6 @@ struct PanelStream {
     const int cg = 32 >> log2P; // columns covered by 32 consecutive doubles
     const int row_in_panel = lane & (P - 1);
     const int col_of_lane = lane >> log2P;
-    int slot = 0;
-    uint32_t phase = 0;
     for (int k = 0; k < n_my; ++k) {
       const int panel = panel0 + rank + k * n_ranks;
       double a[NRHS][4];
@@ -198,10 +210,10 @@ __device__ __forceinline__ void wait_count(const int* counter, int need, int* er
     }
   }
 }
-// one thread, after the barrier that follows the tile's last store: publish "one more tile of this front is complete"
+// one thread, after the barrier that follows the tile's last store: publish "one more tile of this front is complete".
+// One release-reduction: the stores of the whole block (ordered before it by the barrier) become visible before the count
 __device__ __forceinline__ void signal_count(int* counter) {
-  __threadfence();
-  atomicAdd(counter, 1);
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(counter) : "memory");
 }
 // ---- trace build only (python -m pecs_b200.build --variant trace): per-block timestamps of the level kernels, the ground
 // truth about what overlaps with what (scripts/trace_step.py).  Record = {tag << 32 | block, start, dependencies met, end}
@@ -227,7 +239,7 @@ __device__ __forceinline__ void trace_record(int tag, unsigned long long t0, uns
   g_trace[4 * (size_t)k + 3] = t2;
 }
 #define PECS_TRACE_T(name) const unsigned long long name = trace_now()
-#define PECS_TRACE_REC(tag, a, b, c) if (threadIdx.x == 0) trace_record(tag, a, b, c)
+#define PECS_TRACE_REC(tag, a, b, c) if (first_thread == 0) trace_record(tag, a, b, c)
 #else
 #define PECS_TRACE_T(name)
 #define PECS_TRACE_REC(tag, a, b, c)
@@ -249,6 +261,7 @@ struct BlockSmem {
   double* sv;                  // this thread's vector (the block's, or its warp's)
   double* my_ring;
   unsigned long long* my_bars;
+  int* next_tile;              // block tiles: the tile index thread 0 fetched, for everybody
 };
 // vec_doubles: all NRHS vectors of one front (NRHS * padded length)
 template <bool PER_WARP, int CHUNK>
@@ -258,90 +271,122 @@ __device__ __forceinline__ BlockSmem carve(unsigned char* raw, int vec_doubles, 
   double* ring = base + (size_t)vec_doubles * (PER_WARP ? n_warps : 1);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)n_warps * stages * CHUNK);
   return BlockSmem{base + (PER_WARP ? (size_t)warp * vec_doubles : 0), ring + (size_t)warp * stages * CHUNK,
-                   bars + warp * stages};
+                   bars + warp * stages, reinterpret_cast<int*>(bars + n_warps * stages)};
 }
+
+// A level kernel is ONE RESIDENT WAVE of thread blocks that take tiles off a work counter until the level is done
+// (block tiles: a block per tile at a time; one-warp tiles: every warp for itself).  The per-block-timestamp trace of
+// round 2 (profiles/r02_trace_*.log) showed why: with a block per tile the Poisson levels were bound by the rate at
+// which the GPU can START thread blocks -- 4 096 blocks of 3 us of work each, 2 TB/s -- and every block paid its
+// prologue (descriptor, barrier init, first table chunk, counter polls: 2 us) in front of 5-20 us of work.  Here the
+// prologue is paid once per block, the ring and its barriers live across tiles, and the index of the next tile is
+// fetched while the current one is being worked on.  Tiles come off the counter in list order and a tile only ever
+// waits for tiles of EARLIER kernels of the chain, all of whose blocks are already running: no deadlock.
+template <bool PER_WARP>
+struct TileFetcher {
+  int* work;
+  int* shared_next; // block tiles
+  int pending = 0;  // the index fetched ahead (thread 0 / lane 0)
+  __device__ __forceinline__ TileFetcher(int* work_, int* shared_next_) : work(work_), shared_next(shared_next_) {}
+  __device__ __forceinline__ void fetch_ahead() {
+    if ((PER_WARP ? (threadIdx.x & 31) : threadIdx.x) == 0) pending = atomicAdd(work, 1);
+  }
+  // everybody gets the index fetched ahead.  Block tiles: the two barriers also fence the shared vector between tiles
+  __device__ __forceinline__ int take() {
+    if (PER_WARP) return __shfl_sync(0xffffffffu, pending, 0);
+    __syncthreads(); // the previous tile is finished everywhere: vector, shared index free
+    if (threadIdx.x == 0) *shared_next = pending;
+    __syncthreads();
+    return *shared_next;
+  }
+};
 
 template <bool PER_WARP, int CHUNK, int NRHS>
 __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
                                                                         int n_tiles, int vec_doubles, int stages,
                                                                         SolveVectors io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PECS_TRACE_T(trace_t0);
   const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles * NRHS, stages);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
-  if (PER_WARP && tile_index >= n_tiles) return;
-  const SolveTile tile = tiles[tile_index];
+  const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
   init_pipeline(sm.my_bars, stages);
-  PanelStream<CHUNK> stream(t.fwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.my_ring, sm.my_bars,
-                            stages);
-  stream.start();
+  PanelStream<CHUNK> stream(sm.my_ring, sm.my_bars, stages);
+  TileFetcher<PER_WARP> fetcher(io.work, sm.next_tile);
   if (io.grid_wait) grid_dependency_wait();
   release_dependents();
-  const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
-  // the children's updates (their forward tiles) must be complete
-  if (first_thread == 0) {
-    if (tile.dep[0] >= 0) wait_count(io.done_fwd + tile.dep[0], tile.need[0], io.error);
-    if (tile.dep[1] >= 0) wait_count(io.done_fwd + tile.dep[1], tile.need[1], io.error);
-  }
-  if (PER_WARP)
-    __syncwarp();
-  else
-    __syncthreads();
-  PECS_TRACE_T(trace_t1);
-  const int* omap = t.out_map + tile.bd_off;
-#pragma unroll
-  for (int r = 0; r < NRHS; ++r) {
-    const double* cb = io.cbuf + (size_t)r * io.cbuf_stride;
-    const double* c0 = tile.cbuf_off[0] >= 0 ? cb + tile.cbuf_off[0] : nullptr;
-    const double* c1 = tile.cbuf_off[1] >= 0 ? cb + tile.cbuf_off[1] : nullptr;
-    const double* w_in = io.w_in + (size_t)r * io.n_stride;
-    double* w_fin = io.w_fin + (size_t)r * io.n_stride;
-    double* sv = sm.sv + r * vec_doubles;
-    // finalised pivot right-hand side: w_P = b_P - what the children eliminated into it
-    const int count = max(tile.np, tile.cols_pad);
-    for (int l = first_thread; l < count; l += n_threads) {
-      double v = 0.0;
-      if (l < tile.np) {
-        v = ld_step(w_in + tile.p0 + l);
-        if (c0) v -= ld_step(c0 + l);
-        if (c1) v -= ld_step(c1 + l);
-        if (tile.first) w_fin[tile.p0 + l] = v;
-      }
-      if (l < tile.cols_pad) sv[l] = v;
+  fetcher.fetch_ahead();
+  for (;;) {
+    const int tile_index = fetcher.take();
+    if (tile_index >= n_tiles) break;
+    PECS_TRACE_T(trace_t0);
+    const SolveTile tile = tiles[tile_index];
+    stream.begin(t.fwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps);
+    stream.start();
+    fetcher.fetch_ahead();
+    // the children's updates (their forward tiles) must be complete: two threads poll the two counters side by side
+    if (io.use_counters) {
+      if (first_thread < 2 && tile.dep[first_thread] >= 0)
+        wait_count(io.done_fwd + tile.dep[first_thread], tile.need[first_thread], io.error);
+      if (PER_WARP)
+        __syncwarp();
+      else
+        __syncthreads();
     }
-    if (tile.np == 0) {
-      // a front without pivots (its region fell apart into unconnected pieces) only hands its children's updates on
-      double* out = io.cbuf + (size_t)r * io.cbuf_stride + tile.out_off;
-      for (int row = first_thread; row < tile.nb; row += n_threads) {
-        double carry = 0.0;
-        if (c0) carry += ld_step(c0 + tile.np + row);
-        if (c1) carry += ld_step(c1 + tile.np + row);
-        out[omap[row]] = carry;
-      }
-    }
-  }
-  if (PER_WARP)
-    __syncwarp();
-  else
-    __syncthreads();
-  stream.template run<NRHS>(sm.sv, vec_doubles, tile.nb, [&](int row, const double (&dot)[NRHS]) {
+    PECS_TRACE_T(trace_t1);
+    const int* omap = t.out_map + tile.bd_off;
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) {
-      double* cb = io.cbuf + (size_t)r * io.cbuf_stride;
-      double carry = 0.0;
-      if (tile.cbuf_off[0] >= 0) carry += ld_step(cb + tile.cbuf_off[0] + tile.np + row);
-      if (tile.cbuf_off[1] >= 0) carry += ld_step(cb + tile.cbuf_off[1] + tile.np + row);
-      cb[tile.out_off + omap[row]] = carry + dot[r];
+      const double* cb = io.cbuf + (size_t)r * io.cbuf_stride;
+      const double* c0 = tile.cbuf_off[0] >= 0 ? cb + tile.cbuf_off[0] : nullptr;
+      const double* c1 = tile.cbuf_off[1] >= 0 ? cb + tile.cbuf_off[1] : nullptr;
+      const double* w_in = io.w_in + (size_t)r * io.n_stride;
+      double* w_fin = io.w_fin + (size_t)r * io.n_stride;
+      double* sv = sm.sv + r * vec_doubles;
+      // finalised pivot right-hand side: w_P = b_P - what the children eliminated into it
+      const int count = max(tile.np, tile.cols_pad);
+      for (int l = first_thread; l < count; l += n_threads) {
+        double v = 0.0;
+        if (l < tile.np) {
+          v = ld_step(w_in + tile.p0 + l);
+          if (c0) v -= ld_step(c0 + l);
+          if (c1) v -= ld_step(c1 + l);
+          if (tile.first) w_fin[tile.p0 + l] = v;
+        }
+        if (l < tile.cols_pad) sv[l] = v;
+      }
+      if (tile.np == 0) {
+        // a front without pivots (its region fell apart into unconnected pieces) only hands its children's updates on
+        double* out = io.cbuf + (size_t)r * io.cbuf_stride + tile.out_off;
+        for (int row = first_thread; row < tile.nb; row += n_threads) {
+          double carry = 0.0;
+          if (c0) carry += ld_step(c0 + tile.np + row);
+          if (c1) carry += ld_step(c1 + tile.np + row);
+          out[omap[row]] = carry;
+        }
+      }
     }
-  });
-  if (PER_WARP)
-    __syncwarp();
-  else
-    __syncthreads();
-  if (first_thread == 0) signal_count(io.done_fwd + tile.front);
-  PECS_TRACE_T(trace_t2);
-  PECS_TRACE_REC(io.tag, trace_t0, trace_t1, trace_t2);
+    if (PER_WARP)
+      __syncwarp();
+    else
+      __syncthreads();
+    stream.template run<NRHS>(sm.sv, vec_doubles, tile.nb, [&](int row, const double (&dot)[NRHS]) {
+#pragma unroll
+      for (int r = 0; r < NRHS; ++r) {
+        double* cb = io.cbuf + (size_t)r * io.cbuf_stride;
+        double carry = 0.0;
+        if (tile.cbuf_off[0] >= 0) carry += ld_step(cb + tile.cbuf_off[0] + tile.np + row);
+        if (tile.cbuf_off[1] >= 0) carry += ld_step(cb + tile.cbuf_off[1] + tile.np + row);
+        cb[tile.out_off + omap[row]] = carry + dot[r];
+      }
+    });
+    if (PER_WARP)
+      __syncwarp();
+    else
+      __syncthreads();
+    if (io.use_counters && first_thread == 0 && tile.out_off >= 0) signal_count(io.done_fwd + tile.front);
+    PECS_TRACE_T(trace_t2);
+    PECS_TRACE_REC(io.tag, trace_t0, trace_t1, trace_t2);
+  }
   if (!io.grid_wait) grid_dependency_wait(); // completion stays transitive along the kernel chain
 }
 
@@ -350,85 +395,90 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
                                                                          int n_tiles, int vec_doubles, int stages,
                                                                          SolveVectors io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PECS_TRACE_T(trace_t0);
   const BlockSmem sm = carve<PER_WARP, CHUNK>(smem_raw, vec_doubles * NRHS, stages);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  const int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x;
-  if (PER_WARP && tile_index >= n_tiles) return;
-  const SolveTile tile = tiles[tile_index];
+  const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
   init_pipeline(sm.my_bars, stages);
-  PanelStream<CHUNK> stream(t.bwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps, sm.my_ring, sm.my_bars,
-                            stages);
-  stream.start();
+  PanelStream<CHUNK> stream(sm.my_ring, sm.my_bars, stages);
+  TileFetcher<PER_WARP> fetcher(io.work, sm.next_tile);
   if (io.grid_wait) grid_dependency_wait();
   release_dependents();
-  const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
-  // x of every ancestor (the nearest one with tiles waited for its own ancestors), this front's finalised right-hand
-  // side (its forward tiles), and -- a front without boundary reads its children's updates itself -- the children
-  if (first_thread == 0) {
-    if (tile.up >= 0) wait_count(io.done_bwd + tile.up, tile.need_up, io.error);
-    wait_count(io.done_fwd + tile.front, tile.need_self, io.error);
-    if (tile.first) {
-      if (tile.dep[0] >= 0) wait_count(io.done_fwd + tile.dep[0], tile.need[0], io.error);
-      if (tile.dep[1] >= 0) wait_count(io.done_fwd + tile.dep[1], tile.need[1], io.error);
+  fetcher.fetch_ahead();
+  for (;;) {
+    const int tile_index = fetcher.take();
+    if (tile_index >= n_tiles) break;
+    PECS_TRACE_T(trace_t0);
+    const SolveTile tile = tiles[tile_index];
+    stream.begin(t.bwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps);
+    stream.start();
+    fetcher.fetch_ahead();
+    // x of every ancestor (the nearest one with tiles waited for its own ancestors), this front's finalised right-hand
+    // side (its forward tiles), and -- a front without boundary reads its children's updates itself -- the children
+    // (four threads poll the up-to-four counters side by side: one L2 round trip instead of four)
+    if (io.use_counters) {
+      if (first_thread == 0 && tile.up >= 0) wait_count(io.done_bwd + tile.up, tile.need_up, io.error);
+      if (first_thread == 1) wait_count(io.done_fwd + tile.front, tile.need_self, io.error);
+      if (tile.first && (first_thread == 2 || first_thread == 3) && tile.dep[first_thread - 2] >= 0)
+        wait_count(io.done_fwd + tile.dep[first_thread - 2], tile.need[first_thread - 2], io.error);
+      if (PER_WARP)
+        __syncwarp();
+      else
+        __syncthreads();
     }
-  }
-  if (PER_WARP)
-    __syncwarp();
-  else
-    __syncthreads();
-  PECS_TRACE_T(trace_t1);
-  {
-    const int np = tile.np, m = tile.np + tile.nb;
-    const int* bd = t.bd_index + tile.bd_off;
+    PECS_TRACE_T(trace_t1);
+    {
+      const int np = tile.np, m = tile.np + tile.nb;
+      const int* bd = t.bd_index + tile.bd_off;
 #pragma unroll
-    for (int r = 0; r < NRHS; ++r) {
-      double* sv = sm.sv + r * vec_doubles;
-      if (tile.first) {
-        // no boundary, hence no forward tile: w_P = b_P - what the children eliminated into it, finalised here
-        const double* cb = io.cbuf + (size_t)r * io.cbuf_stride;
-        const double* c0 = tile.cbuf_off[0] >= 0 ? cb + tile.cbuf_off[0] : nullptr;
-        const double* c1 = tile.cbuf_off[1] >= 0 ? cb + tile.cbuf_off[1] : nullptr;
-        const double* w_in = io.w_in + (size_t)r * io.n_stride;
-        for (int l = first_thread; l < tile.cols_pad; l += n_threads) {
-          double v = 0.0;
-          if (l < np) {
-            v = ld_step(w_in + tile.p0 + l);
-            if (c0) v -= ld_step(c0 + l);
-            if (c1) v -= ld_step(c1 + l);
+      for (int r = 0; r < NRHS; ++r) {
+        double* sv = sm.sv + r * vec_doubles;
+        if (tile.first) {
+          // no boundary, hence no forward tile: w_P = b_P - what the children eliminated into it, finalised here
+          const double* cb = io.cbuf + (size_t)r * io.cbuf_stride;
+          const double* c0 = tile.cbuf_off[0] >= 0 ? cb + tile.cbuf_off[0] : nullptr;
+          const double* c1 = tile.cbuf_off[1] >= 0 ? cb + tile.cbuf_off[1] : nullptr;
+          const double* w_in = io.w_in + (size_t)r * io.n_stride;
+          for (int l = first_thread; l < tile.cols_pad; l += n_threads) {
+            double v = 0.0;
+            if (l < np) {
+              v = ld_step(w_in + tile.p0 + l);
+              if (c0) v -= ld_step(c0 + l);
+              if (c1) v -= ld_step(c1 + l);
+            }
+            sv[l] = v;
           }
-          sv[l] = v;
+        } else {
+          const double* wp = io.w_fin + (size_t)r * io.n_stride + tile.p0;
+          const double* xp = io.x_perm + (size_t)r * io.n_stride;
+          for (int l = first_thread; l < tile.cols_pad; l += n_threads)
+            sv[l] = l < np ? ld_step(wp + l) : (l < m ? ld_step(xp + bd[l - np]) : 0.0);
         }
-      } else {
-        const double* wp = io.w_fin + (size_t)r * io.n_stride + tile.p0;
-        const double* xp = io.x_perm + (size_t)r * io.n_stride;
-        for (int l = first_thread; l < tile.cols_pad; l += n_threads)
-          sv[l] = l < np ? ld_step(wp + l) : (l < m ? ld_step(xp + bd[l - np]) : 0.0);
       }
     }
-  }
-  if (PER_WARP)
-    __syncwarp();
-  else
-    __syncthreads();
-  stream.template run<NRHS>(sm.sv, vec_doubles, tile.np, [&](int row, const double (&x)[NRHS]) {
-    const int i = t.iperm[tile.p0 + row];
+    if (PER_WARP)
+      __syncwarp();
+    else
+      __syncthreads();
+    stream.template run<NRHS>(sm.sv, vec_doubles, tile.np, [&](int row, const double (&x)[NRHS]) {
+      const int i = t.iperm[tile.p0 + row];
 #pragma unroll
-    for (int r = 0; r < NRHS; ++r) {
-      io.x_perm[(size_t)r * io.n_stride + tile.p0 + row] = x[r];
-      double* solution = io.solution[r];
-      const double v = ld_step(solution + i) + x[r]; // increment form: the right-hand side was the residual of `solution`
-      solution[i] = v;
-      for (int m = 0; m < io.n_mirror[r]; ++m) io.mirror[r][m][i] = v; // peer copies (sharded step)
-    }
-  });
-  if (PER_WARP)
-    __syncwarp();
-  else
-    __syncthreads();
-  if (first_thread == 0) signal_count(io.done_bwd + tile.front);
-  PECS_TRACE_T(trace_t2);
-  PECS_TRACE_REC(io.tag, trace_t0, trace_t1, trace_t2);
+      for (int r = 0; r < NRHS; ++r) {
+        io.x_perm[(size_t)r * io.n_stride + tile.p0 + row] = x[r];
+        double* solution = io.solution[r];
+        const double v = ld_step(solution + i) + x[r]; // increment form: the right-hand side was the residual of `solution`
+        solution[i] = v;
+        for (int m = 0; m < io.n_mirror[r]; ++m) io.mirror[r][m][i] = v; // peer copies (sharded step)
+      }
+    });
+    if (PER_WARP)
+      __syncwarp();
+    else
+      __syncthreads();
+    // only fronts some deeper front waits for publish their completion (leaf fronts, half of all, do not)
+    if (io.use_counters && first_thread == 0 && tile.signal_bwd) signal_count(io.done_bwd + tile.front);
+    PECS_TRACE_T(trace_t2);
+    PECS_TRACE_REC(io.tag, trace_t0, trace_t1, trace_t2);
+  }
   if (!io.grid_wait) grid_dependency_wait(); // completion stays transitive along the kernel chain
 }
 
@@ -453,12 +503,31 @@ void configure_solve_kernels(int max_smem_bytes) {
   configure_one<true, 2>(max_smem_bytes);
 }
 
-void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                          int stages, const SolveVectors& io, cudaStream_t s) {
+int level_grid(bool forward, bool per_warp, int n_rhs, int n_tiles, int vec_doubles, int warps, int stages) {
+  if (n_tiles == 0) return 0;
+  const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, n_rhs);
+  const void* kernel = nullptr;
+#define PECS_PICK(PW, NR) \
+  kernel = forward ? (const void*)forward_level_kernel<PW, kChunkDoubles, NR> : (const void*)backward_level_kernel<PW, kChunkDoubles, NR>
+  if (n_rhs == 2) {
+    if (per_warp) PECS_PICK(true, 2); else PECS_PICK(false, 2);
+  } else {
+    if (per_warp) PECS_PICK(true, 1); else PECS_PICK(false, 1);
+  }
+#undef PECS_PICK
+  int per_sm = 0, dev = 0, sms = 0;
+  PECS_CUDA(cudaGetDevice(&dev));
+  PECS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PECS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
+  const int units = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
+  return std::max(1, std::min(units, std::max(per_sm, 1) * sms));
+}
+
+void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int grid, bool per_warp, int vec_doubles,
+                          int warps, int stages, const SolveVectors& io, cudaStream_t s) {
   if (n_tiles == 0) return;
   const int vec = (vec_doubles + 15) / 16 * 16;
   const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, io.n_rhs);
-  const int grid = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
 #define PECS_LAUNCH(PW, NR) \
   launch_pdl(forward_level_kernel<PW, kChunkDoubles, NR>, grid, warps * 32, smem, s, t, tiles, n_tiles, vec, stages, io)
   if (io.n_rhs == 2) {
@@ -469,12 +538,11 @@ void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_ti
 #undef PECS_LAUNCH
 }
 
-void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                           int stages, const SolveVectors& io, cudaStream_t s) {
+void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int grid, bool per_warp, int vec_doubles,
+                           int warps, int stages, const SolveVectors& io, cudaStream_t s) {
   if (n_tiles == 0) return;
   const int vec = (vec_doubles + 15) / 16 * 16;
   const size_t smem = solve_smem_bytes(vec_doubles, per_warp, warps, stages, io.n_rhs);
-  const int grid = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
 #define PECS_LAUNCH(PW, NR) \
   launch_pdl(backward_level_kernel<PW, kChunkDoubles, NR>, grid, warps * 32, smem, s, t, tiles, n_tiles, vec, stages, io)
   if (io.n_rhs == 2) {

@@ -25,7 +25,7 @@ struct SolveTile {
   int dep[2], need[2];     // children whose forward tiles must all be complete before this tile reads their updates
   int up, need_up;         // backward: nearest ancestor that has backward tiles (-1: none) and how many it has
   int need_self;           // backward: forward tiles of this front (they publish its finalised right-hand side)
-  int pad_;
+  int signal_bwd;          // backward: some descendant's tile waits for this front (else nothing needs its counter)
 };
 
 struct SolveTables {
@@ -56,7 +56,9 @@ struct SolveVectors {
   // completion counters of the fronts (zeroed at the start of every solve): forward tiles done / backward tiles done
   int* done_fwd;
   int* done_bwd;
+  int* work;       // this launch's tile counter: blocks (or warps) take the next tile of the level off it
   int* error;      // set to 1 if a counter wait ever gave up (bounded spin: a logic error must not hang the GPU)
+  int use_counters; // 0: every kernel waits for its whole predecessor grid, the counters are neither read nor written
   int tag;         // identifies the launch in the trace build (-DPECS_B200_TRACE=1, scripts/trace_step.py); unused otherwise
   int grid_wait;   // 1: wait for the whole predecessor grid BEFORE reading anything (first kernel behind a producer
                    // that signals no counters, or dataflow switched off); 0: counters only, grid wait at the very end
@@ -69,15 +71,20 @@ constexpr int kSolveWarps = 16;
 // mbarrier per slot
 inline size_t solve_smem_bytes(int vec_doubles, bool per_warp, int warps, int stages, int n_rhs = 1) {
   const size_t vec = ((size_t)vec_doubles + 15) / 16 * 16 * (per_warp ? warps : 1) * n_rhs;
-  return (vec + (size_t)warps * stages * kChunkDoubles) * sizeof(double) + (size_t)warps * stages * sizeof(unsigned long long);
+  return (vec + (size_t)warps * stages * kChunkDoubles) * sizeof(double) + (size_t)warps * stages * sizeof(unsigned long long) +
+         16; // + the shared tile index
 }
 
-// forward sweep of one level.  per_warp: one small front per warp.
-void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                          int stages, const SolveVectors& io, cudaStream_t s);
+// forward sweep of one level.  per_warp: one small front per warp.  grid: thread blocks of the launch (one resident
+// wave at most, level_grid() below); they take the n_tiles tiles off io.work
+void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int grid, bool per_warp, int vec_doubles,
+                          int warps, int stages, const SolveVectors& io, cudaStream_t s);
 // backward sweep of one level; writes x_perm and ADDS the result to the caller's solution vectors (increment form)
-void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, bool per_warp, int vec_doubles, int warps,
-                           int stages, const SolveVectors& io, cudaStream_t s);
+void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int grid, bool per_warp, int vec_doubles,
+                           int warps, int stages, const SolveVectors& io, cudaStream_t s);
+// thread blocks of a level launch: enough for every tile, but never more than fit on the device at once (occupancy of
+// the kernel variant at this block shape x number of SMs)
+int level_grid(bool forward, bool per_warp, int n_rhs, int n_tiles, int vec_doubles, int warps, int stages);
 // out[i] = in[index[i]]
 void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s);
 // opt in to large dynamic shared memory once per process
