@@ -40,10 +40,8 @@ struct DeviceSystem {
   SolvePlan plan;
   DeviceBuffer<double> fwd, bwd, cbuf, w_in, w_fin, x_perm;
   DeviceBuffer<int> bd_index, out_map, iperm;
-  // [0, F) forward tiles done per front, [F, 2F) backward tiles done, [2F, 2F + L) tile counters of the L level launches
-  // of a solve, [2F + L] error word
+  // completion counters of the fronts: [0, F) forward tiles done, [F, 2F) backward tiles done, [2F] error word
   DeviceBuffer<int> done;
-  int n_fwd_launches = 0;
   // one sweep of one level: large fronts cut into block tiles, small fronts one warp each
   struct Sweep {
     DeviceBuffer<SolveTile> block_tiles, warp_tiles;
@@ -268,11 +266,9 @@ struct DeviceSystem {
         if (out.bt.size() <= 148 * 4 && !env_int("PECS_B200_SOLVE_STAGES", 0)) sw.stages = std::max(sw.stages, 4);
         sw.grid_block = level_grid(which == 0, false, n_rhs, (int)out.bt.size(), sw.vec_block, sw.warps, sw.stages);
         sw.grid_warp = level_grid(which == 0, true, n_rhs, (int)out.wt.size(), sw.vec_warp, solve_warps(), sw.stages_warp);
-        const int n = (out.bt.empty() ? 0 : 1) + (out.wt.empty() ? 0 : 1);
-        launches_per_solve += n;
-        if (which == 0) n_fwd_launches += n;
+        launches_per_solve += (out.bt.empty() ? 0 : 1) + (out.wt.empty() ? 0 : 1);
       }
-    done.resize(2 * (size_t)n_fronts + launches_per_solve + 1);
+    done.resize(2 * (size_t)n_fronts + 1);
     done.zero();
   }
 
@@ -296,8 +292,7 @@ struct DeviceSystem {
     const size_t n_fronts = plan.fronts.size();
     io.done_fwd = done.get();
     io.done_bwd = done.get() + n_fronts;
-    io.work = done.get() + 2 * n_fronts;
-    io.error = done.get() + 2 * n_fronts + launches_per_solve;
+    io.error = done.get() + 2 * n_fronts;
     io.grid_wait = dataflow_enabled() ? 0 : 1;
     io.use_counters = dataflow_enabled() ? 1 : 0;
     return io;
@@ -311,12 +306,12 @@ struct DeviceSystem {
   // that produces the residual, so that the chain residual -> forward levels -> backward levels is one unbroken chain
   // of programmatic launches
   void reset_counters(cudaStream_t s) {
-    PECS_CUDA(cudaMemsetAsync(done.get(), 0, (2 * plan.fronts.size() + launches_per_solve) * sizeof(int), s));
+    PECS_CUDA(cudaMemsetAsync(done.get(), 0, 2 * plan.fronts.size() * sizeof(int), s));
   }
   int error_flag() const {
     int e = 0;
     if (done.size() > 0)
-      PECS_CUDA(cudaMemcpy(&e, done.get() + 2 * plan.fronts.size() + launches_per_solve, sizeof(int), cudaMemcpyDeviceToHost));
+      PECS_CUDA(cudaMemcpy(&e, done.get() + 2 * plan.fronts.size(), sizeof(int), cudaMemcpyDeviceToHost));
     return e;
   }
   // The kernel that produced the residual signals no counters: the FIRST forward kernel waits for that whole grid
@@ -325,7 +320,6 @@ struct DeviceSystem {
     const SolveTables t = tables();
     const int warps = solve_warps();
     bool first = true;
-    int launch = 0;
     for (int d = (int)levels.size() - 1; d >= 0; --d) {
       Sweep& sw = levels[d].fwd;
       for (int per_warp = 1; per_warp >= 0; --per_warp) {
@@ -333,7 +327,6 @@ struct DeviceSystem {
         if (tiles.size() == 0) continue;
         SolveVectors v = io;
         v.tag = trace_id * 10000 + d * 2 + per_warp;
-        v.work = io.work + launch++;
         if (first) v.grid_wait = 1;
         first = false;
         if (per_warp)
@@ -346,22 +339,14 @@ struct DeviceSystem {
   void backward_sweep(SolveVectors io, cudaStream_t s) {
     const SolveTables t = tables();
     const int warps = solve_warps();
-    int* const work = io.work + n_fwd_launches;
-    int launch = 0;
     for (size_t d = 0; d < levels.size(); ++d) {
       Sweep& sw = levels[d].bwd;
       io.tag = trace_id * 10000 + 1000 + (int)d * 2;
-      if (sw.block_tiles.size() > 0) {
-        io.work = work + launch++;
-        launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), sw.grid_block, false, sw.vec_block, sw.warps,
-                              sw.stages, io, s);
-      }
+      launch_backward_level(t, sw.block_tiles.get(), (int)sw.block_tiles.size(), sw.grid_block, false, sw.vec_block, sw.warps,
+                            sw.stages, io, s);
       io.tag += 1;
-      if (sw.warp_tiles.size() > 0) {
-        io.work = work + launch++;
-        launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), sw.grid_warp, true, sw.vec_warp, warps,
-                              sw.stages_warp, io, s);
-      }
+      launch_backward_level(t, sw.warp_tiles.get(), (int)sw.warp_tiles.size(), sw.grid_warp, true, sw.vec_warp, warps,
+                            sw.stages_warp, io, s);
     }
   }
   // w_in = rhs - A solution (rows in elimination order)

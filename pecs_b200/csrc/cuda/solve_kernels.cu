@@ -34,6 +34,7 @@
 #include "solve_kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "device_util.cuh"
 
@@ -261,7 +262,6 @@ struct BlockSmem {
   double* sv;                  // this thread's vector (the block's, or its warp's)
   double* my_ring;
   unsigned long long* my_bars;
-  int* next_tile;              // block tiles: the tile index thread 0 fetched, for everybody
 };
 // vec_doubles: all NRHS vectors of one front (NRHS * padded length)
 template <bool PER_WARP, int CHUNK>
@@ -271,35 +271,16 @@ __device__ __forceinline__ BlockSmem carve(unsigned char* raw, int vec_doubles, 
   double* ring = base + (size_t)vec_doubles * (PER_WARP ? n_warps : 1);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)n_warps * stages * CHUNK);
   return BlockSmem{base + (PER_WARP ? (size_t)warp * vec_doubles : 0), ring + (size_t)warp * stages * CHUNK,
-                   bars + warp * stages, reinterpret_cast<int*>(bars + n_warps * stages)};
+                   bars + warp * stages};
 }
 
-// A level kernel is ONE RESIDENT WAVE of thread blocks that take tiles off a work counter until the level is done
-// (block tiles: a block per tile at a time; one-warp tiles: every warp for itself).  The per-block-timestamp trace of
-// round 2 (profiles/r02_trace_*.log) showed why: with a block per tile the Poisson levels were bound by the rate at
-// which the GPU can START thread blocks -- 4 096 blocks of 3 us of work each, 2 TB/s -- and every block paid its
-// prologue (descriptor, barrier init, first table chunk, counter polls: 2 us) in front of 5-20 us of work.  Here the
-// prologue is paid once per block, the ring and its barriers live across tiles, and the index of the next tile is
-// fetched while the current one is being worked on.  Tiles come off the counter in list order and a tile only ever
-// waits for tiles of EARLIER kernels of the chain, all of whose blocks are already running: no deadlock.
-template <bool PER_WARP>
-struct TileFetcher {
-  int* work;
-  int* shared_next; // block tiles
-  int pending = 0;  // the index fetched ahead (thread 0 / lane 0)
-  __device__ __forceinline__ TileFetcher(int* work_, int* shared_next_) : work(work_), shared_next(shared_next_) {}
-  __device__ __forceinline__ void fetch_ahead() {
-    if ((PER_WARP ? (threadIdx.x & 31) : threadIdx.x) == 0) pending = atomicAdd(work, 1);
-  }
-  // everybody gets the index fetched ahead.  Block tiles: the two barriers also fence the shared vector between tiles
-  __device__ __forceinline__ int take() {
-    if (PER_WARP) return __shfl_sync(0xffffffffu, pending, 0);
-    __syncthreads(); // the previous tile is finished everywhere: vector, shared index free
-    if (threadIdx.x == 0) *shared_next = pending;
-    __syncthreads();
-    return *shared_next;
-  }
-};
+// Tiles map to thread blocks statically (block tiles: tile = blockIdx; one-warp tiles: one per warp), a launch normally has
+// a block per tile and the loop below runs once.  The loop exists for launches with FEWER blocks than tiles
+// (PECS_B200_LEVEL_WAVES: grids capped at so many resident waves).  Measured with the per-block-timestamp trace
+// (profiles/r02_trace_*.log): a single resident wave per level that takes tiles off a counter is SLOWER (electron solve
+// 776 us against 651 us): the blocks of level k+1 then occupy the SM slots for the whole level while they spin on
+// counters of level k, whose remaining tiles wait for slots -- the hardware's block scheduler, which recycles a slot per
+// tile, is the better dynamic scheduler here.
 
 template <bool PER_WARP, int CHUNK, int NRHS>
 __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTables t, const SolveTile* __restrict__ tiles,
@@ -311,18 +292,14 @@ __global__ void __launch_bounds__(kSolveWarps * 32) forward_level_kernel(SolveTa
   const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
   init_pipeline(sm.my_bars, stages);
   PanelStream<CHUNK> stream(sm.my_ring, sm.my_bars, stages);
-  TileFetcher<PER_WARP> fetcher(io.work, sm.next_tile);
   if (io.grid_wait) grid_dependency_wait();
   release_dependents();
-  fetcher.fetch_ahead();
-  for (;;) {
-    const int tile_index = fetcher.take();
-    if (tile_index >= n_tiles) break;
+  const int tile_stride = (int)gridDim.x * (PER_WARP ? n_warps : 1);
+  for (int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x; tile_index < n_tiles; tile_index += tile_stride) {
     PECS_TRACE_T(trace_t0);
     const SolveTile tile = tiles[tile_index];
     stream.begin(t.fwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps);
     stream.start();
-    fetcher.fetch_ahead();
     // the children's updates (their forward tiles) must be complete: two threads poll the two counters side by side
     if (io.use_counters) {
       if (first_thread < 2 && tile.dep[first_thread] >= 0)
@@ -400,18 +377,14 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
   const int first_thread = PER_WARP ? lane : threadIdx.x, n_threads = PER_WARP ? 32 : blockDim.x;
   init_pipeline(sm.my_bars, stages);
   PanelStream<CHUNK> stream(sm.my_ring, sm.my_bars, stages);
-  TileFetcher<PER_WARP> fetcher(io.work, sm.next_tile);
   if (io.grid_wait) grid_dependency_wait();
   release_dependents();
-  fetcher.fetch_ahead();
-  for (;;) {
-    const int tile_index = fetcher.take();
-    if (tile_index >= n_tiles) break;
+  const int tile_stride = (int)gridDim.x * (PER_WARP ? n_warps : 1);
+  for (int tile_index = PER_WARP ? blockIdx.x * n_warps + warp : blockIdx.x; tile_index < n_tiles; tile_index += tile_stride) {
     PECS_TRACE_T(trace_t0);
     const SolveTile tile = tiles[tile_index];
     stream.begin(t.bwd + tile.table_off, tile, PER_WARP ? 0 : warp, PER_WARP ? 1 : n_warps);
     stream.start();
-    fetcher.fetch_ahead();
     // x of every ancestor (the nearest one with tiles waited for its own ancestors), this front's finalised right-hand
     // side (its forward tiles), and -- a front without boundary reads its children's updates itself -- the children
     // (four threads poll the up-to-four counters side by side: one L2 round trip instead of four)
@@ -520,7 +493,12 @@ int level_grid(bool forward, bool per_warp, int n_rhs, int n_tiles, int vec_doub
   PECS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   PECS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
   const int units = per_warp ? (n_tiles + warps - 1) / warps : n_tiles;
-  return std::max(1, std::min(units, std::max(per_sm, 1) * sms));
+  static const int waves = [] {
+    const char* e = std::getenv("PECS_B200_LEVEL_WAVES");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (waves <= 0) return units; // default: a block per tile (one-warp tiles: per `warps` tiles)
+  return std::max(1, std::min(units, waves * std::max(per_sm, 1) * sms));
 }
 
 void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int grid, bool per_warp, int vec_doubles,

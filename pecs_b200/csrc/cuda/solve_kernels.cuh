@@ -56,7 +56,6 @@ struct SolveVectors {
   // completion counters of the fronts (zeroed at the start of every solve): forward tiles done / backward tiles done
   int* done_fwd;
   int* done_bwd;
-  int* work;       // this launch's tile counter: blocks (or warps) take the next tile of the level off it
   int* error;      // set to 1 if a counter wait ever gave up (bounded spin: a logic error must not hang the GPU)
   int use_counters; // 0: every kernel waits for its whole predecessor grid, the counters are neither read nor written
   int tag;         // identifies the launch in the trace build (-DPECS_B200_TRACE=1, scripts/trace_step.py); unused otherwise
@@ -71,19 +70,17 @@ constexpr int kSolveWarps = 16;
 // mbarrier per slot
 inline size_t solve_smem_bytes(int vec_doubles, bool per_warp, int warps, int stages, int n_rhs = 1) {
   const size_t vec = ((size_t)vec_doubles + 15) / 16 * 16 * (per_warp ? warps : 1) * n_rhs;
-  return (vec + (size_t)warps * stages * kChunkDoubles) * sizeof(double) + (size_t)warps * stages * sizeof(unsigned long long) +
-         16; // + the shared tile index
+  return (vec + (size_t)warps * stages * kChunkDoubles) * sizeof(double) + (size_t)warps * stages * sizeof(unsigned long long);
 }
 
-// forward sweep of one level.  per_warp: one small front per warp.  grid: thread blocks of the launch (one resident
-// wave at most, level_grid() below); they take the n_tiles tiles off io.work
+// forward sweep of one level.  per_warp: one small front per warp.  grid: thread blocks of the launch (level_grid() below)
 void launch_forward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int grid, bool per_warp, int vec_doubles,
                           int warps, int stages, const SolveVectors& io, cudaStream_t s);
 // backward sweep of one level; writes x_perm and ADDS the result to the caller's solution vectors (increment form)
 void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_tiles, int grid, bool per_warp, int vec_doubles,
                            int warps, int stages, const SolveVectors& io, cudaStream_t s);
-// thread blocks of a level launch: enough for every tile, but never more than fit on the device at once (occupancy of
-// the kernel variant at this block shape x number of SMs)
+// thread blocks of a level launch: one per tile (one-warp tiles: one per `warps` tiles); with PECS_B200_LEVEL_WAVES=k
+// at most k resident waves (occupancy of the kernel variant at this block shape x number of SMs), the blocks then loop
 int level_grid(bool forward, bool per_warp, int n_rhs, int n_tiles, int vec_doubles, int warps, int stages);
 // out[i] = in[index[i]]
 void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s);
