@@ -388,6 +388,10 @@ def run_gpu_arm(args):
             sh["strong_scaling_efficiency"] = sh["steps_per_s"] / one_gpu / world
             sh["one_gpu_steps_per_s"] = one_gpu
             line["sharded"] = sh
+    # ---- the reference's DEFAULT input end to end (cfg1 = input_file.prm verbatim: g=4, l=1, 1000 steps, 100 time stamps,
+    # reference main.cpp -> run_full_system): setup + time loop + the 101 output stamps + restart files, wall clock
+    if rank == 0 and world == 1 and not args.no_cfg1:
+        line["cfg1_default_input"] = measure_default_input(device, args)
     if rank == 0:
         # CPU baseline on this box's host cores (rank 0, N = 1 only): bounded sample of the same workload (the two
         # refinements below it, MEASURED exponent); `--impl reference` runs the workload itself
@@ -409,6 +413,39 @@ def run_gpu_arm(args):
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def measure_default_input(device, args):
+    """BASELINE.json configs[0] on the GPU path: `run_full_system` of input_file.prm as the reference's main() runs it."""
+    import shutil
+    import tempfile
+    import pecs_b200 as pecs
+    out = {"workload": "input_file.prm verbatim: global refinements 4, local 1 (15360 DoF per carrier), 1000 IMEX steps, "
+                       "100 time stamps (303 .vtu files + 4 restart files)"}
+    tmp = tempfile.mkdtemp(prefix="pecs_cfg1_")
+    try:
+        t0 = time.perf_counter()
+        prob = pecs.SolarCellProblem(pecs.default_input_file(4, 1), device=device)
+        prob.set_output(tmp)
+        prob.run_full_system()
+        out["run_full_system_wall_seconds"] = time.perf_counter() - t0
+        out["files_written"] = len(os.listdir(tmp))
+        ms = prob.step_timed(1000)[0]
+        out["steps_per_s_time_loop_only"] = 1000 / (ms * 1e-3)
+        out["ms_per_step"] = ms / 1000
+        out["gpu_launches_per_step"] = prob.info(0)
+        out["finite"] = bool(all(__import__("numpy").isfinite(prob.get_solution(w)).all() for w in range(5)))
+        prob.close()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    if not args.no_cpu_baseline:
+        from oracle import cpu_arm
+        t0 = time.perf_counter()
+        cpu = cpu_arm.run(4, 1, 200, 1, os.cpu_count())
+        out["cpu_steps_per_s"] = cpu["steps_per_s"]
+        out["cpu_note"] = (f"oracle assembly + SuperLU on {cpu['threads']} host threads, 200 timed steps of the same input "
+                           f"(time loop only, no output), setup {sum(cpu['setup_seconds'].values()):.1f} s")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- sharded step
@@ -512,6 +549,7 @@ def main():
                     help="--impl reference: wall-clock budget; the workload itself is run when its estimated cost fits")
     ap.add_argument("--cpu-no-full", action="store_true", help="--impl reference: samples + extrapolation only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg1", action="store_true", help="skip the end-to-end run of the reference's default input")
     ap.add_argument("--no-sharded", action="store_true", help="N = 2 / 4: skip the sharded-step measurement")
     ap.add_argument("--no-validate", action="store_true", help="skip the parity check of the benchmarked workload")
     ap.add_argument("--exchange", choices=["nccl", "p2p"], default="p2p",

@@ -67,6 +67,10 @@ enum {
   PECS_P_RHO_N_E, PECS_P_RHO_P_E, PECS_P_RHO_R_E, PECS_P_RHO_O_E,
   PECS_P_PHI_BI, PECS_P_PHI_APP, PECS_P_PHI_SCH, PECS_P_SCH_LOCATION,
   PECS_P_TRANSIENT,    /* transient_or_steady of assemble_LDG_system */
+  /* Shockley-Read-Hall recombination R(rho_n, rho_p) (reference include/SolarCell.hpp:86-98; the reference's function
+     returns 0.0 with the formula commented out, which is PECS_P_SRH == 0, the default):
+     R = (n_i^2 - rho_n rho_p) / (tau_n (rho_n - n_i) + tau_p (rho_p - n_i)), added to both semiconductor carriers */
+  PECS_P_SRH, PECS_P_N_INTRINSIC, PECS_P_TAU_N, PECS_P_TAU_P,
   PECS_P_COUNT
 };
 

@@ -34,12 +34,14 @@ DEFAULT_PRM = {  # reference input_file.prm
     "characteristic length": 1.0e-4, "characteristic time": 1.0e-12, "electrolyte permittivity": 1000.0,
     "illumination status": True, "insulated": True, "intrinsic density": 2.564e9, "photon flux": 1.2e17,
     "schottky bias": 0.0, "schottky status": True, "semiconductor permittivity": 11.9,
+    "electron recombination time": 5e-5, "hole recombination time": 5e-5,
+    "srh recombination": False,  # not a key of the reference: its SRH_Recombination returns 0.0 (SolarCell.hpp:86-98)
 }
 
 # include/pecs_b200.h PECS_P_* slots of the 32-double parameter block the oracle's C API takes
 PARAM_SLOTS = ["delta_t", "penalty", "mu_n", "mu_p", "mu_r", "mu_o", "eps_s", "eps_e", "lambda2", "k_et", "k_ht", "v_n",
                "v_p", "gen_flux", "gen_alpha", "gen_location", "rho_n_e", "rho_p_e", "rho_r_e", "rho_o_e", "phi_bi",
-               "phi_app", "phi_sch", "sch_location", "transient"]
+               "phi_app", "phi_sch", "sch_location", "transient", "srh", "n_intrinsic", "tau_n", "tau_p"]
 
 
 def scaled_parameters(prm=None):
@@ -64,6 +66,8 @@ def scaled_parameters(prm=None):
         "rho_n_e": 2.0, "rho_p_e": 0.0, "rho_r_e": 30.0, "rho_o_e": 29.0,  # InitialConditions.cpp:20,43,61,79
         "phi_bi": p["built in bias"] / U_T, "phi_app": p["applied bias"] / U_T, "phi_sch": p["schottky bias"] / U_T,
         "sch_location": p["mesh height"], "transient": 1.0,
+        "srh": 1.0 if p["srh recombination"] else 0.0, "n_intrinsic": p["intrinsic density"] / C,
+        "tau_n": p["electron recombination time"] / T, "tau_p": p["hole recombination time"] / T,
     }
     out = np.zeros(32)
     for k, name in enumerate(PARAM_SLOTS):

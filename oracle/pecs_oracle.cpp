@@ -559,7 +559,14 @@ void SolarCellProblem::project_initial_conditions() {
 double SolarCellProblem::generation(const Tensor1& p) const { // reference Generation.cpp:29-44
   return prm[P_GEN_ALPHA] * prm[P_GEN_FLUX] * std::exp(prm[P_GEN_ALPHA] * (p.c[1] - prm[P_GEN_LOCATION]));
 }
-static double SRH_Recombination(double, double) { return 0.0; } // reference SolarCell.hpp:86-98
+// reference include/SolarCell.hpp:86-98.  The reference's function returns 0.0 and carries the Shockley-Read-Hall formula
+// as a comment; P_SRH != 0 switches that commented formula on, exactly as written there.
+static double SRH_Recombination(double electron_density, double hole_density, const double* prm) {
+  if (prm[P_SRH] == 0.0) return 0.0;
+  const double ni = prm[P_N_INTRINSIC];
+  return (ni * ni - electron_density * hole_density) /
+         (prm[P_TAU_N] * (electron_density - ni) + prm[P_TAU_P] * (hole_density - ni));
+}
 
 namespace {
 // FEValues[Density].get_function_values
@@ -609,9 +616,9 @@ void SolarCellProblem::assemble_local_semiconductor_rhs(int cell, std::vector<do
     for (int i = 0; i < 12; ++i) {
       const double psi_i_density = carrier_fe_values.density_value(i, q);
       const Tensor1 psi_i_current = carrier_fe_values.current_value(i, q);
-      rhs1[i] += (psi_i_density * gen[q] + psi_i_density * SRH_Recombination(old1[q], old2[q]) +
+      rhs1[i] += (psi_i_density * gen[q] + psi_i_density * SRH_Recombination(old1[q], old2[q], prm) +
                   z1 * (psi_i_current * E[q]) * inverse_perm * old1[q]) * carrier_fe_values.JxW(q);
-      rhs2[i] += (psi_i_density * gen[q] + psi_i_density * SRH_Recombination(old1[q], old2[q]) +
+      rhs2[i] += (psi_i_density * gen[q] + psi_i_density * SRH_Recombination(old1[q], old2[q], prm) +
                   z2 * (psi_i_current * E[q]) * inverse_perm * old2[q]) * carrier_fe_values.JxW(q);
     }
   FEFaceValues face_values, neighbor_face_values;

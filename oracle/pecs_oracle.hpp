@@ -23,7 +23,7 @@ enum { FACE_SAME_LEVEL = 0, FACE_BOUNDARY = 1, FACE_HAS_CHILDREN = 2, FACE_COARS
 enum ParamIndex {
   P_DELTA_T = 0, P_PENALTY, P_MU_N, P_MU_P, P_MU_R, P_MU_O, P_EPS_S, P_EPS_E, P_LAMBDA2, P_K_ET, P_K_HT, P_V_N, P_V_P,
   P_GEN_FLUX, P_GEN_ALPHA, P_GEN_LOCATION, P_RHO_N_E, P_RHO_P_E, P_RHO_R_E, P_RHO_O_E, P_PHI_BI, P_PHI_APP, P_PHI_SCH,
-  P_SCH_LOCATION, P_TRANSIENT, P_COUNT
+  P_SCH_LOCATION, P_TRANSIENT, P_SRH, P_N_INTRINSIC, P_TAU_N, P_TAU_P, P_COUNT
 };
 
 struct Mesh {

@@ -62,6 +62,9 @@ PECS_HD void assemble_local_carrier_rhs(const AssemblyScratch& scratch, const pe
   pecs::rhsmath::production_cell_terms(scratch.vertices.x, scratch.vertices.y, scratch.carrier_1_density,
                                        scratch.carrier_2_density, scratch.Poisson_flux, scratch.generation_integrals, p.inv_dt,
                                        p.charge1 * p.inv_eps, p.charge2 * p.inv_eps, o1, o1 + 4, o1 + 8, o2, o2 + 4, o2 + 8);
+  if (p.srh) // SRH_Recombination, reference SolarCell.hpp:86-98 (0.0 there; the commented formula when switched on)
+    pecs::rhsmath::srh_cell_terms(scratch.vertices.x, scratch.vertices.y, scratch.carrier_1_density, scratch.carrier_2_density,
+                                  p.n_i, p.tau_n, p.tau_p, o1 + 8, o2 + 8);
   if (!scratch.at_boundary) return;
   double b[6][4] = {};
   pecs::rhsmath::boundary_terms_accumulate<PECS_KIND_PRODUCTION>(

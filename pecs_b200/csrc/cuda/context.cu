@@ -129,7 +129,7 @@ struct DeviceSystem {
   static int panels_per_tile(int64_t level_panels, int warps) {
     const int forced = env_int("PECS_B200_SOLVE_PANELS_PER_TILE", 0);
     if (forced) return forced;
-    const int64_t want_tiles = 148 * 16;
+    const int64_t want_tiles = env_int("PECS_B200_TILE_TARGET", 148 * 16);
     return (int)std::min<int64_t>(64, std::max<int64_t>(warps, (level_panels + want_tiles - 1) / want_tiles));
   }
 

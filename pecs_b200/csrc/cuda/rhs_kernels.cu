@@ -124,9 +124,10 @@ __device__ __forceinline__ void carrier_cell_terms(const DomainView& d, const Rh
           const double y = v.y[0] * N[0] + v.y[1] * N[1] + v.y[2] * N[2] + v.y[3] * N[3];
           gen = p.gen_scale * exp(p.gen_alpha * (y - p.gen_location));
         }
-        // SRH_Recombination == 0.0 (reference SolarCell.hpp:86-98)
-        src1 = (rho1 * p.inv_dt + gen) * JxW;
-        src2 = (rho2 * p.inv_dt + gen) * JxW;
+        // SRH_Recombination (reference SolarCell.hpp:86-98): 0.0 unless switched on
+        const double R = p.srh ? rhsmath::srh_recombination(rho1, rho2, p.n_i, p.tau_n, p.tau_p) : 0.0;
+        src1 = (rho1 * p.inv_dt + gen + R) * JxW;
+        src2 = (rho2 * p.inv_dt + gen + R) * JxW;
       } else {
         double x, y;
         fe::map_point(v, xi, eta, x, y);
@@ -389,8 +390,17 @@ __device__ __forceinline__ void store_cell(const CarrierPass& w, int c, const do
   }
 }
 
+// Shockley-Read-Hall terms of one cell.  The production kernels are compiled TWICE (template parameter SRH): the
+// instantiation the reference's configuration runs (SRH_Recombination == 0.0) contains nothing of this, so its registers
+// and code are exactly those of the kernel without the switch; the other one calls this out of line
+__device__ __noinline__ void srh_terms(const double vx[4], const double vy[4], const double r1[4], const double r2[4],
+                                       const RhsParams& p, double rh1[4], double rh2[4]) {
+  rhsmath::srh_cell_terms(vx, vy, r1, r2, p.n_i, p.tau_n, p.tau_p, rh1, rh2);
+}
+
 // one boundary record: cell terms + face terms of its cell, single writer of the cell's 24 rows.  Three dependent
 // round trips to memory at most: {record, cell index} -> {vertices, densities, flux dofs, neighbour densities} -> fluxes
+template <bool SRH>
 __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const double* X) {
   const DomainView& d = w.d;
   const size_t n = (size_t)d.n_cells;
@@ -419,6 +429,7 @@ __device__ __noinline__ void boundary_record(const CarrierPass& w, int r, const 
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
   rhsmath::production_cell_terms(v.x, v.y, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
                         jy1, rh1, jx2, jy2, rh2);
+  if (SRH && w.p.srh) srh_terms(v.x, v.y, r1, r2, w.p, rh1, rh2); // w.p.srh: the semiconductor pass only
   double bx1[4] = {0, 0, 0, 0}, by1[4] = {0, 0, 0, 0}, bh1[4] = {0, 0, 0, 0};
   double bx2[4] = {0, 0, 0, 0}, by2[4] = {0, 0, 0, 0}, bh2[4] = {0, 0, 0, 0};
   rhsmath::boundary_terms_accumulate<PECS_KIND_PRODUCTION>(w.p, rec, geom, v, r1, r2, q1, q2, bx1, by1, bh1, bx2, by2, bh2);
@@ -445,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 4)
   if ((int)blockIdx.x < btiles_total) {
     const int sel = (int)blockIdx.x < btiles_a ? 0 : 1;
     const int r = ((int)blockIdx.x - (sel ? btiles_a : 0)) * kThreads + tid;
-    if (r < pp.pass[sel].d.n_bcells) boundary_record(pp.pass[sel], r, X);
+    if (r < pp.pass[sel].d.n_bcells) boundary_record<false>(pp.pass[sel], r, X);
     return;
   }
   int* iring = reinterpret_cast<int*>(ring + kRingDoubles);
@@ -496,14 +507,14 @@ __global__ void __launch_bounds__(kThreads, 4)
 
 // One-thread-per-cell production kernel on the sum-factorised cell terms (no staging): the variant for meshes too
 // small to fill a resident wave, and the A/B partner of the streaming kernel (PECS_B200_RHS_KERNEL=1).
-template <int MIN_BLOCKS, int THREADS>
+template <int MIN_BLOCKS, int THREADS, bool SRH>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     carrier_rhs_direct_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a, int btiles_a, int btiles_total,
                               const double* X) {
   if ((int)blockIdx.x < btiles_total) { // leading blocks: one boundary tile each (see the streaming kernel)
     const int sel = (int)blockIdx.x < btiles_a ? 0 : 1;
     const int r = ((int)blockIdx.x - (sel ? btiles_a : 0)) * THREADS + threadIdx.x;
-    if (r < pp.pass[sel].d.n_bcells) boundary_record(pp.pass[sel], r, X);
+    if (r < pp.pass[sel].d.n_bcells) boundary_record<SRH>(pp.pass[sel], r, X);
     return;
   }
   const int block = (int)blockIdx.x - btiles_total;
@@ -527,6 +538,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
   double jx1[4], jy1[4], rh1[4], jx2[4], jy2[4], rh2[4];
   rhsmath::production_cell_terms(vx, vy, r1, r2, Xf, gen, w.p.inv_dt, w.p.charge1 * w.p.inv_eps, w.p.charge2 * w.p.inv_eps, jx1,
                         jy1, rh1, jx2, jy2, rh2);
+  if (SRH && w.p.srh) srh_terms(vx, vy, r1, r2, w.p, rh1, rh2); // w.p.srh: the semiconductor pass only
   store_cell<true>(w, c, jx1, jy1, rh1, jx2, jy2, rh2);
 }
 
@@ -671,7 +683,8 @@ void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, co
   const CarrierPassPair pp{{a, b}};
   // production: the sum-factorised kernels on the static cell tables (variant 0 keeps the point-by-point kernel that
   // also serves the manufactured problems; it is the parity partner of the other two in tests/test_gpu_extra.py)
-  const int variant = (kind == PECS_KIND_PRODUCTION && a.d.nodal_int) ? carrier_rhs_variant() : 0;
+  int variant = (kind == PECS_KIND_PRODUCTION && a.d.nodal_int) ? carrier_rhs_variant() : 0;
+  if (variant >= 2 && variant < 11 && (a.p.srh || b.p.srh)) variant = 1; // the streaming kernel has no SRH instantiation
   const int btiles_a = blocks_for(a.d.n_bcells), btiles_b = blocks_for(b.d.n_bcells), btiles = btiles_a + btiles_b;
   if (variant == 1 || (variant >= 11 && variant <= 15)) {
     // 1: 128 threads, 4 blocks per SM (no spills).  11: compiled for 5 blocks per SM; 14 / 15: 64- / 32-thread blocks
@@ -681,10 +694,14 @@ void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, co
       const int ba = nb(a.d.n_cells), bb = nb(b.d.n_cells), ta = nb(a.d.n_bcells), tb = nb(b.d.n_bcells);
       kernel<<<ta + tb + ba + bb, threads, 0, s>>>(pp, ba, ta, ta + tb, X);
     };
-    if (variant == 1) launch(carrier_rhs_direct_kernel<4, 128>, 128);
-    if (variant == 11) launch(carrier_rhs_direct_kernel<5, 128>, 128);
-    if (variant == 14) launch(carrier_rhs_direct_kernel<8, 64>, 64);
-    if (variant == 15) launch(carrier_rhs_direct_kernel<16, 32>, 32);
+    if (a.p.srh || b.p.srh) { // Shockley-Read-Hall recombination on: the second instantiation, one launch shape
+      launch(carrier_rhs_direct_kernel<4, 128, true>, 128);
+      return;
+    }
+    if (variant == 1) launch(carrier_rhs_direct_kernel<4, 128, false>, 128);
+    if (variant == 11) launch(carrier_rhs_direct_kernel<5, 128, false>, 128);
+    if (variant == 14) launch(carrier_rhs_direct_kernel<8, 64, false>, 64);
+    if (variant == 15) launch(carrier_rhs_direct_kernel<16, 32, false>, 32);
     return;
   }
   if (variant >= 2) {

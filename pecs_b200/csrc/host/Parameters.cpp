@@ -36,6 +36,9 @@ const Entry kEntries[] = {
     {"physical", "illumination status", "false", "false"},
     {"physical", "insulated", "false", "false"},
     {"physical", "schottky status", "false", "false"},
+    // not a key of the reference (its SRH_Recombination returns 0.0, include/SolarCell.hpp:86-98): switches the
+    // Shockley-Read-Hall formula that function carries as a comment on
+    {"physical", "srh recombination", "false", "false"},
     {"physical", "characteristic length", "1.0e-4", "1.0"},
     {"physical", "characteristic density", "1.0e16", "1.0"},
     {"physical", "characteristic time", "1.0e-12", "1.0"},
@@ -186,6 +189,7 @@ void Parameters::parse_and_scale_parameters(ParameterHandler& prm) {
   illum_or_dark = prm.get_bool("illumination status");
   insulated = prm.get_bool("insulated");
   schottky_status = prm.get_bool("schottky status");
+  srh_recombination = prm.get_bool("srh recombination");
   scaled_applied_bias = prm.get_double("applied bias");
   scaled_built_in_bias = prm.get_double("built in bias");
   scaled_schottky_bias = prm.get_double("schottky bias");

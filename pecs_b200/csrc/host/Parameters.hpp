@@ -72,6 +72,7 @@ struct Parameters {
   double characteristic_length = 0, characteristic_time = 0, characteristic_denisty = 0;
   double scaled_domain_length = 0, scaled_domain_height = 0, scaled_radius_one = 0, scaled_radius_two = 0;
   bool illum_or_dark = false, insulated = false, restart_status = false, schottky_status = false;
+  bool srh_recombination = false; // extension: the reference's SRH_Recombination returns 0.0 (include/SolarCell.hpp:86-98)
   double scaled_applied_bias = 0, scaled_built_in_bias = 0, scaled_schottky_bias = 0;
   double rescale_current = 0, rescaled_k_et = 0, rescaled_k_ht = 0;
 

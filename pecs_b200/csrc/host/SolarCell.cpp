@@ -160,6 +160,10 @@ void SolarCellProblem::fill_params(double p[32]) const {
   // the reference never calls Schottky_Bias::set_location; the intended location is the top
   p[PECS_P_SCH_LOCATION] = sim_params.scaled_domain_height;
   p[PECS_P_TRANSIENT] = (kind == PECS_KIND_TEST_STEADY) ? 0.0 : 1.0;
+  p[PECS_P_SRH] = (kind == PECS_KIND_PRODUCTION && sim_params.srh_recombination) ? 1.0 : 0.0;
+  p[PECS_P_N_INTRINSIC] = sim_params.scaled_intrinsic_density;
+  p[PECS_P_TAU_N] = sim_params.scaled_electron_recombo_t;
+  p[PECS_P_TAU_P] = sim_params.scaled_hole_recombo_t;
 }
 
 // ------------------------------------------------------------------------------------------- setup pieces

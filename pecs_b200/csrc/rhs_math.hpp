@@ -25,6 +25,8 @@ struct RhsParams {
   double k_et, k_ht, v_n, v_p;
   double doping;       // N_D - N_A (semiconductor) or 0 (electrolyte)
   double time;         // manufactured right-hand sides
+  int srh;             // Shockley-Read-Hall recombination on (semiconductor only; 0 = the reference's function body)
+  double n_i, tau_n, tau_p;
 };
 
 // the scalars of subdomain w (0 semiconductor, 1 electrolyte) from the PECS_P_* parameter block of the problem
@@ -50,6 +52,10 @@ inline RhsParams make_rhs_params(const double* p, int kind, int w) {
   r.v_p = p[PECS_P_V_P];
   r.doping = w == 0 ? p[PECS_P_RHO_N_E] - p[PECS_P_RHO_P_E] : 0.0; // N_D = electrons_e, N_A = holes_e (SolarCell.cpp:542-548)
   r.time = 0.0;
+  r.srh = (w == 0 && kind == PECS_KIND_PRODUCTION && p[PECS_P_SRH] != 0.0) ? 1 : 0;
+  r.n_i = p[PECS_P_N_INTRINSIC];
+  r.tau_n = p[PECS_P_TAU_N];
+  r.tau_p = p[PECS_P_TAU_P];
   return r;
 }
 
@@ -85,6 +91,38 @@ PECS_HD void static_cell_integrals(const fe::CellVerts& v, bool with_generation,
         g[a] += N[a] * (gen * JxW);
       }
     }
+}
+
+// reference include/SolarCell.hpp:86-98, the formula the reference carries as a comment (its function returns 0.0)
+PECS_HD double srh_recombination(double electron_density, double hole_density, double n_i, double tau_n, double tau_p) {
+  return (n_i * n_i - electron_density * hole_density) / (tau_n * (electron_density - n_i) + tau_p * (hole_density - n_i));
+}
+// int N_a R(rho_n, rho_p) over one cell, added to the density rows of BOTH carriers (reference SolarCell.cpp:1160-1187).
+// R is not polynomial in the densities: it is evaluated point by point on the 3 x 3 Gauss rule (one division per
+// point); the production kernels call this only when the switch is on, out of line of the sum-factorised terms.
+PECS_HD void srh_cell_terms(const double vx[4], const double vy[4], const double r1[4], const double r2[4], double n_i,
+                            double tau_n, double tau_p, double rh1[4], double rh2[4]) {
+  fe::CellVerts v;
+  for (int a = 0; a < 4; ++a) {
+    v.x[a] = vx[a];
+    v.y[a] = vy[a];
+  }
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int qy = 0; qy < 3; ++qy)
+    for (int qx = 0; qx < 3; ++qx) {
+      const double xi = fe::gauss_x(qx), eta = fe::gauss_x(qy), w = fe::gauss_w(qx) * fe::gauss_w(qy);
+      const fe::Jac j = fe::jacobian(v, xi, eta);
+      double N[4];
+      fe::shape(xi, eta, N);
+      const double rho_n = N[0] * r1[0] + N[1] * r1[1] + N[2] * r1[2] + N[3] * r1[3];
+      const double rho_p = N[0] * r2[0] + N[1] * r2[1] + N[2] * r2[2] + N[3] * r2[3];
+      const double R = srh_recombination(rho_n, rho_p, n_i, tau_n, tau_p) * (j.det * w);
+      for (int a = 0; a < 4; ++a) acc[a] += N[a] * R;
+    }
+  for (int a = 0; a < 4; ++a) {
+    rh1[a] += acc[a];
+    rh2[a] += acc[a];
+  }
 }
 
 // Cell terms of both carriers of one production cell from values in registers, sum-factorised over the 3 x 3 tensor

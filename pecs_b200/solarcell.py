@@ -18,7 +18,7 @@ SEMICONDUCTOR_MESH, ELECTROLYTE_MESH, POISSON_MESH = 0, 1, 2
 # include/pecs_b200.h PECS_P_*
 PARAM_NAMES = ["delta_t", "penalty", "mu_n", "mu_p", "mu_r", "mu_o", "eps_s", "eps_e", "lambda2", "k_et", "k_ht",
                "v_n", "v_p", "gen_flux", "gen_alpha", "gen_location", "rho_n_e", "rho_p_e", "rho_r_e", "rho_o_e",
-               "phi_bi", "phi_app", "phi_sch", "sch_location", "transient"]
+               "phi_bi", "phi_app", "phi_sch", "sch_location", "transient", "srh", "n_intrinsic", "tau_n", "tau_p"]
 
 (INFO_LAUNCHES_PER_STEP, INFO_FACTOR_BYTES, INFO_SOLVE_BYTES_PER_STEP, INFO_TREE_LEVELS_MAX, INFO_RHS_BYTES_PER_STEP,
  INFO_HOST_STEP_H2D_BYTES, INFO_HOST_STEP_D2H_BYTES, INFO_SOLVE_WAIT_ERRORS, INFO_SHARED_FACTOR_PAIRS) = range(9)
@@ -47,7 +47,9 @@ def default_input_file(global_refinements=4, local_refinements=1, **overrides):
                      "characteristic time": "1.0e-12", "electrolyte permittivity": "1000",
                      "illumination status": "true", "insulated": "true", "intrinsic density": "2.564e9",
                      "photon flux": "1.2e17", "schottky bias": "0.0", "schottky status": "true",
-                     "semiconductor permittivity": "11.9"},
+                     "semiconductor permittivity": "11.9",
+                     # not in the reference's file (its SRH_Recombination returns 0.0): switches the formula on
+                     "srh recombination": "false"},
         "reductants": {"mobility": "1.0"},
     }
     for key, value in overrides.items():

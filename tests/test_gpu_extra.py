@@ -95,6 +95,9 @@ CASES = {
     # dark, no Schottky contact, not insulated with an applied bias: every boundary branch the default input skips
     "dark_biased": (2, 1, {"physical__illumination_status": False, "physical__schottky_status": False,
                            "physical__insulated": False, "physical__applied_bias": 0.2}),
+    # non-zero Shockley-Read-Hall recombination (the formula the reference carries as a comment), O(1) here
+    "srh_on": (3, 1, {"physical__srh_recombination": True, "physical__intrinsic_density": 0.5e16,
+                      "electrons__recombination_time": 2e-12, "holes__recombination_time": 1e-12}),
 }
 
 

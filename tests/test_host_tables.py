@@ -153,7 +153,11 @@ def test_ldg_matrices_do_not_depend_on_the_thread_count(tmp_path):
 @pytest.mark.parametrize("g,l,overrides", [
     (3, 1, {}), (3, 2, {"mesh__radius_one": 0.2}),
     (2, 1, {"physical__illumination_status": False, "physical__schottky_status": False, "physical__insulated": False,
-            "physical__applied_bias": 0.2})])
+            "physical__applied_bias": 0.2}),
+    # Shockley-Read-Hall recombination switched on (the formula the reference carries as a comment, SolarCell.hpp:86-98)
+    # with lifetimes and intrinsic density that make it an O(1) term of the right-hand side
+    (3, 1, {"physical__srh_recombination": True, "physical__intrinsic_density": 0.5e16,
+            "electrons__recombination_time": 2e-12, "holes__recombination_time": 1e-12})])
 def test_production_rhs_arithmetic_matches_oracle_on_cpu(g, l, overrides):
     """The arithmetic of the production RHS kernels -- csrc/rhs_math.hpp: static generation integrals, sum-factorised
     cell terms, static face geometry and the Dirichlet / interface / Schottky face terms, the very inline functions

@@ -39,7 +39,7 @@ def test_oracle_grid_equals_product_tables(g, l, overrides):
         for key in ("material_id", "level", "face_kind", "neighbor", "neighbor2", "boundary_id"):
             assert np.array_equal(mine[key], theirs[key]), (which, key)
         np.testing.assert_allclose(mine["nb_parent_diameter"], theirs["nb_parent_diameter"], rtol=1e-15, atol=0)
-    np.testing.assert_allclose(ogrid.scaled_parameters(to_prm(g, l, overrides))[:25], prob.params[:25], rtol=1e-15)
+    np.testing.assert_allclose(ogrid.scaled_parameters(to_prm(g, l, overrides))[:29], prob.params[:29], rtol=1e-15)
     prob.close()
 
 
