@@ -125,11 +125,20 @@ struct DeviceSystem {
       }
     }
   }
-  // panels per block tile: one per warp, more only when the level is so large that the tile count would explode
+  // Panels per block tile: one per warp at least; on the large levels as many as leave about `tile_target` tiles.
+  // Every tile pays a fixed prologue and epilogue (descriptor, first table chunk, counter polls, release: 2-3 us against
+  // 5-20 us of streaming), so FEWER, LARGER tiles win as long as the device stays full -- and with the levels of a chain
+  // and the solves of a step overlapping it does: measured at cfg3 (profiles/r02_tune_*.log), step time by target
+  // 2368 (round 1) 2.338 ms, 1184 2.290, 592 2.214, 444 2.189, 296 2.116, 148 2.135; a LONE solve (sharded step: one
+  // or two carriers per GPU) is best at 444 (0.705 ms against 0.751 at 296 and 0.964 at 148).
+  static int& tile_target() {
+    static int target = 296;
+    return target;
+  }
   static int panels_per_tile(int64_t level_panels, int warps) {
     const int forced = env_int("PECS_B200_SOLVE_PANELS_PER_TILE", 0);
     if (forced) return forced;
-    const int64_t want_tiles = env_int("PECS_B200_TILE_TARGET", 148 * 16);
+    const int64_t want_tiles = env_int("PECS_B200_TILE_TARGET", tile_target());
     return (int)std::min<int64_t>(64, std::max<int64_t>(warps, (level_panels + want_tiles - 1) / want_tiles));
   }
 
@@ -226,7 +235,7 @@ struct DeviceSystem {
             sw.vec_block = std::max(sw.vec_block, T.cols_pad);
           }
         }
-        sw.stages_warp = env_int("PECS_B200_SOLVE_STAGES_WARP", 4);
+        sw.stages_warp = env_int("PECS_B200_SOLVE_STAGES_WARP", 3); // 3 x 2 KB per warp: more warps resident than with 4
       }
     }
     // dependencies: forward = the two children; backward = the nearest ancestor that has backward tiles, the front's
@@ -954,6 +963,7 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     ctx->kind = desc->kind;
     ctx->full = desc->full_system != 0;
     ctx->owned = desc->owned_species ? (desc->owned_species & 0xF) : 0xF;
+    DeviceSystem::tile_target() = ctx->owned == 0xF ? 296 : 444; // a shard's solves run alone: see panels_per_tile
     std::memcpy(ctx->params, desc->params, sizeof(ctx->params));
     PECS_CUDA(cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking));
     for (int k = 0; k < 4; ++k) {

@@ -244,6 +244,11 @@ bool schur_reduction_enabled() {
 }
 
 int default_leaf_nodes(bool poisson) {
+  if (poisson)
+    if (const char* e = std::getenv("PECS_B200_POISSON_LEAF_NODES")) {
+      const int v = std::atoi(e);
+      if (v > 0) return v;
+    }
   if (const char* e = std::getenv("PECS_B200_LEAF_NODES")) {
     const int v = std::atoi(e);
     if (v > 0) return v;
