@@ -50,18 +50,6 @@ pecs_status pecs_solarcell_write_patches(pecs_solarcell* p, int32_t which, const
  * out = { int k_et (rho_n - rho_n^e) rho_o ds, int k_ht (rho_p - rho_p^e) rho_r ds }, from host state vectors
  * states[PECS_ELECTRONS..PECS_OXIDANTS] or, with states == NULL, from the current device state */
 pecs_status pecs_solarcell_interface_currents(pecs_solarcell* p, const double* const states[4], double out[2]);
-/* CPU check of the arithmetic the production RHS kernels run (pecs_b200/csrc/rhs_math.hpp is compiled into both the
- * kernels and this function): the carrier right-hand sides of subdomain `which` (0 / 1) from host states -- u1, u2 the
- * two carrier vectors of the subdomain, o1, o2 those of the other subdomain (interface traces; NULL: cell terms only, no
- * face terms), X the Poisson vector; rhs1 / rhs2 in the [Jx|Jy|rho] layout.  Test infrastructure: the product's per-step
- * path never calls it. */
-pecs_status pecs_solarcell_selftest_carrier_rhs(pecs_solarcell* p, int32_t which, const double* u1, const double* u2,
-                                                const double* o1, const double* o2, const double* X, double* rhs1,
-                                                double* rhs2);
-/* the same for the potential rows of the Poisson right-hand side (static int N_a table + charge row; rows of the Poisson
- * cells, phi_rows[n_poisson_cells]) and for the RT0 field at the patch vertices of the output path (field[4n][2]) */
-pecs_status pecs_solarcell_selftest_poisson_rows(pecs_solarcell* p, const double* const densities[4], double* phi_rows);
-pecs_status pecs_solarcell_selftest_field_patches(pecs_solarcell* p, const double* X, double scale, double* field);
 /* the four PostProcessor scales {potential, field, density, current} (reference source/PostProcessor.cpp:14-18) */
 pecs_status pecs_solarcell_output_scales(const pecs_solarcell* p, double scales[4]);
 /* test_steady_state / test_transient / test_DD_Poisson at one refinement level; errors[4] = {u, J, Phi, D} */
@@ -111,11 +99,6 @@ int32_t pecs_solarcell_plan_levels(pecs_solarcell* p, int32_t which, int32_t lea
 /* per-front listing of the same plan: out[8*f..8*f+7] = depth, np, nb, log2 of the forward / backward panel height,
  * forward / backward "one warp per front" flags, parent; returns the number of fronts (<= max_fronts written) */
 int64_t pecs_solarcell_plan_fronts(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, int32_t* out, int64_t max_fronts);
-/* Additionally runs the HOST numeric factorisation and the host reference of the two solve sweeps on rhs b, so
- * that the CPU test-suite can check plan + factor tables against the matrix (residual) without a GPU. */
-pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,
-                                                 double* x);
-
 #ifdef __cplusplus
 }
 #endif

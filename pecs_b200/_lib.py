@@ -74,10 +74,6 @@ SIGNATURES = {
     "pecs_solarcell_finish_output": (C.c_int, [VOIDP]),
     "pecs_solarcell_write_patches": (C.c_int, [VOIDP, C.c_int32, c_double_p, C.c_int32, C.c_char_p]),
     "pecs_solarcell_interface_currents": (C.c_int, [VOIDP, C.POINTER(c_double_p), c_double_p]),
-    "pecs_solarcell_selftest_carrier_rhs": (C.c_int, [VOIDP, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p,
-                                                     c_double_p, c_double_p, c_double_p]),
-    "pecs_solarcell_selftest_poisson_rows": (C.c_int, [VOIDP, C.POINTER(c_double_p), c_double_p]),
-    "pecs_solarcell_selftest_field_patches": (C.c_int, [VOIDP, c_double_p, C.c_double, c_double_p]),
     "pecs_solarcell_output_scales": (C.c_int, [VOIDP, c_double_p]),
     "pecs_solarcell_run_test": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p]),
     "pecs_solarcell_ctx": (VOIDP, [VOIDP]),
@@ -103,10 +99,34 @@ SIGNATURES = {
     "pecs_solarcell_plan_stats": (C.c_int, [VOIDP, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "pecs_solarcell_plan_levels": (C.c_int32, [VOIDP, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int32]),
     "pecs_solarcell_plan_fronts": (C.c_int64, [VOIDP, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int64]),
-    "pecs_solarcell_selftest_direct_solve": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p, c_double_p]),
 }
 
+# ---- include/pecs_b200_selftest.h: the TEST library (CPU checkers; not part of the product, loaded on demand) ----
+SELFTEST_SIGNATURES = {
+    "pecs_solarcell_selftest_carrier_rhs": (C.c_int, [VOIDP, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p,
+                                                     c_double_p, c_double_p, c_double_p]),
+    "pecs_solarcell_selftest_poisson_rows": (C.c_int, [VOIDP, C.POINTER(c_double_p), c_double_p]),
+    "pecs_solarcell_selftest_field_patches": (C.c_int, [VOIDP, c_double_p, C.c_double, c_double_p]),
+    "pecs_solarcell_selftest_direct_solve": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p, c_double_p]),
+}
+SELFTEST_LIB_PATH = os.path.join(_HERE, "lib", "libpecs_b200_selftest.so")
+
 _lib = None
+_selftest = None
+
+
+def load_selftest():
+    """libpecs_b200_selftest.so (tests only): CPU evaluation of the device formulas and of the setup tables"""
+    global _selftest
+    if _selftest is None:
+        load()
+        lib = C.CDLL(SELFTEST_LIB_PATH)
+        for name, (restype, argtypes) in SELFTEST_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _selftest = lib
+    return _selftest
 
 
 def load():
@@ -117,7 +137,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise OSError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(pecs_b200 has no Python/CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)  # the test library resolves the host classes against it
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = restype

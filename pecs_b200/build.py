@@ -33,8 +33,17 @@ def sources():
     return cpp, cu
 
 
+# TEST library (csrc/selftest): CPU checkers of the device formulas and the setup tables, linked AGAINST the product
+# library, never into it (include/pecs_b200_selftest.h)
+SELFTEST_LIB = os.path.join(HERE, "lib", "libpecs_b200_selftest.so")
+
+
+def selftest_sources():
+    return sorted(glob.glob(os.path.join(CSRC, "selftest", "*.cpp")))
+
+
 def headers():
-    pats = ["*.hpp", "*.cuh", "host/*.hpp", "cuda/*.cuh", "../../include/*.h"]
+    pats = ["*.hpp", "*.cuh", "host/*.hpp", "cuda/*.cuh", "selftest/*.hpp", "../../include/*.h"]
     return [h for p in pats for h in glob.glob(os.path.join(CSRC, p))]
 
 
@@ -84,6 +93,15 @@ def build(force=False, jobs=None, verbose=False, variant=None):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    if not variant:
+        tobjs = [compile_one(src, force, newest_header, OBJ)[0] for src in selftest_sources()]
+        if tobjs and (force or not os.path.exists(SELFTEST_LIB) or
+                      os.path.getmtime(SELFTEST_LIB) < max(os.path.getmtime(o) for o in tobjs + [LIB])):
+            cmd = [HOST_CXX, "-shared", "-fopenmp", "-o", SELFTEST_LIB] + tobjs + \
+                  ["-L" + os.path.dirname(LIB), "-lpecs_b200", "-Wl,-rpath,$ORIGIN"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

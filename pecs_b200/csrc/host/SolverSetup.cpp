@@ -256,48 +256,6 @@ int default_leaf_nodes(bool poisson) {
   return 16;
 }
 
-namespace {
-struct CarrierRef {
-  const MeshTables* mesh;
-  const CsrMatrix* A;
-};
-CarrierRef carrier_ref(SOLARCELL::SolarCellProblem& s, int which) {
-  if (which < 0 || which > 3) throw StatusError(PECS_ERR_INVALID, "system selector must be 0..4");
-  const bool semi = which <= 1;
-  const ChargeCarrierSpace::CarrierPair& pair = semi ? s.electron_hole_pair : s.redox_pair;
-  return {semi ? &s.semiconductor_triangulation.tables() : &s.electrolyte_triangulation.tables(),
-          (which % 2 == 0) ? &pair.carrier_1.system_matrix : &pair.carrier_2.system_matrix};
-}
-} // namespace
-
-void solve_system_host(SOLARCELL::SolarCellProblem& s, int which, int leaf_nodes, const double* b, double* x) {
-  std::vector<double> fwd, bwd;
-  if (which == PECS_POISSON || !schur_reduction_enabled()) {
-    const SolvePlan plan = plan_for_system(s, which, leaf_nodes);
-    const CsrMatrix& A = which == PECS_POISSON ? s.Poisson_object.system_matrix : *carrier_ref(s, which).A;
-    factorize_host(plan, A, fwd, bwd);
-    solve_host(plan, fwd, bwd, b, x);
-    return;
-  }
-  const CarrierRef ref = carrier_ref(s, which);
-  const int n = ref.mesh->n_cells, nq = 8 * n, nu = 4 * n;
-  SchurReduction R;
-  if (!build_schur_reduction(*ref.A, n, R)) throw StatusError(PECS_ERR_INTERNAL, "carrier (q,q) block couples cells");
-  pecs_domain_desc d{};
-  d.n_cells = n;
-  d.vertices = ref.mesh->vertices.data();
-  const NodeLayout L = carrier_density_nodes(d);
-  const SolvePlan plan = plan_from_layout(R.S, L, leaf_nodes > 0 ? leaf_nodes : default_leaf_nodes(false));
-  factorize_host(plan, R.S, fwd, bwd);
-  std::vector<double> t(nu), rt(nu), q1(nq), q2(nq);
-  R.T1.vmult(t.data(), b);                       // T1 r_q
-  for (int i = 0; i < nu; ++i) rt[i] = b[nq + i] - t[i];
-  solve_host(plan, fwd, bwd, rt.data(), x + nq); // u
-  R.Ainv.vmult(q1.data(), b);
-  R.T2.vmult(q2.data(), x + nq);
-  for (int i = 0; i < nq; ++i) x[i] = q1[i] - q2[i];
-}
-
 SolvePlan plan_for_system(SOLARCELL::SolarCellProblem& s, int which, int leaf_nodes) {
   if (which == PECS_POISSON) {
     pecs_poisson_desc d{};

@@ -48,8 +48,5 @@ int default_leaf_nodes(bool poisson);
 
 // convenience for the host classes / CPU tests: which = 0..3 species, 4 Poisson; leaf_nodes <= 0 -> default
 SolvePlan plan_for_system(SOLARCELL::SolarCellProblem& problem, int which, int leaf_nodes);
-// host reference of the complete solve of system `which` exactly as the device does it (Schur reduction for the
-// carriers unless disabled, nested-dissection tables, two sweeps): CPU verification of the setup tables only.
-void solve_system_host(SOLARCELL::SolarCellProblem& problem, int which, int leaf_nodes, const double* b, double* x);
 
 } // namespace pecs

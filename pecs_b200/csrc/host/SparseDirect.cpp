@@ -531,45 +531,4 @@ void factorize_host(const SolvePlan& plan, const CsrMatrix& A, std::vector<doubl
   }
 }
 
-void solve_host(const SolvePlan& plan, const std::vector<double>& fwd, const std::vector<double>& bwd, const double* b,
-                double* x) {
-  const int n = plan.n;
-  std::vector<double> w(n), xp(n), cbuf((size_t)std::max<int64_t>(plan.upd_entries, 1), 0.0);
-  for (int i = 0; i < n; ++i) w[plan.perm[i]] = b[i];
-  for (int d = (int)plan.levels.size() - 1; d >= 0; --d)
-    for (int f : plan.levels[d]) {
-      const Front& F = plan.fronts[f];
-      const int np = F.np, nb = F.nb;
-      // finalise the pivot right-hand side with what the children eliminated into it
-      for (int c = 0; c < 2; ++c)
-        if (F.cbuf_off[c] >= 0)
-          for (int l = 0; l < np; ++l) w[F.p0 + l] -= cbuf[(size_t)F.cbuf_off[c] + l];
-      if (F.parent < 0) continue;
-      const Front& P = plan.fronts[F.parent];
-      double* out = cbuf.data() + P.cbuf_off[F.which_child];
-      const int* omap = plan.out_map.data() + F.bd_off;
-      for (int i = 0; i < nb; ++i) {
-        double carry = 0.0;
-        for (int c = 0; c < 2; ++c)
-          if (F.cbuf_off[c] >= 0) carry += cbuf[(size_t)F.cbuf_off[c] + np + i];
-        double s = 0;
-        for (int j = 0; j < np; ++j) s += fwd[(size_t)F.fwd.index(i, j)] * w[F.p0 + j];
-        out[omap[i]] = carry + s;
-      }
-    }
-  for (size_t d = 0; d < plan.levels.size(); ++d)
-    for (int f : plan.levels[d]) {
-      const Front& F = plan.fronts[f];
-      const int np = F.np, nb = F.nb;
-      const int* bd = plan.bd(F);
-      for (int i = 0; i < np; ++i) {
-        double s = 0;
-        for (int j = 0; j < np; ++j) s += bwd[(size_t)F.bwd.index(i, j)] * w[F.p0 + j];
-        for (int j = 0; j < nb; ++j) s += bwd[(size_t)F.bwd.index(i, np + j)] * xp[bd[j]];
-        xp[F.p0 + i] = s;
-      }
-    }
-  for (int i = 0; i < n; ++i) x[i] = xp[plan.perm[i]];
-}
-
 } // namespace pecs

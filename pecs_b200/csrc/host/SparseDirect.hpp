@@ -127,8 +127,6 @@ CsrMatrix permute_csr(const CsrMatrix& A, const std::vector<int>& perm, bool tra
 // when a pivot block cannot be inverted.
 void factorize_host(const SolvePlan& plan, const CsrMatrix& A, std::vector<double>& fwd, std::vector<double>& bwd);
 
-// Host reference of the two solve sweeps (used by the CPU tests to validate plan + factor tables).
-void solve_host(const SolvePlan& plan, const std::vector<double>& fwd, const std::vector<double>& bwd, const double* b,
-                double* x);
+// (the host reference of the two solve sweeps lives in the test library, csrc/selftest/selftest.cpp)
 
 } // namespace pecs

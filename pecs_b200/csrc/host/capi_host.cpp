@@ -7,38 +7,14 @@
 
 #include "../../../include/pecs_b200_host.h"
 #include "../error.hpp"
-#include "../Assembly.hpp"
-#include "../rhs_math.hpp"
+#include "capi_internal.hpp"
 #include "SolarCell.hpp"
 #include "SolverSetup.hpp"
 
-struct pecs_solarcell {
-  ParameterSpace::ParameterHandler prm;
-  std::unique_ptr<SOLARCELL::SolarCellProblem> problem;
-};
-
 namespace {
 using SOLARCELL::SolarCellProblem;
-
-template <class F>
-pecs_status guarded(F&& f) {
-  try {
-    f();
-    return PECS_OK;
-  } catch (const pecs::StatusError& e) {
-    pecs::set_last_error(e.what());
-    return e.status;
-  } catch (const std::exception& e) {
-    pecs::set_last_error(e.what());
-    return PECS_ERR_INTERNAL;
-  }
-}
-const pecs::Triangulation& tria(const pecs_solarcell* p, int which) {
-  if (which == 0) return p->problem->semiconductor_triangulation;
-  if (which == 1) return p->problem->electrolyte_triangulation;
-  if (which == 2) return p->problem->Poisson_triangulation;
-  throw pecs::StatusError(PECS_ERR_INVALID, "mesh selector must be 0, 1 or 2");
-}
+using pecs::capi::guarded;
+using pecs::capi::tria;
 ChargeCarrierSpace::Carrier& carrier(const pecs_solarcell* p, int which) {
   SolarCellProblem& s = *p->problem;
   switch (which) {
@@ -124,120 +100,6 @@ pecs_status pecs_solarcell_interface_currents(pecs_solarcell* p, const double* c
   return guarded([&] {
     if (!out) throw pecs::StatusError(PECS_ERR_INVALID, "interface_currents: out is NULL");
     p->problem->interface_currents(states, out);
-  });
-}
-pecs_status pecs_solarcell_selftest_carrier_rhs(pecs_solarcell* p, int32_t which, const double* u1, const double* u2,
-                                                const double* o1, const double* o2, const double* X, double* rhs1,
-                                                double* rhs2) {
-  return guarded([&] {
-    if (which < 0 || which > 1 || !u1 || !u2 || !X || !rhs1 || !rhs2)
-      throw pecs::StatusError(PECS_ERR_INVALID, "selftest_carrier_rhs: bad argument");
-    SolarCellProblem& s = *p->problem;
-    const pecs::MeshTables& mesh = tria(p, which).tables();
-    const std::vector<int>& to_poisson = which == 0 ? s.s_2_p_map : s.e_2_p_map;
-    const std::vector<int>& face_dof = s.Poisson_object.dofs.face_dof;
-    double prm[32];
-    s.fill_params(prm);
-    const pecs::RhsParams rp = pecs::make_rhs_params(prm, PECS_KIND_PRODUCTION, which);
-    const size_t n = (size_t)mesh.n_cells;
-    const size_t n_other = (size_t)tria(p, 1 - which).tables().n_cells;
-    // interface neighbour of a cell of this subdomain (one interface face per cell at most)
-    std::vector<int> nb_cell(n, -1), nb_face(n, 0);
-    const std::vector<int>& mine_c = which == 0 ? s.semi_interface_cells : s.elec_interface_cells;
-    const std::vector<int>& other_c = which == 0 ? s.elec_interface_cells : s.semi_interface_cells;
-    const std::vector<int>& other_f = which == 0 ? s.elec_interface_faces : s.semi_interface_faces;
-    for (size_t k = 0; k < mine_c.size(); ++k) {
-      nb_cell[mine_c[k]] = other_c[k];
-      nb_face[mine_c[k]] = other_f[k];
-    }
-    // one AssemblyScratch / CopyData per cell, exactly what a device thread holds in registers (csrc/Assembly.hpp)
-    for (size_t c = 0; c < n; ++c) {
-      Assembly::AssemblyScratch scratch;
-      const double* vt = mesh.vtx((int)c);
-      for (int a = 0; a < 4; ++a) {
-        scratch.vertices.x[a] = vt[2 * a];
-        scratch.vertices.y[a] = vt[2 * a + 1];
-        scratch.carrier_1_density[a] = u1[8 * n + 4 * c + a];
-        scratch.carrier_2_density[a] = u2[8 * n + 4 * c + a];
-        scratch.Poisson_flux[a] = X[face_dof[4 * (size_t)to_poisson[c] + a]];
-        scratch.neighbor_carrier_1_density[a] = scratch.neighbor_carrier_2_density[a] = 0.0;
-      }
-      double m[4];
-      pecs::rhsmath::static_cell_integrals(scratch.vertices, rp.gen_scale != 0.0, rp.gen_scale, rp.gen_alpha, rp.gen_location, m,
-                                           scratch.generation_integrals);
-      // face terms exactly as cuda/rhs_kernels.cu boundary_record adds them (skipped when o1 / o2 are not given)
-      scratch.faces = pecs::rhsmath::BoundaryRecord{{-1, -1, -1, -1}, nb_cell[c], nb_face[c]};
-      bool boundary = false;
-      for (int f = 0; f < 4; ++f)
-        if (mesh.face_kind[4 * c + f] == pecs::FACE_BOUNDARY) {
-          scratch.faces.id[f] = mesh.boundary_id[4 * c + f];
-          boundary = true;
-        }
-      scratch.at_boundary = boundary && o1 && o2;
-      if (scratch.at_boundary) {
-        pecs::rhsmath::boundary_geometry(scratch.vertices, rp.tau, &scratch.face_geometry[0][0]);
-        if (scratch.faces.nb_cell >= 0)
-          for (int a = 0; a < 4; ++a) {
-            scratch.neighbor_carrier_1_density[a] = o1[8 * n_other + 4 * (size_t)scratch.faces.nb_cell + a];
-            scratch.neighbor_carrier_2_density[a] = o2[8 * n_other + 4 * (size_t)scratch.faces.nb_cell + a];
-          }
-      }
-      Assembly::DriftDiffusion::CopyData data;
-      Assembly::assemble_local_carrier_rhs(scratch, rp, data);
-      // the "copier": cell c owns rows 4c..4c+3 of every component block (reference SolarCell.cpp:999-1035)
-      for (int k = 0; k < 3; ++k)
-        for (int a = 0; a < 4; ++a) {
-          rhs1[4 * k * n + 4 * c + a] = data.local_carrier_1_rhs[4 * k + a];
-          rhs2[4 * k * n + 4 * c + a] = data.local_carrier_2_rhs[4 * k + a];
-        }
-    }
-  });
-}
-pecs_status pecs_solarcell_selftest_poisson_rows(pecs_solarcell* p, const double* const densities[4], double* phi_rows) {
-  return guarded([&] {
-    if (!densities || !phi_rows) throw pecs::StatusError(PECS_ERR_INVALID, "selftest_poisson_rows: bad argument");
-    SolarCellProblem& s = *p->problem;
-    double prm[32];
-    s.fill_params(prm);
-    for (int w = 0; w < (s.full_system ? 2 : 1); ++w) {
-      const pecs::MeshTables& mesh = tria(p, w).tables();
-      const std::vector<int>& to_poisson = w == 0 ? s.s_2_p_map : s.e_2_p_map;
-      const pecs::RhsParams rp = pecs::make_rhs_params(prm, PECS_KIND_PRODUCTION, w);
-      const size_t n = (size_t)mesh.n_cells;
-      const double *u1 = densities[2 * w], *u2 = densities[2 * w + 1];
-      if (!u1 || !u2) throw pecs::StatusError(PECS_ERR_INVALID, "selftest_poisson_rows: missing carrier vector");
-      for (size_t c = 0; c < n; ++c) {
-        pecs::fe::CellVerts v;
-        const double* vt = mesh.vtx((int)c);
-        for (int a = 0; a < 4; ++a) {
-          v.x[a] = vt[2 * a];
-          v.y[a] = vt[2 * a + 1];
-        }
-        double m[4], g[4];
-        pecs::rhsmath::static_cell_integrals(v, false, 0.0, 0.0, 0.0, m, g);
-        phi_rows[to_poisson[c]] = pecs::rhsmath::poisson_charge_row(rp, m, u1 + 8 * n + 4 * c, u2 + 8 * n + 4 * c);
-      }
-    }
-  });
-}
-pecs_status pecs_solarcell_selftest_field_patches(pecs_solarcell* p, const double* X, double scale, double* field) {
-  return guarded([&] {
-    if (!X || !field) throw pecs::StatusError(PECS_ERR_INVALID, "selftest_field_patches: bad argument");
-    SolarCellProblem& s = *p->problem;
-    const pecs::MeshTables& mesh = s.Poisson_triangulation.tables();
-    const std::vector<int>& face_dof = s.Poisson_object.dofs.face_dof;
-    for (size_t c = 0; c < (size_t)mesh.n_cells; ++c) {
-      pecs::fe::CellVerts v;
-      const double* vt = mesh.vtx((int)c);
-      double Xf[4];
-      for (int a = 0; a < 4; ++a) {
-        v.x[a] = vt[2 * a];
-        v.y[a] = vt[2 * a + 1];
-        Xf[a] = X[face_dof[4 * c + a]];
-      }
-      for (int a = 0; a < 4; ++a)
-        pecs::rhsmath::rt0_field_at_vertex(v, Xf, a, scale, field[2 * (4 * c + a)], field[2 * (4 * c + a) + 1]);
-    }
   });
 }
 pecs_status pecs_solarcell_output_scales(const pecs_solarcell* p, double scales[4]) {
@@ -435,11 +297,4 @@ int64_t pecs_solarcell_plan_fronts(pecs_solarcell* p, int32_t which, int32_t lea
     return -1;
   }
 }
-pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,
-                                                 double* x) {
-  return guarded([&] {
-    pecs::solve_system_host(*p->problem, which, leaf_nodes, b, x);
-  });
-}
-
 } // extern "C"

@@ -180,7 +180,7 @@ class SolarCellProblem:
         if o1 is not None:
             o1, o2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (o1, o2))
         r1, r2 = np.zeros_like(u1), np.zeros_like(u2)
-        check(self._lib.pecs_solarcell_selftest_carrier_rhs(
+        check(_lib.load_selftest().pecs_solarcell_selftest_carrier_rhs(
             self._h, which, _dp(u1), _dp(u2), _dp(o1) if o1 is not None else None, _dp(o2) if o2 is not None else None,
             _dp(X), _dp(r1), _dp(r2)))
         return r1, r2
@@ -190,14 +190,14 @@ class SolarCellProblem:
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in densities]
         ptrs = (_lib.c_double_p * 4)(*[_dp(a) for a in arrs])
         out = np.zeros(self.n_cells(POISSON_MESH))
-        check(self._lib.pecs_solarcell_selftest_poisson_rows(self._h, ptrs, _dp(out)))
+        check(_lib.load_selftest().pecs_solarcell_selftest_poisson_rows(self._h, ptrs, _dp(out)))
         return out
 
     def selftest_field_patches(self, X, scale):
         """CPU evaluation of the RT0 field at the patch vertices as the output kernel computes it -> [4n, 2]"""
         X = np.ascontiguousarray(X, dtype=np.float64)
         out = np.zeros((4 * self.n_cells(POISSON_MESH), 2))
-        check(self._lib.pecs_solarcell_selftest_field_patches(self._h, _dp(X), float(scale), _dp(out)))
+        check(_lib.load_selftest().pecs_solarcell_selftest_field_patches(self._h, _dp(X), float(scale), _dp(out)))
         return out
 
     def run_test(self, kind, n_refine):
@@ -429,7 +429,7 @@ class SolarCellProblem:
     def selftest_direct_solve(self, which, b, leaf_nodes=0):
         b = np.ascontiguousarray(b, np.float64)
         x = np.zeros_like(b)
-        check(self._lib.pecs_solarcell_selftest_direct_solve(self._h, which, leaf_nodes, _dp(b), _dp(x)))
+        check(_lib.load_selftest().pecs_solarcell_selftest_direct_solve(self._h, which, leaf_nodes, _dp(b), _dp(x)))
         return x
 
     # ---- post-processing ----

@@ -13,9 +13,9 @@ from pecs_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
+def _declared_symbols(headers=("pecs_b200.h", "pecs_b200_host.h")):
     names = set()
-    for header in ("pecs_b200.h", "pecs_b200_host.h"):
+    for header in headers:
         text = open(os.path.join(ROOT, "include", header)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names |= set(re.findall(r"\b(pecs_[a-z0-9_]+)\s*\(", text))
@@ -29,6 +29,19 @@ def test_every_declared_symbol_is_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     assert declared == set(_lib.SIGNATURES), "python binding and headers disagree"
+
+
+def test_cpu_checkers_live_in_the_test_library_only():
+    """the CPU evaluation of the device formulas and the host reference of the solve sweeps are test
+    infrastructure -- exported by libpecs_b200_selftest.so (include/pecs_b200_selftest.h), absent from the product"""
+    product = open(_lib.LIB_PATH, "rb").read()
+    declared = _declared_symbols(("pecs_b200_selftest.h",))
+    assert declared == set(_lib.SELFTEST_SIGNATURES) and len(declared) == 4
+    test_lib = _lib.load_selftest()
+    for name in declared:
+        assert hasattr(test_lib, name)
+        assert name.encode() not in product, f"{name} is still in the product library"
+    assert b"solve_host" not in product and b"solve_system_host" not in product
 
 
 def test_oracle_is_not_linked_into_the_product():
