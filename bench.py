@@ -26,21 +26,38 @@ METRIC = "IMEX steps/sec at ~1M DoF/carrier"
 UNIT = "steps/s"
 
 
+def source_sha16(files):
+    import hashlib
+    h = hashlib.sha256()
+    for rel in files:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic():
-    """DRAM bytes per step of the solve kernels from the committed ncu pass (profiles/r01_solve_traffic.json), or None"""
-    path = os.path.join(ROOT, "profiles", "r01_solve_traffic.json")
+    """DRAM bytes per step of the solve kernels from the committed ncu pass (profiles/r02_solve_traffic.json, written by
+    scripts/summarize_launches.py) -- or None when that pass was taken from OTHER kernel sources than the ones in the
+    tree (the file carries their hash): a stale figure is not reported."""
+    path = os.path.join(ROOT, "profiles", "r02_solve_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get("dram_bytes_per_step")
+            d = json.load(f)
+        if d.get("kernel_source_sha16") == source_sha16(["pecs_b200/csrc/cuda/solve_kernels.cu",
+                                                          "pecs_b200/csrc/cuda/solve_kernels.cuh",
+                                                          "pecs_b200/csrc/cuda/schur_kernels.cu"]):
+            return d.get("dram_bytes_per_step")
     return None
 
 
 def measured_rhs_traffic():
-    """DRAM bytes of one launch of the carrier RHS kernel from the committed ncu capture, or None"""
-    path = os.path.join(ROOT, "profiles", "r01_rhs_traffic.json")
+    """DRAM bytes of one launch of the carrier RHS kernel from the committed ncu capture, or None (same hash rule)"""
+    path = os.path.join(ROOT, "profiles", "r02_rhs_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            d = json.load(f)
+        if d.get("kernel_source_sha16") == source_sha16(["pecs_b200/csrc/cuda/rhs_kernels.cu", "pecs_b200/csrc/rhs_math.hpp"]):
+            return d.get("dram_bytes_per_launch")
     return None
 
 

@@ -23,6 +23,9 @@ def init_distributed(backend=None):
         return rank, local, world, None
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    # rank 0 prints ONE JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION, set on some boxes) goes to stdout
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if not dist.is_initialized():
         dist.init_process_group(backend=backend or "nccl", rank=rank, world_size=world)
     return rank, local, world, dist

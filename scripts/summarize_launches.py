@@ -56,7 +56,21 @@ for k, t in table.items():
     print(f"  {k:34s} {t['launches']:4d} launches {t['us']:10.1f} us {100 * t['us'] / total_us:5.1f} %  "
           f"{t['dram'] / 1e6:10.1f} MB DRAM")
 solve = {k: t for k, t in table.items() if re.search(r"level_kernel|ell_|gather", k)}
-out = {"dram_bytes_per_step": sum(t["dram"] for t in solve.values()),
+import hashlib  # noqa: E402
+import os  # noqa: E402
+
+
+def kernel_source_hash():
+    """sha256 of the sources of the solve kernels: bench.py refuses a traffic file taken from other kernels"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha256()
+    for rel in ("pecs_b200/csrc/cuda/solve_kernels.cu", "pecs_b200/csrc/cuda/solve_kernels.cuh", "pecs_b200/csrc/cuda/schur_kernels.cu"):
+        h.update(open(os.path.join(root, rel), "rb").read())
+    return h.hexdigest()[:16]
+
+
+out = {"kernel_source_sha16": kernel_source_hash(),
+       "dram_bytes_per_step": sum(t["dram"] for t in solve.values()),
        "launches": sum(t["launches"] for t in solve.values()),
        "sum_isolated_durations_ms": sum(t["us"] for t in solve.values()) / 1e3,
        "share_of_step_isolated": sum(t["us"] for t in solve.values()) / total_us,
