@@ -23,11 +23,23 @@ def init_distributed(backend=None):
         return rank, local, world, None
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    # rank 0 prints ONE JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION, set on some boxes) goes to stdout
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     if not dist.is_initialized():
         dist.init_process_group(backend=backend or "nccl", rank=rank, world_size=world)
+        if (backend or "nccl") == "nccl":
+            # rank 0 prints ONE JSON line on stdout: NCCL writes its "NCCL version ..." banner there when the first
+            # communicator is created (NCCL_DEBUG=VERSION / WARN on some boxes), so create it now with fd 1 parked on fd 2
+            import sys
+            import torch
+            sys.stdout.flush()
+            saved = os.dup(1)
+            try:
+                os.dup2(2, 1)
+                torch.cuda.set_device(local)
+                dist.barrier(device_ids=[local])
+                torch.cuda.synchronize()
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
     return rank, local, world, dist
 
 
