@@ -88,7 +88,11 @@ struct DeviceSystem {
   }
   // warps per thread block.  Measured (scripts/tune_solve.py, cfg3): 4 warps beat 8 -- smaller blocks, more of them
   // resident, finer tiles
-  static int solve_warps() { return std::min(kSolveWarps, env_int("PECS_B200_SOLVE_WARPS", kWarpsPerFront)); }
+  static int solve_warps() {
+    return std::min(kSolveWarps, env_int("PECS_B200_WARP_TILE_WARPS", env_int("PECS_B200_SOLVE_WARPS", kWarpsPerFront)));
+  }
+  // one-warp tiles a warp works off one after the other (the launch then has 1 / loop of the blocks)
+  static int warp_tile_loop() { return env_int("PECS_B200_WARP_TILE_LOOP", 1); }
   // Shape of the block-tile launch of one level: warps per block and ring depth.  What counts is the number of bytes
   // in flight per SM (ncu: a bulk copy takes 2-4 us under load, so ~44 GB/s per SM needs > 128 KB in flight) and that at
   // least two blocks are resident (one stages its vector while the other streams).  Levels with small vectors reach
@@ -130,15 +134,22 @@ struct DeviceSystem {
   // 5-20 us of streaming), so FEWER, LARGER tiles win as long as the device stays full -- and with the levels of a chain
   // and the solves of a step overlapping it does: measured at cfg3 (profiles/r02_tune_*.log), step time by target
   // 2368 (round 1) 2.338 ms, 1184 2.290, 592 2.214, 444 2.189, 296 2.116, 148 2.135; a LONE solve (sharded step: one
-  // or two carriers per GPU) is best at 444 (0.705 ms against 0.751 at 296 and 0.964 at 148).
-  static int& tile_target() {
-    static int target = 296;
-    return target;
-  }
-  static int panels_per_tile(int64_t level_panels, int warps) {
+  // or two carriers per GPU) is best at 444 (0.705 ms against 0.751 at 296 and 0.964 at 148): ShapePolicy below.
+  // How the levels of THIS system are cut into thread blocks (set before build(); the PECS_B200_* switches override).
+  // Defaults = a system that runs next to other solves of a step; a shard's carrier solves run ALONE on their GPU and
+  // want finer large levels and fatter blocks on the sparse ones (shard_policy()).
+  struct ShapePolicy {
+    int tile_target = 296;          // tiles per large level
+    int sparse_warps = 8;           // SPARSE levels (see build()): warps per block, one panel each ...
+    int sparse_stages = 4;          // ... ring depth
+    int sparse_panels = 148 * 32;   // a level is sparse if it has at most this many panels ...
+    int sparse_panel_doubles = 2048; // ... of at most this size on average
+  } policy;
+  static ShapePolicy shard_policy() { return ShapePolicy{444, 16, 2, 148 * 64, 8192}; }
+  int panels_per_tile(int64_t level_panels, int warps) const {
     const int forced = env_int("PECS_B200_SOLVE_PANELS_PER_TILE", 0);
     if (forced) return forced;
-    const int64_t want_tiles = env_int("PECS_B200_TILE_TARGET", tile_target());
+    const int64_t want_tiles = env_int("PECS_B200_TILE_TARGET", policy.tile_target);
     return (int)std::min<int64_t>(64, std::max<int64_t>(warps, (level_panels + want_tiles - 1) / want_tiles));
   }
 
@@ -196,7 +207,30 @@ struct DeviceSystem {
           }
         }
         pick_shape(vec_block, n_rhs, sw.warps, sw.stages, sw.chunk);
-        const int ppt = panels_per_tile(panels, sw.warps);
+        int64_t level_doubles = 0;
+        for (int f : plan.levels[d]) {
+          const PanelTable& T = which == 0 ? plan.fronts[f].fwd : plan.fronts[f].bwd;
+          if (!T.small && T.n_panels() > 0) level_doubles += T.size();
+        }
+        int ppt = panels_per_tile(panels, sw.warps);
+        // SPARSE levels -- few bytes in many small panels (the Poisson tree: 13-18 MB per level in 2 500-3 700 panels of
+        // 5 KB; the lower carrier levels): all panels of the level fit on the device at once, ONE per warp, so the level
+        // costs one panel's latency instead of a tile's worth of them.  Fat blocks (many warps share the staged vector),
+        // every warp exactly one panel.
+        // *Measured* at cfg3 (profiles/r02_tune_j.log, _k.log): 8 warps x 4 stages: Poisson solve 0.298 -> 0.269 ms, step
+        // 2.112 -> 2.084 ms; 16 warps x 2 stages on levels up to 64 KB panels: a LONE carrier solve 0.755 -> 0.669 ms
+        // (but the step 2.195 ms: fat blocks of three concurrent solves get in each other's way).
+        const char* off = std::getenv("PECS_B200_SPARSE_WARPS");
+        const int sparse_warps = off ? std::atoi(off) : policy.sparse_warps; // PECS_B200_SPARSE_WARPS=0 switches it off
+        if (sparse_warps > 0 && panels > 0 && panels <= (int64_t)env_int("PECS_B200_SPARSE_PANELS", policy.sparse_panels) &&
+            level_doubles / std::max<int64_t>(panels, 1) <= env_int("PECS_B200_SPARSE_PANEL_DOUBLES", policy.sparse_panel_doubles)) {
+          const int st = env_int("PECS_B200_SPARSE_STAGES", policy.sparse_stages);
+          if (solve_smem_bytes(vec_block, false, sparse_warps, st, n_rhs) + 1024 <= 227 * 1024) {
+            sw.warps = std::min(sparse_warps, kSolveWarps);
+            sw.stages = st;
+            ppt = sw.warps;
+          }
+        }
         for (int f : plan.levels[d]) {
           const Front& F = plan.fronts[f];
           const PanelTable& T = which == 0 ? F.fwd : F.bwd;
@@ -275,6 +309,7 @@ struct DeviceSystem {
         if (out.bt.size() <= 148 * 4 && !env_int("PECS_B200_SOLVE_STAGES", 0)) sw.stages = std::max(sw.stages, 4);
         sw.grid_block = level_grid(which == 0, false, n_rhs, (int)out.bt.size(), sw.vec_block, sw.warps, sw.stages);
         sw.grid_warp = level_grid(which == 0, true, n_rhs, (int)out.wt.size(), sw.vec_warp, solve_warps(), sw.stages_warp);
+        if (warp_tile_loop() > 1) sw.grid_warp = std::max(1, (sw.grid_warp + warp_tile_loop() - 1) / warp_tile_loop());
         launches_per_solve += (out.bt.empty() ? 0 : 1) + (out.wt.empty() ? 0 : 1);
       }
     done.resize(2 * (size_t)n_fronts + 1);
@@ -363,8 +398,10 @@ struct DeviceSystem {
     launch_ell_combine(n, rhs, iperm.get(), EllTerm{&matrix_rows, solution, -1.0}, EllTerm{}, EllTerm{}, w_in.get(), s);
   }
   // solution = A^-1 rhs in increment form (one right-hand side; mirrors of this system apply)
-  void solve(const double* rhs, double* solution, cudaStream_t s) {
-    reset_counters(s);
+  // reset = false: the caller has zeroed the counters earlier on this stream (the step does it while the carrier solves
+  // run, so the memset is off the critical path in front of the Poisson solve)
+  void solve(const double* rhs, double* solution, cudaStream_t s, bool reset = true) {
+    if (reset) reset_counters(s);
     residual(rhs, solution, s);
     SolveVectors io = vectors(w_in.get(), 0, 1, &solution);
     io.n_mirror[0] = n_mirror;
@@ -704,13 +741,13 @@ void enqueue_carrier_rhs(pecs_ctx* ctx, int which, cudaStream_t s) {
     launch_carrier_rhs(carrier_pass(ctx, which == 2 ? 0 : which), none, ctx->kind, ctx->p_solution.get(), s);
 }
 void enqueue_poisson_rhs(pecs_ctx* ctx, cudaStream_t s) {
-  // flux rows: the static Dirichlet data; potential rows: the charge integrals of both subdomains, one launch
-  PECS_CUDA(cudaMemcpyAsync(ctx->p_rhs.get(), ctx->p_static.get(), ctx->p_rhs.bytes(), cudaMemcpyDeviceToDevice, s));
+  // flux rows: the static Dirichlet data; potential rows: the charge integrals of both subdomains -- ONE launch
   const CarrierPass none{};
-  launch_poisson_cell_rhs(carrier_pass(ctx, 0), ctx->full ? carrier_pass(ctx, 1) : none, ctx->kind, ctx->p_rhs.get(), s);
+  launch_poisson_cell_rhs(carrier_pass(ctx, 0), ctx->full ? carrier_pass(ctx, 1) : none, ctx->kind, ctx->p_static.get(),
+                          ctx->n_rt, ctx->p_rhs.get(), s);
 }
-void enqueue_poisson_solve(pecs_ctx* ctx, cudaStream_t s) {
-  ctx->p_system.solve(ctx->p_rhs.get(), ctx->p_solution.get(), s);
+void enqueue_poisson_solve(pecs_ctx* ctx, cudaStream_t s, bool reset_counters = true) {
+  ctx->p_system.solve(ctx->p_rhs.get(), ctx->p_solution.get(), s, reset_counters);
   launch_distribute(ctx->n_constraints, ctx->c_dof.get(), ctx->c_master.get(), ctx->c_weight.get(),
                     ctx->p_solution.get(), s);
 }
@@ -848,6 +885,9 @@ int deferred_currents_mode() {
 }
 bool deferred_currents_enabled() { return deferred_currents_mode() != 0; }
 void enqueue_step(pecs_ctx* ctx, double* const* host = nullptr) {
+  // the Poisson solve's completion counters: zeroed first thing, long before that solve (which is alone on the critical
+  // path at the end of the step) needs them
+  ctx->p_system.reset_counters(ctx->main);
   enqueue_carrier_rhs(ctx, 2, ctx->main);
   int n_copies = 0;
   // the recovery of the LDG currents (outputs only) overlaps the Poisson part; not in the sharded step, whose
@@ -855,7 +895,7 @@ void enqueue_step(pecs_ctx* ctx, double* const* host = nullptr) {
   const bool defer = !ctx->p2p.active && deferred_currents_enabled();
   enqueue_full_solve(ctx, host, &n_copies, defer);
   enqueue_poisson_rhs(ctx, ctx->main);
-  enqueue_poisson_solve(ctx, ctx->main);
+  enqueue_poisson_solve(ctx, ctx->main, false);
   if (defer) {
     const int n_species = ctx->full ? 4 : (ctx->kind == PECS_KIND_PRODUCTION ? 2 : 1);
     for (int k = 0; k < n_species; ++k)
@@ -963,7 +1003,9 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     ctx->kind = desc->kind;
     ctx->full = desc->full_system != 0;
     ctx->owned = desc->owned_species ? (desc->owned_species & 0xF) : 0xF;
-    DeviceSystem::tile_target() = ctx->owned == 0xF ? 296 : 444; // a shard's solves run alone: see panels_per_tile
+    if (ctx->owned != 0xF) // a shard's carrier solves run alone on their GPU (the Poisson system keeps the default)
+      for (DeviceDomain& D : ctx->dom)
+        for (DeviceSystem& S : D.system) S.policy = DeviceSystem::shard_policy();
     std::memcpy(ctx->params, desc->params, sizeof(ctx->params));
     PECS_CUDA(cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking));
     for (int k = 0; k < 4; ++k) {

@@ -545,7 +545,13 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 // ------------------------------------------------------------------------------------------ Poisson cells
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) poisson_cell_rhs_kernel(const __grid_constant__ CarrierPassPair pp, int blocks_a,
+                                                                    const double* __restrict__ static_rows, int n_static,
                                                                     double* __restrict__ poisson_rhs) {
+  // the flux rows are time independent (Dirichlet / Schottky face data, evaluated once: poisson_face_rhs_kernel); the
+  // reference zeroes and re-assembles the whole vector every step, so they are re-written here, by the same launch
+  // (round 1 spent a separate device-to-device copy node on them, on the critical path between the carrier solves and
+  // the Poisson solve)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_static; i += gridDim.x * blockDim.x) poisson_rhs[i] = static_rows[i];
   const bool first = (int)blockIdx.x < blocks_a;
   const CarrierPass& w = pp.pass[first ? 0 : 1];
   const DomainView& d = w.d;
@@ -728,11 +734,13 @@ void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, co
 #undef CALL
 }
 
-void launch_poisson_cell_rhs(const CarrierPass& a, const CarrierPass& b, int kind, double* poisson_rhs, cudaStream_t s) {
+void launch_poisson_cell_rhs(const CarrierPass& a, const CarrierPass& b, int kind, const double* static_rows, int n_static,
+                             double* poisson_rhs, cudaStream_t s) {
   const int blocks_a = blocks_for(a.d.n_cells), blocks_b = blocks_for(b.d.n_cells);
   if (blocks_a + blocks_b == 0) return;
   const CarrierPassPair pp{{a, b}};
-#define CALL(K) poisson_cell_rhs_kernel<K><<<blocks_a + blocks_b, kThreads, 0, s>>>(pp, blocks_a, poisson_rhs)
+#define CALL(K) \
+  poisson_cell_rhs_kernel<K><<<blocks_a + blocks_b, kThreads, 0, s>>>(pp, blocks_a, static_rows, n_static, poisson_rhs)
   PECS_DISPATCH_KIND(kind, CALL)
 #undef CALL
 }

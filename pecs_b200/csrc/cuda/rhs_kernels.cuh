@@ -52,7 +52,8 @@ int carrier_rhs_variant();
 // (SURVEY K1-K3); X = Poisson solution (electric field)
 void launch_carrier_rhs(const CarrierPass& a, const CarrierPass& b, int kind, const double* X, cudaStream_t s);
 // potential rows of the Poisson rhs: -int (doping + z1 rho1 + z2 rho2) per matched cell, both passes, one launch
-void launch_poisson_cell_rhs(const CarrierPass& a, const CarrierPass& b, int kind, double* poisson_rhs, cudaStream_t s);
+void launch_poisson_cell_rhs(const CarrierPass& a, const CarrierPass& b, int kind, const double* static_rows, int n_static,
+                             double* poisson_rhs, cudaStream_t s);
 
 // Poisson boundary faces: time-independent, evaluated once into a static vector
 struct PoissonFaceView {

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call H: the state to be judged -- full GPU suite, the default bench line, ncu launch list + full captures
-tag=${1:-r02h}
+tag=${1:-r02l}
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -x -q --durations=8 -s > gpurun_out/pytest_$tag.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_$tag.log
@@ -25,7 +25,7 @@ ncu -i gpurun_out/rhs_$tag.ncu-rep --page raw --csv > gpurun_out/rhs_${tag}_raw.
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:level_kernel --launch-skip 160 -c 60 -o gpurun_out/levels_$tag -f \
   python scripts/profile_step.py --steps 2 > gpurun_out/ncu_levels_$tag.log 2>&1
 ncu -i gpurun_out/levels_$tag.ncu-rep --page raw --csv > gpurun_out/levels_${tag}_raw.csv 2>/dev/null
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:level_kernel|ell_combine|distribute|poisson_cell' --launch-skip 400 -c 45 -o gpurun_out/poisson_$tag -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:level_kernel|ell_combine|distribute|poisson_cell' --launch-skip 290 -c 45 -o gpurun_out/poisson_$tag -f \
   python scripts/profile_step.py --steps 2 > gpurun_out/ncu_poisson_$tag.log 2>&1
 ncu -i gpurun_out/poisson_$tag.ncu-rep --page raw --csv > gpurun_out/poisson_${tag}_raw.csv 2>/dev/null
 rm -f gpurun_out/*_$tag.ncu-rep
