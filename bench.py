@@ -264,6 +264,7 @@ def run_gpu_arm(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     device = local
+    pinned_cores = None
     if dist is not None:
         import torch
         torch.cuda.set_device(device)
@@ -292,6 +293,8 @@ def run_gpu_arm(args):
     value = world * K / (ms_max * 1e-3)
 
     # ---- end to end through the host-buffer entry point: H2D of the five states, one step, D2H of the five states
+    if dist is not None:  # N > 1: every rank on cores of its GPU's NUMA node (after the multi-threaded setup, before the
+        pinned_cores = sweep.pin_to_gpu_numa_node(local, world)  # page-locked buffers are allocated and first touched)
     states = prob.pinned_states()
     for w in range(5):
         states[w][:] = prob.get_solution(w)
@@ -362,7 +365,8 @@ def run_gpu_arm(args):
                        if world > 1 else "single context",
                        "l2": "inputs larger than L2: every step streams the factor tables "
                              f"({factor_bytes / 1e9:.1f} GB) once; the isolated RHS timing flushes L2 (256 MB memset + 256 MB read sweep, so evictions are clean)",
-                       "setup_seconds": t_setup},
+                       "setup_seconds": t_setup,
+                       "host_cores_of_rank_0": (f"{pinned_cores[0]}-{pinned_cores[-1]}" if pinned_cores else "not pinned")},
             "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes,
                     "what": "pecs_step_host on pinned host states: upload of what a step reads (4 density blocks + "

@@ -223,6 +223,13 @@ int64_t pecs_output_doubles(const pecs_ctx* ctx, int32_t which);
 pecs_status pecs_output_snapshot(pecs_ctx* ctx, const double scales[4], double* const host[3]);
 pecs_status pecs_output_wait(pecs_ctx* ctx);
 
+/* I-V post-processing on the device: the two charge-transfer currents through the
+ * semiconductor-electrolyte interface in scaled units, integrals of the step's interface terms (reference
+ * source/SolarCell.cpp:1265-1347) over the current device state:
+ *   out = { int k_et (rho_n - rho_n^e) rho_o ds,  int k_ht (rho_p - rho_p^e) rho_r ds }.
+ * One small kernel over the interface cells + an ordered sum of the per-cell values; synchronises the context. */
+pecs_status pecs_interface_currents(pecs_ctx* ctx, double out[2]);
+
 /* measurement support for bench.py: run n_steps and report device times measured with CUDA events on the
  * context's own streams.  ms[0] = whole region.  sectioned == 0: n_steps replays of the step graph; sectioned == 1:
  * ms[1..5] = the reference's five TimerOutput sections summed over the steps, launched one by one

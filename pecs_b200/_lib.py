@@ -57,6 +57,7 @@ SIGNATURES = {
     "pecs_output_doubles": (C.c_int64, [VOIDP, C.c_int32]),
     "pecs_output_snapshot": (C.c_int, [VOIDP, c_double_p, C.POINTER(c_double_p)]),
     "pecs_output_wait": (C.c_int, [VOIDP]),
+    "pecs_interface_currents": (C.c_int, [VOIDP, c_double_p]),
     "pecs_step_timed": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p]),
     "pecs_time_kernel": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p, c_int32_p]),
     "pecs_get_info": (C.c_int64, [VOIDP, C.c_int32]),

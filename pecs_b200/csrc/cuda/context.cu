@@ -1474,6 +1474,28 @@ pecs_status pecs_output_snapshot(pecs_ctx* ctx, const double scales[4], double* 
   });
 }
 
+pecs_status pecs_interface_currents(pecs_ctx* ctx, double out[2]) {
+  return guarded([&] {
+    require(ctx != nullptr && out != nullptr, "pecs_interface_currents: NULL argument");
+    require(ctx->full && ctx->kind == PECS_KIND_PRODUCTION, "pecs_interface_currents: needs the full production system");
+    PECS_CUDA(cudaSetDevice(ctx->device));
+    sync_all(ctx);
+    const int n = ctx->dom[0].n_bcells;
+    out[0] = out[1] = 0.0;
+    if (n == 0) return;
+    DeviceBuffer<double> partial(2 * (size_t)n);
+    launch_interface_currents(carrier_pass(ctx, 0), partial.get(), ctx->main);
+    PECS_CUDA(cudaGetLastError());
+    std::vector<double> h(2 * (size_t)n);
+    PECS_CUDA(cudaMemcpyAsync(h.data(), partial.get(), partial.bytes(), cudaMemcpyDeviceToHost, ctx->main));
+    PECS_CUDA(cudaStreamSynchronize(ctx->main));
+    for (int r = 0; r < n; ++r) { // record order: deterministic
+      out[0] += h[2 * (size_t)r];
+      out[1] += h[2 * (size_t)r + 1];
+    }
+  });
+}
+
 pecs_status pecs_output_wait(pecs_ctx* ctx) {
   return guarded([&] {
     require(ctx != nullptr, "pecs_output_wait: NULL context");

@@ -646,6 +646,42 @@ __global__ void poisson_face_rhs_kernel(PoissonFaceView fv, PoissonFaceParams p,
   atomicAdd(static_rhs + dof, acc);
 }
 
+// I-V post-processing on the device: the two interface integrals of the step's charge-transfer terms
+// (reference SolarCell.cpp:1265-1347), one thread per boundary record of the SEMICONDUCTOR, both values per record into
+// partial[2 r], partial[2 r + 1] (zero for records without an interface face); the caller adds them up in record order
+// on the host (a few hundred values: deterministic, no atomics).
+__global__ void interface_current_kernel(CarrierPass w, double* partial) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const DomainView& d = w.d;
+  if (r >= d.n_bcells) return;
+  double i_et = 0.0, i_ht = 0.0;
+  const rhsmath::BoundaryRecord rec = load_record(d, r);
+  if (rec.nb_cell >= 0) {
+    const size_t n = (size_t)d.n_cells, c = (size_t)d.bcell[r];
+    double rn[4], rp[4], rr[4], ro[4], geom[4][4];
+    load4_step(w.u1 + 8 * n + 4 * c, rn);
+    load4_step(w.u2 + 8 * n + 4 * c, rp);
+    load4_step(w.o1 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, rr);
+    load4_step(w.o2 + 8 * (size_t)w.other_n_cells + 4 * (size_t)rec.nb_cell, ro);
+    load_geometry(d, r, geom);
+    for (int f = 0; f < 4; ++f) {
+      if (rec.id[f] != PECS_INTERFACE) continue;
+      for (int q = 0; q < 3; ++q) {
+        const double t = fe::gauss_x(q), W = geom[f][2] * fe::gauss_w(q);
+        double xi, eta, N[4], Nn[4];
+        fe::face_point(f, t, xi, eta);
+        fe::shape(xi, eta, N);
+        fe::face_point(rec.nb_face, t, xi, eta); // same quadrature index on both sides
+        fe::shape(xi, eta, Nn);
+        i_et += w.p.k_et * (rhsmath::trace(N, rn) - w.p.rho1_e) * rhsmath::trace(Nn, ro) * W;
+        i_ht += w.p.k_ht * (rhsmath::trace(N, rp) - w.p.rho2_e) * rhsmath::trace(Nn, rr) * W;
+      }
+    }
+  }
+  partial[2 * r] = i_et;
+  partial[2 * r + 1] = i_ht;
+}
+
 __global__ void distribute_kernel(int n, const int* __restrict__ dof, const int* __restrict__ master,
                                   const double* __restrict__ weight, double* x) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -748,6 +784,11 @@ void launch_poisson_cell_rhs(const CarrierPass& a, const CarrierPass& b, int kin
 void launch_poisson_face_rhs(const PoissonFaceView& v, const PoissonFaceParams& p, double* static_rhs, cudaStream_t s) {
   if (v.n_faces == 0) return;
   poisson_face_rhs_kernel<<<blocks_for(v.n_faces), kThreads, 0, s>>>(v, p, static_rhs);
+}
+
+void launch_interface_currents(const CarrierPass& semiconductor, double* partial, cudaStream_t s) {
+  if (semiconductor.d.n_bcells == 0) return;
+  interface_current_kernel<<<blocks_for(semiconductor.d.n_bcells), kThreads, 0, s>>>(semiconductor, partial);
 }
 
 void launch_distribute(int n_constraints, const int* dof, const int* master, const double* weight, double* x,

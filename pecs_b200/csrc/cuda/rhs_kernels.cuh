@@ -76,6 +76,9 @@ struct PoissonFaceParams {
 void launch_poisson_face_rhs(const PoissonFaceView& v, const PoissonFaceParams& p, double* static_rhs, cudaStream_t s);
 
 // ConstraintMatrix::distribute on the device
+// I-V post-processing: per boundary record of the semiconductor {int k_et (rho_n - rho_n^e) rho_o, int k_ht (rho_p - rho_p^e) rho_r}
+// over its interface face (zero without one) -> partial[2 n_bcells]
+void launch_interface_currents(const CarrierPass& semiconductor, double* partial, cudaStream_t s);
 void launch_distribute(int n_constraints, const int* dof, const int* master, const double* weight, double* x,
                        cudaStream_t s);
 

@@ -533,13 +533,10 @@ void SolarCellProblem::interface_currents(const double* const states[4], double 
       u[k] = states[k];
     }
   } else {
+    // from the device state: integrated ON the device (pecs_interface_currents), nothing is downloaded but the result
     require_ctx(ctx, "SolarCellProblem::interface_currents");
-    ChargeCarrierSpace::Carrier* carriers[4] = {&electron_hole_pair.carrier_1, &electron_hole_pair.carrier_2,
-                                                 &redox_pair.carrier_1, &redox_pair.carrier_2};
-    for (int k = 0; k < 4; ++k) {
-      carriers[k]->pull_solution();
-      u[k] = carriers[k]->solution.data();
-    }
+    check(pecs_interface_currents(ctx, out), "SolarCellProblem::interface_currents");
+    return;
   }
   double prm[32];
   fill_params(prm);

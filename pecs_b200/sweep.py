@@ -43,6 +43,31 @@ def init_distributed(backend=None):
     return rank, local, world, dist
 
 
+def pin_to_gpu_numa_node(local_rank, local_world):
+    """Pin this rank's host threads to cores of its GPU's NUMA node (NVML's ideal CPU affinity of the device), and to its
+    own share of them when several ranks report the same set (the end-to-end sweep moves 50 MB per step
+    and rank through host memory).  Returns the core list, or None when NVML / sched_setaffinity are unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        index = local_rank
+        if visible and all(t.strip().isdigit() for t in visible.split(",")):
+            index = int(visible.split(",")[local_rank])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cores = [c for c in cores if c in os.sched_getaffinity(0)]
+        if not cores:
+            return None
+        share = max(1, len(cores) // max(local_world, 1))
+        mine = cores[local_rank * share:(local_rank + 1) * share] or cores
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
+
+
 def barrier(dist, device=None):
     if dist is not None:
         if device is not None:
