@@ -792,8 +792,7 @@ __global__ void p2p_wait_published_kernel(const unsigned long long* mine) {
   __threadfence_system();
 }
 
-int deferred_currents_mode();
-__global__ void completion_fence_kernel() {}
+bool deferred_currents_enabled();
 // Solve `count` (1 or 2) carriers of one subdomain, k0 first, on stream s.  count == 2 only for a shared pair: both
 // right-hand sides ride on ONE pass over the tables (reduction, two sweeps, recovery).
 // densities_final[r]: recorded on s as soon as the new densities are complete, i.e. before the LDG currents are
@@ -833,10 +832,8 @@ void enqueue_carrier_solve(pecs_ctx* ctx, int w, int k0, int count, cudaStream_t
   S.forward_sweep(io, s);
   if (ctx->p2p.active) p2p_wait_assembled_kernel<<<1, 1, 0, s>>>(ctx->p2p.flags.get(), ctx->p2p.world);
   S.backward_sweep(io, s);
-  if (densities_final) {
-    if (deferred_currents_mode() == 2) completion_fence_kernel<<<1, 1, 0, s>>>(); // experiment, scripts/race_repro.py
+  if (densities_final)
     for (int i = 0; i < count; ++i) PECS_CUDA(cudaEventRecord(densities_final[i], s));
-  }
   if (count == 2)
     launch_ell_combine2(nq, nullptr, nullptr, nullptr, EllTerm{&red.Ainv, r[0], 1.0, r[1]},
                         EllTerm{&red.T2, x[0] + nq, -1.0, x[1] + nq}, EllTerm{}, x[0], x[1], s);
@@ -875,15 +872,15 @@ void enqueue_full_solve(pecs_ctx* ctx, double* const* host = nullptr, int* n_cop
     k += count - 1;
   }
 }
-// OFF by default.  Measured +1 % (2.49 -> 2.46 ms per step at cfg3), but one of three complete GPU suite runs with it
-// failed tests/test_gpu_parity.py::test_states_after_n_steps with a 5.6e-6 density difference after 25 steps that a
-// determinism check (scripts/race_check.py, 59 x 25 steps, bit-identical) did not reproduce; until that is explained
-// the step keeps the v15 topology (PECS_B200_DEFER_CURRENTS=1 enables the overlap).
-int deferred_currents_mode() {
+// OFF by default (PECS_B200_DEFER_CURRENTS=1 enables it).  Round 1 saw one parity failure in a suite run with this overlap
+// on and could not explain it; round 2 could not reproduce it in 6 380 repetitions over every schedule, removed the two
+// ordering hazards an audit found and keeps a regression test on the switch
+// (tests/test_gpu_extra.py::test_step_scheduling_variants_match_oracle).  It is worth +0.3 % on the device-timed step
+// and +6 % end to end (downloads start earlier); the default stays the plain topology.
+bool deferred_currents_enabled() {
   const char* e = std::getenv("PECS_B200_DEFER_CURRENTS");
-  return e && (*e == '1' || *e == '2') ? *e - '0' : 0;
+  return e && *e == '1';
 }
-bool deferred_currents_enabled() { return deferred_currents_mode() != 0; }
 void enqueue_step(pecs_ctx* ctx, double* const* host = nullptr) {
   // the Poisson solve's completion counters: zeroed first thing, long before that solve (which is alone on the critical
   // path at the end of the step) needs them

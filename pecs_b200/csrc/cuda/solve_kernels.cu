@@ -455,11 +455,6 @@ __global__ void __launch_bounds__(kSolveWarps * 32) backward_level_kernel(SolveT
   if (!io.grid_wait) grid_dependency_wait(); // completion stays transitive along the kernel chain
 }
 
-__global__ void gather_kernel(int n, const int* __restrict__ index, const double* __restrict__ in, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[index[i]];
-}
-
 } // namespace
 
 template <bool PER_WARP, int NRHS>
@@ -558,10 +553,5 @@ extern "C" int pecs_trace_read(unsigned long long* out, int max_records) {
 }
 namespace pecs {
 #endif
-
-void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s) {
-  if (n == 0) return;
-  gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, index, in, out);
-}
 
 } // namespace pecs

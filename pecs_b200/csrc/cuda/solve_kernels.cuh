@@ -82,8 +82,6 @@ void launch_backward_level(const SolveTables& t, const SolveTile* tiles, int n_t
 // thread blocks of a level launch: one per tile (one-warp tiles: one per `warps` tiles); with PECS_B200_LEVEL_WAVES=k
 // at most k resident waves (occupancy of the kernel variant at this block shape x number of SMs), the blocks then loop
 int level_grid(bool forward, bool per_warp, int n_rhs, int n_tiles, int vec_doubles, int warps, int stages);
-// out[i] = in[index[i]]
-void launch_gather(int n, const int* index, const double* in, double* out, cudaStream_t s);
 // opt in to large dynamic shared memory once per process
 void configure_solve_kernels(int max_smem_bytes);
 
