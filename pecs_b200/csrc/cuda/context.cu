@@ -1012,20 +1012,6 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
       PECS_CUDA(cudaEventCreateWithFlags(&ctx->dens[k], cudaEventDisableTiming));
     }
     PECS_CUDA(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
-    // PECS_B200_STAGGER=1: the kernels of the carrier solves get descending priorities (electrons first, the redox pair
-    // last), so that the solves FINISH one after the other instead of together and the downloads of pecs_step_host
-    // (started per species when its solve is done) spread over the step instead of piling up behind it
-    if (const char* e = std::getenv("PECS_B200_STAGGER")) {
-      if (*e == '1') {
-        int least = 0, greatest = 0;
-        PECS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        const int span = least - greatest; // greatest is the numerically smallest value
-        for (int k = 0; k < 4; ++k)
-          stream_priority_hints().set(ctx->side[k], greatest + std::min(span, k < 2 ? k : 2 + (k - 2)));
-        stream_priority_hints().set(ctx->main, greatest);
-      }
-    }
-
     const pecs_poisson_desc& P = desc->poisson;
     require(P.n_cells > 0 && P.vertices && P.face_dof && P.n_rt > 0, "poisson: empty tables");
     ctx->n_rt = P.n_rt;

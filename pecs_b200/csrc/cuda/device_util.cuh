@@ -110,38 +110,6 @@ __device__ __forceinline__ void ld_vec4(const double* p, double v[4]) {
 
 // Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream is still
 // running and synchronises itself with griddepcontrol.wait (wait_for_predecessor).  PECS_B200_PDL=0 launches plainly.
-// Optional scheduling priority of the kernels launched on a stream (captured into graph kernel nodes as the launch
-// attribute; stream priorities themselves are not): the context staggers the carrier solves of the host-buffer step with
-// it so that their downloads do not all start at the same moment (context.cu: PECS_B200_STAGGER).
-struct StreamPriorityHints {
-  cudaStream_t stream[8] = {};
-  int priority[8] = {};
-  int n = 0;
-  void set(cudaStream_t s, int p) {
-    for (int k = 0; k < n; ++k)
-      if (stream[k] == s) {
-        priority[k] = p;
-        return;
-      }
-    if (n < 8) {
-      stream[n] = s;
-      priority[n++] = p;
-    }
-  }
-  bool find(cudaStream_t s, int& p) const {
-    for (int k = 0; k < n; ++k)
-      if (stream[k] == s) {
-        p = priority[k];
-        return true;
-      }
-    return false;
-  }
-};
-inline StreamPriorityHints& stream_priority_hints() {
-  static StreamPriorityHints h;
-  return h;
-}
-
 template <class... KArgs, class... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
   static const bool pdl = [] {
@@ -153,21 +121,11 @@ inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
   cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  int n_attr = 0;
-  if (pdl) {
-    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
-    ++n_attr;
-  }
-  int priority = 0;
-  if (stream_priority_hints().find(s, priority)) {
-    attr[n_attr].id = cudaLaunchAttributePriority;
-    attr[n_attr].val.priority = priority;
-    ++n_attr;
-  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = n_attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
