@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <future>
@@ -33,6 +35,19 @@
 #include "solve_kernels.cuh"
 
 namespace pecs {
+
+// PECS_B200_SETUP_TIMING=1: wall-clock phases of pecs_ctx_create on stderr (where the one-time cost goes)
+struct SetupTimer {
+  bool on = std::getenv("PECS_B200_SETUP_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "pecs_ctx_create: %-44s %.2f s\n", what, std::chrono::duration<double>(now - t).count());
+    t = now;
+  }
+};
 
 // ------------------------------------------------------------------------------------------------ one factorised system
 struct DeviceSystem {
@@ -157,6 +172,7 @@ struct DeviceSystem {
     build(A, plan_from_layout(A, layout, leaf_nodes), factor_on_device);
   }
   void build(const CsrMatrix& A, SolvePlan&& ready_plan, bool factor_on_device, int right_hand_sides = 1) {
+    SetupTimer timer;
     n = A.n;
     n_rhs = right_hand_sides;
     plan = std::move(ready_plan);
@@ -171,8 +187,10 @@ struct DeviceSystem {
     x_perm.resize((size_t)n_rhs * n);
     fwd.resize((size_t)std::max<int64_t>(plan.fwd_entries, 2));
     bwd.resize((size_t)std::max<int64_t>(plan.bwd_entries, 2));
+    timer.lap("  system: index tables, ELL of the matrix, buffers");
     if (factor_on_device) {
       factorize_device(plan, A, fwd.get(), bwd.get());
+      timer.lap("  system: numeric factorisation on the device");
     } else {
       std::vector<double> hf, hb;
       factorize_host(plan, A, hf, hb);
@@ -314,6 +332,7 @@ struct DeviceSystem {
       }
     done.resize(2 * (size_t)n_fronts + 1);
     done.zero();
+    timer.lap("  system: tile lists of the level kernels");
   }
 
   // solution += A^-1 w, all on stream s; w = residual of the current content of `solution`, in elimination order
@@ -672,7 +691,9 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
   // factorise the two fixed carrier matrices
   for (int k = 0; k < 2; ++k) {
     if (!prepared[k].valid()) continue; // not solved here: manufactured tests only solve carrier_1; other shards' carriers
+    SetupTimer wait;
     PreparedSystem ps = prepared[k].get();
+    wait.lap("  wait for the host preparation (Schur reduction, dissection, plan)");
     if (ps.reduced) {
       DeviceDomain::Reduced& red = D.reduced[k];
       red.active = true;
@@ -1049,8 +1070,11 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
       return ps;
     });
     // on any failure below the futures' destructors wait for the host threads before desc goes away
+    SetupTimer timer;
     setup_domain(*ctx, 0, desc->semiconductor, P, desc->interface_pairs, factor_on_device, prepared[0]);
+    timer.lap("semiconductor: wait for plans, factorise, upload");
     if (ctx->full) setup_domain(*ctx, 1, desc->electrolyte, P, desc->interface_pairs, factor_on_device, prepared[1]);
+    timer.lap("electrolyte: wait for plans, factorise, upload");
 
     // Poisson vectors, constraints, static boundary data
     const int np = ctx->n_pdofs();
@@ -1110,6 +1134,7 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
       ctx->p_system.trace_id = 4;
       ctx->p_system.build(ps.A, std::move(ps.plan), factor_on_device);
     }
+    timer.lap("Poisson: static data, plan, factorise, upload");
     size_t smem = ctx->p_system.max_smem_bytes();
     for (int w = 0; w < ctx->n_domains(); ++w)
       for (int k = 0; k < 2; ++k) smem = std::max(smem, ctx->dom[w].system[k].max_smem_bytes());
@@ -1117,6 +1142,7 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
       throw StatusError(PECS_ERR_INTERNAL, "a front's vector does not fit into shared memory");
     PECS_CUDA(cudaDeviceSynchronize());
     if (ctx->kind == PECS_KIND_PRODUCTION) build_step_graph(ctx.get());
+    timer.lap("step graph capture");
     PECS_CUDA(cudaGetLastError());
     *out = ctx.release();
   });
