@@ -264,16 +264,31 @@ void cusolver_check(cusolverStatus_t s, const char* what) {
     throw StatusError(PECS_ERR_CUDA, std::string(what) + ": cuSOLVER status " + std::to_string((int)s));
 }
 
-struct Handles {
+// The large fronts of a level are independent: they are factorised on kLanes streams side by side, each with its own
+// cuSOLVER / cuBLAS handle, work space, pivot vector and info word.  (Round 1 ran them one after the other on the
+// default stream: getrf of a 200..1300-row block fills a fraction of the device, and the numeric factorisation was 60 %
+// of pecs_ctx_create at cfg3: 1.5-2.3 s per carrier system, profiles/r02_setup_timing_q.log.)  The lanes are BLOCKING
+// streams: the legacy default stream, on which the assembly / extend-add / small-front / pack kernels of the level run,
+// orders itself with them in both directions, so no events are needed.
+constexpr int kLanes = 8;
+struct Lane {
+  cudaStream_t stream = nullptr;
   cublasHandle_t blas = nullptr;
   cusolverDnHandle_t solver = nullptr;
+  DeviceBuffer<double> work;
+  DeviceBuffer<int> ipiv, info;
+};
+struct Handles {
+  Lane lane[kLanes];
   Handles() {
-    cublas_check(cublasCreate(&blas), "cublasCreate");
-    cusolver_check(cusolverDnCreate(&solver), "cusolverDnCreate");
-  }
-  ~Handles() {
-    if (solver) cusolverDnDestroy(solver);
-    if (blas) cublasDestroy(blas);
+    for (Lane& l : lane) {
+      PECS_CUDA(cudaStreamCreate(&l.stream)); // blocking with respect to the legacy default stream, on purpose
+      cublas_check(cublasCreate(&l.blas), "cublasCreate");
+      cusolver_check(cusolverDnCreate(&l.solver), "cusolverDnCreate");
+      cublas_check(cublasSetStream(l.blas, l.stream), "cublasSetStream");
+      cusolver_check(cusolverDnSetStream(l.solver, l.stream), "cusolverDnSetStream");
+      l.info.resize(1);
+    }
   }
 };
 
@@ -301,12 +316,17 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, 
   PECS_CUDA(cudaMemset(d_fwd, 0, (size_t)std::max<int64_t>(plan.fwd_entries, 2) * sizeof(double)));
   PECS_CUDA(cudaMemset(d_bwd, 0, (size_t)std::max<int64_t>(plan.bwd_entries, 2) * sizeof(double)));
 
-  // cuSOLVER / cuBLAS initialisation costs about a second: one set of handles per process
-  static Handles* handles = new Handles();
-  Handles& h = *handles;
-  DeviceBuffer<double> Fcur, Fchild, work, Gs, Bs;
+  // cuSOLVER / cuBLAS initialisation costs about a second: one set of handles per process and device
+  static Handles* handles_of[64] = {};
+  int device = 0;
+  PECS_CUDA(cudaGetDevice(&device));
+  if (!handles_of[device & 63]) handles_of[device & 63] = new Handles();
+  Handles& h = *handles_of[device & 63];
+  for (Lane& l : h.lane)
+    if (l.ipiv.size() < (size_t)std::max(plan.max_np, 1)) l.ipiv.resize((size_t)std::max(plan.max_np, 1));
+  DeviceBuffer<double> Fcur, Fchild, Gs, Bs;
   DeviceBuffer<FactorFront> d_cur, d_child;
-  DeviceBuffer<int> ipiv((size_t)std::max(plan.max_np, 1)), info(1), cl, small_list;
+  DeviceBuffer<int> cl, small_list;
   std::vector<int> index_in_level(plan.fronts.size(), -1);
 
   for (int d = (int)plan.levels.size() - 1; d >= 0; --d) {
@@ -368,7 +388,23 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, 
                                                      d_error.get());
       PECS_CUDA(cudaGetLastError());
     }
+    if (!large.empty()) {
+      // work space of the lanes: sized once per level (a resize is a device-wide synchronisation)
+      int lwork_max = 0;
+      for (int k : large) {
+        int lwork = 0;
+        cusolver_check(cusolverDnDgetrf_bufferSize(h.lane[0].solver, ff[k].np, ff[k].np, Fcur.get() + ff[k].F_off,
+                                                   ff[k].np + ff[k].nb, &lwork),
+                       "getrf_bufferSize");
+        lwork_max = std::max(lwork_max, lwork);
+      }
+      for (Lane& l : h.lane)
+        if (l.work.size() < (size_t)lwork_max) l.work.resize((size_t)lwork_max);
+    }
+    int next_lane = 0;
     for (int k : large) {
+      Lane& l = h.lane[next_lane];
+      next_lane = (next_lane + 1) % kLanes;
       const FactorFront& x = ff[k];
       const int np = x.np, nb = x.nb, m = np + nb;
       double* M = Fcur.get() + x.F_off;
@@ -377,24 +413,21 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, 
       // col-major view of the row-major F_PP (ld m) is F_PP^T; getrf/getrs on it give (F_PP^T)^-1 = Inv^T, whose
       // col-major storage with leading dimension ldb IS the row-major Inv with row stride ldb: it lands in the table.
       const int ldb = m, ldf = np;
-      int lwork = 0;
-      cusolver_check(cusolverDnDgetrf_bufferSize(h.solver, np, np, M, m, &lwork), "getrf_bufferSize");
-      if ((size_t)lwork > work.size()) work.resize((size_t)lwork);
-      cusolver_check(cusolverDnDgetrf(h.solver, np, np, M, m, work.get(), ipiv.get(), info.get()), "getrf");
-      check_info_kernel<<<1, 1>>>(info.get(), d_error.get());
-      set_identity_kernel<<<(np * np + 255) / 256, 256>>>(B, np, ldb);
-      cusolver_check(cusolverDnDgetrs(h.solver, CUBLAS_OP_N, np, np, M, m, ipiv.get(), B, ldb, info.get()), "getrs");
+      cusolver_check(cusolverDnDgetrf(l.solver, np, np, M, m, l.work.get(), l.ipiv.get(), l.info.get()), "getrf");
+      check_info_kernel<<<1, 1, 0, l.stream>>>(l.info.get(), d_error.get());
+      set_identity_kernel<<<(np * np + 255) / 256, 256, 0, l.stream>>>(B, np, ldb);
+      cusolver_check(cusolverDnDgetrs(l.solver, CUBLAS_OP_N, np, np, M, m, l.ipiv.get(), B, ldb, l.info.get()), "getrs");
       if (nb > 0) {
         const double one = 1.0, zero = 0.0, minus = -1.0;
         // (-H)^T = -F_PB^T Inv^T : C(nb x np, ld ldb) = -A(nb x np: F_PB memory, ld m) * B(np x np: Inv memory, ld ldb)
-        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, np, np, &minus, M + np, m, B, ldb, &zero, B + np, ldb),
+        cublas_check(cublasDgemm(l.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, np, np, &minus, M + np, m, B, ldb, &zero, B + np, ldb),
                      "dgemm H");
         // G^T = Inv^T F_BP^T : C(np x nb, ld ldf) = A(np x np: Inv memory, ld ldb) * B(np x nb: F_BP memory, ld m)
-        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, np, nb, np, &one, B, ldb, M + (size_t)np * m, m, &zero,
+        cublas_check(cublasDgemm(l.blas, CUBLAS_OP_N, CUBLAS_OP_N, np, nb, np, &one, B, ldb, M + (size_t)np * m, m, &zero,
                                  G, ldf),
                      "dgemm G");
         // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * B(np x nb: G memory, ld ldf)
-        cublas_check(cublasDgemm(h.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, nb, np, &minus, M + np, m, G, ldf, &one,
+        cublas_check(cublasDgemm(l.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, nb, np, &minus, M + np, m, G, ldf, &one,
                                  M + (size_t)np * m + np, m),
                      "dgemm U");
       }
