@@ -171,7 +171,8 @@ struct DeviceSystem {
   void build(const CsrMatrix& A, const NodeLayout& layout, int leaf_nodes, bool factor_on_device) {
     build(A, plan_from_layout(A, layout, leaf_nodes), factor_on_device);
   }
-  void build(const CsrMatrix& A, SolvePlan&& ready_plan, bool factor_on_device, int right_hand_sides = 1) {
+  void build(const CsrMatrix& A, SolvePlan&& ready_plan, bool factor_on_device, int right_hand_sides = 1,
+             const CsrMatrix* A_permuted = nullptr, const CsrMatrix* A_permuted_transposed = nullptr) {
     SetupTimer timer;
     n = A.n;
     n_rhs = right_hand_sides;
@@ -189,7 +190,10 @@ struct DeviceSystem {
     bwd.resize((size_t)std::max<int64_t>(plan.bwd_entries, 2));
     timer.lap("  system: index tables, ELL of the matrix, buffers");
     if (factor_on_device) {
-      factorize_device(plan, A, fwd.get(), bwd.get());
+      if (A_permuted && A_permuted_transposed)
+        factorize_device(plan, *A_permuted, *A_permuted_transposed, fwd.get(), bwd.get());
+      else
+        factorize_device(plan, A, fwd.get(), bwd.get());
       timer.lap("  system: numeric factorisation on the device");
     } else {
       std::vector<double> hf, hb;
@@ -571,8 +575,14 @@ CsrMatrix copy_csr(const pecs_csr& a, int expected_n, const char* name) {
 struct PreparedSystem {
   bool present = false, reduced = false;
   CsrMatrix A;       // the matrix that is factorised (S when reduced)
+  CsrMatrix Ap, Apt; // P A P^T and its transpose in elimination order, for the device factorisation
   SchurReduction R;
   SolvePlan plan;
+  void permute() {
+    if (!device_factorization_enabled()) return;
+    Ap = permute_csr(A, plan.perm, false);
+    Apt = permute_csr(A, plan.perm, true);
+  }
 };
 
 PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k) {
@@ -588,6 +598,7 @@ PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k) {
     ps.A = std::move(A);
     ps.plan = plan_from_layout(ps.A, carrier_nodes(d), default_leaf_nodes(false));
   }
+  ps.permute();
   return ps;
 }
 
@@ -699,14 +710,14 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
       red.active = true;
       const int n_rhs = (k == 0 && D.shared_pair) ? 2 : 1;
       D.system[k].trace_id = 2 * which + k;
-      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, n_rhs);
+      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, n_rhs, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr);
       red.T1.upload(ps.R.T1, &D.system[k].plan.iperm); // r~ is produced directly in elimination order
       red.Ainv.upload(ps.R.Ainv);
       red.T2.upload(ps.R.T2);
       red.rtilde.resize((size_t)n_rhs * 4 * (size_t)n);
     } else {
       if (D.shared_pair) throw StatusError(PECS_ERR_INTERNAL, "shared factorisation needs the Schur-reduced system");
-      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device);
+      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, 1, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr);
     }
   }
 }
@@ -1067,6 +1078,7 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
       ps.present = true;
       ps.A = copy_csr(P.system_matrix, n_pdofs, "poisson: system matrix size");
       ps.plan = poisson_plan(ps.A, P, default_leaf_nodes(true));
+      ps.permute();
       return ps;
     });
     // on any failure below the futures' destructors wait for the host threads before desc goes away
@@ -1132,7 +1144,7 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     {
       PreparedSystem ps = prepared_poisson.get();
       ctx->p_system.trace_id = 4;
-      ctx->p_system.build(ps.A, std::move(ps.plan), factor_on_device);
+      ctx->p_system.build(ps.A, std::move(ps.plan), factor_on_device, 1, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr);
     }
     timer.lap("Poisson: static data, plan, factorise, upload");
     size_t smem = ctx->p_system.max_smem_bytes();

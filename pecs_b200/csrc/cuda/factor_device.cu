@@ -300,10 +300,14 @@ bool device_factorization_enabled() {
 }
 
 void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, double* d_bwd) {
+  const CsrMatrix Ap = permute_csr(A, plan.perm, false), Apt = permute_csr(A, plan.perm, true);
+  factorize_device(plan, Ap, Apt, d_fwd, d_bwd);
+}
+
+void factorize_device(const SolvePlan& plan, const CsrMatrix& Ap, const CsrMatrix& Apt, double* d_fwd, double* d_bwd) {
   DeviceBuffer<int> bd_index_buf;
   bd_index_buf.upload(plan.bd_index.data(), std::max<size_t>(plan.bd_index.size(), 1));
   const int* d_bd_index = bd_index_buf.get();
-  const CsrMatrix Ap = permute_csr(A, plan.perm, false), Apt = permute_csr(A, plan.perm, true);
   DeviceBuffer<int> rp, col, trp, tcol, d_error(1);
   DeviceBuffer<double> val, tval;
   rp.upload(Ap.row_ptr);

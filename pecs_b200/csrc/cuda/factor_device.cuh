@@ -12,5 +12,9 @@ bool device_factorization_enabled();
 
 // Fills the forward / backward tables (already allocated on the device, zero-initialised inside) of `plan`.
 void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, double* d_bwd);
+// the same with P A P^T and its transpose (P = plan.perm) already formed: the two host permutations cost about as much
+// as the device work, so pecs_ctx_create forms them on the concurrent preparation threads
+void factorize_device(const SolvePlan& plan, const CsrMatrix& A_permuted, const CsrMatrix& A_permuted_transposed, double* d_fwd,
+                      double* d_bwd);
 
 } // namespace pecs
