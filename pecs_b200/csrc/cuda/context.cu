@@ -558,50 +558,6 @@ void require(bool ok, const char* what) {
   if (!ok) throw StatusError(PECS_ERR_INVALID, what);
 }
 
-CsrMatrix copy_csr(const pecs_csr& a, int expected_n, const char* name) {
-  require(a.n == expected_n && a.row_ptr && a.col && a.val, name);
-  CsrMatrix A;
-  A.n = a.n;
-  A.row_ptr.assign(a.row_ptr, a.row_ptr + a.n + 1);
-  const size_t nnz = (size_t)A.row_ptr[a.n];
-  A.col.assign(a.col, a.col + nnz);
-  A.val.assign(a.val, a.val + nnz);
-  return A;
-}
-
-// Host half of building one linear system -- copy of the matrix, Schur reduction of the currents, nested dissection and
-// the symbolic front layout -- needs no device and dominates pecs_ctx_create; the (up to) five systems are prepared
-// concurrently on host threads, then factorised on the device one after the other.
-struct PreparedSystem {
-  bool present = false, reduced = false;
-  CsrMatrix A;       // the matrix that is factorised (S when reduced)
-  CsrMatrix Ap, Apt; // P A P^T and its transpose in elimination order, for the device factorisation
-  SchurReduction R;
-  SolvePlan plan;
-  void permute() {
-    if (!device_factorization_enabled()) return;
-    Ap = permute_csr(A, plan.perm, false);
-    Apt = permute_csr(A, plan.perm, true);
-  }
-};
-
-PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k) {
-  PreparedSystem ps;
-  ps.present = true;
-  const int n = d.n_cells;
-  CsrMatrix A = copy_csr(d.system_matrix[k], 12 * n, "domain: system matrix size");
-  if (schur_reduction_enabled() && build_schur_reduction(A, n, ps.R)) {
-    ps.reduced = true;
-    ps.A = ps.R.S;
-    ps.plan = plan_from_layout(ps.A, carrier_density_nodes(d), default_leaf_nodes(false));
-  } else {
-    ps.A = std::move(A);
-    ps.plan = plan_from_layout(ps.A, carrier_nodes(d), default_leaf_nodes(false));
-  }
-  ps.permute();
-  return ps;
-}
-
 // bitwise equality of two constant matrices handed over the ABI
 bool same_matrix(const pecs_csr& a, const pecs_csr& b) {
   if (a.n != b.n || !a.row_ptr || !b.row_ptr || !a.col || !b.col || !a.val || !b.val) return false;
@@ -1069,18 +1025,12 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
         if (ctx->kind != PECS_KIND_PRODUCTION && k == 1) break; // the manufactured tests only solve carrier_1
         if (!(ctx->owned >> (2 * w + k) & 1)) continue;          // another shard owns this carrier
         if (k == 1 && ctx->dom[w].shared_pair) continue;         // served by carrier_1's factorisation
-        prepared[w][k] = std::async(std::launch::async, [d, k] { return prepare_carrier(*d, k); });
+        prepared[w][k] = std::async(std::launch::async, [d, k, factor_on_device] { return prepare_carrier(*d, k, factor_on_device); });
       }
     }
     const int n_pdofs = ctx->n_pdofs();
-    std::future<PreparedSystem> prepared_poisson = std::async(std::launch::async, [&P, n_pdofs] {
-      PreparedSystem ps;
-      ps.present = true;
-      ps.A = copy_csr(P.system_matrix, n_pdofs, "poisson: system matrix size");
-      ps.plan = poisson_plan(ps.A, P, default_leaf_nodes(true));
-      ps.permute();
-      return ps;
-    });
+    std::future<PreparedSystem> prepared_poisson = std::async(
+        std::launch::async, [&P, n_pdofs, factor_on_device] { return prepare_poisson(P, n_pdofs, factor_on_device); });
     // on any failure below the futures' destructors wait for the host threads before desc goes away
     SetupTimer timer;
     setup_domain(*ctx, 0, desc->semiconductor, P, desc->interface_pairs, factor_on_device, prepared[0]);

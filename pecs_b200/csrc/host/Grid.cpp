@@ -1,6 +1,8 @@
 // Grid.cpp -- see Grid.hpp.
 #include "Grid.hpp"
 
+#include <future>
+
 #include <iostream>
 
 namespace Grid_Maker {
@@ -91,29 +93,21 @@ void Grid::make_grids(Triangulation& semiconductor_triang, Triangulation& electr
   else
     make_semiconductor_grid(Poisson_triang);
 
-  semiconductor_triang.refine_global((int)n_global_refine);
-  electrolyte_triang.refine_global((int)n_global_refine);
-  Poisson_triang.refine_global((int)n_global_refine);
-
-  // boundary-layer cells are refined n_local_refine more times (reference Grid.cpp:70-106)
-  for (unsigned int r = 0; r < n_local_refine; ++r) {
-    semiconductor_triang.refine_material({semi_boundary_layer_id});
-    electrolyte_triang.refine_material({elec_boundary_layer_id});
-    Poisson_triang.refine_material({semi_boundary_layer_id, elec_boundary_layer_id});
-  }
-
-  make_Dirichlet_boundaries(semiconductor_triang);
-  make_Dirichlet_boundaries(electrolyte_triang);
-  make_Dirichlet_boundaries(Poisson_triang);
-  if (insulated) {
-    make_Neumann_boundaries(Poisson_triang);
-    make_Neumann_boundaries(semiconductor_triang);
-    make_Neumann_boundaries(electrolyte_triang);
-  }
-  if (schottky) {
-    make_Schottky_boundaries(semiconductor_triang);
-    make_Schottky_boundaries(Poisson_triang);
-  }
+  // from here on the three triangulations share nothing: refined and marked side by side
+  // (boundary-layer cells are refined n_local_refine more times, reference Grid.cpp:70-106)
+  auto finish = [&](Triangulation& t, std::vector<int> layer_ids, bool schottky_edge) {
+    t.refine_global((int)n_global_refine);
+    for (unsigned int r = 0; r < n_local_refine; ++r) t.refine_material(layer_ids);
+    make_Dirichlet_boundaries(t);
+    if (insulated) make_Neumann_boundaries(t);
+    if (schottky && schottky_edge) make_Schottky_boundaries(t);
+  };
+  std::future<void> electrolyte = std::async(std::launch::async, [&] { finish(electrolyte_triang, {elec_boundary_layer_id}, false); });
+  std::future<void> poisson =
+      std::async(std::launch::async, [&] { finish(Poisson_triang, {semi_boundary_layer_id, elec_boundary_layer_id}, true); });
+  finish(semiconductor_triang, {semi_boundary_layer_id}, true);
+  electrolyte.get();
+  poisson.get();
 }
 
 void Grid::make_Dirichlet_boundaries(Triangulation& triangulation) {

@@ -111,43 +111,131 @@ CsrMatrix LDG::assemble_mass_matrix(const MeshTables& mesh, double delta_t) cons
   return tl.compress();
 }
 
-void LDG::assemble_system_matrices(const MeshTables& mesh, int dirichlet_id, double mu1, double mu2, double delta_t,
-                                   double transient_or_steady, double penalty, CsrMatrix& matrix_1,
-                                   CsrMatrix& matrix_2) const {
-  CarrierDofs dofs{mesh.n_cells};
-  // one chunk of triplets per thread over a contiguous range of cells; compressed in chunk order, so the result does
-  // not depend on the number of threads (reference LDG.cpp:283-426 assembles the flux terms sequentially)
-  const double t_begin = omp_get_wtime();
-  const int n_chunks = std::max(1, std::min(omp_get_max_threads(), mesh.n_cells / 64));
-  pecs::PairedTripletChunks chunks(dofs.n_dofs(), n_chunks);
-  const double beta[2] = {1.0 / std::sqrt(2.0), 1.0 / std::sqrt(2.0)};
-  const double mass_scale = transient_or_steady / delta_t;
+// keeps a value in a register as it is: the compiler cannot contract the product that made it with a later sum
+#if defined(__x86_64__)
+#define PECS_ROUNDED(x) __asm__("" : "+x"(x))
+#elif defined(__aarch64__)
+#define PECS_ROUNDED(x) __asm__("" : "+w"(x))
+#else
+#define PECS_ROUNDED(x) __asm__("" : "+m"(x))
+#endif
 
-#pragma omp parallel for schedule(static, 1) num_threads(n_chunks)
-  for (int chunk = 0; chunk < n_chunks; ++chunk) {
-  pecs::PairedTripletChunks::Chunk& out = chunks.chunk(chunk);
-  const int c_begin = (int)((long long)mesh.n_cells * chunk / n_chunks);
-  const int c_end = (int)((long long)mesh.n_cells * (chunk + 1) / n_chunks);
-  out.reserve(250 * (size_t)(c_end - c_begin));
-  auto both = [&](int i, int j, double v) { out.add(i, j, v, v); };
-  double M[4][4], Dx[4][4], Dy[4][4];
-  for (int c = c_begin; c < c_end; ++c) {
+namespace {
+
+// The 12 rows of ONE cell of the two carrier matrices of a pair, gathered: every term that lands in these rows -- the
+// cell integrals, the cell's boundary faces, the interior faces the cell works on, and the interior faces a NEIGHBOUR
+// works on (same level: the lower cell index; hanging: the coarse side, per sub-face; reference LDG.cpp:283-426 visits
+// every face once, from that side) -- added into dense 12 x 12 blocks, one per column cell.  Terms are added in the
+// order a sequential cell loop inserts them (worker cell ascending; within the cell itself: cell part, then faces
+// 0..3), so every entry is the same floating-point sum as in a sequential assembly, whatever runs in parallel.
+struct CellRows {
+  static constexpr int kMaxBlocks = 9; // the cell itself + at most two cells across each face
+  int n_blocks = 0;
+  int cell_of_block[kMaxBlocks];
+  double v1[12][12 * kMaxBlocks], v2[12][12 * kMaxBlocks];
+
+  int block(int cell) {
+    for (int k = 0; k < n_blocks; ++k)
+      if (cell_of_block[k] == cell) return k;
+    cell_of_block[n_blocks] = cell;
+    for (int r = 0; r < 12; ++r)
+      for (int j = 0; j < 12; ++j) v1[r][12 * n_blocks + j] = v2[r][12 * n_blocks + j] = 0.0;
+    return n_blocks++;
+  }
+  // a and b are ROUNDED terms (no fused multiply-add of the product that made them with this sum): an entry is then
+  // the same sum of the same terms as in a sequential triplet assembly
+  void add(int row, int blk, int col, double a, double b) {
+    PECS_ROUNDED(a);
+    PECS_ROUNDED(b);
+    v1[row][12 * blk + col] += a;
+    v2[row][12 * blk + col] += b;
+  }
+  void both(int row, int blk, int col, double v) { add(row, blk, col, v, v); }
+};
+
+struct LdgTerms {
+  const MeshTables& mesh;
+  int dirichlet_id;
+  double mu1, mu2, mass_scale, penalty;
+
+  // an interior face seen from its worker (minus) side
+  struct Face {
+    int worker, f, sub, n_parts, plus;
+    double sigma;
+  };
+
+  void face_of_worker(int w, int f, int sub, Face& F) const {
+    const int kind = mesh.face_kind[4 * w + f];
+    const double h = pecs::fe::cell_diameter(load_verts(mesh, w));
+    F.worker = w;
+    F.f = f;
+    F.sub = sub;
+    if (kind == pecs::FACE_SAME_LEVEL) {
+      F.n_parts = 1;
+      F.plus = mesh.neighbor[4 * w + f];
+      F.sigma = penalty / std::min(h, mesh.diameter(F.plus));
+    } else { // FACE_HAS_CHILDREN
+      F.n_parts = 2;
+      F.plus = sub == 0 ? mesh.neighbor[4 * w + f] : mesh.neighbor2[4 * w + f];
+      F.sigma = penalty / std::min(h, mesh.nb_parent_diameter[4 * w + f]);
+    }
+  }
+
+  // rows of cell c from an interior face; c is the worker (minus side) or the plus side
+  void interior(const Face& I, int c, CellRows& R) const {
+    const double beta[2] = {1.0 / std::sqrt(2.0), 1.0 / std::sqrt(2.0)};
+    const double len = 1.0 / I.n_parts;
+    const FaceTables F = face_tables(load_verts(mesh, I.worker), I.f, I.sub * len, len, true, I.f ^ 1);
+    const double n[2] = {F.nx, F.ny};
+    const double sigma = I.sigma;
+    if (c == I.worker) {
+      const int own = R.block(c), other = R.block(I.plus);
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+          for (int d = 0; d < 2; ++d) {
+            const double hp = 0.5 * n[d] + beta[d], hm = 0.5 * n[d] - beta[d];
+            R.both(4 * d + a, own, 8 + b, hp * F.Tmm[a][b]);
+            R.both(4 * d + a, other, 8 + b, hm * F.Tmp[a][b]);
+            R.both(8 + a, own, 4 * d + b, hm * F.Tmm[a][b]);
+            R.both(8 + a, other, 4 * d + b, hp * F.Tmp[a][b]);
+          }
+          R.both(8 + a, own, 8 + b, sigma * F.Tmm[a][b]);
+          R.both(8 + a, other, 8 + b, -sigma * F.Tmp[a][b]);
+        }
+    } else {
+      const int own = R.block(c), other = R.block(I.worker);
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+          for (int d = 0; d < 2; ++d) {
+            const double hp = 0.5 * n[d] + beta[d], hm = 0.5 * n[d] - beta[d];
+            R.both(4 * d + a, other, 8 + b, -hp * F.Tpm[a][b]);
+            R.both(4 * d + a, own, 8 + b, -hm * F.Tpp[a][b]);
+            R.both(8 + a, other, 4 * d + b, -hm * F.Tpm[a][b]);
+            R.both(8 + a, own, 4 * d + b, -hp * F.Tpp[a][b]);
+          }
+          R.both(8 + a, other, 8 + b, -sigma * F.Tpm[a][b]);
+          R.both(8 + a, own, 8 + b, sigma * F.Tpp[a][b]);
+        }
+    }
+  }
+
+  // what cell c itself inserts into its own rows: cell integrals, boundary faces, the interior faces it works on
+  void own_terms(int c, CellRows& R) const {
     const CellVerts v = load_verts(mesh, c);
     const double h = pecs::fe::cell_diameter(v);
+    double M[4][4], Dx[4][4], Dy[4][4];
     cell_tables(v, M, Dx, Dy);
+    const int own = R.block(c);
     for (int a = 0; a < 4; ++a)
       for (int b = 0; b < 4; ++b) {
-        const int ja = dofs.global(c, a), ka = dofs.global(c, 4 + a), ua = dofs.global(c, 8 + a);
-        const int jb = dofs.global(c, b), kb = dofs.global(c, 4 + b), ub = dofs.global(c, 8 + b);
-        out.add(ja, jb, M[a][b] / mu1, M[a][b] / mu2);
-        out.add(ka, kb, M[a][b] / mu1, M[a][b] / mu2);
-        both(ja, ub, -Dx[a][b]); // -(div p) u
-        both(ka, ub, -Dy[a][b]);
-        both(ua, jb, -Dx[a][b]); // -grad v . q
-        both(ua, kb, -Dy[a][b]);
-        both(ua, ub, mass_scale * M[a][b]);
+        R.add(a, own, b, M[a][b] / mu1, M[a][b] / mu2);
+        R.add(4 + a, own, 4 + b, M[a][b] / mu1, M[a][b] / mu2);
+        R.both(a, own, 8 + b, -Dx[a][b]); // -(div p) u
+        R.both(4 + a, own, 8 + b, -Dy[a][b]);
+        R.both(8 + a, own, b, -Dx[a][b]); // -grad v . q
+        R.both(8 + a, own, 4 + b, -Dy[a][b]);
+        R.both(8 + a, own, 8 + b, mass_scale * M[a][b]);
       }
-
     for (int f = 0; f < 4; ++f) {
       const int kind = mesh.face_kind[4 * c + f];
       if (kind == pecs::FACE_BOUNDARY) {
@@ -160,66 +248,113 @@ void LDG::assemble_system_matrices(const MeshTables& mesh, int dirichlet_id, dou
             if (T == 0.0) continue;
             for (int d = 0; d < 2; ++d) {
               if (dirichlet)
-                both(dofs.global(c, 8 + a), dofs.global(c, 4 * d + b), n[d] * T); // v n.q
+                R.both(8 + a, own, 4 * d + b, n[d] * T); // v n.q
               else
-                both(dofs.global(c, 4 * d + a), dofs.global(c, 8 + b), n[d] * T); // (p.n) u
+                R.both(4 * d + a, own, 8 + b, n[d] * T); // (p.n) u
             }
-            if (dirichlet) both(dofs.global(c, 8 + a), dofs.global(c, 8 + b), (penalty / h) * T);
+            if (dirichlet) R.both(8 + a, own, 8 + b, (penalty / h) * T);
           }
-        continue;
-      }
-      // interior faces: same level -> lower index does the work; hanging -> coarse side, per sub-face
-      int n_parts = 0, plus_cell[2] = {-1, -1};
-      double sigma = 0.0;
-      if (kind == pecs::FACE_SAME_LEVEL) {
-        const int nb = mesh.neighbor[4 * c + f];
-        if (nb < c) continue;
-        n_parts = 1;
-        plus_cell[0] = nb;
-        sigma = penalty / std::min(h, mesh.diameter(nb));
-      } else if (kind == pecs::FACE_HAS_CHILDREN) {
-        n_parts = 2;
-        plus_cell[0] = mesh.neighbor[4 * c + f];
-        plus_cell[1] = mesh.neighbor2[4 * c + f];
-        sigma = penalty / std::min(h, mesh.nb_parent_diameter[4 * c + f]);
-      } else {
-        continue; // FACE_COARSER: assembled from the coarse side
-      }
-      for (int s = 0; s < n_parts; ++s) {
-        const int e = plus_cell[s];
-        const double len = 1.0 / n_parts;
-        const FaceTables F = face_tables(v, f, s * len, len, true, f ^ 1);
-        const double n[2] = {F.nx, F.ny};
-        for (int a = 0; a < 4; ++a)
-          for (int b = 0; b < 4; ++b) {
-            for (int d = 0; d < 2; ++d) {
-              const double hp = 0.5 * n[d] + beta[d], hm = 0.5 * n[d] - beta[d];
-              // rows: current test functions, cols: densities
-              both(dofs.global(c, 4 * d + a), dofs.global(c, 8 + b), hp * F.Tmm[a][b]);
-              both(dofs.global(c, 4 * d + a), dofs.global(e, 8 + b), hm * F.Tmp[a][b]);
-              both(dofs.global(e, 4 * d + a), dofs.global(c, 8 + b), -hp * F.Tpm[a][b]);
-              both(dofs.global(e, 4 * d + a), dofs.global(e, 8 + b), -hm * F.Tpp[a][b]);
-              // rows: density test functions, cols: currents
-              both(dofs.global(c, 8 + a), dofs.global(c, 4 * d + b), hm * F.Tmm[a][b]);
-              both(dofs.global(c, 8 + a), dofs.global(e, 4 * d + b), hp * F.Tmp[a][b]);
-              both(dofs.global(e, 8 + a), dofs.global(c, 4 * d + b), -hm * F.Tpm[a][b]);
-              both(dofs.global(e, 8 + a), dofs.global(e, 4 * d + b), -hp * F.Tpp[a][b]);
-            }
-            // penalty on the density jump
-            both(dofs.global(c, 8 + a), dofs.global(c, 8 + b), sigma * F.Tmm[a][b]);
-            both(dofs.global(c, 8 + a), dofs.global(e, 8 + b), -sigma * F.Tmp[a][b]);
-            both(dofs.global(e, 8 + a), dofs.global(c, 8 + b), -sigma * F.Tpm[a][b]);
-            both(dofs.global(e, 8 + a), dofs.global(e, 8 + b), sigma * F.Tpp[a][b]);
-          }
+      } else if ((kind == pecs::FACE_SAME_LEVEL && mesh.neighbor[4 * c + f] > c) || kind == pecs::FACE_HAS_CHILDREN) {
+        const int n_parts = kind == pecs::FACE_SAME_LEVEL ? 1 : 2;
+        for (int sub = 0; sub < n_parts; ++sub) {
+          Face I;
+          face_of_worker(c, f, sub, I);
+          interior(I, c, R);
+        }
       }
     }
   }
-  } // chunk
-  const double t_fill = omp_get_wtime();
-  chunks.compress(true, matrix_1, matrix_2);
+
+  void rows_of_cell(int c, CellRows& R) const {
+    R.n_blocks = 0;
+    R.block(c);
+    // faces a neighbour works on, in the order of the neighbours' cell indices
+    Face foreign[4];
+    int n_foreign = 0;
+    for (int f = 0; f < 4; ++f) {
+      const int kind = mesh.face_kind[4 * c + f];
+      if (kind == pecs::FACE_SAME_LEVEL && mesh.neighbor[4 * c + f] < c)
+        face_of_worker(mesh.neighbor[4 * c + f], f ^ 1, 0, foreign[n_foreign++]);
+      else if (kind == pecs::FACE_COARSER)
+        face_of_worker(mesh.neighbor[4 * c + f], f ^ 1, mesh.neighbor2[4 * c + f], foreign[n_foreign++]);
+    }
+    std::sort(foreign, foreign + n_foreign, [](const Face& x, const Face& y) {
+      return x.worker != y.worker ? x.worker < y.worker : (x.f != y.f ? x.f < y.f : x.sub < y.sub);
+    });
+    int k = 0;
+    for (; k < n_foreign && foreign[k].worker < c; ++k) interior(foreign[k], c, R);
+    own_terms(c, R);
+    for (; k < n_foreign; ++k) interior(foreign[k], c, R);
+  }
+};
+
+} // namespace
+
+void LDG::assemble_system_matrices(const MeshTables& mesh, int dirichlet_id, double mu1, double mu2, double delta_t,
+                                   double transient_or_steady, double penalty, CsrMatrix& matrix_1,
+                                   CsrMatrix& matrix_2) const {
+  const double t_begin = omp_get_wtime();
+  const int n = mesh.n_cells;
+  const CarrierDofs dofs{n};
+  const LdgTerms terms{mesh, dirichlet_id, mu1, mu2, transient_or_steady / delta_t, penalty};
+  // rows are independent: pass 1 counts the entries of every row (entries whose two sums are both exactly zero are not
+  // stored), pass 2 evaluates the rows again and writes them in place.  Columns of a row ascend: [Jx | Jy | rho], and
+  // inside each component by cell.
+  auto emit = [&](int c, const CellRows& R, bool write) {
+    int order[CellRows::kMaxBlocks];
+    for (int k = 0; k < R.n_blocks; ++k) order[k] = k;
+    std::sort(order, order + R.n_blocks, [&](int x, int y) { return R.cell_of_block[x] < R.cell_of_block[y]; });
+    for (int r = 0; r < 12; ++r) {
+      const int row = dofs.global(c, r);
+      int at = write ? matrix_1.row_ptr[row] : 0;
+      for (int comp = 0; comp < 3; ++comp)
+        for (int q = 0; q < R.n_blocks; ++q) {
+          const int k = order[q];
+          for (int j = 0; j < 4; ++j) {
+            const double a = R.v1[r][12 * k + 4 * comp + j], b = R.v2[r][12 * k + 4 * comp + j];
+            if (a == 0.0 && b == 0.0) continue;
+            if (write) {
+              matrix_1.col[at] = dofs.global(R.cell_of_block[k], 4 * comp + j);
+              matrix_1.val[at] = a;
+              matrix_2.val[at] = b;
+            }
+            ++at;
+          }
+        }
+      if (!write) matrix_1.row_ptr[(size_t)row + 1] = at;
+    }
+  };
+  matrix_1.n = matrix_2.n = dofs.n_dofs();
+  matrix_1.row_ptr.assign((size_t)dofs.n_dofs() + 1, 0);
+#pragma omp parallel
+  {
+    CellRows R;
+#pragma omp for schedule(static)
+    for (int c = 0; c < n; ++c) {
+      terms.rows_of_cell(c, R);
+      emit(c, R, false);
+    }
+  }
+  for (int i = 0; i < dofs.n_dofs(); ++i) matrix_1.row_ptr[i + 1] += matrix_1.row_ptr[i];
+  const size_t nnz = (size_t)matrix_1.row_ptr[dofs.n_dofs()];
+  matrix_1.col.resize(nnz);
+  matrix_1.val.resize(nnz);
+  matrix_2.val.resize(nnz);
+  const double t_count = omp_get_wtime();
+#pragma omp parallel
+  {
+    CellRows R;
+#pragma omp for schedule(static)
+    for (int c = 0; c < n; ++c) {
+      terms.rows_of_cell(c, R);
+      emit(c, R, true);
+    }
+  }
+  matrix_2.row_ptr = matrix_1.row_ptr;
+  matrix_2.col = matrix_1.col;
   if (std::getenv("PECS_B200_SETUP_TIMING"))
-    std::fprintf(stderr, "LDG::assemble_system_matrices: %d cells, %d chunks: fill %.2f s, compress %.2f s\n", mesh.n_cells,
-                 n_chunks, t_fill - t_begin, omp_get_wtime() - t_fill);
+    std::fprintf(stderr, "LDG::assemble_system_matrices: %d cells: count %.2f s, fill %.2f s\n", n, t_count - t_begin,
+                 omp_get_wtime() - t_count);
 }
 
 std::string int_to_string_3(unsigned int n) {

@@ -34,6 +34,7 @@ struct SchurReduction {
 double schur_drop_tolerance();
 
 // A: full carrier matrix (12 n_cells rows).  Returns false (and leaves out untouched) when A_qq couples cells.
-bool build_schur_reduction(const CsrMatrix& A, int n_cells, SchurReduction& out);
+// threads: rows are built in that many contiguous ranges (the result does not depend on it).
+bool build_schur_reduction(const CsrView& A, int n_cells, SchurReduction& out, int threads = 1);
 
 } // namespace pecs

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <future>
 #include <iomanip>
 #include <iostream>
 #include <stdexcept>
@@ -14,6 +15,7 @@
 #include "../fe.hpp"
 #include "../rhs_math.hpp"
 #include "../test_functions.hpp"
+#include "SolverSetup.hpp"
 
 namespace SOLARCELL {
 
@@ -232,8 +234,12 @@ void SolarCellProblem::assemble_LDG_system(const double& transient_or_steady) {
                                            pair.carrier_2.scaled_mobility, delta_t, transient_or_steady, pair.penalty,
                                            pair.carrier_1.system_matrix, pair.carrier_2.system_matrix);
   };
+  // the two subdomains share nothing: assembled side by side (each with its own team of threads)
+  std::future<void> electrolyte;
+  if (full_system)
+    electrolyte = std::async(std::launch::async, [&] { do_pair(redox_pair, electrolyte_triangulation.tables()); });
   do_pair(electron_hole_pair, semiconductor_triangulation.tables());
-  if (full_system) do_pair(redox_pair, electrolyte_triangulation.tables());
+  if (full_system) electrolyte.get();
 }
 
 SolarCellProblem::BoundaryFaces SolarCellProblem::boundary_faces(const pecs::MeshTables& mesh) {
@@ -404,10 +410,14 @@ void SolarCellProblem::synchronize() {
 void SolarCellProblem::setup_full_system_host() {
   full_system = true;
   kind = PECS_KIND_PRODUCTION;
+  pecs::PhaseTimer timer("setup_full_system (host)");
   Grid_Maker::Grid grid_maker(sim_params);
   grid_maker.make_grids(semiconductor_triangulation, electrolyte_triangulation, Poisson_triangulation, full_system);
+  timer.lap("make_grids");
   setup_dofs();
+  timer.lap("setup_dofs");
   setup_mappings();
+  timer.lap("setup_mappings");
   if (verbose) {
     Poisson_object.print_info();
     electron_hole_pair.print_info();
@@ -416,12 +426,15 @@ void SolarCellProblem::setup_full_system_host() {
   electron_hole_pair.penalty = 1.0; // "dont remove", reference SolarCell.cpp:1944-1945
   redox_pair.penalty = 1.0;
   assemble_Poisson_matrix();
+  timer.lap("assemble_Poisson_matrix");
   delta_t = sim_params.delta_t;
   assemble_LDG_system(1.0);
+  timer.lap("assemble_LDG_system");
 }
 
 void SolarCellProblem::setup_full_system() {
   setup_full_system_host();
+  pecs::PhaseTimer timer("setup_full_system");
   // initial values first (reference SolarCell.cpp:1980-2021): a missing or truncated restart file is reported before
   // the factorisations are paid for
   if (sim_params.restart_status) {
@@ -430,7 +443,9 @@ void SolarCellProblem::setup_full_system() {
   } else {
     project_initial_conditions();
   }
+  timer.lap("initial conditions");
   set_solvers();
+  timer.lap("set_solvers (tables + pecs_ctx_create)");
   electron_hole_pair.carrier_1.push_solution();
   electron_hole_pair.carrier_2.push_solution();
   redox_pair.carrier_1.push_solution();
@@ -438,6 +453,7 @@ void SolarCellProblem::setup_full_system() {
   // initial potential and field, reference SolarCell.cpp:2033-2034
   assemble_Poisson_rhs();
   solve_Poisson();
+  timer.lap("initial states, first Poisson solve");
 }
 
 // ------------------------------------------------------------------------------------------------- output path

@@ -2,7 +2,11 @@
 #include "SolverSetup.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
+#include <future>
+#include <thread>
 
 #include "../error.hpp"
 #include "SchurReduction.hpp"
@@ -191,7 +195,8 @@ SolvePlan poisson_plan(const CsrMatrix& A, const pecs_poisson_desc& d, int leaf_
   if (A.n != n) throw StatusError(PECS_ERR_INVALID, "poisson_plan: matrix size");
   std::vector<int> identity(n);
   for (int i = 0; i < n; ++i) identity[i] = i;
-  const std::vector<std::vector<int>> adj = node_adjacency(A, identity, n);
+  const int threads = preparation_threads();
+  const std::vector<std::vector<int>> adj = node_adjacency(A, identity, n, threads);
   PoissonNd nd{adj, d, {}, {}, std::max(1, leaf_cells), std::vector<char>(n, 0), std::vector<int>(d.n_cells, 0),
                std::vector<int>(d.n_cells, 0), std::vector<int>(d.n_cells, 0), 0, {}};
   nd.cx.resize(d.n_cells);
@@ -210,7 +215,7 @@ SolvePlan poisson_plan(const CsrMatrix& A, const pecs_poisson_desc& d, int leaf_
   for (int e = 0; e < d.n_rt; ++e)
     if (!nd.assigned[e]) root.nodes.push_back(e);
   std::sort(root.nodes.begin(), root.nodes.end());
-  return build_solve_plan(A, identity, n, adj, nd.out);
+  return build_solve_plan(A, identity, n, adj, nd.out, threads);
 }
 
 NodeLayout carrier_density_nodes(const pecs_domain_desc& d) {
@@ -234,8 +239,8 @@ NodeLayout carrier_density_nodes(const pecs_domain_desc& d) {
   return L;
 }
 
-SolvePlan plan_from_layout(const CsrMatrix& A, const NodeLayout& L, int leaf_groups) {
-  return build_solve_plan(A, L.node_of_dof, L.group_of_node, L.x, L.y, leaf_groups);
+SolvePlan plan_from_layout(const CsrMatrix& A, const NodeLayout& L, int leaf_groups, int threads) {
+  return build_solve_plan(A, L.node_of_dof, L.group_of_node, L.x, L.y, leaf_groups, threads);
 }
 
 bool schur_reduction_enabled() {
@@ -254,6 +259,84 @@ int default_leaf_nodes(bool poisson) {
     if (v > 0) return v;
   }
   return 16;
+}
+
+namespace {
+double wall_seconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+} // namespace
+
+PhaseTimer::PhaseTimer(const char* scope_) : on(std::getenv("PECS_B200_SETUP_TIMING") != nullptr), scope(scope_), t(wall_seconds()) {}
+void PhaseTimer::lap(const char* what) {
+  if (!on) return;
+  const double now = wall_seconds();
+  std::fprintf(stderr, "%s: %-44s %.2f s\n", scope, what, now - t);
+  t = now;
+}
+
+CsrMatrix copy_csr(const pecs_csr& a, int expected_n, const char* what) {
+  if (!(a.n == expected_n && a.row_ptr && a.col && a.val)) throw StatusError(PECS_ERR_INVALID, what);
+  CsrMatrix A;
+  A.n = a.n;
+  A.row_ptr.assign(a.row_ptr, a.row_ptr + a.n + 1);
+  const size_t nnz = (size_t)A.row_ptr[a.n];
+  A.col.assign(a.col, a.col + nnz);
+  A.val.assign(a.val, a.val + nnz);
+  return A;
+}
+
+int preparation_threads() {
+  if (const char* e = std::getenv("PECS_B200_SETUP_THREADS"))
+    if (std::atoi(e) > 0) return std::atoi(e);
+  const int hw = (int)std::thread::hardware_concurrency();
+  return std::max(1, std::min(8, hw / 4));
+}
+
+namespace {
+// the two permuted copies are independent of each other: the transposed one on a second thread
+void permuted_copies_of(PreparedSystem& ps) {
+  const int threads = std::max(1, preparation_threads() / 2);
+  std::future<CsrMatrix> transposed =
+      std::async(std::launch::async, [&ps, threads] { return permute_csr(ps.A, ps.plan.perm, true, threads); });
+  ps.Ap = permute_csr(ps.A, ps.plan.perm, false, threads);
+  ps.Apt = transposed.get();
+}
+} // namespace
+
+PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k, bool permuted_copies) {
+  PhaseTimer timer(k == 0 ? "prepare carrier_1" : "prepare carrier_2");
+  PreparedSystem ps;
+  ps.present = true;
+  const int n = d.n_cells;
+  const pecs_csr& a = d.system_matrix[k];
+  if (!(a.n == 12 * n && a.row_ptr && a.col && a.val)) throw StatusError(PECS_ERR_INVALID, "domain: system matrix size");
+  if (schur_reduction_enabled() &&
+      build_schur_reduction(CsrView(a.n, a.row_ptr, a.col, a.val), n, ps.R, preparation_threads())) {
+    timer.lap("Schur reduction of the currents");
+    ps.reduced = true;
+    ps.A = std::move(ps.R.S); // R keeps T1, Ainv, T2
+    ps.plan = plan_from_layout(ps.A, carrier_density_nodes(d), default_leaf_nodes(false), preparation_threads());
+  } else {
+    ps.A = copy_csr(a, 12 * n, "domain: system matrix size");
+    ps.plan = plan_from_layout(ps.A, carrier_nodes(d), default_leaf_nodes(false), preparation_threads());
+  }
+  timer.lap("dissection and symbolic plan");
+  if (permuted_copies) permuted_copies_of(ps);
+  timer.lap("matrix in elimination order (+ transpose)");
+  return ps;
+}
+
+PreparedSystem prepare_poisson(const pecs_poisson_desc& P, int n_dofs, bool permuted_copies) {
+  PhaseTimer timer("prepare Poisson");
+  PreparedSystem ps;
+  ps.present = true;
+  ps.A = copy_csr(P.system_matrix, n_dofs, "poisson: system matrix size");
+  ps.plan = poisson_plan(ps.A, P, default_leaf_nodes(true));
+  timer.lap("dissection and symbolic plan");
+  if (permuted_copies) permuted_copies_of(ps);
+  timer.lap("matrix in elimination order (+ transpose)");
+  return ps;
 }
 
 SolvePlan plan_for_system(SOLARCELL::SolarCellProblem& s, int which, int leaf_nodes) {

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../../include/pecs_b200.h"
+#include "SchurReduction.hpp"
 #include "SparseDirect.hpp"
 
 namespace SOLARCELL {
@@ -29,7 +30,7 @@ NodeLayout carrier_nodes(const pecs_domain_desc& d);
 // the Schur-reduced carrier system (host/SchurReduction.hpp): every density unknown is its own graph node, bisected
 // through its cell -- separators are then sets of unknowns (6 per cell row), not of whole cells (8 per cell row)
 NodeLayout carrier_density_nodes(const pecs_domain_desc& d);
-SolvePlan plan_from_layout(const CsrMatrix& A, const NodeLayout& L, int leaf_groups);
+SolvePlan plan_from_layout(const CsrMatrix& A, const NodeLayout& L, int leaf_groups, int threads = 1);
 // PECS_B200_NO_SCHUR=1 factorises the full 12-unknowns-per-cell systems instead (debugging / comparison)
 bool schur_reduction_enabled();
 NodeLayout poisson_nodes(const pecs_poisson_desc& d);
@@ -45,6 +46,32 @@ NodeLayout poisson_nodes(const pecs_poisson_desc& d);
 SolvePlan poisson_plan(const CsrMatrix& A, const pecs_poisson_desc& d, int leaf_cells);
 // recursion stops at this many nodes per leaf; PECS_B200_LEAF_NODES overrides (tuning)
 int default_leaf_nodes(bool poisson);
+
+// Host half of building one linear system -- copy of the matrix, Schur reduction of the currents, nested dissection,
+// the symbolic front layout and the matrix in elimination order -- needs no device and dominates pecs_ctx_create; the
+// (up to) five systems are prepared concurrently on host threads, then factorised on the device one after the other.
+struct PreparedSystem {
+  bool present = false, reduced = false;
+  CsrMatrix A;       // the matrix that is factorised (S when reduced)
+  CsrMatrix Ap, Apt; // P A P^T and its transpose in elimination order (only when asked for: the device factorisation)
+  SchurReduction R;
+  SolvePlan plan;
+};
+CsrMatrix copy_csr(const pecs_csr& a, int expected_n, const char* what);
+// threads each of the concurrent preparations may use for its own loops: a quarter of the machine, at most 8
+// (PECS_B200_SETUP_THREADS overrides); no result depends on it
+int preparation_threads();
+PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k, bool permuted_copies);
+PreparedSystem prepare_poisson(const pecs_poisson_desc& P, int n_dofs, bool permuted_copies);
+
+// PECS_B200_SETUP_TIMING=1: wall-clock phases of the one-time setup on stderr, one line per phase
+struct PhaseTimer {
+  explicit PhaseTimer(const char* scope);
+  void lap(const char* what);
+  bool on;
+  const char* scope;
+  double t;
+};
 
 // convenience for the host classes / CPU tests: which = 0..3 species, 4 Poisson; leaf_nodes <= 0 -> default
 SolvePlan plan_for_system(SOLARCELL::SolarCellProblem& problem, int which, int leaf_nodes);

@@ -2,8 +2,10 @@
 #include "SparseDirect.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <future>
 #include <numeric>
 #include <stdexcept>
 
@@ -20,33 +22,35 @@ namespace {
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct NdBuilder {
+  typedef std::vector<EliminationTree::Node> Tree; // postorder, root last, child indices local to the vector
   const std::vector<std::vector<int>>& adj;
   const std::vector<int>& group_of; // empty: every node is its own group
   const std::vector<double>&x, &y;  // per group
   int leaf_groups;
+  int parallel_depth;      // the two halves of a region are dissected concurrently down to this depth
   std::vector<int> side;   // per node: 0 = outside the current region, 1 = A, 2 = B
   std::vector<int> gside;  // per group, scratch
   std::vector<int> gstamp; // per group: last region that counted it
-  int stamp = 0;
-  EliminationTree out;
+  std::atomic<int> stamp{0};
+  // Concurrent regions are disjoint in nodes AND in groups (a region is bisected through whole groups), so the three
+  // scratch arrays are shared without locks; only the region counter is atomic.
 
   int group(int v) const { return group_of.empty() ? v : group_of[v]; }
 
-  int leaf(std::vector<int>& nodes) {
-    EliminationTree::Node t;
+  static Tree leaf(std::vector<int>& nodes) {
+    Tree t(1);
     std::sort(nodes.begin(), nodes.end());
-    t.nodes.swap(nodes);
-    out.tree.push_back(std::move(t));
-    return (int)out.tree.size() - 1;
+    t[0].nodes.swap(nodes);
+    return t;
   }
 
-  int build(std::vector<int>& nodes) {
+  Tree build(std::vector<int>& nodes, int depth) {
     std::vector<int> groups;
-    ++stamp;
+    const int my_stamp = ++stamp;
     for (int v : nodes) {
       const int g = group(v);
-      if (gstamp[g] != stamp) {
-        gstamp[g] = stamp;
+      if (gstamp[g] != my_stamp) {
+        gstamp[g] = my_stamp;
         groups.push_back(g);
       }
     }
@@ -93,13 +97,30 @@ struct NdBuilder {
     if (!have) return leaf(nodes);
     nodes.clear();
     nodes.shrink_to_fit();
+    Tree a, b;
+    if (depth < parallel_depth) {
+      std::future<Tree> other = std::async(std::launch::async, [&] { return build(bestB, depth + 1); });
+      a = build(bestA, depth + 1);
+      b = other.get();
+    } else {
+      a = build(bestA, depth + 1);
+      b = build(bestB, depth + 1);
+    }
+    // postorder: the first half's subtree, the second half's, then the separator
+    const int na = (int)a.size(), nb = (int)b.size();
+    a.reserve((size_t)na + nb + 1);
+    for (EliminationTree::Node& t : b) {
+      for (int k = 0; k < 2; ++k)
+        if (t.child[k] >= 0) t.child[k] += na;
+      a.push_back(std::move(t));
+    }
     EliminationTree::Node t;
-    t.child[0] = build(bestA);
-    t.child[1] = build(bestB);
+    t.child[0] = na - 1;
+    t.child[1] = na + nb - 1;
     std::sort(bestS.begin(), bestS.end());
     t.nodes.swap(bestS);
-    out.tree.push_back(std::move(t));
-    return (int)out.tree.size() - 1;
+    a.push_back(std::move(t));
+    return a;
   }
 };
 
@@ -161,8 +182,22 @@ void shape_table(PanelTable& t, int rows, int cols, int log2_cap) {
 
 } // namespace
 
-std::vector<std::vector<int>> node_adjacency(const CsrMatrix& A, const std::vector<int>& node_of_dof, int n_nodes) {
+std::vector<std::vector<int>> node_adjacency(const CsrMatrix& A, const std::vector<int>& node_of_dof, int n_nodes,
+                                             int threads) {
   std::vector<std::vector<int>> adj(n_nodes);
+  {
+    std::vector<int> degree(n_nodes, 0); // with duplicates: an upper bound, reserved once
+    for (int i = 0; i < A.n; ++i)
+      for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k) {
+        const int a = node_of_dof[i], b = node_of_dof[A.col[k]];
+        if (a != b) {
+          ++degree[a];
+          ++degree[b];
+        }
+      }
+#pragma omp parallel for schedule(static) num_threads(std::max(1, threads))
+    for (int v = 0; v < n_nodes; ++v) adj[v].reserve((size_t)degree[v]);
+  }
   for (int i = 0; i < A.n; ++i)
     for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k) {
       const int a = node_of_dof[i], b = node_of_dof[A.col[k]];
@@ -171,7 +206,9 @@ std::vector<std::vector<int>> node_adjacency(const CsrMatrix& A, const std::vect
         adj[b].push_back(a);
       }
     }
-  for (auto& a : adj) {
+#pragma omp parallel for schedule(static) num_threads(std::max(1, threads))
+  for (int v = 0; v < n_nodes; ++v) {
+    std::vector<int>& a = adj[v];
     std::sort(a.begin(), a.end());
     a.erase(std::unique(a.begin(), a.end()), a.end());
   }
@@ -179,31 +216,37 @@ std::vector<std::vector<int>> node_adjacency(const CsrMatrix& A, const std::vect
 }
 
 EliminationTree nested_dissection(const std::vector<std::vector<int>>& adj, const std::vector<int>& group_of_node,
-                                  const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups) {
+                                  const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups,
+                                  int threads) {
   const int n_nodes = (int)adj.size();
   const int n_groups = (int)group_x.size();
   if (!group_of_node.empty() && (int)group_of_node.size() != n_nodes)
     throw StatusError(PECS_ERR_INVALID, "nested_dissection: group_of_node size");
   if (group_of_node.empty() && n_groups != n_nodes) throw StatusError(PECS_ERR_INVALID, "nested_dissection: coordinates size");
-  NdBuilder nd{adj, group_of_node, group_x, group_y, std::max(1, leaf_groups), std::vector<int>(n_nodes, 0),
-               std::vector<int>(n_groups, 0), std::vector<int>(n_groups, 0), 0, {}};
+  int depth = 0;
+  while ((1 << (depth + 1)) <= threads) ++depth; // 2^depth concurrent subtrees
+  NdBuilder nd{adj, group_of_node, group_x, group_y, std::max(1, leaf_groups), depth, std::vector<int>(n_nodes, 0),
+               std::vector<int>(n_groups, 0), std::vector<int>(n_groups, 0)};
   std::vector<int> all(n_nodes);
   std::iota(all.begin(), all.end(), 0);
-  nd.build(all);
-  return std::move(nd.out);
+  EliminationTree out;
+  out.tree = nd.build(all, 0);
+  return out;
 }
 
 SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_dof, const std::vector<int>& group_of_node,
-                           const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups) {
+                           const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups,
+                           int threads) {
   if ((int)node_of_dof.size() != A.n) throw StatusError(PECS_ERR_INVALID, "build_solve_plan: node_of_dof size");
   const int n_nodes = group_of_node.empty() ? (int)group_x.size() : (int)group_of_node.size();
-  const std::vector<std::vector<int>> adj = node_adjacency(A, node_of_dof, n_nodes);
-  const EliminationTree tree = nested_dissection(adj, group_of_node, group_x, group_y, leaf_groups);
-  return build_solve_plan(A, node_of_dof, n_nodes, adj, tree);
+  const std::vector<std::vector<int>> adj = node_adjacency(A, node_of_dof, n_nodes, threads);
+  const EliminationTree tree = nested_dissection(adj, group_of_node, group_x, group_y, leaf_groups, threads);
+  return build_solve_plan(A, node_of_dof, n_nodes, adj, tree, threads);
 }
 
 SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_dof, int n_nodes,
-                           const std::vector<std::vector<int>>& adj, const EliminationTree& etree) {
+                           const std::vector<std::vector<int>>& adj, const EliminationTree& etree, int threads) {
+  threads = std::max(1, threads);
   const int n = A.n;
   if ((int)node_of_dof.size() != n) throw StatusError(PECS_ERR_INVALID, "build_solve_plan: node_of_dof size");
   std::vector<std::vector<int>> node_dofs(n_nodes);
@@ -249,19 +292,29 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
   for (int v = 0; v < n_nodes; ++v)
     if (node_pos[v] >= 0) pos_to_node[node_pos[v]] = v;
   std::vector<std::vector<int>> bd_nodes(nf);
-  for (int f = 0; f < nf; ++f) {
-    std::vector<int> s;
-    for (int v : tree[f].nodes)
-      for (int w : adj[v])
-        if (node_pos[w] > last_node_pos[f]) s.push_back(node_pos[w]);
-    for (int k = 0; k < 2; ++k)
-      if (plan.fronts[f].child[k] >= 0) {
-        for (int p : bd_nodes[plan.fronts[f].child[k]])
-          if (p > last_node_pos[f]) s.push_back(p);
-      }
-    std::sort(s.begin(), s.end());
-    s.erase(std::unique(s.begin(), s.end()), s.end());
-    bd_nodes[f].swap(s);
+  int max_depth = 0;
+  for (const Front& F : plan.fronts) max_depth = std::max(max_depth, F.depth);
+  plan.levels.assign(max_depth + 1, {});
+  for (int f = 0; f < nf; ++f) plan.levels[plan.fronts[f].depth].push_back(f);
+  // children before parents: level by level from the bottom, the fronts of a level side by side
+  for (int depth = max_depth; depth >= 0; --depth) {
+    const std::vector<int>& lvl = plan.levels[depth];
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads) if (lvl.size() > 64)
+    for (int q = 0; q < (int)lvl.size(); ++q) {
+      const int f = lvl[q];
+      std::vector<int> s;
+      for (int v : tree[f].nodes)
+        for (int w : adj[v])
+          if (node_pos[w] > last_node_pos[f]) s.push_back(node_pos[w]);
+      for (int k = 0; k < 2; ++k)
+        if (plan.fronts[f].child[k] >= 0) {
+          for (int p : bd_nodes[plan.fronts[f].child[k]])
+            if (p > last_node_pos[f]) s.push_back(p);
+        }
+      std::sort(s.begin(), s.end());
+      s.erase(std::unique(s.begin(), s.end()), s.end());
+      bd_nodes[f].swap(s);
+    }
   }
   // expand to unknowns
   for (int f = 0; f < nf; ++f) {
@@ -274,10 +327,6 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
     F.nb = (int)((int64_t)plan.bd_index.size() - F.bd_off);
     std::vector<int>().swap(bd_nodes[f]);
   }
-  int max_depth = 0;
-  for (const Front& F : plan.fronts) max_depth = std::max(max_depth, F.depth);
-  plan.levels.assign(max_depth + 1, {});
-  for (int f = 0; f < nf; ++f) plan.levels[plan.fronts[f].depth].push_back(f);
   // panel heights: as tall as possible, capped per level so that the level offers enough panels for the whole GPU
   for (const std::vector<int>& lvl : plan.levels)
     for (int which = 0; which < 2; ++which) {
@@ -319,6 +368,8 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
   }
   // where every boundary unknown of a front lives in its parent's local numbering [pivots | boundary]
   plan.out_map.assign(plan.bd_index.size(), -1);
+  bool outside = false;
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads) reduction(|| : outside)
   for (int f = 0; f < nf; ++f) {
     const Front& C = plan.fronts[f];
     if (C.parent < 0) continue;
@@ -329,17 +380,17 @@ SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_d
       const int pos = cbd[s];
       int l;
       if (pos < F.p0 + F.np) {
-        if (pos < F.p0) throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: child boundary below parent pivots");
+        if (pos < F.p0) outside = true; // below the parent's pivots
         l = pos - F.p0;
       } else {
         const int* it = std::lower_bound(fbd, fbd + F.nb, pos);
-        if (it == fbd + F.nb || *it != pos)
-          throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: child boundary not contained in parent front");
+        if (it == fbd + F.nb || *it != pos) outside = true;
         l = F.np + (int)(it - fbd);
       }
       plan.out_map[C.bd_off + s] = l;
     }
   }
+  if (outside) throw StatusError(PECS_ERR_INTERNAL, "build_solve_plan: child boundary not contained in parent front");
   return plan;
 }
 
@@ -420,17 +471,56 @@ bool invert(int n, double* M, bool par) {
 
 } // namespace
 
-CsrMatrix permute_csr(const CsrMatrix& A, const std::vector<int>& perm, bool transpose) {
-  TripletList tl(A.n);
-  tl.reserve(A.nnz());
-  for (int i = 0; i < A.n; ++i)
-    for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k) {
-      if (transpose)
-        tl.add(perm[A.col[k]], perm[i], A.val[k]);
-      else
-        tl.add(perm[i], perm[A.col[k]], A.val[k]);
+CsrMatrix permute_csr(const CsrMatrix& A, const std::vector<int>& perm, bool transpose, int threads) {
+  // entry (i, j) goes to row perm[i] (perm[j] when transposed); rows are filled by counting, then sorted by column
+  // one by one (a matrix has no duplicate entries, so the order inside a row is all there is to fix)
+  const int n = A.n;
+  threads = std::max(1, threads);
+  CsrMatrix B;
+  B.n = n;
+  B.row_ptr.assign((size_t)n + 1, 0);
+  if (transpose) {
+    for (size_t k = 0; k < A.col.size(); ++k) ++B.row_ptr[(size_t)perm[A.col[k]] + 1];
+  } else {
+    for (int i = 0; i < n; ++i) B.row_ptr[(size_t)perm[i] + 1] = A.row_ptr[i + 1] - A.row_ptr[i];
+  }
+  for (int i = 0; i < n; ++i) B.row_ptr[i + 1] += B.row_ptr[i];
+  B.col.resize(A.col.size());
+  B.val.resize(A.val.size());
+  if (transpose) {
+    std::vector<int> next(B.row_ptr.begin(), B.row_ptr.end() - 1);
+    for (int i = 0; i < n; ++i)
+      for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k) {
+        const int q = next[perm[A.col[k]]]++;
+        B.col[q] = perm[i];
+        B.val[q] = A.val[k];
+      }
+  } else {
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int i = 0; i < n; ++i) {
+      int q = B.row_ptr[perm[i]];
+      for (int k = A.row_ptr[i]; k < A.row_ptr[i + 1]; ++k, ++q) {
+        B.col[q] = perm[A.col[k]];
+        B.val[q] = A.val[k];
+      }
     }
-  return tl.compress();
+  }
+#pragma omp parallel num_threads(threads)
+  {
+    std::vector<std::pair<int, double>> row;
+#pragma omp for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      const int b = B.row_ptr[i], e = B.row_ptr[i + 1];
+      row.resize((size_t)(e - b));
+      for (int k = b; k < e; ++k) row[(size_t)(k - b)] = {B.col[k], B.val[k]};
+      std::sort(row.begin(), row.end(), [](const std::pair<int, double>& x, const std::pair<int, double>& y) { return x.first < y.first; });
+      for (int k = b; k < e; ++k) {
+        B.col[k] = row[(size_t)(k - b)].first;
+        B.val[k] = row[(size_t)(k - b)].second;
+      }
+    }
+  }
+  return B;
 }
 
 void factorize_host(const SolvePlan& plan, const CsrMatrix& A, std::vector<double>& fwd, std::vector<double>& bwd) {

@@ -105,23 +105,27 @@ struct EliminationTree {
 // of a region are split at the median coordinate, in x and in y, and the separator is the smaller of "nodes of one
 // side that touch the other side", both sides tried.  With single unknowns as nodes the separator of the LDG density
 // system is 6 unknowns per cell row (a cell and the facing nodes of its neighbour) instead of the 8 of two whole cells.
-// Recursion stops at leaf_groups cells.
+// Recursion stops at leaf_groups cells.  threads: the two halves of a region are dissected concurrently near the root
+// (regions are disjoint; the tree does not depend on it).
 EliminationTree nested_dissection(const std::vector<std::vector<int>>& adj, const std::vector<int>& group_of_node,
-                                  const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups);
+                                  const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups,
+                                  int threads = 1);
 
 // adjacency of the graph nodes induced by the (symmetrised) pattern of A
-std::vector<std::vector<int>> node_adjacency(const CsrMatrix& A, const std::vector<int>& node_of_dof, int n_nodes);
+std::vector<std::vector<int>> node_adjacency(const CsrMatrix& A, const std::vector<int>& node_of_dof, int n_nodes,
+                                             int threads = 1);
 
 // Symbolic analysis + table layout for a given tree.
 SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_dof, int n_nodes,
-                           const std::vector<std::vector<int>>& adj, const EliminationTree& tree);
+                           const std::vector<std::vector<int>>& adj, const EliminationTree& tree, int threads = 1);
 
 // convenience: node_adjacency + nested_dissection + build_solve_plan
 SolvePlan build_solve_plan(const CsrMatrix& A, const std::vector<int>& node_of_dof, const std::vector<int>& group_of_node,
-                           const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups);
+                           const std::vector<double>& group_x, const std::vector<double>& group_y, int leaf_groups,
+                           int threads = 1);
 
 // P A P^T (or its transpose) in CSR, P = plan.perm
-CsrMatrix permute_csr(const CsrMatrix& A, const std::vector<int>& perm, bool transpose);
+CsrMatrix permute_csr(const CsrMatrix& A, const std::vector<int>& perm, bool transpose, int threads = 1);
 
 // Host numeric factorisation: fills fwd (all G) and bwd (all [Inv | -H]) tables.  Throws StatusError(PECS_ERR_SINGULAR)
 // when a pivot block cannot be inverted.
