@@ -671,6 +671,7 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
       red.Ainv.upload(ps.R.Ainv);
       red.T2.upload(ps.R.T2);
       red.rtilde.resize((size_t)n_rhs * 4 * (size_t)n);
+      wait.lap("  system in all (build + reduction tables T1, Ainv, T2)");
     } else {
       if (D.shared_pair) throw StatusError(PECS_ERR_INTERNAL, "shared factorisation needs the Schur-reduced system");
       D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, 1, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr);

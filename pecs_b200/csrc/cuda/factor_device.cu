@@ -328,9 +328,38 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& Ap, const CsrMatri
   Handles& h = *handles_of[device & 63];
   for (Lane& l : h.lane)
     if (l.ipiv.size() < (size_t)std::max(plan.max_np, 1)) l.ipiv.resize((size_t)std::max(plan.max_np, 1));
+  // work buffers sized ONCE for the largest level: an allocation or a release per level is a device-wide
+  // synchronisation and the most expensive host call of the whole loop
   DeviceBuffer<double> Fcur, Fchild, Gs, Bs;
   DeviceBuffer<FactorFront> d_cur, d_child;
   DeviceBuffer<int> cl, small_list;
+  {
+    size_t F_max = 1, Gs_max = 1, Bs_max = 1, cl_max = 1, fronts_max = 1;
+    for (const std::vector<int>& lvl : plan.levels) {
+      size_t F_total = 0, Gs_total = 0, Bs_total = 0, cl_total = 0;
+      for (int f : lvl) {
+        const Front& F = plan.fronts[f];
+        F_total += (size_t)(F.np + F.nb) * (F.np + F.nb);
+        Gs_total += (size_t)F.nb * F.np;
+        Bs_total += (size_t)F.np * (F.np + F.nb);
+        for (int c = 0; c < 2; ++c)
+          if (F.child[c] >= 0) cl_total += (size_t)plan.fronts[F.child[c]].nb;
+      }
+      F_max = std::max(F_max, F_total);
+      Gs_max = std::max(Gs_max, Gs_total);
+      Bs_max = std::max(Bs_max, Bs_total);
+      cl_max = std::max(cl_max, cl_total);
+      fronts_max = std::max(fronts_max, lvl.size());
+    }
+    Fcur.resize(F_max);
+    Fchild.resize(F_max);
+    Gs.resize(Gs_max);
+    Bs.resize(Bs_max);
+    cl.resize(cl_max);
+    d_cur.resize(fronts_max);
+    d_child.resize(fronts_max);
+    small_list.resize(fronts_max);
+  }
   std::vector<int> index_in_level(plan.fronts.size(), -1);
 
   for (int d = (int)plan.levels.size() - 1; d >= 0; --d) {
@@ -369,16 +398,12 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& Ap, const CsrMatri
       (F.np <= kSmallFrontMaxNp ? small : large).push_back((int)k);
     }
     for (size_t k = 0; k < lvl.size(); ++k) index_in_level[lvl[k]] = (int)k;
-    Fcur.resize((size_t)F_total);
-    Fcur.zero();
-    if ((size_t)Gs_total > Gs.size()) Gs.resize((size_t)Gs_total);
-    if ((size_t)Bs_total > Bs.size()) Bs.resize((size_t)Bs_total);
-    d_cur.upload(ff);
+    if (F_total > 0) PECS_CUDA(cudaMemsetAsync(Fcur.get(), 0, (size_t)F_total * sizeof(double)));
+    PECS_CUDA(cudaMemcpy(d_cur.get(), ff.data(), ff.size() * sizeof(FactorFront), cudaMemcpyHostToDevice));
     const int nfl = (int)lvl.size();
     assemble_kernel<<<nfl, 128>>>(d_cur.get(), d_bd_index, rp.get(), col.get(), val.get(), trp.get(), tcol.get(),
                                   tval.get(), Fcur.get(), d_error.get());
     if (cl_total > 0) {
-      cl.resize((size_t)cl_total);
       for (int c = 0; c < 2; ++c) {
         child_local_kernel<<<nfl, 128>>>(d_cur.get(), d_child.get(), d_bd_index, c, cl.get(), d_error.get());
         const dim3 grid(nfl, std::max(1, std::min(max_child_nb, 1024)));
@@ -387,7 +412,7 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& Ap, const CsrMatri
     }
     PECS_CUDA(cudaGetLastError());
     if (!small.empty()) {
-      small_list.upload(small);
+      PECS_CUDA(cudaMemcpy(small_list.get(), small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice));
       small_front_kernel<<<(int)small.size(), 256>>>(d_cur.get(), small_list.get(), Fcur.get(), Gs.get(), Bs.get(),
                                                      d_error.get());
       PECS_CUDA(cudaGetLastError());

@@ -15,6 +15,7 @@ void DeviceEll::upload(const CsrMatrix& A, const std::vector<int>* row_order) {
   n = A.n;
   // slots per row in both formats
   int w1 = 0, w4 = 0;
+#pragma omp parallel for schedule(static) reduction(max : w1, w4)
   for (int i = 0; i < n; ++i) {
     w1 = std::max(w1, A.row_ptr[i + 1] - A.row_ptr[i]);
     int groups = 0, last = -1;
@@ -30,7 +31,8 @@ void DeviceEll::upload(const CsrMatrix& A, const std::vector<int>* row_order) {
   width = block == 4 ? w4 : w1;
   std::vector<int> c((size_t)n * width, 0);
   std::vector<double> v((size_t)n * width * block, 0.0);
-  for (int i = 0; i < n; ++i) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) { // row i owns entry i of every slot: no two rows write the same place
     const int r = row_order ? (*row_order)[i] : i;
     if (block == 1) {
       for (int k = A.row_ptr[r]; k < A.row_ptr[r + 1]; ++k) {
