@@ -140,6 +140,11 @@ typedef struct pecs_ctx pecs_ctx;
 const char* pecs_last_error(void);
 /* number of CUDA devices visible to the library (0 when there is none or the driver is missing) */
 int32_t pecs_device_count(void);
+/* Optional: pays the one-time costs of a device's first pecs_ctx_create ahead of it -- CUDA context, the library's kernel
+ * image, the cuSOLVER / cuBLAS handles of the setup factorisation -- so that a caller can overlap them with its own host
+ * work (SolarCellProblem::setup_full_system calls it on a second thread while it builds grids and matrices).  Has no
+ * counterpart in the reference and changes no result; pecs_ctx_create does the same work itself when it was not called. */
+pecs_status pecs_device_warmup(int32_t device);
 
 /* replaces: end of setup + SolarCellProblem::set_solvers, reference source/SolarCell.cpp:1733-1747 */
 pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out);

@@ -29,6 +29,7 @@ SIGNATURES = {
     # ---- include/pecs_b200.h ----
     "pecs_last_error": (C.c_char_p, []),
     "pecs_device_count": (C.c_int32, []),
+    "pecs_device_warmup": (C.c_int, [C.c_int32]),
     "pecs_ctx_create": (C.c_int, [VOIDP, C.POINTER(VOIDP)]),
     "pecs_ctx_destroy": (None, [VOIDP]),
     "pecs_set_state": (C.c_int, [VOIDP, C.c_int32, c_double_p]),

@@ -970,6 +970,23 @@ int32_t pecs_device_count(void) {
   return n;
 }
 
+pecs_status pecs_device_warmup(int32_t device) {
+  return guarded([&] {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+      cudaGetLastError();
+      throw StatusError(PECS_ERR_NO_DEVICE, "pecs_device_warmup: no CUDA device visible");
+    }
+    require(device >= 0 && device < n_dev, "pecs_device_warmup: device ordinal out of range");
+    PECS_CUDA(cudaSetDevice(device));
+    PECS_CUDA(cudaFree(nullptr)); // the context
+    int max_optin = 0;
+    PECS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    configure_solve_kernels(max_optin); // loads the kernel image
+    if (device_factorization_enabled()) warm_factor_handles();
+  });
+}
+
 pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
   return guarded([&] {
     require(desc && out, "pecs_ctx_create: NULL argument");
@@ -983,7 +1000,6 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     require(desc->device >= 0 && desc->device < n_dev, "pecs_ctx_create: device ordinal out of range");
     require(desc->kind >= PECS_KIND_PRODUCTION && desc->kind <= PECS_KIND_TEST_DD_POISSON, "pecs_ctx_create: unknown kind");
     require(desc->params[PECS_P_DELTA_T] > 0.0, "pecs_ctx_create: delta_t must be positive");
-    PECS_CUDA(cudaSetDevice(desc->device));
     std::unique_ptr<pecs_ctx> ctx(new pecs_ctx());
     ctx->device = desc->device;
     ctx->kind = desc->kind;
@@ -993,27 +1009,14 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
       for (DeviceDomain& D : ctx->dom)
         for (DeviceSystem& S : D.system) S.policy = DeviceSystem::shard_policy();
     std::memcpy(ctx->params, desc->params, sizeof(ctx->params));
-    PECS_CUDA(cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking));
-    for (int k = 0; k < 4; ++k) {
-      PECS_CUDA(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
-      PECS_CUDA(cudaEventCreateWithFlags(&ctx->join[k], cudaEventDisableTiming));
-      PECS_CUDA(cudaEventCreateWithFlags(&ctx->copied[k], cudaEventDisableTiming));
-      PECS_CUDA(cudaEventCreateWithFlags(&ctx->dens[k], cudaEventDisableTiming));
-    }
-    PECS_CUDA(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
     const pecs_poisson_desc& P = desc->poisson;
     require(P.n_cells > 0 && P.vertices && P.face_dof && P.n_rt > 0, "poisson: empty tables");
     ctx->n_rt = P.n_rt;
     ctx->n_pcells = P.n_cells;
     const bool factor_on_device = device_factorization_enabled();
-    // large dynamic shared memory for the level kernels: before the systems are built, their launch grids are sized by
-    // the occupancy of the kernels at their block shapes (level_grid)
-    int max_optin = 0;
-    PECS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    configure_solve_kernels(max_optin);
-
     fill_rhs_params(*ctx);
-    // host preparation of all systems at once (threads), device work in order
+    // host preparation of all systems at once (threads) -- started before anything touches the device --, device work
+    // in order
     std::future<PreparedSystem> prepared[2][2];
     for (int w = 0; w < ctx->n_domains(); ++w) {
       const pecs_domain_desc* d = w == 0 ? &desc->semiconductor : &desc->electrolyte;
@@ -1032,6 +1035,23 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     const int n_pdofs = ctx->n_pdofs();
     std::future<PreparedSystem> prepared_poisson = std::async(
         std::launch::async, [&P, n_pdofs, factor_on_device] { return prepare_poisson(P, n_pdofs, factor_on_device); });
+    // The device is touched only now, with the host preparations under way: the first context of a process pays 1.5-2 s
+    // for the CUDA context, the kernel image and the solver handles (less what pecs_device_warmup has already done).
+    PECS_CUDA(cudaSetDevice(desc->device));
+    PECS_CUDA(cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; ++k) {
+      PECS_CUDA(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+      PECS_CUDA(cudaEventCreateWithFlags(&ctx->join[k], cudaEventDisableTiming));
+      PECS_CUDA(cudaEventCreateWithFlags(&ctx->copied[k], cudaEventDisableTiming));
+      PECS_CUDA(cudaEventCreateWithFlags(&ctx->dens[k], cudaEventDisableTiming));
+    }
+    PECS_CUDA(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
+    // large dynamic shared memory for the level kernels: before the systems are built, their launch grids are sized by
+    // the occupancy of the kernels at their block shapes (level_grid)
+    int max_optin = 0;
+    PECS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    configure_solve_kernels(max_optin);
+    if (factor_on_device) warm_factor_handles();
     // on any failure below the futures' destructors wait for the host threads before desc goes away
     SetupTimer timer;
     setup_domain(*ctx, 0, desc->semiconductor, P, desc->interface_pairs, factor_on_device, prepared[0]);

@@ -11,6 +11,10 @@
 // comments); a last kernel per level packs them into the panel layout the solve kernels stream.
 #include "factor_device.cuh"
 
+#include <mutex>
+#include <string>
+#include <thread>
+
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 
@@ -281,18 +285,46 @@ struct Lane {
 struct Handles {
   Lane lane[kLanes];
   Handles() {
-    for (Lane& l : lane) {
-      PECS_CUDA(cudaStreamCreate(&l.stream)); // blocking with respect to the legacy default stream, on purpose
-      cublas_check(cublasCreate(&l.blas), "cublasCreate");
-      cusolver_check(cusolverDnCreate(&l.solver), "cusolverDnCreate");
-      cublas_check(cublasSetStream(l.blas, l.stream), "cublasSetStream");
-      cusolver_check(cusolverDnSetStream(l.solver, l.stream), "cusolverDnSetStream");
-      l.info.resize(1);
-    }
+    // every lane's handles on a thread of its own: cusolverDnCreate + cublasCreate take 0.1-0.2 s each
+    int device = 0;
+    PECS_CUDA(cudaGetDevice(&device));
+    std::string failure[kLanes];
+    std::thread maker[kLanes];
+    for (int k = 0; k < kLanes; ++k)
+      maker[k] = std::thread([this, k, device, &failure] {
+        try {
+          Lane& l = lane[k];
+          PECS_CUDA(cudaSetDevice(device));
+          PECS_CUDA(cudaStreamCreate(&l.stream)); // blocking with respect to the legacy default stream, on purpose
+          cublas_check(cublasCreate(&l.blas), "cublasCreate");
+          cusolver_check(cusolverDnCreate(&l.solver), "cusolverDnCreate");
+          cublas_check(cublasSetStream(l.blas, l.stream), "cublasSetStream");
+          cusolver_check(cusolverDnSetStream(l.solver, l.stream), "cusolverDnSetStream");
+          l.info.resize(1);
+        } catch (const std::exception& e) {
+          failure[k] = e.what();
+        }
+      });
+    for (std::thread& t : maker) t.join();
+    for (const std::string& f : failure)
+      if (!f.empty()) throw StatusError(PECS_ERR_CUDA, "factorize_device: " + f);
   }
 };
 
+// cuSOLVER / cuBLAS initialisation costs about a second: one set of handles per process and device
+Handles& handles_of_current_device() {
+  static std::mutex guard;
+  static Handles* handles_of[64] = {};
+  int device = 0;
+  PECS_CUDA(cudaGetDevice(&device));
+  std::lock_guard<std::mutex> lock(guard);
+  if (!handles_of[device & 63]) handles_of[device & 63] = new Handles();
+  return *handles_of[device & 63];
+}
+
 } // namespace
+
+void warm_factor_handles() { handles_of_current_device(); }
 
 bool device_factorization_enabled() {
   const char* e = std::getenv("PECS_B200_HOST_FACTOR");
@@ -320,12 +352,7 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& Ap, const CsrMatri
   PECS_CUDA(cudaMemset(d_fwd, 0, (size_t)std::max<int64_t>(plan.fwd_entries, 2) * sizeof(double)));
   PECS_CUDA(cudaMemset(d_bwd, 0, (size_t)std::max<int64_t>(plan.bwd_entries, 2) * sizeof(double)));
 
-  // cuSOLVER / cuBLAS initialisation costs about a second: one set of handles per process and device
-  static Handles* handles_of[64] = {};
-  int device = 0;
-  PECS_CUDA(cudaGetDevice(&device));
-  if (!handles_of[device & 63]) handles_of[device & 63] = new Handles();
-  Handles& h = *handles_of[device & 63];
+  Handles& h = handles_of_current_device();
   for (Lane& l : h.lane)
     if (l.ipiv.size() < (size_t)std::max(plan.max_np, 1)) l.ipiv.resize((size_t)std::max(plan.max_np, 1));
   // work buffers sized ONCE for the largest level: an allocation or a release per level is a device-wide

@@ -9,6 +9,8 @@ namespace pecs {
 // The device factorisation is the default; PECS_B200_HOST_FACTOR=1 selects the host reference implementation
 // (host/SparseDirect.cpp::factorize_host) for debugging -- setup only, never the per-step path.
 bool device_factorization_enabled();
+// creates the current device's cuSOLVER / cuBLAS handles of factorize_device now (about a second, once per process and device)
+void warm_factor_handles();
 
 // Fills the forward / backward tables (already allocated on the device, zero-initialised inside) of `plan`.
 void factorize_device(const SolvePlan& plan, const CsrMatrix& A, double* d_fwd, double* d_bwd);

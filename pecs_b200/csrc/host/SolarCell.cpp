@@ -433,6 +433,10 @@ void SolarCellProblem::setup_full_system_host() {
 }
 
 void SolarCellProblem::setup_full_system() {
+  // the device's one-time costs (context, kernel image, solver handles) are paid while the host builds its tables; a
+  // failure here is reported by set_solvers, which does the same work itself
+  const int warm_device = device;
+  std::future<void> warm = std::async(std::launch::async, [warm_device] { (void)pecs_device_warmup(warm_device); });
   setup_full_system_host();
   pecs::PhaseTimer timer("setup_full_system");
   // initial values first (reference SolarCell.cpp:1980-2021): a missing or truncated restart file is reported before
@@ -444,7 +448,7 @@ void SolarCellProblem::setup_full_system() {
     project_initial_conditions();
   }
   timer.lap("initial conditions");
-  set_solvers();
+  set_solvers(); // waits for what is left of the warm-up where it first needs the device, its host preparations running
   timer.lap("set_solvers (tables + pecs_ctx_create)");
   electron_hole_pair.carrier_1.push_solution();
   electron_hole_pair.carrier_2.push_solution();
