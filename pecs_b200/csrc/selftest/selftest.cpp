@@ -243,5 +243,60 @@ pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t whic
   });
 }
 
+pecs_status pecs_solarcell_selftest_prepared_hashes(pecs_solarcell* p, int32_t which, uint64_t hashes[8]) {
+  return guarded([&] {
+    if (!hashes || which < 0 || which > PECS_POISSON)
+      throw pecs::StatusError(PECS_ERR_INVALID, "selftest_prepared_hashes: bad argument");
+    SolarCellProblem& s = *p->problem;
+    auto bytes = [](const void* q, size_t n) {
+      uint64_t v = 1469598103934665603ull; // FNV-1a
+      const unsigned char* b = static_cast<const unsigned char*>(q);
+      for (size_t i = 0; i < n; ++i) v = (v ^ b[i]) * 1099511628211ull;
+      return v;
+    };
+    auto matrix = [&](const pecs::CsrMatrix& M) {
+      return bytes(M.row_ptr.data(), M.row_ptr.size() * sizeof(int)) ^ 3 * bytes(M.col.data(), M.col.size() * sizeof(int)) ^
+             5 * bytes(M.val.data(), M.val.size() * sizeof(double));
+    };
+    auto as_csr = [](const pecs::CsrMatrix& M) {
+      pecs_csr c;
+      c.n = M.n;
+      c.row_ptr = M.row_ptr.data();
+      c.col = M.col.data();
+      c.val = M.val.data();
+      return c;
+    };
+    pecs::PreparedSystem ps;
+    if (which == PECS_POISSON) {
+      pecs_poisson_desc d{};
+      const pecs::MeshTables& P = s.Poisson_triangulation.tables();
+      d.n_cells = P.n_cells;
+      d.vertices = P.vertices.data();
+      d.n_rt = s.Poisson_object.dofs.n_rt;
+      d.face_dof = s.Poisson_object.dofs.face_dof.data();
+      d.system_matrix = as_csr(s.Poisson_object.system_matrix);
+      ps = pecs::prepare_poisson(d, s.Poisson_object.system_matrix.n, true);
+    } else {
+      const bool semi = which <= 1;
+      const pecs::MeshTables& M = semi ? s.semiconductor_triangulation.tables() : s.electrolyte_triangulation.tables();
+      const ChargeCarrierSpace::CarrierPair& pair = semi ? s.electron_hole_pair : s.redox_pair;
+      pecs_domain_desc d{};
+      d.n_cells = M.n_cells;
+      d.vertices = M.vertices.data();
+      d.system_matrix[0] = as_csr(pair.carrier_1.system_matrix);
+      d.system_matrix[1] = as_csr(pair.carrier_2.system_matrix);
+      ps = pecs::prepare_carrier(d, which % 2, true);
+    }
+    hashes[0] = matrix(ps.A);
+    hashes[1] = matrix(ps.R.T1);
+    hashes[2] = matrix(ps.R.T2);
+    hashes[3] = matrix(ps.R.Ainv);
+    hashes[4] = bytes(ps.plan.perm.data(), ps.plan.perm.size() * sizeof(int));
+    hashes[5] = bytes(ps.plan.bd_index.data(), ps.plan.bd_index.size() * sizeof(int)) ^
+                3 * bytes(ps.plan.out_map.data(), ps.plan.out_map.size() * sizeof(int));
+    hashes[6] = matrix(ps.Ap);
+    hashes[7] = matrix(ps.Apt);
+  });
+}
 
 } // extern "C"

@@ -432,6 +432,13 @@ class SolarCellProblem:
         check(_lib.load_selftest().pecs_solarcell_selftest_direct_solve(self._h, which, leaf_nodes, _dp(b), _dp(x)))
         return x
 
+    def selftest_prepared_hashes(self, which):
+        """hashes of everything the host preparation of system `which` produces (tests: independent of the thread count)"""
+        import ctypes
+        h = (ctypes.c_uint64 * 8)()
+        check(_lib.load_selftest().pecs_solarcell_selftest_prepared_hashes(self._h, which, h))
+        return tuple(int(v) for v in h)
+
     # ---- post-processing ----
     def ldg_errors(self, which, time):
         e = np.zeros(2)

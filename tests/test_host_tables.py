@@ -126,8 +126,9 @@ def test_oracle_matches_golden():
 
 
 def test_ldg_matrices_do_not_depend_on_the_thread_count(tmp_path):
-    """host/LDG.cpp assembles the system matrices in per-thread chunks and compresses them in chunk order, so the
-    sums of duplicates are taken in the order of a sequential assembly whatever the number of threads: bit-identical"""
+    """host/LDG.cpp assembles the system matrices cell by cell in gather form (every cell evaluates all terms of its own
+    12 rows, in the order a sequential face loop would insert them), the cells in parallel: bit-identical whatever the
+    number of threads"""
     import subprocess
     import sys
     code = (

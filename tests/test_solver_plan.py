@@ -81,3 +81,20 @@ def test_plans_on_the_other_configurations(g, l, overrides):
         assert np.linalg.norm(A @ x - b) <= 1e-9 * np.linalg.norm(b)
     fronts = prob.plan_fronts(pecs.POISSON)
     assert (fronts[:, 1] >= 0).all() and fronts[:, 1].sum() == prob.matrix(pecs.POISSON).shape[0]
+
+
+def test_host_preparation_does_not_depend_on_the_thread_count(monkeypatch):
+    """Schur reduction, nested dissection, symbolic plan and the permuted matrices are built on several threads at setup
+    (SolverSetup.cpp: preparation_threads); every table must come out bit-identical whatever the number of threads."""
+    prob = pecs.SolarCellProblem(pecs.default_input_file(4, 1))
+    prob.setup_full_system_host()
+    try:
+        for which in (pecs.ELECTRONS, pecs.OXIDANTS, pecs.POISSON):
+            seen = {}
+            for threads in (1, 2, 3, 8):
+                monkeypatch.setenv("PECS_B200_SETUP_THREADS", str(threads))
+                seen[threads] = prob.selftest_prepared_hashes(which)
+            assert len(set(seen.values())) == 1, (which, seen)
+            assert seen[1][4] != 0 and seen[1][6] != seen[1][7]
+    finally:
+        prob.close()
