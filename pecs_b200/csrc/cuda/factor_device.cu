@@ -11,6 +11,8 @@
 // comments); a last kernel per level packs them into the panel layout the solve kernels stream.
 #include "factor_device.cuh"
 
+#include <chrono>
+#include <cstdio>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -200,28 +202,97 @@ __global__ void __launch_bounds__(256) small_front_kernel(const FactorFront* __r
   }
   // NOTE: row swaps were applied to F_PP only; F_PB rows were not swapped, which is right: P F_PP = LU-like
   // elimination acts on [F_PP | I], and B now holds F_PP^-1 exactly (no permutation left over).
-  // -H = -Inv * F_PB
-  for (int e = tid; e < np * nb; e += nt) {
-    const int i = e / nb, j = e % nb;
-    double s = 0.0;
-    for (int k = 0; k < np; ++k) s += B[(size_t)i * ldb + k] * M[(size_t)k * m + np + j];
-    B[(size_t)i * ldb + np + j] = -s;
+  // -H = -Inv F_PB, G = F_BP Inv and the Schur complement F_BB -= G F_PB follow in small_front_products_kernel.
+}
+
+// The three products of the small fronts of a level, tiled over the whole device.  (They used to be the tail of
+// small_front_kernel, one thread block per front, one dot product from global memory per thread: fine for thousands of
+// leaf fronts, but a front with 100 pivots and 1 000-1 400 boundary unknowns then kept ONE block busy for 60-90 ms:
+// levels 6-8 of a carrier tree were 220 of the 390 ms of a factorisation.)  A tile is 64 x 64 entries of the result,
+// 256 threads x (4 x 4), the operands staged through shared memory 16 columns of the inner dimension at a time.  Every
+// entry is still the fused-multiply-add chain over k = 0, 1, 2, ... of the old loops: the tables are bit-identical.
+//   stage 0: -H = -Inv F_PB (tiles first)  and  G = F_BP Inv;    stage 1: F_BB -= G F_PB
+__global__ void __launch_bounds__(256) small_front_products_kernel(const FactorFront* __restrict__ fronts,
+                                                                   const int* __restrict__ small_list, int stage, double* Fbuf,
+                                                                   double* Gs, double* Bs) {
+  const FactorFront F = fronts[small_list[blockIdx.x]];
+  const int np = F.np, nb = F.nb, m = np + nb;
+  if (nb == 0) return;
+  double* Mf = Fbuf + F.F_off; // rows 0..np-1: [. | F_PB], rows np..: [F_BP | F_BB]
+  double* Bt = Bs + F.Bs_off;  // [Inv | -H], row stride m
+  double* Gt = Gs + F.Gs_off;  // nb x np
+  const int tp = (np + 63) / 64, tb = (nb + 63) / 64;
+  // C (rows x cols) = sign * A (rows x inner, lda) * Bm (inner x cols, ldbm)  [+ C when accumulate]
+  const double *A, *Bm;
+  double* C;
+  int rows, cols, lda, ldbm, ldc, tile = (int)blockIdx.y;
+  bool negate, accumulate;
+  const int inner = np;
+  if (stage == 0) {
+    if (tile < tp * tb) { // -H
+      A = Bt, lda = m, Bm = Mf + np, ldbm = m, C = Bt + np, ldc = m;
+      rows = np, cols = nb, negate = true, accumulate = false;
+    } else if ((tile -= tp * tb) < tb * tp) { // G
+      A = Mf + (size_t)np * m, lda = m, Bm = Bt, ldbm = m, C = Gt, ldc = np;
+      rows = nb, cols = np, negate = false, accumulate = false;
+    } else {
+      return;
+    }
+  } else {
+    if (tile >= tb * tb) return;
+    A = Gt, lda = np, Bm = Mf + np, ldbm = m, C = Mf + (size_t)np * m + np, ldc = m;
+    rows = nb, cols = nb, negate = true, accumulate = true;
   }
-  // G = F_BP * Inv
-  for (int e = tid; e < nb * np; e += nt) {
-    const int i = e / np, j = e % np;
-    double s = 0.0;
-    for (int k = 0; k < np; ++k) s += M[(size_t)(np + i) * m + k] * B[(size_t)k * ldb + j];
-    G[(size_t)i * g_rs + (size_t)j * g_cs] = s;
+  const int tiles_across = (cols + 63) / 64;
+  const int i0 = (tile / tiles_across) * 64, j0 = (tile % tiles_across) * 64;
+  __shared__ double As[16][65], Bsm[16][64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < inner; k0 += 16) {
+    const int kn = min(16, inner - k0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + 256 * q;
+      {
+        const int r = e >> 4, c = e & 15; // A: 64 rows x 16 inner, the inner index fastest
+        As[c][r] = (i0 + r < rows && c < kn) ? A[(size_t)(i0 + r) * lda + k0 + c] : 0.0;
+      }
+      {
+        const int r = e >> 6, c = e & 63; // Bm: 16 inner x 64 columns
+        Bsm[r][c] = (r < kn && j0 + c < cols) ? Bm[(size_t)(k0 + r) * ldbm + j0 + c] : 0.0;
+      }
+    }
+    __syncthreads();
+    for (int k = 0; k < kn; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][4 * ty + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bsm[k][4 * tx + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // F_BB -= G * F_PB
-  for (int e = tid; e < nb * nb; e += nt) {
-    const int i = e / nb, j = e % nb;
-    double s = 0.0;
-    for (int k = 0; k < np; ++k) s += G[(size_t)i * g_rs + (size_t)k * g_cs] * M[(size_t)k * m + np + j];
-    M[(size_t)(np + i) * m + np + j] -= s;
-  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = i0 + 4 * ty + i, c = j0 + 4 * tx + j;
+      if (r < rows && c < cols) {
+        double* out = C + (size_t)r * ldc + c;
+        if (accumulate)
+          *out -= acc[i][j];
+        else
+          *out = negate ? -acc[i][j] : acc[i][j];
+      }
+    }
 }
 
 // row-major scratch operators -> panels; grid.x = front, grid.y strides over the entries
@@ -389,7 +460,11 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& Ap, const CsrMatri
   }
   std::vector<int> index_in_level(plan.fronts.size(), -1);
 
+  // PECS_B200_SETUP_TIMING=2: wall-clock per level on stderr (each level ends with a device synchronisation anyway)
+  const char* timing_env = std::getenv("PECS_B200_SETUP_TIMING");
+  const bool level_timing = timing_env && std::atoi(timing_env) >= 2;
   for (int d = (int)plan.levels.size() - 1; d >= 0; --d) {
+    const auto level_begin = std::chrono::steady_clock::now();
     const std::vector<int>& lvl = plan.levels[d];
     std::vector<FactorFront> ff(lvl.size());
     std::vector<int> small, large;
@@ -442,6 +517,18 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& Ap, const CsrMatri
       PECS_CUDA(cudaMemcpy(small_list.get(), small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice));
       small_front_kernel<<<(int)small.size(), 256>>>(d_cur.get(), small_list.get(), Fcur.get(), Gs.get(), Bs.get(),
                                                      d_error.get());
+      int tiles0 = 0, tiles1 = 0;
+      for (int k : small) {
+        const int tp = (ff[k].np + 63) / 64, tb = (ff[k].nb + 63) / 64;
+        tiles0 = std::max(tiles0, 2 * tp * tb);
+        tiles1 = std::max(tiles1, tb * tb);
+      }
+      if (tiles0 > 0) {
+        small_front_products_kernel<<<dim3((unsigned)small.size(), (unsigned)tiles0), 256>>>(d_cur.get(), small_list.get(), 0,
+                                                                                              Fcur.get(), Gs.get(), Bs.get());
+        small_front_products_kernel<<<dim3((unsigned)small.size(), (unsigned)tiles1), 256>>>(d_cur.get(), small_list.get(), 1,
+                                                                                              Fcur.get(), Gs.get(), Bs.get());
+      }
       PECS_CUDA(cudaGetLastError());
     }
     if (!large.empty()) {
@@ -457,36 +544,58 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& Ap, const CsrMatri
       for (Lane& l : h.lane)
         if (l.work.size() < (size_t)lwork_max) l.work.resize((size_t)lwork_max);
     }
-    int next_lane = 0;
-    for (int k : large) {
-      Lane& l = h.lane[next_lane];
-      next_lane = (next_lane + 1) % kLanes;
-      const FactorFront& x = ff[k];
-      const int np = x.np, nb = x.nb, m = np + nb;
-      double* M = Fcur.get() + x.F_off;
-      double* B = Bs.get() + x.Bs_off;
-      double* G = Gs.get() + x.Gs_off;
-      // col-major view of the row-major F_PP (ld m) is F_PP^T; getrf/getrs on it give (F_PP^T)^-1 = Inv^T, whose
-      // col-major storage with leading dimension ldb IS the row-major Inv with row stride ldb: it lands in the table.
-      const int ldb = m, ldf = np;
-      cusolver_check(cusolverDnDgetrf(l.solver, np, np, M, m, l.work.get(), l.ipiv.get(), l.info.get()), "getrf");
-      check_info_kernel<<<1, 1, 0, l.stream>>>(l.info.get(), d_error.get());
-      set_identity_kernel<<<(np * np + 255) / 256, 256, 0, l.stream>>>(B, np, ldb);
-      cusolver_check(cusolverDnDgetrs(l.solver, CUBLAS_OP_N, np, np, M, m, l.ipiv.get(), B, ldb, l.info.get()), "getrs");
-      if (nb > 0) {
-        const double one = 1.0, zero = 0.0, minus = -1.0;
-        // (-H)^T = -F_PB^T Inv^T : C(nb x np, ld ldb) = -A(nb x np: F_PB memory, ld m) * B(np x np: Inv memory, ld ldb)
-        cublas_check(cublasDgemm(l.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, np, np, &minus, M + np, m, B, ldb, &zero, B + np, ldb),
-                     "dgemm H");
-        // G^T = Inv^T F_BP^T : C(np x nb, ld ldf) = A(np x np: Inv memory, ld ldb) * B(np x nb: F_BP memory, ld m)
-        cublas_check(cublasDgemm(l.blas, CUBLAS_OP_N, CUBLAS_OP_N, np, nb, np, &one, B, ldb, M + (size_t)np * m, m, &zero,
-                                 G, ldf),
-                     "dgemm G");
-        // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * B(np x nb: G memory, ld ldf)
-        cublas_check(cublasDgemm(l.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, nb, np, &minus, M + np, m, G, ldf, &one,
-                                 M + (size_t)np * m + np, m),
-                     "dgemm U");
-      }
+    // Every front costs about a millisecond of HOST time (getrf alone is dozens of launches), far more than the device
+    // needs for it: the lanes are fed by one host thread each.  Ordering: the level's assembly kernels were issued to
+    // the legacy default stream before the threads start and the pack kernel is issued after they have joined, so the
+    // blocking lane streams order themselves with both.
+    if (!large.empty()) {
+      int device = 0;
+      PECS_CUDA(cudaGetDevice(&device));
+      const int n_feeders = (int)std::min<size_t>(kLanes, large.size());
+      std::exception_ptr failure[kLanes];
+      auto feed = [&](int lane_index) {
+        try {
+          PECS_CUDA(cudaSetDevice(device));
+          Lane& l = h.lane[lane_index];
+          for (size_t q = (size_t)lane_index; q < large.size(); q += (size_t)n_feeders) {
+            const int k = large[q];
+            const FactorFront& x = ff[k];
+            const int np = x.np, nb = x.nb, m = np + nb;
+            double* M = Fcur.get() + x.F_off;
+            double* B = Bs.get() + x.Bs_off;
+            double* G = Gs.get() + x.Gs_off;
+            // col-major view of the row-major F_PP (ld m) is F_PP^T; getrf/getrs on it give (F_PP^T)^-1 = Inv^T, whose
+            // col-major storage with leading dimension ldb IS the row-major Inv with row stride ldb: it lands in the table.
+            const int ldb = m, ldf = np;
+            cusolver_check(cusolverDnDgetrf(l.solver, np, np, M, m, l.work.get(), l.ipiv.get(), l.info.get()), "getrf");
+            check_info_kernel<<<1, 1, 0, l.stream>>>(l.info.get(), d_error.get());
+            set_identity_kernel<<<(np * np + 255) / 256, 256, 0, l.stream>>>(B, np, ldb);
+            cusolver_check(cusolverDnDgetrs(l.solver, CUBLAS_OP_N, np, np, M, m, l.ipiv.get(), B, ldb, l.info.get()), "getrs");
+            if (nb > 0) {
+              const double one = 1.0, zero = 0.0, minus = -1.0;
+              // (-H)^T = -F_PB^T Inv^T : C(nb x np, ld ldb) = -A(nb x np: F_PB memory, ld m) * B(np x np: Inv memory, ld ldb)
+              cublas_check(cublasDgemm(l.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, np, np, &minus, M + np, m, B, ldb, &zero, B + np, ldb),
+                           "dgemm H");
+              // G^T = Inv^T F_BP^T : C(np x nb, ld ldf) = A(np x np: Inv memory, ld ldb) * B(np x nb: F_BP memory, ld m)
+              cublas_check(cublasDgemm(l.blas, CUBLAS_OP_N, CUBLAS_OP_N, np, nb, np, &one, B, ldb, M + (size_t)np * m, m, &zero,
+                                       G, ldf),
+                           "dgemm G");
+              // U^T = F_BB^T - F_PB^T G^T : C(nb x nb, ld m) -= A(nb x np: F_PB memory, ld m) * B(np x nb: G memory, ld ldf)
+              cublas_check(cublasDgemm(l.blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, nb, np, &minus, M + np, m, G, ldf, &one,
+                                       M + (size_t)np * m + np, m),
+                           "dgemm U");
+            }
+          }
+        } catch (...) {
+          failure[lane_index] = std::current_exception();
+        }
+      };
+      std::thread feeder[kLanes];
+      for (int t = 1; t < n_feeders; ++t) feeder[t] = std::thread(feed, t);
+      feed(0);
+      for (int t = 1; t < n_feeders; ++t) feeder[t].join();
+      for (int t = 0; t < n_feeders; ++t)
+        if (failure[t]) std::rethrow_exception(failure[t]);
     }
     {
       long long max_entries = 1;
@@ -499,6 +608,16 @@ void factorize_device(const SolvePlan& plan, const CsrMatrix& Ap, const CsrMatri
     PECS_CUDA(cudaMemcpy(&herr, d_error.get(), sizeof(int), cudaMemcpyDeviceToHost));
     if (herr == 3) throw StatusError(PECS_ERR_SINGULAR, "factorize_device: singular pivot block in a small front");
     if (herr != 0) throw StatusError(PECS_ERR_INTERNAL, "factorize_device: matrix entry outside the symbolic front structure");
+    if (level_timing) {
+      int max_np = 0, max_nb = 0;
+      for (const FactorFront& x : ff) {
+        max_np = std::max(max_np, x.np);
+        max_nb = std::max(max_nb, x.nb);
+      }
+      std::fprintf(stderr, "factorize_device: level %2d: %6zu fronts (%zu by cuSOLVER), np <= %4d, nb <= %4d, %7.2f ms\n", d,
+                   ff.size(), large.size(), max_np, max_nb,
+                   1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - level_begin).count());
+    }
     // this level becomes the child level of the next one
     std::swap(Fcur, Fchild);
     std::swap(d_cur, d_child);
