@@ -80,7 +80,7 @@ def test_matrices_match_oracle(default_problem, which):
     prob, o = default_problem
     A, B = prob.matrix(which), o.matrix(which)
     assert A.nnz == B.nnz
-    assert abs(A - B).max() <= 1e-13 * abs(B).max()
+    assert abs(A - B).max() <= 1e-14 * abs(B).max()  # measured 4e-16 .. 2e-15 (VERDICT r1 item 7 asks for 1e-14)
 
 
 def test_carrier_matrix_structure(default_problem):
