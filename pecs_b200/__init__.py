@@ -7,4 +7,4 @@ C ABI of include/pecs_b200.h.  See DESIGN.md and INTEGRATION.md.
 from ._lib import PecsError, LIB_PATH, load  # noqa: F401
 from .solarcell import (SolarCellProblem, KIND_PRODUCTION, KIND_TEST_STEADY, KIND_TEST_TRANSIENT,  # noqa: F401
                         KIND_TEST_DD_POISSON, ELECTRONS, HOLES, REDUCTANTS, OXIDANTS, POISSON, PARAM_NAMES,
-                        default_input_file, device_count)
+                        default_input_file, device_count, device_warmup)

@@ -28,6 +28,11 @@ def device_count():
     return int(_lib.load().pecs_device_count())
 
 
+def device_warmup(device=0):
+    """pay a device's first-context costs now (CUDA context, kernel image, solver handles); optional, changes no result"""
+    check(_lib.load().pecs_device_warmup(int(device)))
+
+
 def default_input_file(global_refinements=4, local_refinements=1, **overrides):
     """Text of the reference's input_file.prm (reference input_file.prm:1-133) with optional overrides given as
     ``section__key=value`` (spaces in names written as single underscores), e.g. physical__applied_bias=0.1."""

@@ -95,6 +95,16 @@ def test_no_cpu_fallback():
         prob.run_test(pecs.KIND_TEST_TRANSIENT, 2)
 
 
+def test_device_warmup_without_a_device_is_a_clean_error():
+    """the optional warm-up entry reports the missing device like everything else (setup_full_system calls it on a
+    second thread and ignores its status: set_solvers reports the failure)"""
+    if pecs.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pecs.PecsError) as e:
+        pecs.device_warmup(0)
+    assert e.value.status == "PECS_ERR_NO_DEVICE"
+
+
 def test_test_initial_condition_projection():
     """host projection (collocation form) == the oracle's mass-matrix projection"""
     from helpers import make_oracle

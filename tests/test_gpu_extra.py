@@ -38,6 +38,15 @@ def test_golden_fixtures(name, g, overrides):
     prob.close()
 
 
+def test_device_warmup_is_optional_and_repeatable():
+    """pecs_device_warmup pays the first-context costs ahead of pecs_ctx_create; calling it, calling it twice or not at
+    all changes nothing; a bad ordinal is refused"""
+    pecs.device_warmup(0)
+    pecs.device_warmup(0)
+    with pytest.raises(pecs.PecsError):
+        pecs.device_warmup(pecs.device_count())
+
+
 def test_step_host_equals_step():
     """the host-buffer entry point (H2D, step, D2H) is the same arithmetic as the resident path"""
     prob = pecs.SolarCellProblem(pecs.default_input_file(3, 1))
