@@ -7,6 +7,9 @@
 #include <cstdlib>
 #include <future>
 #include <thread>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 #include "../error.hpp"
 #include "SchurReduction.hpp"
@@ -289,7 +292,11 @@ CsrMatrix copy_csr(const pecs_csr& a, int expected_n, const char* what) {
 int preparation_threads() {
   if (const char* e = std::getenv("PECS_B200_SETUP_THREADS"))
     if (std::atoi(e) > 0) return std::atoi(e);
-  const int hw = (int)std::thread::hardware_concurrency();
+  int hw = (int)std::thread::hardware_concurrency();
+#ifdef __linux__
+  cpu_set_t allowed; // a rank of a multi-GPU job is pinned to its share of the cores (sweep.pin_to_gpu_numa_node)
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) hw = std::max(1, std::min(hw, CPU_COUNT(&allowed)));
+#endif
   return std::max(1, std::min(8, hw / 4));
 }
 
