@@ -52,7 +52,11 @@ public:
 
 private:
   int n_cells_;
-  std::string points_, connectivity_, offsets_, types_;
+  // The file image.  Everything up to <PointData> (header, points, cells) depends on the mesh only: it is encoded once
+  // and stays at the head of the buffer; every write() encodes the fields behind it and hands the whole image to the
+  // operating system in one call.  One writer per mesh at a time (the output queue runs one stamp after the other).
+  mutable std::vector<char> image_;
+  size_t prefix_bytes_ = 0;
 };
 
 std::string base64_with_header(const void* data, size_t bytes);

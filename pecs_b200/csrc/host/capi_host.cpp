@@ -87,7 +87,10 @@ pecs_status pecs_solarcell_write_patches(pecs_solarcell* p, int32_t which, const
   return guarded([&] {
     if (!patches || time_step_number < 0) throw pecs::StatusError(PECS_ERR_INVALID, "write_patches: bad argument");
     SolarCellProblem& s = *p->problem;
-    const pecs::VtuMesh mesh(tria(p, which).tables());
+    if (which < 0 || which > 2) throw pecs::StatusError(PECS_ERR_INVALID, "write_patches: which must be 0..2");
+    if (!p->patch_mesh[which] || p->patch_mesh[which]->n_cells() != tria(p, which).tables().n_cells)
+      p->patch_mesh[which].reset(new pecs::VtuMesh(tria(p, which).tables()));
+    const pecs::VtuMesh& mesh = *p->patch_mesh[which];
     const std::string dir = directory && *directory ? directory : ".";
     if (which == 2)
       s.Mixed_Assembler.output_rescaled_results(mesh, patches, s.sim_params, (unsigned)time_step_number, dir);

@@ -12,6 +12,9 @@
 struct pecs_solarcell {
   ParameterSpace::ParameterHandler prm;
   std::unique_ptr<SOLARCELL::SolarCellProblem> problem;
+  // geometry of the three meshes for pecs_solarcell_write_patches, encoded at the first call (the meshes do not change
+  // after setup)
+  std::unique_ptr<pecs::VtuMesh> patch_mesh[3];
 };
 
 namespace pecs {
