@@ -25,7 +25,7 @@ pecs_status pecs_solarcell_selftest_field_patches(pecs_solarcell* p, const doubl
 pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t which, int32_t leaf_nodes, const double* b,
                                                  double* x);
 /* The host half of building system `which` (0..3 carriers, 4 Poisson) as pecs_ctx_create runs it -- Schur reduction,
- * nested dissection, symbolic plan, matrix in elimination order -- reduced to hashes: the factorised matrix, T1, T2, A^-1,
+ * nested dissection, symbolic plan, matrix in elimination order -- reduced to hashes: the factorised matrix, T1, T2, A^-1 (each with its ELL table),
  * the permutation, the boundary lists + child maps, P A P^T and its transpose.  The preparation is threaded
  * (PECS_B200_SETUP_THREADS); the CPU tests call this with different thread counts and require identical hashes. */
 pecs_status pecs_solarcell_selftest_prepared_hashes(pecs_solarcell* p, int32_t which, uint64_t hashes[8]);

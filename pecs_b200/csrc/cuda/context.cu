@@ -172,7 +172,8 @@ struct DeviceSystem {
     build(A, plan_from_layout(A, layout, leaf_nodes), factor_on_device);
   }
   void build(const CsrMatrix& A, SolvePlan&& ready_plan, bool factor_on_device, int right_hand_sides = 1,
-             const CsrMatrix* A_permuted = nullptr, const CsrMatrix* A_permuted_transposed = nullptr) {
+             const CsrMatrix* A_permuted = nullptr, const CsrMatrix* A_permuted_transposed = nullptr,
+             const HostEll* rows_in_elimination_order = nullptr) {
     SetupTimer timer;
     n = A.n;
     n_rhs = right_hand_sides;
@@ -180,7 +181,10 @@ struct DeviceSystem {
     bd_index.upload(plan.bd_index.data(), std::max<size_t>(plan.bd_index.size(), 1));
     out_map.upload(plan.out_map.data(), std::max<size_t>(plan.out_map.size(), 1));
     iperm.upload(plan.iperm);
-    matrix_rows.upload(A, &plan.iperm);
+    if (rows_in_elimination_order && rows_in_elimination_order->n == A.n)
+      matrix_rows.upload(*rows_in_elimination_order);
+    else
+      matrix_rows.upload(A, &plan.iperm);
     cbuf.resize((size_t)n_rhs * cbuf_stride());
     cbuf.zero(); // slots no child ever writes must read as zero forever
     w_in.resize((size_t)n_rhs * n);
@@ -666,15 +670,23 @@ void setup_domain(pecs_ctx& ctx, int which, const pecs_domain_desc& d, const pec
       red.active = true;
       const int n_rhs = (k == 0 && D.shared_pair) ? 2 : 1;
       D.system[k].trace_id = 2 * which + k;
-      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, n_rhs, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr);
-      red.T1.upload(ps.R.T1, &D.system[k].plan.iperm); // r~ is produced directly in elimination order
-      red.Ainv.upload(ps.R.Ainv);
-      red.T2.upload(ps.R.T2);
+      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, n_rhs, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr,
+                        &ps.ell_A);
+      if (ps.ell_T1.n > 0) {
+        red.T1.upload(ps.ell_T1);
+        red.Ainv.upload(ps.ell_Ainv);
+        red.T2.upload(ps.ell_T2);
+      } else {
+        red.T1.upload(ps.R.T1, &D.system[k].plan.iperm); // r~ is produced directly in elimination order
+        red.Ainv.upload(ps.R.Ainv);
+        red.T2.upload(ps.R.T2);
+      }
       red.rtilde.resize((size_t)n_rhs * 4 * (size_t)n);
       wait.lap("  system in all (build + reduction tables T1, Ainv, T2)");
     } else {
       if (D.shared_pair) throw StatusError(PECS_ERR_INTERNAL, "shared factorisation needs the Schur-reduced system");
-      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, 1, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr);
+      D.system[k].build(ps.A, std::move(ps.plan), factor_on_device, 1, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr,
+                        &ps.ell_A);
     }
   }
 }
@@ -1115,7 +1127,8 @@ pecs_status pecs_ctx_create(const pecs_problem_desc* desc, pecs_ctx** out) {
     {
       PreparedSystem ps = prepared_poisson.get();
       ctx->p_system.trace_id = 4;
-      ctx->p_system.build(ps.A, std::move(ps.plan), factor_on_device, 1, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr);
+      ctx->p_system.build(ps.A, std::move(ps.plan), factor_on_device, 1, ps.Ap.n ? &ps.Ap : nullptr, ps.Apt.n ? &ps.Apt : nullptr,
+                          &ps.ell_A);
     }
     timer.lap("Poisson: static data, plan, factorise, upload");
     size_t smem = ctx->p_system.max_smem_bytes();

@@ -21,6 +21,7 @@ struct DeviceEll {
   DeviceBuffer<double> val;
   // row_order (optional): ELL row i holds row (*row_order)[i] of A
   void upload(const CsrMatrix& A, const std::vector<int>* row_order = nullptr);
+  void upload(const HostEll& table); // built ahead (the preparation threads of pecs_ctx_create)
   size_t bytes() const { return col.bytes() + val.bytes(); }
 };
 

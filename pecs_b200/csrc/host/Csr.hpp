@@ -39,6 +39,17 @@ struct CsrView {
   CsrView(const CsrMatrix& A) : n(A.n), row_ptr(A.row_ptr.data()), col(A.col.data()), val(A.val.data()) {}
 };
 
+// ELL layout of a fixed matrix as the device kernels stream it (cuda/schur_kernels.cuh): slot-major, one thread per row,
+// unit stride across the rows; block == 4: a slot is one aligned group of four columns (9 B per stored entry instead of
+// 12).  Built on the host (host/EllTable.cpp) -- at setup by the preparation threads -- and uploaded as it is.
+struct HostEll {
+  int n = 0, width = 0, block = 1;
+  std::vector<int> col;    // [width][n]
+  std::vector<double> val; // [width * block][n]
+};
+// row_order (optional): ELL row i holds row (*row_order)[i] of A.  PECS_B200_ELL_SCALAR forces block = 1.
+HostEll build_ell(const CsrMatrix& A, const std::vector<int>* row_order = nullptr, int threads = 1);
+
 // Triplet accumulator; duplicates are summed in insertion order when compressed.
 class TripletList {
 public:

@@ -311,7 +311,19 @@ void permuted_copies_of(PreparedSystem& ps) {
 }
 } // namespace
 
-PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k, bool permuted_copies) {
+namespace {
+void ell_tables_of(PreparedSystem& ps) {
+  const int threads = preparation_threads();
+  ps.ell_A = build_ell(ps.A, &ps.plan.iperm, threads);
+  if (ps.reduced) {
+    ps.ell_T1 = build_ell(ps.R.T1, &ps.plan.iperm, threads); // r~ is produced directly in elimination order
+    ps.ell_Ainv = build_ell(ps.R.Ainv, nullptr, threads);
+    ps.ell_T2 = build_ell(ps.R.T2, nullptr, threads);
+  }
+}
+} // namespace
+
+PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k, bool for_device) {
   PhaseTimer timer(k == 0 ? "prepare carrier_1" : "prepare carrier_2");
   PreparedSystem ps;
   ps.present = true;
@@ -329,20 +341,24 @@ PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k, bool permuted_c
     ps.plan = plan_from_layout(ps.A, carrier_nodes(d), default_leaf_nodes(false), preparation_threads());
   }
   timer.lap("dissection and symbolic plan");
-  if (permuted_copies) permuted_copies_of(ps);
+  if (for_device) permuted_copies_of(ps);
   timer.lap("matrix in elimination order (+ transpose)");
+  if (for_device) ell_tables_of(ps);
+  timer.lap("ELL tables");
   return ps;
 }
 
-PreparedSystem prepare_poisson(const pecs_poisson_desc& P, int n_dofs, bool permuted_copies) {
+PreparedSystem prepare_poisson(const pecs_poisson_desc& P, int n_dofs, bool for_device) {
   PhaseTimer timer("prepare Poisson");
   PreparedSystem ps;
   ps.present = true;
   ps.A = copy_csr(P.system_matrix, n_dofs, "poisson: system matrix size");
   ps.plan = poisson_plan(ps.A, P, default_leaf_nodes(true));
   timer.lap("dissection and symbolic plan");
-  if (permuted_copies) permuted_copies_of(ps);
+  if (for_device) permuted_copies_of(ps);
   timer.lap("matrix in elimination order (+ transpose)");
+  if (for_device) ell_tables_of(ps);
+  timer.lap("ELL tables");
   return ps;
 }
 

@@ -56,13 +56,17 @@ struct PreparedSystem {
   CsrMatrix Ap, Apt; // P A P^T and its transpose in elimination order (only when asked for: the device factorisation)
   SchurReduction R;
   SolvePlan plan;
+  // what the device streams besides the factor tables, in its ELL layout: the rows of A in elimination order (residual
+  // of the increment form) and, for a reduced carrier system, T1 (rows in elimination order), A_qq^-1 and T2
+  HostEll ell_A, ell_T1, ell_Ainv, ell_T2;
 };
 CsrMatrix copy_csr(const pecs_csr& a, int expected_n, const char* what);
 // threads each of the concurrent preparations may use for its own loops: a quarter of the machine, at most 8
 // (PECS_B200_SETUP_THREADS overrides); no result depends on it
 int preparation_threads();
-PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k, bool permuted_copies);
-PreparedSystem prepare_poisson(const pecs_poisson_desc& P, int n_dofs, bool permuted_copies);
+// for_device: also the permuted copies of the matrix and the ELL tables
+PreparedSystem prepare_carrier(const pecs_domain_desc& d, int k, bool for_device);
+PreparedSystem prepare_poisson(const pecs_poisson_desc& P, int n_dofs, bool for_device);
 
 // PECS_B200_SETUP_TIMING=1: wall-clock phases of the one-time setup on stderr, one line per phase
 struct PhaseTimer {

@@ -287,10 +287,14 @@ pecs_status pecs_solarcell_selftest_prepared_hashes(pecs_solarcell* p, int32_t w
       d.system_matrix[1] = as_csr(pair.carrier_2.system_matrix);
       ps = pecs::prepare_carrier(d, which % 2, true);
     }
-    hashes[0] = matrix(ps.A);
-    hashes[1] = matrix(ps.R.T1);
-    hashes[2] = matrix(ps.R.T2);
-    hashes[3] = matrix(ps.R.Ainv);
+    auto ell = [&](const pecs::HostEll& E) {
+      return bytes(E.col.data(), E.col.size() * sizeof(int)) ^ 7 * bytes(E.val.data(), E.val.size() * sizeof(double)) ^
+             (uint64_t)(E.width * 8 + E.block);
+    };
+    hashes[0] = matrix(ps.A) ^ 11 * ell(ps.ell_A);
+    hashes[1] = matrix(ps.R.T1) ^ 11 * ell(ps.ell_T1);
+    hashes[2] = matrix(ps.R.T2) ^ 11 * ell(ps.ell_T2);
+    hashes[3] = matrix(ps.R.Ainv) ^ 11 * ell(ps.ell_Ainv);
     hashes[4] = bytes(ps.plan.perm.data(), ps.plan.perm.size() * sizeof(int));
     hashes[5] = bytes(ps.plan.bd_index.data(), ps.plan.bd_index.size() * sizeof(int)) ^
                 3 * bytes(ps.plan.out_map.data(), ps.plan.out_map.size() * sizeof(int));
