@@ -29,6 +29,12 @@ pecs_status pecs_solarcell_selftest_direct_solve(pecs_solarcell* p, int32_t whic
  * the permutation, the boundary lists + child maps, P A P^T and its transpose.  The preparation is threaded
  * (PECS_B200_SETUP_THREADS); the CPU tests call this with different thread counts and require identical hashes. */
 pecs_status pecs_solarcell_selftest_prepared_hashes(pecs_solarcell* p, int32_t which, uint64_t hashes[8]);
+/* The ELL layout the device streams (HostEll: slot-major, groups of four columns) against the CSR matrix it was built
+ * from: table 0..3 = S, T1, A^-1, T2 of carrier `which`; y_ell = the slot-by-slot arithmetic of the device kernel on the
+ * host table (rows of S and T1 in a scrambled order, as on the device), y_csr = the CSR product in the same row order;
+ * shape = {rows, slots per row, columns per slot}. */
+pecs_status pecs_solarcell_selftest_ell_matvec(pecs_solarcell* p, int32_t which, int32_t table, const double* x, double* y_ell,
+                                               double* y_csr, int32_t* shape);
 
 #ifdef __cplusplus
 }

@@ -111,6 +111,8 @@ SELFTEST_SIGNATURES = {
     "pecs_solarcell_selftest_field_patches": (C.c_int, [VOIDP, c_double_p, C.c_double, c_double_p]),
     "pecs_solarcell_selftest_direct_solve": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "pecs_solarcell_selftest_prepared_hashes": (C.c_int, [VOIDP, C.c_int32, C.POINTER(C.c_uint64)]),
+    "pecs_solarcell_selftest_ell_matvec": (C.c_int, [VOIDP, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p,
+                                                    C.POINTER(C.c_int32)]),
 }
 SELFTEST_LIB_PATH = os.path.join(_HERE, "lib", "libpecs_b200_selftest.so")
 

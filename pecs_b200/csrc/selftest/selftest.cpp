@@ -303,4 +303,46 @@ pecs_status pecs_solarcell_selftest_prepared_hashes(pecs_solarcell* p, int32_t w
   });
 }
 
+pecs_status pecs_solarcell_selftest_ell_matvec(pecs_solarcell* p, int32_t which, int32_t table, const double* x, double* y_ell,
+                                               double* y_csr, int32_t* shape) {
+  return guarded([&] {
+    if (!x || !y_ell || !y_csr || !shape || which < 0 || which > 3 || table < 0 || table > 3)
+      throw pecs::StatusError(PECS_ERR_INVALID, "selftest_ell_matvec: bad argument");
+    SolarCellProblem& s = *p->problem;
+    const bool semi = which <= 1;
+    const ChargeCarrierSpace::CarrierPair& pair = semi ? s.electron_hole_pair : s.redox_pair;
+    const pecs::MeshTables& mesh = semi ? s.semiconductor_triangulation.tables() : s.electrolyte_triangulation.tables();
+    const pecs::CsrMatrix& A = which % 2 == 0 ? pair.carrier_1.system_matrix : pair.carrier_2.system_matrix;
+    pecs::SchurReduction R;
+    if (!pecs::build_schur_reduction(A, mesh.n_cells, R))
+      throw pecs::StatusError(PECS_ERR_INTERNAL, "carrier (q,q) block couples cells");
+    const pecs::CsrMatrix& M = table == 0 ? R.S : table == 1 ? R.T1 : table == 2 ? R.Ainv : R.T2;
+    // rows in a scrambled order, as the device tables of S and T1 are stored in elimination order
+    std::vector<int> order(M.n);
+    for (int i = 0; i < M.n; ++i) order[i] = (int)(((long long)i * 7919) % M.n);
+    const bool reorder = table <= 1 && M.n % 7919 != 0;
+    const pecs::HostEll E = pecs::build_ell(M, reorder ? &order : nullptr, 3);
+    shape[0] = E.n;
+    shape[1] = E.width;
+    shape[2] = E.block;
+    // exactly the arithmetic of ell_row in cuda/schur_kernels.cu, slot by slot
+    for (int i = 0; i < E.n; ++i) {
+      double acc = 0.0;
+      for (int k = 0; k < E.width; ++k) {
+        const int j = E.col[(size_t)k * E.n + i];
+        if (E.block == 4) {
+          const double* v = E.val.data() + (size_t)4 * k * E.n + i;
+          acc += (v[0] * x[j] + v[E.n] * x[j + 1]) + (v[2 * (size_t)E.n] * x[j + 2] + v[3 * (size_t)E.n] * x[j + 3]);
+        } else {
+          acc += E.val[(size_t)k * E.n + i] * x[j];
+        }
+      }
+      y_ell[i] = acc;
+    }
+    std::vector<double> y(M.n);
+    M.vmult(y.data(), x);
+    for (int i = 0; i < M.n; ++i) y_csr[i] = y[reorder ? order[i] : i];
+  });
+}
+
 } // extern "C"

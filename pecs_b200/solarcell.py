@@ -444,6 +444,17 @@ class SolarCellProblem:
         check(_lib.load_selftest().pecs_solarcell_selftest_prepared_hashes(self._h, which, h))
         return tuple(int(v) for v in h)
 
+    def selftest_ell_matvec(self, which, table, x):
+        """(y from the host ELL table with the device kernel's arithmetic, y from the CSR matrix, (rows, slots, block))"""
+        import ctypes
+        n = self.n_cells(which // 2)
+        rows = (4 * n, 4 * n, 8 * n, 8 * n)[table]
+        x = np.ascontiguousarray(x, np.float64)
+        y_ell, y_csr = np.zeros(rows), np.zeros(rows)
+        shape = (ctypes.c_int32 * 3)()
+        check(_lib.load_selftest().pecs_solarcell_selftest_ell_matvec(self._h, which, table, _dp(x), _dp(y_ell), _dp(y_csr), shape))
+        return y_ell, y_csr, tuple(shape)
+
     # ---- post-processing ----
     def ldg_errors(self, which, time):
         e = np.zeros(2)

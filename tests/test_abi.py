@@ -36,7 +36,7 @@ def test_cpu_checkers_live_in_the_test_library_only():
     infrastructure -- exported by libpecs_b200_selftest.so (include/pecs_b200_selftest.h), absent from the product"""
     product = open(_lib.LIB_PATH, "rb").read()
     declared = _declared_symbols(("pecs_b200_selftest.h",))
-    assert declared == set(_lib.SELFTEST_SIGNATURES) and len(declared) == 5
+    assert declared == set(_lib.SELFTEST_SIGNATURES) and len(declared) == 6
     test_lib = _lib.load_selftest()
     for name in declared:
         assert hasattr(test_lib, name)

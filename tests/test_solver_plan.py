@@ -98,3 +98,14 @@ def test_host_preparation_does_not_depend_on_the_thread_count(monkeypatch):
             assert seen[1][4] != 0 and seen[1][6] != seen[1][7]
     finally:
         prob.close()
+
+
+@pytest.mark.parametrize("table,cols", [(0, 4), (1, 8), (2, 8), (3, 4)])
+def test_ell_tables_reproduce_the_csr_product(problem, table, cols):
+    """the ELL layout the device kernels stream (groups of four columns per slot where that is smaller) is the matrix:
+    S, T1, A^-1 and T2 of a carrier, with the kernel's own slot-by-slot arithmetic, against the CSR product"""
+    n = problem.n_cells(0)
+    x = np.random.default_rng(11 + table).standard_normal(cols * n)
+    y_ell, y_csr, (rows, width, block) = problem.selftest_ell_matvec(pecs.HOLES, table, x)
+    assert rows == y_csr.size and width > 0 and block in (1, 4)
+    assert abs(y_ell - y_csr).max() <= 1e-13 * abs(y_csr).max()
